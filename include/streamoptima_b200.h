@@ -1,0 +1,145 @@
+/*
+ * streamoptima_b200.h -- C ABI of the B200-native (sm_100a) per-block encode hot path of StreamOptima.
+ *
+ * The reference (Suyashagarw/StreamOptima) is pure Python and has no FFI layer; its boundary for this path is the
+ * Python class surface `Y_Video_codec` (Encoder.py:24, :1790, :1544).  This header declares what the two per-frame
+ * flows of that class call into once they are replaced:
+ *
+ *     Encoder.py:1582  complete_intra_flow   ->  so_encode_intra
+ *     Encoder.py:1644  complete_inter_flow   ->  so_encode_inter
+ *     Encoder.py:1790  encode() frame loop   ->  so_encode_sequence   (host buffers in / out, H2D + D2H inside)
+ *     Encoder.py:1864  reference-list FIFO   ->  so_ref_reset / so_ref_push
+ *     Encoder.py:1419  differential_encoder_frame  -> so_format_mv_frame      (host, text)
+ *     Encoder.py:1522  entropy_encoder_frame       -> so_format_residual_frame (host, text)
+ *
+ * Conventions: plain C symbols; every call returns 0 on success or a negative SO_E_* code, with a message available
+ * from so_last_error(); no exceptions or Python objects cross the ABI; frame buffers are caller-owned; a context is
+ * bound to one CUDA device and is not thread-safe (one context per GPU worker process); device work is enqueued on
+ * the caller's cudaStream_t (passed as void*) and is asynchronous unless stated otherwise.
+ *
+ * There is no CPU fallback: every entry point that computes fails with SO_E_CUDA when no sm_100 device is present.
+ */
+#ifndef STREAMOPTIMA_B200_H
+#define STREAMOPTIMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO_ABI_VERSION 1
+
+/* error codes */
+#define SO_OK          0
+#define SO_E_INVALID  -1   /* bad argument / unsupported parameter combination      */
+#define SO_E_CUDA     -2   /* CUDA runtime / driver error (message has the detail)   */
+#define SO_E_NOMEM    -3
+#define SO_E_STATE    -4   /* call sequence error (e.g. inter frame with empty ring)  */
+#define SO_E_RC       -5   /* no QP in the rate table satisfies the row budget (the reference crashes here, Encoder.py:1576) */
+
+/* so_params.flags */
+#define SO_FLAG_FME     1u   /* FMEEnable : half-pel search (Encoder.py:388, :697)     */
+#define SO_FLAG_FAST_ME 2u   /* fast_me   : 3x3 around the predictor (Encoder.py:719)  */
+#define SO_FLAG_VBS     4u   /* VBSEnable : 4-way split with RD decision (Encoder.py:512-573) */
+
+#define SO_MAX_REF 8
+
+/* Encoder parameters; mirrors the Y_Video_codec constructor (Encoder.py:24). */
+typedef struct so_params {
+    int32_t width;          /* w_pixels, multiple of block_size (Encoder.py:1382)              */
+    int32_t height;         /* h_pixels, multiple of block_size                                */
+    int32_t block_size;     /* i : 4, 8 or 16                                                  */
+    int32_t search_range;   /* r : integer-pel range; half-pel search covers +-2r (Encoder.py:1649) */
+    int32_t qp;             /* Qp (const_init_Qp); 0 .. log2(block_size)+7                      */
+    int32_t intra_dur;      /* I_Period                                                        */
+    int32_t n_ref_frames;   /* nRefFrames, 1 .. SO_MAX_REF                                     */
+    uint32_t flags;         /* SO_FLAG_*                                                       */
+    int32_t rc_flag;        /* RCFlag: 0 off, 1 row-level table RC, 2 = 1 + scene-cut re-encode */
+    int32_t parallel_mode;  /* ParallelMode 0, 1 or 2 (3 is broken in the reference)           */
+    double  lam;            /* lambda of the RD cost (Encoder.py:1158); used only with VBS     */
+    int64_t intra_thresh;   /* scene-cut threshold on quantized_sized (Encoder.py:1852)        */
+    int32_t max_batch;      /* independent units (streams / closed GOPs) encoded per launch    */
+    int32_t reserved;
+} so_params;
+
+/* Per-frame statistics written by the encode calls (device or host memory, see each call). */
+typedef struct so_frame_stats {
+    uint64_t sse;           /* sum of squared error recon vs input -> PSNR (Encoder.py:1869)   */
+    uint64_t mae_num;       /* numerator of "MAE per Frame" (Encoder.py:583); see mae_den      */
+    uint32_t mae_den;       /* average_mae = (mae_num / mae_den) / n_blocks                    */
+    uint32_t mae_inf;       /* !=0: some block had no valid candidate -> average_mae = inf (quirk Q3) */
+    uint32_t qsize;         /* quantized_sized: sum of RLE symbol counts (Encoder.py:1614,1683) */
+    uint32_t frame_type;    /* 0 intra, 1 inter (after the scene-cut decision)                 */
+} so_frame_stats;
+
+/* Output planes of one frame.  All pointers are DEVICE pointers for so_encode_intra/inter.
+ *   split  u8  [n_blocks]            0 whole block, 1 four sub-blocks (Z order)
+ *   mv     i16 [n_blocks][4][3]      P: (dx,dy,ref) in slot 0 or the four sub-block vectors; I: offset in [k][0]
+ *   levels i16 [height][width]       quantised coefficients at the pixel position of their (sub-)block
+ *   recon  u8  [height][width]       reconstructed frame
+ *   row_sizes u32 [height/block_size]  RLE symbols per block row (bits_spent_per_row, Encoder.py:1627)
+ */
+typedef struct so_frame_out {
+    uint8_t*  split;
+    int16_t*  mv;
+    int16_t*  levels;
+    uint8_t*  recon;
+    uint32_t* row_sizes;
+    so_frame_stats* stats;
+} so_frame_out;
+
+typedef struct so_ctx so_ctx;
+
+int         so_abi_version(void);
+const char* so_last_error(const so_ctx* ctx);          /* ctx may be NULL: error of the last failed create */
+int         so_device_count(void);                     /* number of visible sm_100 devices, or SO_E_CUDA  */
+
+int  so_ctx_create(so_ctx** out, const so_params* p, int device);
+void so_ctx_destroy(so_ctx* ctx);
+
+/* Row QPs for rate control (RCFlag>0): data-independent (Encoder.py:1599-1609), computed by the host wrapper and
+ * shared by every frame.  n must equal height/block_size. */
+int so_set_row_qps(so_ctx* ctx, const int32_t* qp_rows, int n);
+
+/* Reference ring (Encoder.py:1798, :1864-1867).  unit selects one of max_batch independent chains. */
+int so_ref_reset(so_ctx* ctx, int unit, void* stream);                 /* ring := [constant-128 float frame] */
+int so_ref_push(so_ctx* ctx, int unit, const uint8_t* recon_dev, void* stream);   /* FIFO append of a uint8 frame [height][width] */
+
+/* One frame of one unit; cur_dev is u8 [height][width] on the device.  Asynchronous on `stream`.
+ * so_encode_inter does NOT push the reconstruction into the ring (the caller decides, which is what makes
+ * teacher-forced parity tests possible). */
+int so_encode_intra(so_ctx* ctx, int unit, const uint8_t* cur_dev, const so_frame_out* out, void* stream);
+int so_encode_inter(so_ctx* ctx, int unit, const uint8_t* cur_dev, const so_frame_out* out, void* stream);
+
+/* Whole-sequence encode of `n_units` independent sequences of `n_frames` frames each, HOST buffers in and out
+ * (pinned or pageable).  Restates the frame loop of Encoder.py:1829-1871 including frame typing, the reference
+ * FIFO, ParallelMode 1/2 semantics and the RCFlag=2 scene-cut re-encode.  Synchronous.
+ *   frames     u8  [n_units][n_frames][height][width]
+ *   split      u8  [n_units][n_frames][n_blocks]
+ *   mv         i16 [n_units][n_frames][n_blocks][4][3]
+ *   levels     i16 [n_units][n_frames][height][width]      (may be NULL: not copied back)
+ *   recon      u8  [n_units][n_frames][height][width]      (may be NULL)
+ *   row_sizes  u32 [n_units][n_frames][height/block_size]  (may be NULL)
+ *   stats          [n_units][n_frames]
+ */
+int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames,
+                       uint8_t* split, int16_t* mv, int16_t* levels, uint8_t* recon,
+                       uint32_t* row_sizes, so_frame_stats* stats);
+
+/* Timing of the last so_encode_sequence, CUDA events on the context stream (ms): [0] whole device region,
+ * [1] motion-estimation kernels, [2] transform/quant/recon kernels, [3] number of kernel launches. */
+int so_last_timing(const so_ctx* ctx, double out[4]);
+
+/* Host-side text formatters, byte-identical to the reference's (Encoder.py:1419-1542 with canonical integers).
+ * Return the number of bytes written (excluding the terminating NUL), or the required size (negative) when cap
+ * is too small.  qp_rows may be NULL (RCFlag off). */
+int64_t so_format_mv_frame(int frame_type, const uint8_t* split, const int16_t* mv, int n_blocks, int blocks_per_row,
+                           const int32_t* qp_rows, char* dst, int64_t cap);
+int64_t so_format_residual_frame(const uint8_t* split, const int16_t* levels, int width, int height, int block_size,
+                                 char* dst, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMOPTIMA_B200_H */

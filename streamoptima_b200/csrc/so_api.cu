@@ -1,0 +1,715 @@
+// C ABI + host-side orchestration of the StreamOptima B200 encode path (see include/streamoptima_b200.h).
+// Host logic restates the frame loop of Encoder.py:1790-1898 and the two per-frame flows (:1582, :1644).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "so_kernels.cuh"
+
+#define CU(expr)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            set_err(ctx, std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+            return SO_E_CUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+static_assert(sizeof(so_params) == 64 && sizeof(so_frame_stats) == 32, "ABI struct layout (mirrored in _native.py)");
+static std::string g_create_err;
+
+struct so_ctx {
+    so_params p{};
+    int device = 0;
+    cudaStream_t stream = nullptr;          // used by so_encode_sequence
+    std::string err;
+    FrameGeom g{};
+    int nblk = 0, batch = 1;
+    size_t frame_px = 0;
+    // reference ring: [unit][slot][phase][H][pitch]
+    uint8_t* ring = nullptr;
+    size_t plane_bytes = 0, slot_stride = 0, unit_stride = 0;
+    int nslots = 0;
+    std::vector<int> list;                  // ring slots in list order (oldest first)
+    std::vector<char> slot_u8;              // slot holds a uint8 reconstruction (false: the float 128 frame)
+    std::vector<int> slot_wrap;             // wrap mode the half-pel planes of the slot were built with (-1 none)
+    // scratch
+    MeResult *me_parent = nullptr, *me_sub = nullptr;
+    int16_t* res_frame = nullptr;
+    int32_t* band = nullptr;
+    int* qp_rows_dev = nullptr;
+    std::vector<int> qp_rows;
+    // sequence buffers
+    uint8_t *sq_frames = nullptr, *sq_split = nullptr, *sq_recon = nullptr;
+    int16_t *sq_mv = nullptr, *sq_levels = nullptr;
+    uint32_t* sq_rows = nullptr;
+    so_frame_stats* sq_stats = nullptr;
+    size_t sq_cap_frames = 0;               // capacity in (unit*frame) frames
+    double timing[4] = {0, 0, 0, 0};
+    long launches = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_me, ev_tq;
+    bool timing_on = false;
+};
+
+static void set_err(so_ctx* ctx, const std::string& s) {
+    if (ctx) ctx->err = s; else g_create_err = s;
+}
+
+extern "C" int so_abi_version(void) { return SO_ABI_VERSION; }
+extern "C" const char* so_last_error(const so_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int so_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return SO_E_CUDA; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d);
+        if (major == 10) ++ok;
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------------------------
+static int upload_tables(so_ctx* ctx) {
+    double dct[340];
+    uint16_t pos[340];
+    const int sizes[4] = {2, 4, 8, 16};
+    const int offs[4] = {0, 4, 20, 84};
+    for (int s = 0; s < 4; ++s) {
+        const int N = sizes[s];
+        for (int k = 0; k < N; ++k)
+            for (int n = 0; n < N; ++n) {
+                const double sc = (k == 0) ? std::sqrt(1.0 / N) : std::sqrt(2.0 / N);
+                dct[offs[s] + k * N + n] = sc * std::cos(M_PI * k * (2 * n + 1) / (2.0 * N));
+            }
+        int p = 0;
+        for (int d = 0; d < 2 * N - 1; ++d) {
+            int i = d < N ? 0 : d - N + 1, j = d < N ? d : N - 1;
+            while (i < N && j >= 0) { pos[offs[s] + i * N + j] = (uint16_t)p++; ++i; --j; }
+        }
+    }
+    CU(cudaMemcpyToSymbol(c_dct, dct, sizeof(dct)));
+    CU(cudaMemcpyToSymbol(c_scanpos, pos, sizeof(pos)));
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+static void free_seq(so_ctx* c) {
+    cudaFree(c->sq_frames); cudaFree(c->sq_split); cudaFree(c->sq_recon); cudaFree(c->sq_mv);
+    cudaFree(c->sq_levels); cudaFree(c->sq_rows); cudaFree(c->sq_stats);
+    c->sq_frames = c->sq_split = c->sq_recon = nullptr; c->sq_mv = c->sq_levels = nullptr;
+    c->sq_rows = nullptr; c->sq_stats = nullptr; c->sq_cap_frames = 0;
+}
+
+extern "C" void so_ctx_destroy(so_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_seq(c);
+    cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->res_frame); cudaFree(c->band);
+    cudaFree(c->qp_rows_dev);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
+    so_ctx* ctx = nullptr;
+    if (!out || !p) { set_err(nullptr, "null argument"); return SO_E_INVALID; }
+    *out = nullptr;
+    auto bad = [&](const char* m) { set_err(nullptr, m); return SO_E_INVALID; };
+    if (p->block_size != 4 && p->block_size != 8 && p->block_size != 16) return bad("block_size must be 4, 8 or 16");
+    if (p->width <= 0 || p->height <= 0 || p->width % p->block_size || p->height % p->block_size)
+        return bad("width/height must be positive multiples of block_size (Encoder.py:1382)");
+    if (p->search_range < 0 || p->search_range > 16) return bad("search_range must be 0..16");
+    if (p->n_ref_frames < 1 || p->n_ref_frames > SO_MAX_REF) return bad("n_ref_frames must be 1..8");
+    if (p->qp < 0 || p->qp > 15) return bad("qp out of range");
+    if (p->parallel_mode < 0 || p->parallel_mode > 2) return bad("parallel_mode must be 0, 1 or 2 (3 is broken in the reference)");
+    if (p->rc_flag < 0 || p->rc_flag > 2) return bad("rc_flag must be 0, 1 or 2");
+    if ((p->flags & SO_FLAG_VBS) && p->block_size == 4) return bad("VBS with block_size 4 (2x2 sub-blocks) is not supported");
+    if ((p->flags & SO_FLAG_VBS) && (p->flags & SO_FLAG_FAST_ME) && p->parallel_mode != 0)
+        return bad("VBS + fast_me in ParallelMode 1/2 raises UnboundLocalError in the reference (Encoder.py:616)");
+    if (p->intra_dur < 1) return bad("intra_dur must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        set_err(nullptr, "no usable CUDA device (this library has no CPU fallback)");
+        return SO_E_CUDA;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) { set_err(nullptr, "device is not sm_100 (kernels are built for sm_100a only)"); return SO_E_CUDA; }
+
+    ctx = new so_ctx();
+    ctx->p = *p;
+    ctx->device = device;
+    ctx->batch = p->max_batch > 0 ? p->max_batch : 1;
+    FrameGeom& g = ctx->g;
+    g.W = p->width; g.H = p->height; g.bs = p->block_size;
+    g.pitch = (g.W + 15) / 16 * 16;
+    g.nbx = g.W / g.bs; g.nby = g.H / g.bs;
+    g.r = p->search_range;
+    g.fme = (p->flags & SO_FLAG_FME) ? 1 : 0;
+    g.R = g.fme ? 2 * g.r : g.r;
+    g.nref = 1;
+    ctx->nblk = g.nbx * g.nby;
+    ctx->frame_px = (size_t)g.W * g.H;
+    auto fail = [&](int code) { g_create_err = ctx->err; so_ctx_destroy(ctx); return code; };
+#define CUC(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return fail(SO_E_CUDA); } } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->nslots = p->n_ref_frames;
+    ctx->plane_bytes = (size_t)g.pitch * g.H;
+    ctx->slot_stride = ctx->plane_bytes * 4;
+    ctx->unit_stride = ctx->slot_stride * ctx->nslots;
+    CUC(cudaMalloc(&ctx->ring, ctx->unit_stride * ctx->batch));
+    CUC(cudaMemset(ctx->ring, 0, ctx->unit_stride * ctx->batch));
+    CUC(cudaMalloc(&ctx->me_parent, sizeof(MeResult) * ctx->nblk * ctx->batch));
+    CUC(cudaMalloc(&ctx->me_sub, sizeof(MeResult) * ctx->nblk * 4 * ctx->batch));
+    CUC(cudaMalloc(&ctx->res_frame, sizeof(int16_t) * ctx->frame_px * ctx->batch));
+    CUC(cudaMalloc(&ctx->band, sizeof(int32_t) * ctx->frame_px * ctx->batch));
+    CUC(cudaMalloc(&ctx->qp_rows_dev, sizeof(int) * g.nby));
+    ctx->slot_u8.assign(ctx->nslots, 0);
+    ctx->slot_wrap.assign(ctx->nslots, -1);
+    if (upload_tables(ctx) != SO_OK) return fail(SO_E_CUDA);
+    *out = ctx;
+    return SO_OK;
+}
+
+extern "C" int so_set_row_qps(so_ctx* ctx, const int32_t* qp_rows, int n) {
+    if (!ctx) return SO_E_INVALID;
+    if (!qp_rows || n != ctx->g.nby) { set_err(ctx, "qp_rows must have height/block_size entries"); return SO_E_INVALID; }
+    for (int i = 0; i < n; ++i)
+        if (qp_rows[i] < 0 || qp_rows[i] > 15) { set_err(ctx, "row qp out of range"); return SO_E_INVALID; }
+    CU(cudaSetDevice(ctx->device));
+    ctx->qp_rows.assign(qp_rows, qp_rows + n);
+    CU(cudaMemcpy(ctx->qp_rows_dev, qp_rows, sizeof(int) * n, cudaMemcpyHostToDevice));
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reference ring
+// ---------------------------------------------------------------------------------------------------------
+static uint8_t* slot_ptr(so_ctx* c, int slot) { return c->ring + (size_t)slot * c->slot_stride; }
+
+static int take_free_slot(so_ctx* c) {
+    for (int s = 0; s < c->nslots; ++s) {
+        bool used = false;
+        for (int l : c->list) used = used || (l == s);
+        if (!used) return s;
+    }
+    return -1;
+}
+
+extern "C" int so_ref_reset(so_ctx* ctx, int /*unit*/, void* stream) {
+    if (!ctx) return SO_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->list.clear();
+    const int s = 0;
+    // ref_frames = [np.ones((h, w)) * 128]  (Encoder.py:1798): a float frame -> never triggers the uint8 wrap
+    const size_t n16 = ctx->slot_stride / 16;
+    ring_fill_kernel<<<dim3((unsigned)((n16 + 255) / 256), ctx->batch), 256, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, n16, 0x80808080u);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    ctx->list.push_back(s);
+    ctx->slot_u8[s] = 0;
+    ctx->slot_wrap[s] = 0;          // planes of a constant frame are the constant in both modes
+    return SO_OK;
+}
+
+// FIFO append (Encoder.py:1864-1867); recon_dev is [batch][H][W] dense with unit stride src_unit_stride
+static int ring_push(so_ctx* ctx, const uint8_t* recon_dev, size_t src_unit_stride, int units, cudaStream_t st) {
+    if ((int)ctx->list.size() >= ctx->p.n_ref_frames) ctx->list.erase(ctx->list.begin());
+    const int s = take_free_slot(ctx);
+    if (s < 0) { set_err(ctx, "reference ring has no free slot"); return SO_E_STATE; }
+    const FrameGeom& g = ctx->g;
+    ring_store_kernel<<<dim3((g.W / 4 + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, g.pitch, recon_dev, src_unit_stride, g.W, g.H);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    ctx->list.push_back(s);
+    ctx->slot_u8[s] = 1;
+    ctx->slot_wrap[s] = -1;
+    return SO_OK;
+}
+
+extern "C" int so_ref_push(so_ctx* ctx, int /*unit*/, const uint8_t* recon_dev, void* stream) {
+    if (!ctx || !recon_dev) return SO_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    return ring_push(ctx, recon_dev, ctx->frame_px, ctx->batch, (cudaStream_t)stream);
+}
+
+static RefRing make_ring(so_ctx* c) {
+    RefRing r;
+    r.base = c->ring; r.unit_stride = c->unit_stride; r.slot_stride = c->slot_stride; r.plane_stride = c->plane_bytes;
+    for (int i = 0; i < SO_MAX_REF; ++i) r.slot[i] = i < (int)c->list.size() ? c->list[i] : 0;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------------------------------------
+template <int BS, int NDX, int G>
+static cudaError_t launch_me_full(const MeFullArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    static bool attr_done[16] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!attr_done[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(me_full_kernel<BS, NDX, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done[dev & 15] = true;
+    }
+    me_full_kernel<BS, NDX, G><<<grid, threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int BS, int NDX>
+static cudaError_t launch_me_full_g(int G, const MeFullArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    return G == 3 ? launch_me_full<BS, NDX, 3>(a, grid, threads, smem, st) : launch_me_full<BS, NDX, 1>(a, grid, threads, smem, st);
+}
+
+template <int BS>
+static cudaError_t launch_me_full_n(int NDX, int G, const MeFullArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    switch (NDX) {
+        case 1: return launch_me_full_g<BS, 1>(G, a, grid, threads, smem, st);
+        case 2: return launch_me_full_g<BS, 2>(G, a, grid, threads, smem, st);
+        case 3: return launch_me_full_g<BS, 3>(G, a, grid, threads, smem, st);
+        case 5: return launch_me_full_g<BS, 5>(G, a, grid, threads, smem, st);
+        default: return launch_me_full_g<BS, 9>(G, a, grid, threads, smem, st);
+    }
+}
+
+// exhaustive search of every bs x bs block of the frame (bs = parent or sub-block size) -> out[unit][nblocks]
+static int run_me_full(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
+                       size_t out_stride, cudaStream_t st) {
+    MeFullArgs a{};
+    a.g = ctx->g;
+    a.g.bs = bs; a.g.nbx = ctx->g.W / bs; a.g.nby = ctx->g.H / bs;
+    a.g.nref = (int)ctx->list.size();
+    a.ring = make_ring(ctx);
+    a.ring.base += (size_t)unit0 * ctx->unit_stride;
+    a.cur = cur + (size_t)unit0 * cur_stride;
+    a.cur_unit_stride = cur_stride;
+    a.out = out + (size_t)unit0 * out_stride;
+    a.out_unit_stride = out_stride;
+    a.nph = a.g.fme ? 4 : 1;
+    const int nb = a.g.nbx * a.g.nby;
+    a.items_per_unit = nb * a.g.nref * a.nph;
+    const int r = a.g.r;
+    int ndx = (2 * r) / 4 + 1;
+    const int avail[5] = {1, 2, 3, 5, 9};
+    int NDX = 9;
+    for (int v : avail) if (v >= ndx) { NDX = v; break; }
+    const int G = ((2 * r + 1) % 3 == 0 || r >= 8) ? 3 : 1;
+    a.NG = (2 * r + 1 + G - 1) / G;
+    a.rows = bs + 2 * r;
+    const int NW = NDX + bs / 4 - 1;
+    int wp16 = (NW * 4 + 15) / 16;
+    if (wp16 % 2 == 0) wp16 += 1;
+    a.wpitch = wp16 * 16;
+    // bank-conflict-free continuation across the four shifted copies: copy_stride/16 == NG*G*wpitch/16 (mod 8)
+    int cs16 = a.rows * wp16;
+    const int want = (a.NG * G * wp16) % 8;
+    while (cs16 % 8 != want) ++cs16;
+    a.copy_stride = cs16 * 16;
+    a.item_stride = 4 * a.copy_stride;
+    a.WI = 16;
+    size_t smem = (size_t)a.WI * 8 + (size_t)a.WI * bs * bs + (size_t)a.WI * a.item_stride;
+    while (smem > 200 * 1024 && a.WI > 1) { a.WI /= 2; smem = (size_t)a.WI * 8 + (size_t)a.WI * bs * bs + (size_t)a.WI * a.item_stride; }
+    const int total = a.WI * 4 * a.NG;
+    const int rounds = (total + 383) / 384;
+    int threads = ((total + rounds - 1) / rounds + 31) / 32 * 32;
+    if (threads > 384) threads = 384;
+    a.tma = 0;
+    dim3 grid((a.items_per_unit + a.WI - 1) / a.WI, units);
+    CU(cudaMemsetAsync(a.out, 0xFF, sizeof(MeResult) * out_stride * (units - 1) + sizeof(MeResult) * nb, st));
+    cudaError_t e;
+    if (bs == 16) e = launch_me_full_n<16>(NDX, G, a, grid, threads, smem, st);
+    else if (bs == 8) e = launch_me_full_n<8>(NDX, G, a, grid, threads, smem, st);
+    else e = launch_me_full_n<4>(NDX, G, a, grid, threads, smem, st);
+    if (e != cudaSuccess) { set_err(ctx, std::string("me_full_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
+    for (int u = 0; u < units; ++u) {
+        me_unpack_kernel<<<(nb + 255) / 256, 256, 0, st>>>(a.out + (size_t)u * out_stride, nb, a.g.R);
+        ctx->launches++;
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SO_OK;
+}
+
+static FlowArgs make_flow(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, const so_frame_out* o, size_t out_frames_stride,
+                          int unit0, int qp_rd) {
+    // out_frames_stride: number of frames between consecutive units in the output arrays
+    FlowArgs a{};
+    a.g = ctx->g;
+    a.g.nref = (int)ctx->list.size();
+    a.ring = make_ring(ctx);
+    a.cur = cur; a.cur_unit_stride = cur_stride;
+    a.unit0 = unit0;
+    a.vbs = (ctx->p.flags & SO_FLAG_VBS) ? 1 : 0;
+    a.fast = 0; a.chain = 0; a.nref_fast = ctx->p.n_ref_frames;
+    a.qp_final = ctx->p.qp;
+    a.qp_rd = qp_rd;
+    a.qp_rows = (ctx->p.rc_flag > 0) ? ctx->qp_rows_dev : nullptr;
+    a.lam = ctx->p.lam;
+    a.me_parent = ctx->me_parent; a.me_sub = ctx->me_sub;
+    a.me_parent_stride = ctx->nblk; a.me_sub_stride = (size_t)ctx->nblk * 4;
+    a.res_frame = ctx->res_frame; a.band = ctx->band;
+    a.split = o->split; a.mv = o->mv; a.levels = o->levels; a.recon = o->recon; a.row_sizes = o->row_sizes; a.stats = o->stats;
+    a.split_stride = out_frames_stride * ctx->nblk;
+    a.mv_stride = out_frames_stride * ctx->nblk * 12;
+    a.frame_stride = out_frames_stride * ctx->frame_px;
+    a.rows_stride = out_frames_stride * ctx->g.nby;
+    a.stats_stride = out_frames_stride;
+    return a;
+}
+
+__global__ void stats_init_kernel(so_frame_stats* st, size_t stride, uint32_t* rows, size_t rows_stride, int nrows, uint32_t den, uint32_t type) {
+    so_frame_stats* s = st + blockIdx.x * stride;
+    if (threadIdx.x == 0) { s->sse = 0; s->mae_num = 0; s->mae_den = den; s->mae_inf = 0; s->qsize = 0; s->frame_type = type; }
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) rows[blockIdx.x * rows_stride + i] = 0;
+}
+
+static inline int nthreads_px(int bs) { return bs * bs < 32 ? 32 : bs * bs; }
+
+static int check_out(so_ctx* ctx, const so_frame_out* o) {
+    if (!o || !o->split || !o->mv || !o->levels || !o->recon || !o->row_sizes || !o->stats) {
+        set_err(ctx, "so_frame_out has null members"); return SO_E_INVALID;
+    }
+    if (ctx->p.rc_flag > 0 && ctx->qp_rows.empty()) { set_err(ctx, "rc_flag > 0 requires so_set_row_qps"); return SO_E_STATE; }
+    return SO_OK;
+}
+
+static void ev_pair(so_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, cudaStream_t st, bool start) {
+    if (!ctx->timing_on) return;
+    if (start) {
+        if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+            for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+        }
+        cudaEvent_t a = ctx->ev_pool[ctx->ev_used++], b = ctx->ev_pool[ctx->ev_used++];
+        v.emplace_back(a, b);
+        cudaEventRecord(a, st);
+    } else {
+        cudaEventRecord(v.back().second, st);
+    }
+}
+
+static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, const so_frame_out* o, size_t ofs,
+                             int unit0, int units, int qp_rd, cudaStream_t st) {
+    const FrameGeom& g = ctx->g;
+    FlowArgs a = make_flow(ctx, cur, cur_stride, o, ofs, unit0, qp_rd);
+    stats_init_kernel<<<units, 64, 0, st>>>(o->stats + unit0 * a.stats_stride, a.stats_stride, o->row_sizes + unit0 * a.rows_stride,
+                                            a.rows_stride, g.nby, (uint32_t)(g.bs * g.bs), 0u);
+    dim3 grid(ctx->nblk, units);
+    const int nt = nthreads_px(g.bs);
+    const size_t ism = sizeof(unsigned) * 4 * (2 * g.r + 1);
+    ev_pair(ctx, ctx->ev_me, st, true);
+    if (g.bs == 16) intra_search_kernel<16><<<grid, 256, ism, st>>>(a);
+    else if (g.bs == 8) intra_search_kernel<8><<<grid, 128, ism, st>>>(a);
+    else intra_search_kernel<4><<<grid, 64, ism, st>>>(a);
+    ev_pair(ctx, ctx->ev_me, st, false);
+    ev_pair(ctx, ctx->ev_tq, st, true);
+    if (g.bs == 16) intra_finish_kernel<16><<<grid, nt, 0, st>>>(a);
+    else if (g.bs == 8) intra_finish_kernel<8><<<grid, nt, 0, st>>>(a);
+    else intra_finish_kernel<4><<<grid, nt, 0, st>>>(a);
+    dim3 grid2(g.nby, units);
+    if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
+    else if (g.bs == 8) intra_recon_kernel<8><<<grid2, nt, 0, st>>>(a);
+    else intra_recon_kernel<4><<<grid2, nt, 0, st>>>(a);
+    ev_pair(ctx, ctx->ev_tq, st, false);
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    return SO_OK;
+}
+
+static int ensure_planes(so_ctx* ctx, int units, cudaStream_t st) {
+    if (!ctx->g.fme) return SO_OK;
+    bool all_u8 = true;
+    for (int s : ctx->list) all_u8 = all_u8 && ctx->slot_u8[s];
+    const int wrap = all_u8 ? 1 : 0;                 // np.copy(list) is uint8 only if every frame is (quirk Q1)
+    const FrameGeom& g = ctx->g;
+    for (int s : ctx->list) {
+        if (!ctx->slot_u8[s]) continue;              // the constant frame: planes were filled at reset
+        if (ctx->slot_wrap[s] == wrap) continue;
+        halfpel_planes_kernel<<<dim3((g.W + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, ctx->plane_bytes,
+                                                                                 g.W, g.H, g.pitch, wrap);
+        ctx->launches++;
+        ctx->slot_wrap[s] = wrap;
+    }
+    CU(cudaGetLastError());
+    return SO_OK;
+}
+
+static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, const so_frame_out* o, size_t ofs,
+                             int unit0, int units, cudaStream_t st) {
+    const FrameGeom& g = ctx->g;
+    if (ctx->list.empty()) { set_err(ctx, "inter frame with an empty reference list (call so_ref_reset)"); return SO_E_STATE; }
+    int rc = ensure_planes(ctx, ctx->batch, st);
+    if (rc) return rc;
+    FlowArgs a = make_flow(ctx, cur, cur_stride, o, ofs, unit0, ctx->p.qp);
+    const bool parallel = ctx->p.parallel_mode != 0;
+    const bool use_fast = (ctx->p.flags & SO_FLAG_FAST_ME) && ctx->p.parallel_mode != 1;      // Encoder.py:641
+    a.fast = use_fast ? 1 : 0;
+    a.chain = parallel ? 0 : 1;
+    a.nref_fast = parallel ? 1 : ctx->p.n_ref_frames;                                        // Encoder.py:590
+    stats_init_kernel<<<units, 64, 0, st>>>(o->stats + unit0 * a.stats_stride, a.stats_stride, o->row_sizes + unit0 * a.rows_stride,
+                                            a.rows_stride, g.nby, use_fast ? 4u : (uint32_t)(g.bs * g.bs), 1u);
+    ctx->launches++;
+    const int nt = nthreads_px(g.bs);
+    ev_pair(ctx, ctx->ev_me, st, true);
+    if (use_fast) {
+        dim3 grid(a.chain ? 1 : ctx->nblk, units);
+        if (g.bs == 16) fast_me_kernel<16><<<grid, nt, 0, st>>>(a);
+        else if (g.bs == 8) fast_me_kernel<8><<<grid, nt, 0, st>>>(a);
+        else fast_me_kernel<4><<<grid, nt, 0, st>>>(a);
+        ctx->launches++;
+    } else {
+        rc = run_me_full(ctx, cur, cur_stride, unit0, units, g.bs, ctx->me_parent, ctx->nblk, st);
+        if (rc) return rc;
+        if (a.vbs) {
+            rc = run_me_full(ctx, cur, cur_stride, unit0, units, g.bs / 2, ctx->me_sub, (size_t)ctx->nblk * 4, st);
+            if (rc) return rc;
+        }
+    }
+    ev_pair(ctx, ctx->ev_me, st, false);
+    ev_pair(ctx, ctx->ev_tq, st, true);
+    dim3 grid(ctx->nblk, units);
+    if (g.bs == 16) inter_finish_kernel<16><<<grid, nt, 0, st>>>(a);
+    else if (g.bs == 8) inter_finish_kernel<8><<<grid, nt, 0, st>>>(a);
+    else inter_finish_kernel<4><<<grid, nt, 0, st>>>(a);
+    ev_pair(ctx, ctx->ev_tq, st, false);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SO_OK;
+}
+
+extern "C" int so_encode_intra(so_ctx* ctx, int /*unit*/, const uint8_t* cur_dev, const so_frame_out* out, void* stream) {
+    if (!ctx || !cur_dev) return SO_E_INVALID;
+    int rc = check_out(ctx, out);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    return encode_intra_impl(ctx, cur_dev, ctx->frame_px, out, 1, 0, ctx->batch, ctx->p.qp, (cudaStream_t)stream);
+}
+
+extern "C" int so_encode_inter(so_ctx* ctx, int /*unit*/, const uint8_t* cur_dev, const so_frame_out* out, void* stream) {
+    if (!ctx || !cur_dev) return SO_E_INVALID;
+    int rc = check_out(ctx, out);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    return encode_inter_impl(ctx, cur_dev, ctx->frame_px, out, 1, 0, ctx->batch, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sequence encode (frame loop of Encoder.py:1829-1871)
+// ---------------------------------------------------------------------------------------------------------
+static int ensure_seq(so_ctx* ctx, size_t nframes_total) {
+    if (nframes_total <= ctx->sq_cap_frames) return SO_OK;
+    free_seq(ctx);
+    const size_t n = nframes_total;
+    CU(cudaMalloc(&ctx->sq_frames, n * ctx->frame_px));
+    CU(cudaMalloc(&ctx->sq_recon, n * ctx->frame_px));
+    CU(cudaMalloc(&ctx->sq_levels, n * ctx->frame_px * sizeof(int16_t)));
+    CU(cudaMalloc(&ctx->sq_split, n * ctx->nblk));
+    CU(cudaMalloc(&ctx->sq_mv, n * ctx->nblk * 12 * sizeof(int16_t)));
+    CU(cudaMalloc(&ctx->sq_rows, n * ctx->g.nby * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->sq_stats, n * sizeof(so_frame_stats)));
+    ctx->sq_cap_frames = n;
+    return SO_OK;
+}
+
+extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames, uint8_t* split, int16_t* mv,
+                                  int16_t* levels, uint8_t* recon, uint32_t* row_sizes, so_frame_stats* stats) {
+    if (!ctx || !frames || !split || !mv || !stats || n_units < 1 || n_frames < 1) return SO_E_INVALID;
+    if (n_units > ctx->batch) { set_err(ctx, "n_units exceeds max_batch of the context"); return SO_E_INVALID; }
+    if (ctx->p.rc_flag > 0 && ctx->qp_rows.empty()) { set_err(ctx, "rc_flag > 0 requires so_set_row_qps"); return SO_E_STATE; }
+    CU(cudaSetDevice(ctx->device));
+    const size_t total = (size_t)n_units * n_frames;
+    int rc = ensure_seq(ctx, total);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const size_t px = ctx->frame_px;
+    const int nby = ctx->g.nby;
+    ctx->launches = 0;
+    ctx->ev_used = 0; ctx->ev_me.clear(); ctx->ev_tq.clear();
+    ctx->timing_on = true;
+    CU(cudaMemcpyAsync(ctx->sq_frames, frames, total * px, cudaMemcpyHostToDevice, st));
+    if (ctx->ev_pool.size() < 2) { for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); } }
+    cudaEvent_t ev0 = ctx->ev_pool[ctx->ev_used++], ev1 = ctx->ev_pool[ctx->ev_used++];
+    CU(cudaEventRecord(ev0, st));
+    rc = so_ref_reset(ctx, 0, st);
+    if (rc) return rc;
+    std::vector<so_frame_stats> hstats(n_units);
+    for (int f = 0; f < n_frames; ++f) {
+        so_frame_out o;
+        o.split = ctx->sq_split + (size_t)f * ctx->nblk;
+        o.mv = ctx->sq_mv + (size_t)f * ctx->nblk * 12;
+        o.levels = ctx->sq_levels + (size_t)f * px;
+        o.recon = ctx->sq_recon + (size_t)f * px;
+        o.row_sizes = ctx->sq_rows + (size_t)f * nby;
+        o.stats = ctx->sq_stats + f;
+        const uint8_t* cur = ctx->sq_frames + (size_t)f * px;
+        const size_t cur_stride = (size_t)n_frames * px;
+        const bool intra = (f % ctx->p.intra_dur == 0) && ctx->p.parallel_mode != 1;       // Encoder.py:1839
+        if (intra) {
+            rc = encode_intra_impl(ctx, cur, cur_stride, &o, n_frames, 0, n_units, ctx->p.qp, st);
+            if (rc) return rc;
+        } else {
+            if (ctx->p.parallel_mode == 1) { rc = so_ref_reset(ctx, 0, st); if (rc) return rc; }   // Encoder.py:1846
+            rc = encode_inter_impl(ctx, cur, cur_stride, &o, n_frames, 0, n_units, st);
+            if (rc) return rc;
+            if (ctx->p.rc_flag > 1) {                                                     // scene cut, Encoder.py:1851-1856
+                CU(cudaStreamSynchronize(st));
+                for (int u = 0; u < n_units; ++u)
+                    CU(cudaMemcpy(&hstats[u], o.stats + (size_t)u * n_frames, sizeof(so_frame_stats), cudaMemcpyDeviceToHost));
+                for (int u = 0; u < n_units; ++u) {
+                    if ((int64_t)hstats[u].qsize > ctx->p.intra_thresh) {
+                        // self.Qp still holds the last row QP of the inter flow: it is the RD QP of this intra pass
+                        rc = encode_intra_impl(ctx, cur, cur_stride, &o, n_frames, u, 1, ctx->qp_rows.back(), st);
+                        if (rc) return rc;
+                    }
+                }
+            }
+        }
+        if (f < n_frames - 1) {
+            rc = ring_push(ctx, o.recon, (size_t)n_frames * px, n_units, st);
+            if (rc) return rc;
+        }
+    }
+    CU(cudaEventRecord(ev1, st));
+    CU(cudaMemcpyAsync(split, ctx->sq_split, total * ctx->nblk, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(mv, ctx->sq_mv, total * ctx->nblk * 12 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if (levels) CU(cudaMemcpyAsync(levels, ctx->sq_levels, total * px * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if (recon) CU(cudaMemcpyAsync(recon, ctx->sq_recon, total * px, cudaMemcpyDeviceToHost, st));
+    if (row_sizes) CU(cudaMemcpyAsync(row_sizes, ctx->sq_rows, total * nby * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(stats, ctx->sq_stats, total * sizeof(so_frame_stats), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->timing_on = false;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    ctx->timing[0] = ms;
+    double me = 0, tq = 0;
+    for (auto& p : ctx->ev_me) { float t = 0; cudaEventElapsedTime(&t, p.first, p.second); me += t; }
+    for (auto& p : ctx->ev_tq) { float t = 0; cudaEventElapsedTime(&t, p.first, p.second); tq += t; }
+    ctx->timing[1] = me; ctx->timing[2] = tq; ctx->timing[3] = (double)ctx->launches;
+    return SO_OK;
+}
+
+extern "C" int so_last_timing(const so_ctx* ctx, double out[4]) {
+    if (!ctx || !out) return SO_E_INVALID;
+    for (int i = 0; i < 4; ++i) out[i] = ctx->timing[i];
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host text formatters (Encoder.py:1419-1542, canonical integers)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct Out {
+    char* dst; int64_t cap; int64_t n = 0;
+    void ch(char c) { if (n < cap) dst[n] = c; ++n; }
+    void str(const char* s) { while (*s) ch(*s++); }
+    void num(long v) {
+        char buf[24]; int k = 0;
+        unsigned long u = v < 0 ? (unsigned long)(-v) : (unsigned long)v;
+        do { buf[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (v < 0) ch('-');
+        while (k) ch(buf[--k]);
+    }
+    void tuple3(long a, long b, long c) { ch('('); num(a); str(", "); num(b); str(", "); num(c); ch(')'); }
+    int64_t finish() { if (n < cap) dst[n] = 0; return n < cap ? n : -(n + 1); }
+};
+}  // namespace
+
+extern "C" int64_t so_format_mv_frame(int frame_type, const uint8_t* split, const int16_t* mv, int n_blocks, int blocks_per_row,
+                                      const int32_t* qp_rows, char* dst, int64_t cap) {
+    Out o{dst, cap};
+    o.num(frame_type); o.ch('|');
+    long ref[3] = {0, 0, 0};
+    long ref_qp = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        if (b) o.ch(';');
+        if (qp_rows && b % blocks_per_row == 0) {
+            const long q = qp_rows[b / blocks_per_row];
+            o.num(q - ref_qp); o.ch('@');
+            ref_qp = q;
+        }
+        const int16_t* m = mv + (size_t)b * 12;
+        if (frame_type == 0) {
+            if (!split[b]) { o.str("0'("); o.num(m[0] - ref[0]); o.ch(')'); ref[0] = m[0]; }
+            else {
+                o.str("1'(");
+                for (int k = 0; k < 4; ++k) { if (k) o.ch(','); o.num(m[k * 3] - ref[0]); ref[0] = m[k * 3]; }
+                o.ch(')');
+            }
+        } else {
+            if (!split[b]) {
+                o.str("0'"); o.tuple3(m[0] - ref[0], m[1] - ref[1], m[2] - ref[2]);
+                ref[0] = m[0]; ref[1] = m[1]; ref[2] = m[2];
+            } else {
+                o.str("1'(");
+                for (int k = 0; k < 4; ++k) {
+                    if (k) o.ch(',');
+                    o.tuple3(m[k * 3] - ref[0], m[k * 3 + 1] - ref[1], m[k * 3 + 2] - ref[2]);
+                    ref[0] = m[k * 3]; ref[1] = m[k * 3 + 1]; ref[2] = m[k * 3 + 2];
+                }
+                o.ch(')');
+            }
+        }
+    }
+    return o.finish();
+}
+
+static void rle_block_text(Out& o, const int16_t* lev, int pitch, int n) {
+    // entropy_encoder_block (Encoder.py:1086-1131) printed as a Python list
+    o.ch('[');
+    bool first = true;
+    auto emit = [&](long v) { if (!first) o.str(", "); first = false; o.num(v); };
+    int16_t vals[256];
+    int nz = 0; long zeros = 0; int flag = 1;
+    for (int d = 0; d < 2 * n - 1; ++d) {
+        int i = d < n ? 0 : d - n + 1, j = d < n ? d : n - 1;
+        for (; i < n && j >= 0; ++i, --j) {
+            const int16_t v = lev[(size_t)i * pitch + j];
+            if (v != 0) {
+                if (flag == 0) { if (zeros) { emit(zeros); zeros = 0; } nz = 0; flag = 1; }
+                vals[nz++] = v;
+            } else {
+                if (flag == 1) { if (nz) { emit(-nz); for (int q = 0; q < nz; ++q) emit(vals[q]); nz = 0; } zeros = 0; flag = 0; }
+                ++zeros;
+            }
+        }
+    }
+    if (nz) { emit(-nz); for (int q = 0; q < nz; ++q) emit(vals[q]); }
+    if (zeros) emit(0);
+    o.ch(']');
+}
+
+extern "C" int64_t so_format_residual_frame(const uint8_t* split, const int16_t* levels, int width, int height, int block_size,
+                                            char* dst, int64_t cap) {
+    Out o{dst, cap};
+    const int nbx = width / block_size, nby = height / block_size, S = block_size / 2;
+    for (int b = 0; b < nbx * nby; ++b) {
+        if (b) o.ch(';');
+        const int x = (b % nbx) * block_size, y = (b / nbx) * block_size;
+        if (!split[b]) {
+            o.str("0'(");
+            rle_block_text(o, levels + (size_t)y * width + x, width, block_size);
+            o.ch(')');
+        } else {
+            o.str("1'(");
+            for (int k = 0; k < 4; ++k) {
+                if (k) o.ch(',');
+                rle_block_text(o, levels + (size_t)(y + (k >> 1) * S) * width + x + (k & 1) * S, width, S);
+            }
+            o.ch(')');
+        }
+    }
+    return o.finish();
+}

@@ -1,0 +1,517 @@
+// Per-frame kernels other than the exhaustive search: half-pel planes, fast ME chain, intra search, the
+// residual/transform/quant/RD/reconstruct "finish" kernels and the intra reconstruction chain.
+#pragma once
+#include "so_common.cuh"
+#include "so_me_full.cuh"
+#include "so_transform.cuh"
+#include "../../include/streamoptima_b200.h"
+
+// ------------------------------------------------------------------------------------------------------------
+// half-pel phase planes (frac_me_reference_frame, Encoder.py:388-406; appendix A1)
+// ------------------------------------------------------------------------------------------------------------
+// plane1 = ceil((a[x]+a[x+1])/2) with the uint8 wrap of the sum when `wrap` (quirk Q1), plane2 = vertical (never
+// wraps: the column pass is float), plane3 = ceil((sh[y]+sh[y+1])/4) on the (possibly wrapped) horizontal sums.
+__global__ void halfpel_planes_kernel(uint8_t* base, size_t unit_stride, size_t plane_stride, int W, int H, int pitch, int wrap) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    uint8_t* p0 = base + blockIdx.z * unit_stride;
+    const uint8_t* a0 = p0 + (size_t)y * pitch;
+    const int xn = min(x + 1, W - 1), yn = min(y + 1, H - 1);
+    const uint8_t* a1 = p0 + (size_t)yn * pitch;
+    int sh0 = a0[x] + a0[xn], sh1 = a1[x] + a1[xn];
+    if (wrap) { sh0 &= 255; sh1 &= 255; }
+    const size_t o = (size_t)y * pitch + x;
+    (p0 + plane_stride)[o] = (uint8_t)((sh0 + 1) >> 1);
+    (p0 + 2 * plane_stride)[o] = (uint8_t)((a0[x] + a1[x] + 1) >> 1);
+    (p0 + 3 * plane_stride)[o] = (uint8_t)((sh0 + sh1 + 3) >> 2);
+}
+
+// dense [H][W] frame -> pitched plane 0 of a ring slot, all units
+__global__ void ring_store_kernel(uint8_t* dst, size_t dst_unit_stride, int pitch, const uint8_t* src, size_t src_unit_stride, int W, int H) {
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x4 * 4 >= W) return;
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(src + blockIdx.z * src_unit_stride + (size_t)y * W + x4 * 4);
+    *reinterpret_cast<uint32_t*>(dst + blockIdx.z * dst_unit_stride + (size_t)y * pitch + x4 * 4) = v;
+}
+
+__global__ void ring_fill_kernel(uint8_t* dst, size_t dst_unit_stride, size_t bytes16, uint32_t v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < bytes16) reinterpret_cast<uint4*>(dst + blockIdx.y * dst_unit_stride)[i] = make_uint4(v, v, v, v);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launch arguments shared by the finish / intra / fast kernels
+// ------------------------------------------------------------------------------------------------------------
+struct FlowArgs {
+    FrameGeom g;                 // g.bs = parent block size
+    RefRing ring;
+    const uint8_t* cur;          // [unit][H][W] dense
+    size_t cur_unit_stride;
+    int unit0;                   // first unit processed by this launch (grid.y / grid.x index is added)
+    int vbs, fast, chain;        // chain: fast ME carries mvp across blocks (ParallelMode 0)
+    int nref_fast;               // refs[:nRefFrames] of fast ME (1 in ParallelMode 2, Encoder.py:590)
+    int qp_final;                // QP when no rate control
+    int qp_rd;                   // QP of self.Q during prediction (RD cost)
+    const int* qp_rows;          // device, per block row, or nullptr
+    double lam;
+    MeResult* me_parent;         // [unit][nblk]
+    MeResult* me_sub;            // [unit][4*nblk], sub grid (2nby x 2nbx)
+    size_t me_parent_stride, me_sub_stride;
+    int16_t* res_frame;          // intra: dequantised residual, [unit][H][W]
+    int32_t* band;               // intra: unclipped reconstruction, [unit][H][W]
+    // outputs (dense per unit)
+    uint8_t* split; int16_t* mv; int16_t* levels; uint8_t* recon; uint32_t* row_sizes; so_frame_stats* stats;
+    size_t split_stride, mv_stride, frame_stride, rows_stride, stats_stride;   // per-unit strides in elements
+};
+
+__device__ __forceinline__ double me_mae(const MeResult& m, int n, int fast) {
+    if (fast) return (double)m.sad;                         // quirk Q4: the "MAE" is the reference index
+    if (m.none) return __longlong_as_double(0x7FF0000000000000LL);
+    return (double)m.sad / (double)(n * n);
+}
+
+// number of RLE symbols of the block(s) whose quantised values are spread one per thread:
+// #non-zeros + #runs (oracle/codec_oracle.py:rle_length).  nzbuf: BS*BS ints of shared memory.
+template <int BS, int N>
+__device__ __forceinline__ int rle_len_cta(int level, int u, int v, int sub_index, int* nzbuf, bool active) {
+    const int p = c_scanpos[tbl_off(N) + u * N + v];
+    const int base = sub_index * N * N;
+    __syncthreads();
+    if (active) nzbuf[base + p] = (level != 0);
+    __syncthreads();
+    const bool nz = active && level != 0;
+    const bool start = active && (p == 0 || nzbuf[base + p] != nzbuf[base + p - 1]);
+    return __syncthreads_count(nz) + __syncthreads_count(start);
+}
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sbuf) {
+    // sbuf: 32 entries
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sbuf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long s = 0;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) s += sbuf[i];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// inter finish: residual -> DCT -> [VBS RD decision] -> quant -> RLE size -> dequant -> IDCT -> reconstruct
+// (inter_prediction tail Encoder.py:564-581, complete_inter_flow :1680-1697, reconstruct_frame :831-932)
+// one CTA per block, one thread per pixel (blockDim = max(BS*BS, 32); extra threads are inactive pixels)
+// ------------------------------------------------------------------------------------------------------------
+template <int BS>
+__global__ void inter_finish_kernel(const FlowArgs a) {
+    constexpr int S = BS / 2;
+    constexpr int P = BS + 1;
+    __shared__ double ws[BS * P];
+    __shared__ int nzbuf[BS * BS];
+    __shared__ unsigned long long sbuf[32];
+    const FrameGeom& g = a.g;
+    const int blk = blockIdx.x, unit = a.unit0 + blockIdx.y;
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int t = threadIdx.x;
+    const bool active = t < BS * BS;
+    const int i = active ? t % BS : 0, j = active ? t / BS : 0;
+    const int x = bx * BS, y = by * BS;
+    const int mult = g.fme ? 2 : 1;
+    RefList rl;
+    for (int r = 0; r < g.nref; ++r)
+        for (int ph = 0; ph < 4; ++ph) rl.plane[r][ph] = a.ring.plane(unit, r, ph);
+
+    const int c = a.cur[unit * a.cur_unit_stride + (size_t)(y + j) * g.W + x + i];
+    const MeResult mp = a.me_parent[unit * a.me_parent_stride + blk];
+    const PredSel selp = pred_select(g, x * mult, y * mult, mp.dx, mp.dy, BS, -1);
+    const int predp = pred_sample(g, rl, selp, mp.ref, i, j);
+    const int resp = c - predp;
+
+    if (active) ws[j * P + i] = (double)resp;
+    transform2d<BS, BS, false>(ws, t);
+    const int tcp = active ? (int)rint(ws[j * P + i]) : 0;
+
+    const bool eligible = a.vbs && bx != 0 && by != 0;
+    const int qrow = a.qp_rows ? a.qp_rows[by] : a.qp_final;
+    int split = 0;
+    double mae_blk = me_mae(mp, BS, a.fast);
+    // sub-block data (computed only when eligible; eligibility is CTA-uniform)
+    const int k = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
+    const int si = i % S, sj = j % S;
+    int tcs = 0, preds_q5 = 0;
+    MeResult ms = mp;
+    if (eligible) {
+        const int sblk = (by * 2 + (k >> 1)) * (g.nbx * 2) + bx * 2 + (k & 1);
+        ms = a.me_sub[unit * a.me_sub_stride + sblk];
+        const int xs = x + (k & 1) * S, ys = y + (k >> 1) * S;
+        const PredSel sels = pred_select(g, xs * mult, ys * mult, ms.dx, ms.dy, S, -1);
+        const int preds = pred_sample(g, rl, sels, ms.ref, si, sj);
+        const PredSel selq = pred_select(g, xs * mult, ys * mult, ms.dx, ms.dy, S, BS);     // quirk Q5
+        preds_q5 = pred_sample(g, rl, selq, ms.ref, si, sj);
+        if (active) ws[j * P + i] = (double)(c - preds);
+        transform2d<BS, S, false>(ws, t);
+        tcs = active ? (int)rint(ws[j * P + i]) : 0;
+        // RD costs with the prediction-time QP (calculate_RD_cost, Encoder.py:1133-1158)
+        const int lenp = rle_len_cta<BS, BS>(quant_rhe(tcp, q_shift(j, i, BS, a.qp_rd)), j, i, 0, nzbuf, active);
+        const int qs = a.qp_rd > 0 ? a.qp_rd - 1 : a.qp_rd;
+        const int lens = rle_len_cta<BS, S>(quant_rhe(tcs, q_shift(sj, si, S, qs)), sj, si, k, nzbuf, active);
+        // vbs_mae = (sum of the four sub MAEs) / 4, accumulated in Z order
+        double vm = 0.0;
+        for (int kk = 0; kk < 4; ++kk) {
+            const int sb = (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1);
+            vm = __dadd_rn(vm, me_mae(a.me_sub[unit * a.me_sub_stride + sb], S, a.fast));
+        }
+        vm = vm / 4.0;
+        const double rd_bs = __dadd_rn(__dmul_rn(a.lam, (double)(16 + 8 * lenp)), mae_blk);
+        const double rd_vbs = __dadd_rn(__dmul_rn(a.lam, (double)(64 + 8 * lens)), vm);
+        split = (rd_bs < rd_vbs) ? 0 : 1;
+        mae_blk = vm;
+    }
+
+    // final quantisation with the row QP (self.Q / self.Qm1 after set_Qp, Encoder.py:1668-1694)
+    int level, shift, pred_rec;
+    if (!split) {
+        shift = q_shift(j, i, BS, qrow);
+        level = quant_rhe(tcp, shift);
+        pred_rec = predp;
+    } else {
+        const int qs = qrow > 0 ? qrow - 1 : qrow;
+        shift = q_shift(sj, si, S, qs);
+        level = quant_rhe(tcs, shift);
+        pred_rec = preds_q5;
+    }
+    const int len = split ? rle_len_cta<BS, S>(level, sj, si, k, nzbuf, active)
+                          : rle_len_cta<BS, BS>(level, j, i, 0, nzbuf, active);
+    if (active) {
+        a.levels[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)level;
+        ws[j * P + i] = (double)(level * (1 << shift));          // rescale_QTC, Encoder.py:820
+    }
+    if (split) transform2d<BS, S, true>(ws, t); else transform2d<BS, BS, true>(ws, t);
+    unsigned long long se = 0;
+    if (active) {
+        const int rec = (pred_rec + (int)rint(ws[j * P + i])) & 0xFF;     // astype(np.uint8) wraps (A5)
+        a.recon[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (uint8_t)rec;
+        const int d = rec - c;
+        se = (unsigned long long)(d * d);
+    }
+    se = block_sum_u64(se, sbuf);
+    if (t == 0) {
+        a.split[unit * a.split_stride + blk] = (uint8_t)split;
+        int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
+        for (int kk = 0; kk < 4; ++kk) {
+            MeResult m = mp;
+            if (split) m = a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)];
+            const bool on = split || kk == 0;
+            mvo[kk * 3 + 0] = on ? m.dx : 0; mvo[kk * 3 + 1] = on ? m.dy : 0; mvo[kk * 3 + 2] = on ? m.ref : 0;
+        }
+        so_frame_stats* st = a.stats + unit * a.stats_stride;
+        atomicAdd(reinterpret_cast<unsigned long long*>(&st->sse), se);
+        atomicAdd(&st->qsize, (unsigned)len);
+        atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
+        // MAE numerator in units of 1/mae_den: full search 1/BS^2 (sub MAEs: sum sad_k/S^2/4 = sum sad_k/BS^2),
+        // fast ME 1/4 (values are reference indices; VBS averages four of them)
+        if (a.fast) {
+            unsigned long long n = (unsigned long long)mp.sad * 4ull;
+            if (eligible) {
+                n = 0;
+                for (int kk = 0; kk < 4; ++kk)
+                    n += a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)].sad;
+            }
+            atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), n);
+        } else {
+            unsigned long long n = mp.sad;
+            bool inf = mp.none;
+            if (eligible) {
+                n = 0; inf = false;
+                for (int kk = 0; kk < 4; ++kk) {
+                    const MeResult m = a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)];
+                    n += m.sad; inf = inf || m.none;
+                }
+            }
+            if (inf) atomicOr(&st->mae_inf, 1u); else atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), n);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fast motion estimation (fast_motion_estimation, Encoder.py:719-742; chained by inter_prediction :581)
+// grid.x = 1 (chain over all blocks) or nblk (ParallelMode 2: mvp = (0,0,0) for every block), grid.y = units
+// The four sub-blocks search the same nine offsets around the same predictor, so their SADs are the quadrant
+// partial sums of the parent's candidates; only the validity tests differ per (sub-)block.
+// ------------------------------------------------------------------------------------------------------------
+template <int BS>
+__global__ void fast_me_kernel(const FlowArgs a) {
+    constexpr int S = BS / 2;
+    __shared__ unsigned int sadq[SO_MAX_REF * 9][4];
+    __shared__ int s_mvp[3];
+    const FrameGeom& g = a.g;
+    const int unit = a.unit0 + blockIdx.y;
+    const int t = threadIdx.x;
+    const bool active = t < BS * BS;
+    const int i = active ? t % BS : 0, j = active ? t / BS : 0;
+    const int mult = g.fme ? 2 : 1;
+    const int nref = min(a.nref_fast, g.nref);
+    const int ncand = nref * 9;
+    const int nblk = g.nbx * g.nby;
+    const int b0 = a.chain ? 0 : blockIdx.x, b1 = a.chain ? nblk : blockIdx.x + 1;
+    const uint8_t* planes[SO_MAX_REF][4];
+    for (int r = 0; r < nref; ++r)
+        for (int ph = 0; ph < 4; ++ph) planes[r][ph] = a.ring.plane(unit, r, ph);
+    if (t < 3) s_mvp[t] = 0;
+    const int Wr = g.fme ? 2 * g.W - 1 : g.W, Hr = g.fme ? 2 * g.H - 1 : g.H;
+    const int q = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
+
+    for (int blk = b0; blk < b1; ++blk) {
+        const int bx = blk % g.nbx, by = blk / g.nbx;
+        const int x = bx * BS, y = by * BS;
+        for (int e = t; e < ncand * 4; e += blockDim.x) sadq[e >> 2][e & 3] = 0;
+        __syncthreads();
+        const int mvx = s_mvp[0], mvy = s_mvp[1], mvr = s_mvp[2];
+        const int c = a.cur[unit * a.cur_unit_stride + (size_t)(y + j) * g.W + x + i];
+        for (int cand = 0; cand < ncand; ++cand) {
+            const int ref = cand / 9, dx = mvx - 1 + (cand % 9) / 3, dy = mvy - 1 + (cand % 3);
+            // sample position of pixel (i,j) for this candidate; out-of-frame samples belong to invalid candidates only
+            const int X = x * mult + dx + mult * i, Y = y * mult + dy + mult * j;
+            int d = 0;
+            if (active && X >= 0 && Y >= 0 && X < Wr && Y < Hr) {
+                const int v = g.fme ? planes[ref][((Y & 1) << 1) | (X & 1)][(size_t)(Y >> 1) * g.pitch + (X >> 1)]
+                                    : planes[ref][0][(size_t)Y * g.pitch + X];
+                d = abs(c - v);
+            }
+            // quadrant sums: reduce within the warp per quadrant, then one shared atomic per warp and quadrant
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const unsigned s = __reduce_add_sync(0xFFFFFFFFu, (unsigned)((active && q == qq) ? d : 0));
+                if ((t & 31) == 0 && s) atomicAdd(&sadq[cand][qq], s);
+            }
+        }
+        __syncthreads();
+        // entity e: 0 = whole block, 1..4 = sub-blocks; scan candidates in (ref, dx, dy) order with strict <
+        const bool eligible = a.vbs && bx != 0 && by != 0;
+        if (t < 5 && (t == 0 || eligible)) {
+            const int e = t;
+            const int n = e == 0 ? BS : S;
+            const int ex = (e == 0 ? x : x + ((e - 1) & 1) * S) * mult, ey = (e == 0 ? y : y + ((e - 1) >> 1) * S) * mult;
+            unsigned best = 0xFFFFFFFFu;
+            int bdx = mvx, bdy = mvy, bref = mvr, best_ref_idx = 0;
+            for (int cand = 0; cand < ncand; ++cand) {
+                const int ref = cand / 9, dx = mvx - 1 + (cand % 9) / 3, dy = mvy - 1 + (cand % 3);
+                const int px = ex + dx, py = ey + dy;
+                const bool ok = px >= 0 && px < Wr - n && py >= 0 && py < Hr - n &&
+                                px + 2 * n >= 0 && px + 2 * n < Wr - n && py + 2 * n >= 0 && py + 2 * n < Hr - n;
+                if (!ok) continue;
+                const unsigned s = e == 0 ? sadq[cand][0] + sadq[cand][1] + sadq[cand][2] + sadq[cand][3] : sadq[cand][e - 1];
+                if (s < best) { best = s; bdx = dx; bdy = dy; bref = ref; best_ref_idx = ref; }
+            }
+            MeResult r;
+            r.dx = (int16_t)bdx; r.dy = (int16_t)bdy; r.ref = (int16_t)bref; r.none = 0; r.sad = (uint32_t)best_ref_idx;
+            if (e == 0) a.me_parent[unit * a.me_parent_stride + blk] = r;
+            else {
+                const int kk = e - 1;
+                a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)] = r;
+            }
+            if (e == 0 && a.chain) { s_mvp[0] = bdx; s_mvp[1] = bdy; s_mvp[2] = bref; }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// intra search (intra_find_best_match_horizontal, Encoder.py:1010-1045; intra_prediction :1272-1338)
+// The search frame holds ORIGINAL pixels left of the current parent block and 128 elsewhere, so all blocks are
+// independent.  Sub-block SADs are the quadrant sums of the parent's candidates (same dx, same pixels).
+// ------------------------------------------------------------------------------------------------------------
+template <int BS>
+__global__ void intra_search_kernel(const FlowArgs a) {
+    constexpr int S = BS / 2;
+    extern __shared__ unsigned int isad[];          // [(2r+1)][4]
+    const FrameGeom& g = a.g;
+    const int blk = blockIdx.x, unit = a.unit0 + blockIdx.y;
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int x = bx * BS, y = by * BS;
+    const int ncand = 2 * g.r + 1;
+    const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
+    for (int e = threadIdx.x; e < ncand * 4; e += blockDim.x) isad[e] = 0;
+    __syncthreads();
+    // task = (candidate, row): left and right half-row SADs against pixels at columns x+dx+i (128 at/after column x)
+    for (int task = threadIdx.x; task < ncand * BS; task += blockDim.x) {
+        const int cand = task / BS, j = task % BS;
+        const int dx = bx == 0 ? 0 : cand - g.r;
+        const uint8_t* row = cur + (size_t)(y + j) * g.W;
+        unsigned sl = 0, sr = 0;
+        for (int i = 0; i < BS; ++i) {
+            const int col = x + dx + i;
+            const int pv = (bx == 0 || col >= x || col < 0) ? 128 : row[col];
+            const int d = abs((int)row[x + i] - pv);
+            if (i < S) sl += d; else sr += d;
+        }
+        const int qrow = j >= S ? 2 : 0;
+        atomicAdd(&isad[cand * 4 + qrow], sl);
+        atomicAdd(&isad[cand * 4 + qrow + 1], sr);
+    }
+    __syncthreads();
+    const bool eligible = a.vbs && bx != 0 && by != 0;
+    if (threadIdx.x < 5 && (threadIdx.x == 0 || eligible)) {
+        const int e = threadIdx.x;
+        const int n = e == 0 ? BS : S;
+        const int ex = e == 0 ? x : x + ((e - 1) & 1) * S;
+        MeResult r;
+        r.dy = 0; r.ref = 0; r.none = 0;
+        if (ex == 0) {          // x == 0: mode -1, predictor 128 (only the whole block can be here: VBS needs x != 0)
+            r.dx = -1;
+            r.sad = isad[0] + isad[1] + isad[2] + isad[3];
+        } else {
+            unsigned best = 0xFFFFFFFFu; int bmv = 0; bool any = false;
+            for (int cand = 0; cand < ncand; ++cand) {
+                const int dx = cand - g.r;
+                if (!(ex + dx >= 0 && ex + dx + n <= g.W)) continue;
+                const unsigned s = e == 0 ? isad[cand * 4] + isad[cand * 4 + 1] + isad[cand * 4 + 2] + isad[cand * 4 + 3]
+                                          : isad[cand * 4 + (e - 1)];
+                if (!any || s < best) { best = s; bmv = dx; any = true; }
+                else if (s == best && abs(dx) <= abs(bmv)) bmv = dx;
+            }
+            r.dx = (int16_t)bmv; r.sad = any ? best : 0; r.none = any ? 0 : 1;
+        }
+        if (e == 0) a.me_parent[unit * a.me_parent_stride + blk] = r;
+        else {
+            const int kk = e - 1;
+            a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)] = r;
+        }
+    }
+}
+
+// intra predictor sample for a (sub-)block at column ex with offset mv, parent block starting at column xpar
+__device__ __forceinline__ int intra_pred(const uint8_t* row, int ex, int mv, int i, int xpar, bool first_col) {
+    if (first_col) return 128;
+    const int col = ex + mv + i;
+    return (col >= xpar || col < 0) ? 128 : row[col];
+}
+
+// intra finish: residual -> DCT -> [RD] -> quant -> levels, RLE size; dequant -> IDCT -> res_frame
+// (intra_prediction :1313-1327, complete_intra_flow :1611-1628, reconstruct_frame_intra :1358-1376)
+template <int BS>
+__global__ void intra_finish_kernel(const FlowArgs a) {
+    constexpr int S = BS / 2;
+    constexpr int P = BS + 1;
+    __shared__ double ws[BS * P];
+    __shared__ int nzbuf[BS * BS];
+    const FrameGeom& g = a.g;
+    const int blk = blockIdx.x, unit = a.unit0 + blockIdx.y;
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int t = threadIdx.x;
+    const bool active = t < BS * BS;
+    const int i = active ? t % BS : 0, j = active ? t / BS : 0;
+    const int x = bx * BS, y = by * BS;
+    const uint8_t* row = a.cur + unit * a.cur_unit_stride + (size_t)(y + j) * g.W;
+    const int c = row[x + i];
+    const MeResult mp = a.me_parent[unit * a.me_parent_stride + blk];
+    const int resp = c - intra_pred(row, x, mp.dx, i, x, bx == 0);
+    if (active) ws[j * P + i] = (double)resp;
+    transform2d<BS, BS, false>(ws, t);
+    const int tcp = active ? (int)rint(ws[j * P + i]) : 0;
+
+    const bool eligible = a.vbs && bx != 0 && by != 0;
+    const int qrow = a.qp_rows ? a.qp_rows[by] : a.qp_final;
+    int split = 0;
+    const int k = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
+    const int si = i % S, sj = j % S;
+    int tcs = 0;
+    unsigned long long mae_n = mp.sad;      // units of 1/BS^2
+    bool mae_inf = mp.none;
+    if (eligible) {
+        const int sb = (by * 2 + (k >> 1)) * (g.nbx * 2) + bx * 2 + (k & 1);
+        const MeResult ms = a.me_sub[unit * a.me_sub_stride + sb];
+        const int xs = x + (k & 1) * S;
+        const int ress = c - intra_pred(row, xs, ms.dx, si, x, false);
+        if (active) ws[j * P + i] = (double)ress;
+        transform2d<BS, S, false>(ws, t);
+        tcs = active ? (int)rint(ws[j * P + i]) : 0;
+        const int lenp = rle_len_cta<BS, BS>(quant_rhe(tcp, q_shift(j, i, BS, a.qp_rd)), j, i, 0, nzbuf, active);
+        const int qs = a.qp_rd > 0 ? a.qp_rd - 1 : a.qp_rd;
+        const int lens = rle_len_cta<BS, S>(quant_rhe(tcs, q_shift(sj, si, S, qs)), sj, si, k, nzbuf, active);
+        double vm = 0.0;
+        unsigned long long vn = 0; bool vinf = false;
+        for (int kk = 0; kk < 4; ++kk) {
+            const MeResult m = a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)];
+            vm = __dadd_rn(vm, me_mae(m, S, 0));
+            vn += m.sad; vinf = vinf || m.none;
+        }
+        vm = vm / 4.0;
+        const double rd_bs = __dadd_rn(__dmul_rn(a.lam, (double)(8 + 8 * lenp)), me_mae(mp, BS, 0));
+        const double rd_vbs = __dadd_rn(__dmul_rn(a.lam, (double)(32 + 8 * lens)), vm);
+        split = (rd_bs < rd_vbs) ? 0 : 1;
+        mae_n = vn; mae_inf = vinf;
+    }
+    int level, shift;
+    if (!split) { shift = q_shift(j, i, BS, qrow); level = quant_rhe(tcp, shift); }
+    else { const int qs = qrow > 0 ? qrow - 1 : qrow; shift = q_shift(sj, si, S, qs); level = quant_rhe(tcs, shift); }
+    const int len = split ? rle_len_cta<BS, S>(level, sj, si, k, nzbuf, active)
+                          : rle_len_cta<BS, BS>(level, j, i, 0, nzbuf, active);
+    if (active) {
+        a.levels[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)level;
+        ws[j * P + i] = (double)(level * (1 << shift));
+    }
+    if (split) transform2d<BS, S, true>(ws, t); else transform2d<BS, BS, true>(ws, t);
+    if (active) a.res_frame[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)rint(ws[j * P + i]);
+    if (t == 0) {
+        a.split[unit * a.split_stride + blk] = (uint8_t)split;
+        int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
+        for (int kk = 0; kk < 4; ++kk) {
+            MeResult m = mp;
+            if (split) m = a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)];
+            const bool on = split || kk == 0;
+            mvo[kk * 3 + 0] = on ? m.dx : 0; mvo[kk * 3 + 1] = 0; mvo[kk * 3 + 2] = 0;
+        }
+        so_frame_stats* st = a.stats + unit * a.stats_stride;
+        atomicAdd(&st->qsize, (unsigned)len);
+        atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
+        if (mae_inf) atomicOr(&st->mae_inf, 1u); else atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), mae_n);
+    }
+}
+
+// intra reconstruction chain (reconstruct_frame_intra, Encoder.py:1378-1414): one CTA per block row, blocks in
+// sequence; the frame being built is int32 and unclipped, the block under construction still reads as 128.
+template <int BS>
+__global__ void intra_recon_kernel(const FlowArgs a) {
+    constexpr int S = BS / 2;
+    __shared__ unsigned long long sbuf[32];
+    const FrameGeom& g = a.g;
+    const int by = blockIdx.x, unit = a.unit0 + blockIdx.y;
+    const int t = threadIdx.x;
+    const bool active = t < BS * BS;
+    const int i = active ? t % BS : 0, j = active ? t / BS : 0;
+    const int y = by * BS;
+    int32_t* band = a.band + unit * a.frame_stride + (size_t)(y + j) * g.W;
+    const int16_t* res = a.res_frame + unit * a.frame_stride + (size_t)(y + j) * g.W;
+    const uint8_t* cur = a.cur + unit * a.cur_unit_stride + (size_t)(y + j) * g.W;
+    uint8_t* rec = a.recon + unit * a.frame_stride + (size_t)(y + j) * g.W;
+    if (active) for (int xx = i; xx < g.W; xx += BS) band[xx] = 128;
+    __syncthreads();
+    unsigned long long se = 0;
+    const int k = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
+    for (int bx = 0; bx < g.nbx; ++bx) {
+        const int blk = by * g.nbx + bx, x = bx * BS;
+        const int split = a.split[unit * a.split_stride + blk];
+        const int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
+        int val = 0;
+        if (active) {
+            const int r = res[x + i];
+            if (bx == 0) val = 128 + r;
+            else if (!split) val = band[x + mvo[0] + i] + r;
+            else val = band[x + (k & 1) * S + mvo[k * 3] + (i % S)] + r;
+        }
+        __syncthreads();
+        if (active) {
+            band[x + i] = val;
+            const int rv = val & 0xFF;
+            rec[x + i] = (uint8_t)rv;
+            const int d = rv - (int)cur[x + i];
+            se += (unsigned long long)(d * d);
+        }
+        __syncthreads();
+    }
+    se = block_sum_u64(se, sbuf);
+    if (t == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&(a.stats + unit * a.stats_stride)->sse), se);
+}
