@@ -78,24 +78,17 @@ extern "C" int so_device_count(void) {
 // tables
 // ---------------------------------------------------------------------------------------------------------
 static int upload_tables(so_ctx* ctx) {
-    double dct[340];
     uint16_t pos[340];
     const int sizes[4] = {2, 4, 8, 16};
     const int offs[4] = {0, 4, 20, 84};
     for (int s = 0; s < 4; ++s) {
         const int N = sizes[s];
-        for (int k = 0; k < N; ++k)
-            for (int n = 0; n < N; ++n) {
-                const double sc = (k == 0) ? std::sqrt(1.0 / N) : std::sqrt(2.0 / N);
-                dct[offs[s] + k * N + n] = sc * std::cos(M_PI * k * (2 * n + 1) / (2.0 * N));
-            }
         int p = 0;
         for (int d = 0; d < 2 * N - 1; ++d) {
             int i = d < N ? 0 : d - N + 1, j = d < N ? d : N - 1;
             while (i < N && j >= 0) { pos[offs[s] + i * N + j] = (uint16_t)p++; ++i; --j; }
         }
     }
-    CU(cudaMemcpyToSymbol(c_dct, dct, sizeof(dct)));
     CU(cudaMemcpyToSymbol(c_scanpos, pos, sizeof(pos)));
     return SO_OK;
 }

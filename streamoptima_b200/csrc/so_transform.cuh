@@ -1,52 +1,34 @@
 // 2-D DCT / IDCT on n x n blocks held in shared memory as double, one thread per 1-D transform.
-// The reference computes dct(dct(X, axis=0, 'ortho'), axis=1, 'ortho') in float64 (Encoder.py:779-784, 810-817);
-// the transform is computed in FP64 here as well so that the only coefficients that can differ from SciPy are
-// exact rounding ties.  dct1d / idct1d are the single place that defines the arithmetic order.
+// The reference computes dct(dct(X, axis=0, 'ortho'), axis=1, 'ortho') in float64 and rounds (Encoder.py:779-784,
+// 810-817).  Exact rounding ties are common, so the 1-D transforms replay SciPy's own sequence of
+// IEEE-754 double operations; FP64 is cheap here (B200: ~64 DFMA/clk/SM, the transform is <1 % of a frame).
 #pragma once
 #include "so_common.cuh"
 
-// Orthonormal DCT-II matrices C[k][n] = s_k * cos(pi*k*(2n+1)/(2N)) for N = 2, 4, 8, 16 (host-filled, FP64).
-// layout: offset(N) = {2:0, 4:4, 8:20, 16:84}; total 340 entries.
-__constant__ double c_dct[340];
+#include "so_dct_ducc.cuh"
+
 // inverse scan position: c_scanpos[offset(N) + u*N + v] = index of (u,v) in the anti-diagonal scan of
-// entropy_encoder_block (Encoder.py:1095-1123)
+// entropy_encoder_block (Encoder.py:1095-1123); offset(N) = {2:0, 4:4, 8:20, 16:84}
 __constant__ uint16_t c_scanpos[340];
 
 __device__ __forceinline__ constexpr int tbl_off(int n) { return n == 2 ? 0 : (n == 4 ? 4 : (n == 8 ? 20 : 84)); }
 
-// in-place forward transform of N values at v[0], v[stride], ...
+// in-place 1-D transforms of N values at v[0], v[stride], ...: the generated straight-line programs that reproduce
+// scipy.fftpack.dct / idct (norm='ortho') bit for bit (tools/dctgen/gen_dct.py, tests/test_dct_model.py)
 template <int N>
 __device__ __forceinline__ void dct1d(double* v, int stride) {
-    double x[N], y[N];
-#pragma unroll
-    for (int n = 0; n < N; ++n) x[n] = v[n * stride];
-    const double* C = c_dct + tbl_off(N);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        double s = 0.0;
-#pragma unroll
-        for (int n = 0; n < N; ++n) s = fma(C[k * N + n], x[n], s);
-        y[k] = s;
-    }
-#pragma unroll
-    for (int k = 0; k < N; ++k) v[k * stride] = y[k];
+    if constexpr (N == 2) ducc_dct2_2(v, stride);
+    else if constexpr (N == 4) ducc_dct2_4(v, stride);
+    else if constexpr (N == 8) ducc_dct2_8(v, stride);
+    else ducc_dct2_16(v, stride);
 }
 
 template <int N>
 __device__ __forceinline__ void idct1d(double* v, int stride) {
-    double x[N], y[N];
-#pragma unroll
-    for (int n = 0; n < N; ++n) x[n] = v[n * stride];
-    const double* C = c_dct + tbl_off(N);
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; ++k) s = fma(C[k * N + n], x[k], s);
-        y[n] = s;
-    }
-#pragma unroll
-    for (int n = 0; n < N; ++n) v[n * stride] = y[n];
+    if constexpr (N == 2) ducc_dct3_2(v, stride);
+    else if constexpr (N == 4) ducc_dct3_4(v, stride);
+    else if constexpr (N == 8) ducc_dct3_8(v, stride);
+    else ducc_dct3_16(v, stride);
 }
 
 // 2-D transform of the BS x BS tile `ws` (row pitch BS+1 doubles) viewed as (BS/N)^2 independent N x N blocks.
