@@ -98,6 +98,9 @@ int         so_device_count(void);                     /* number of visible sm_1
 int  so_ctx_create(so_ctx** out, const so_params* p, int device);
 void so_ctx_destroy(so_ctx* ctx);
 
+/* Change Qp / const_init_Qp for subsequent encodes (set_Qp, Encoder.py:948). */
+int so_set_qp(so_ctx* ctx, int qp);
+
 /* Row QPs for rate control (RCFlag>0): data-independent (Encoder.py:1599-1609), computed by the host wrapper and
  * shared by every frame.  n must equal height/block_size. */
 int so_set_row_qps(so_ctx* ctx, const int32_t* qp_rows, int n);
@@ -127,9 +130,23 @@ int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_fr
                        uint8_t* split, int16_t* mv, int16_t* levels, uint8_t* recon,
                        uint32_t* row_sizes, so_frame_stats* stats);
 
-/* Timing of the last so_encode_sequence, CUDA events on the context stream (ms): [0] whole device region,
- * [1] motion-estimation kernels, [2] transform/quant/recon kernels, [3] number of kernel launches. */
-int so_last_timing(const so_ctx* ctx, double out[4]);
+/* The three stages of so_encode_sequence, separately callable (bench.py times so_seq_run alone with the inputs
+ * already resident in HBM, and the whole so_encode_sequence for the end-to-end figure):
+ *   so_seq_upload   H2D copy of the frames, asynchronous on the context stream
+ *   so_seq_run      the frame loop; outputs stay on the device; asynchronous unless rc_flag == 2
+ *   so_seq_download D2H copy of the requested outputs + stream synchronise
+ *   so_seq_sync     stream synchronise only */
+int so_seq_upload(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames);
+int so_seq_run(so_ctx* ctx);
+int so_seq_download(so_ctx* ctx, uint8_t* split, int16_t* mv, int16_t* levels, uint8_t* recon,
+                    uint32_t* row_sizes, so_frame_stats* stats);
+int so_seq_sync(so_ctx* ctx);
+
+/* Timing of the last so_seq_run, CUDA events on the context stream (ms): [0] whole device region, [1] motion-search
+ * kernels only (exhaustive search: the me_full_kernel launches; fast ME: the chain kernel; intra frames: intra search),
+ * [2] transform/quant/recon kernels, [3] number of kernel launches.  Waits for the run to finish. */
+int so_last_timing(so_ctx* ctx, double out[4]);
+int so_last_me_launches(so_ctx* ctx);    /* number of launches covered by timing [1] */
 
 /* Host-side text formatters, byte-identical to the reference's (Encoder.py:1419-1542 with canonical integers).
  * Return the number of bytes written (excluding the terminating NUL), or the required size (negative) when cap

@@ -192,6 +192,7 @@ class Y_Video_codec:
     def _context(self, block_size, search_range, intra_dur, max_batch=1):
         key = (block_size, search_range, intra_dur, max_batch, self.device)
         if self._ctx is not None and self._ctx_key == key:
+            self._ctx.set_qp(self.const_init_Qp)
             return self._ctx
         if self._ctx is not None:
             self._ctx.close()
@@ -226,24 +227,28 @@ class Y_Video_codec:
             raise ValueError("frame dimensions must be multiples of the block size (Encoder.py:1382)")
         ctx = self._context(block_size, search_range, intra_dur, max_batch=U)
         nblk, rows = ctx.nblk, ctx.rows
-        t_in, a_in = _pinned_empty((U, F, H, W), np.uint8)
+        # pinned staging buffers are cached per shape: cudaHostAlloc of GBs costs more than the encode itself.
+        # NOTE the returned arrays are views of these buffers and are overwritten by the next call.
+        key = (U, F, H, W, nblk, rows)
+        if getattr(self, "_pin_key", None) != key:
+            self._pin = dict(inp=_pinned_empty((U, F, H, W), np.uint8), split=_pinned_empty((U, F, nblk), np.uint8),
+                             mv=_pinned_empty((U, F, nblk, 4, 3), np.int16), rows=_pinned_empty((U, F, rows), np.uint32))
+            self._pin_key = key
+        if want_levels and "lev" not in self._pin:
+            self._pin["lev"] = _pinned_empty((U, F, H, W), np.int16)
+        if want_recon and "rec" not in self._pin:
+            self._pin["rec"] = _pinned_empty((U, F, H, W), np.uint8)
+        a_in = self._pin["inp"][1]
         np.copyto(a_in, arr)
-        t_split, split = _pinned_empty((U, F, nblk), np.uint8)
-        t_mv, mv = _pinned_empty((U, F, nblk, 4, 3), np.int16)
-        t_rows, row_sizes = _pinned_empty((U, F, rows), np.uint32)
-        levels = recon = None
-        t_lev = t_rec = None
-        if want_levels:
-            t_lev, levels = _pinned_empty((U, F, H, W), np.int16)
-        if want_recon:
-            t_rec, recon = _pinned_empty((U, F, H, W), np.uint8)
+        split, mv, row_sizes = self._pin["split"][1], self._pin["mv"][1], self._pin["rows"][1]
+        levels = self._pin["lev"][1] if want_levels else None
+        recon = self._pin["rec"][1] if want_recon else None
         stats = np.zeros((U, F), dtype=_native.STATS_DTYPE)
         rc = ctx.lib.so_encode_sequence(ctx.handle, a_in.ctypes.data, U, F, split.ctypes.data, mv.ctypes.data,
                                         levels.ctypes.data if want_levels else None,
                                         recon.ctypes.data if want_recon else None, row_sizes.ctypes.data, stats.ctypes.data)
         _native.check(ctx.handle, rc)
         self.last_timing = ctx.last_timing()
-        self._keepalive = (t_in, t_split, t_mv, t_rows, t_lev, t_rec)
         return dict(split=split, mv=mv, levels=levels, recon=recon, row_sizes=row_sizes, stats=stats,
                     frame_types=stats["frame_type"].astype(np.uint8))
 

@@ -42,8 +42,9 @@ STATS_DTYPE = [("sse", "<u8"), ("mae_num", "<u8"), ("mae_den", "<u4"), ("mae_inf
                ("frame_type", "<u4")]
 
 # every symbol declared in include/streamoptima_b200.h
-EXPORTS = ["so_abi_version", "so_last_error", "so_device_count", "so_ctx_create", "so_ctx_destroy", "so_set_row_qps",
-           "so_ref_reset", "so_ref_push", "so_encode_intra", "so_encode_inter", "so_encode_sequence", "so_last_timing",
+EXPORTS = ["so_abi_version", "so_last_error", "so_device_count", "so_ctx_create", "so_ctx_destroy", "so_set_qp", "so_set_row_qps",
+           "so_ref_reset", "so_ref_push", "so_encode_intra", "so_encode_inter", "so_encode_sequence", "so_seq_upload", "so_seq_run", "so_seq_download", "so_seq_sync",
+           "so_last_timing", "so_last_me_launches",
            "so_format_mv_frame", "so_format_residual_frame"]
 
 _lib = None
@@ -70,13 +71,19 @@ def load():
     lib.so_ctx_create.argtypes = [C.POINTER(vp), C.POINTER(so_params), i32]
     lib.so_ctx_destroy.argtypes = [vp]
     lib.so_ctx_destroy.restype = None
+    lib.so_set_qp.argtypes = [vp, i32]
     lib.so_set_row_qps.argtypes = [vp, C.POINTER(C.c_int32), i32]
     lib.so_ref_reset.argtypes = [vp, i32, vp]
     lib.so_ref_push.argtypes = [vp, i32, vp, vp]
     lib.so_encode_intra.argtypes = [vp, i32, vp, C.POINTER(so_frame_out), vp]
     lib.so_encode_inter.argtypes = [vp, i32, vp, C.POINTER(so_frame_out), vp]
     lib.so_encode_sequence.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.so_seq_upload.argtypes = [vp, vp, i32, i32]
+    lib.so_seq_run.argtypes = [vp]
+    lib.so_seq_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.so_seq_sync.argtypes = [vp]
     lib.so_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.so_last_me_launches.argtypes = [vp]
     lib.so_format_mv_frame.restype = i64
     lib.so_format_mv_frame.argtypes = [i32, vp, vp, i32, i32, vp, C.c_char_p, i64]
     lib.so_format_residual_frame.restype = i64
@@ -124,6 +131,9 @@ class Context:
 
     __del__ = close
 
+    def set_qp(self, qp):
+        check(self.handle, self.lib.so_set_qp(self.handle, int(qp)))
+
     def set_row_qps(self, qps):
         arr = (C.c_int32 * len(qps))(*[int(q) for q in qps])
         check(self.handle, self.lib.so_set_row_qps(self.handle, arr, len(qps)))
@@ -131,4 +141,5 @@ class Context:
     def last_timing(self):
         out = (C.c_double * 4)()
         check(self.handle, self.lib.so_last_timing(self.handle, out))
-        return dict(device_ms=out[0], me_ms=out[1], tq_ms=out[2], launches=int(out[3]))
+        return dict(device_ms=out[0], me_ms=out[1], tq_ms=out[2], launches=int(out[3]),
+                    me_launches=int(self.lib.so_last_me_launches(self.handle)))

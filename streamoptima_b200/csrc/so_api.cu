@@ -47,7 +47,10 @@ struct so_ctx {
     uint32_t* sq_rows = nullptr;
     so_frame_stats* sq_stats = nullptr;
     size_t sq_cap_frames = 0;               // capacity in (unit*frame) frames
-    double timing[4] = {0, 0, 0, 0};
+    double timing[5] = {0, 0, 0, 0, 0};
+    bool timing_pending = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sq_units = 0, sq_nframes = 0;
     long launches = 0;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -177,6 +180,14 @@ extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
     return SO_OK;
 }
 
+// set_Qp for the whole sequence (Encoder.py:948): changes const_init_Qp of subsequent encodes
+extern "C" int so_set_qp(so_ctx* ctx, int qp) {
+    if (!ctx) return SO_E_INVALID;
+    if (qp < 0 || qp > 15) { set_err(ctx, "qp out of range"); return SO_E_INVALID; }
+    ctx->p.qp = qp;
+    return SO_OK;
+}
+
 extern "C" int so_set_row_qps(so_ctx* ctx, const int32_t* qp_rows, int n) {
     if (!ctx) return SO_E_INVALID;
     if (!qp_rows || n != ctx->g.nby) { set_err(ctx, "qp_rows must have height/block_size entries"); return SO_E_INVALID; }
@@ -245,6 +256,20 @@ static RefRing make_ring(so_ctx* c) {
     r.base = c->ring; r.unit_stride = c->unit_stride; r.slot_stride = c->slot_stride; r.plane_stride = c->plane_bytes;
     for (int i = 0; i < SO_MAX_REF; ++i) r.slot[i] = i < (int)c->list.size() ? c->list[i] : 0;
     return r;
+}
+
+static void ev_pair(so_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, cudaStream_t st, bool start) {
+    if (!ctx->timing_on) return;
+    if (start) {
+        if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+            for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+        }
+        cudaEvent_t a = ctx->ev_pool[ctx->ev_used++], b = ctx->ev_pool[ctx->ev_used++];
+        v.emplace_back(a, b);
+        cudaEventRecord(a, st);
+    } else {
+        cudaEventRecord(v.back().second, st);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -324,9 +349,11 @@ static int run_me_full(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
     dim3 grid((a.items_per_unit + a.WI - 1) / a.WI, units);
     CU(cudaMemsetAsync(a.out, 0xFF, sizeof(MeResult) * out_stride * (units - 1) + sizeof(MeResult) * nb, st));
     cudaError_t e;
+    ev_pair(ctx, ctx->ev_me, st, true);
     if (bs == 16) e = launch_me_full_n<16>(NDX, G, a, grid, threads, smem, st);
     else if (bs == 8) e = launch_me_full_n<8>(NDX, G, a, grid, threads, smem, st);
     else e = launch_me_full_n<4>(NDX, G, a, grid, threads, smem, st);
+    ev_pair(ctx, ctx->ev_me, st, false);
     if (e != cudaSuccess) { set_err(ctx, std::string("me_full_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
     for (int u = 0; u < units; ++u) {
         me_unpack_kernel<<<(nb + 255) / 256, 256, 0, st>>>(a.out + (size_t)u * out_stride, nb, a.g.R);
@@ -378,20 +405,6 @@ static int check_out(so_ctx* ctx, const so_frame_out* o) {
     }
     if (ctx->p.rc_flag > 0 && ctx->qp_rows.empty()) { set_err(ctx, "rc_flag > 0 requires so_set_row_qps"); return SO_E_STATE; }
     return SO_OK;
-}
-
-static void ev_pair(so_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, cudaStream_t st, bool start) {
-    if (!ctx->timing_on) return;
-    if (start) {
-        if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
-            for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
-        }
-        cudaEvent_t a = ctx->ev_pool[ctx->ev_used++], b = ctx->ev_pool[ctx->ev_used++];
-        v.emplace_back(a, b);
-        cudaEventRecord(a, st);
-    } else {
-        cudaEventRecord(v.back().second, st);
-    }
 }
 
 static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, const so_frame_out* o, size_t ofs,
@@ -456,12 +469,13 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
                                             a.rows_stride, g.nby, use_fast ? 4u : (uint32_t)(g.bs * g.bs), 1u);
     ctx->launches++;
     const int nt = nthreads_px(g.bs);
-    ev_pair(ctx, ctx->ev_me, st, true);
     if (use_fast) {
+        ev_pair(ctx, ctx->ev_me, st, true);
         dim3 grid(a.chain ? 1 : ctx->nblk, units);
         if (g.bs == 16) fast_me_kernel<16><<<grid, nt, 0, st>>>(a);
         else if (g.bs == 8) fast_me_kernel<8><<<grid, nt, 0, st>>>(a);
         else fast_me_kernel<4><<<grid, nt, 0, st>>>(a);
+        ev_pair(ctx, ctx->ev_me, st, false);
         ctx->launches++;
     } else {
         rc = run_me_full(ctx, cur, cur_stride, unit0, units, g.bs, ctx->me_parent, ctx->nblk, st);
@@ -471,7 +485,6 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
             if (rc) return rc;
         }
     }
-    ev_pair(ctx, ctx->ev_me, st, false);
     ev_pair(ctx, ctx->ev_tq, st, true);
     dim3 grid(ctx->nblk, units);
     if (g.bs == 16) inter_finish_kernel<16><<<grid, nt, 0, st>>>(a);
@@ -517,26 +530,37 @@ static int ensure_seq(so_ctx* ctx, size_t nframes_total) {
     return SO_OK;
 }
 
-extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames, uint8_t* split, int16_t* mv,
-                                  int16_t* levels, uint8_t* recon, uint32_t* row_sizes, so_frame_stats* stats) {
-    if (!ctx || !frames || !split || !mv || !stats || n_units < 1 || n_frames < 1) return SO_E_INVALID;
+// stage 1: host -> device copy of the input frames (async on the context stream)
+extern "C" int so_seq_upload(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames) {
+    if (!ctx || !frames || n_units < 1 || n_frames < 1) return SO_E_INVALID;
     if (n_units > ctx->batch) { set_err(ctx, "n_units exceeds max_batch of the context"); return SO_E_INVALID; }
-    if (ctx->p.rc_flag > 0 && ctx->qp_rows.empty()) { set_err(ctx, "rc_flag > 0 requires so_set_row_qps"); return SO_E_STATE; }
     CU(cudaSetDevice(ctx->device));
     const size_t total = (size_t)n_units * n_frames;
     int rc = ensure_seq(ctx, total);
     if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->sq_frames, frames, total * ctx->frame_px, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sq_units = n_units; ctx->sq_nframes = n_frames;
+    return SO_OK;
+}
+
+// stage 2: the frame loop on frames already resident in HBM; outputs stay on the device.  Asynchronous unless
+// rc_flag == 2 (the scene-cut decision needs quantized_sized on the host every P frame).
+extern "C" int so_seq_run(so_ctx* ctx) {
+    if (!ctx) return SO_E_INVALID;
+    if (ctx->sq_units < 1) { set_err(ctx, "so_seq_run before so_seq_upload"); return SO_E_STATE; }
+    if (ctx->p.rc_flag > 0 && ctx->qp_rows.empty()) { set_err(ctx, "rc_flag > 0 requires so_set_row_qps"); return SO_E_STATE; }
+    CU(cudaSetDevice(ctx->device));
+    const int n_units = ctx->sq_units, n_frames = ctx->sq_nframes;
     cudaStream_t st = ctx->stream;
     const size_t px = ctx->frame_px;
     const int nby = ctx->g.nby;
     ctx->launches = 0;
     ctx->ev_used = 0; ctx->ev_me.clear(); ctx->ev_tq.clear();
     ctx->timing_on = true;
-    CU(cudaMemcpyAsync(ctx->sq_frames, frames, total * px, cudaMemcpyHostToDevice, st));
     if (ctx->ev_pool.size() < 2) { for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); } }
-    cudaEvent_t ev0 = ctx->ev_pool[ctx->ev_used++], ev1 = ctx->ev_pool[ctx->ev_used++];
-    CU(cudaEventRecord(ev0, st));
-    rc = so_ref_reset(ctx, 0, st);
+    ctx->ev0 = ctx->ev_pool[ctx->ev_used++]; ctx->ev1 = ctx->ev_pool[ctx->ev_used++];
+    CU(cudaEventRecord(ctx->ev0, st));
+    int rc = so_ref_reset(ctx, 0, st);
     if (rc) return rc;
     std::vector<so_frame_stats> hstats(n_units);
     for (int f = 0; f < n_frames; ++f) {
@@ -575,29 +599,72 @@ extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_unit
             if (rc) return rc;
         }
     }
-    CU(cudaEventRecord(ev1, st));
-    CU(cudaMemcpyAsync(split, ctx->sq_split, total * ctx->nblk, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(mv, ctx->sq_mv, total * ctx->nblk * 12 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-    if (levels) CU(cudaMemcpyAsync(levels, ctx->sq_levels, total * px * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-    if (recon) CU(cudaMemcpyAsync(recon, ctx->sq_recon, total * px, cudaMemcpyDeviceToHost, st));
-    if (row_sizes) CU(cudaMemcpyAsync(row_sizes, ctx->sq_rows, total * nby * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(stats, ctx->sq_stats, total * sizeof(so_frame_stats), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord(ctx->ev1, st));
     ctx->timing_on = false;
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    ctx->timing[0] = ms;
-    double me = 0, tq = 0;
-    for (auto& p : ctx->ev_me) { float t = 0; cudaEventElapsedTime(&t, p.first, p.second); me += t; }
-    for (auto& p : ctx->ev_tq) { float t = 0; cudaEventElapsedTime(&t, p.first, p.second); tq += t; }
-    ctx->timing[1] = me; ctx->timing[2] = tq; ctx->timing[3] = (double)ctx->launches;
+    ctx->timing_pending = true;
     return SO_OK;
 }
 
-extern "C" int so_last_timing(const so_ctx* ctx, double out[4]) {
+// stage 3: device -> host copy of the outputs (any pointer except split/mv/stats may be NULL) and synchronise
+extern "C" int so_seq_download(so_ctx* ctx, uint8_t* split, int16_t* mv, int16_t* levels, uint8_t* recon,
+                               uint32_t* row_sizes, so_frame_stats* stats) {
+    if (!ctx) return SO_E_INVALID;
+    if (ctx->sq_units < 1) { set_err(ctx, "so_seq_download before so_seq_upload"); return SO_E_STATE; }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t total = (size_t)ctx->sq_units * ctx->sq_nframes, px = ctx->frame_px;
+    if (split) CU(cudaMemcpyAsync(split, ctx->sq_split, total * ctx->nblk, cudaMemcpyDeviceToHost, st));
+    if (mv) CU(cudaMemcpyAsync(mv, ctx->sq_mv, total * ctx->nblk * 12 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if (levels) CU(cudaMemcpyAsync(levels, ctx->sq_levels, total * px * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if (recon) CU(cudaMemcpyAsync(recon, ctx->sq_recon, total * px, cudaMemcpyDeviceToHost, st));
+    if (row_sizes) CU(cudaMemcpyAsync(row_sizes, ctx->sq_rows, total * ctx->g.nby * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (stats) CU(cudaMemcpyAsync(stats, ctx->sq_stats, total * sizeof(so_frame_stats), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SO_OK;
+}
+
+extern "C" int so_seq_sync(so_ctx* ctx) {
+    if (!ctx) return SO_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SO_OK;
+}
+
+extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames, uint8_t* split, int16_t* mv,
+                                  int16_t* levels, uint8_t* recon, uint32_t* row_sizes, so_frame_stats* stats) {
+    if (!ctx || !frames || !split || !mv || !stats) return SO_E_INVALID;
+    int rc = so_seq_upload(ctx, frames, n_units, n_frames);
+    if (rc) return rc;
+    rc = so_seq_run(ctx);
+    if (rc) return rc;
+    return so_seq_download(ctx, split, mv, levels, recon, row_sizes, stats);
+}
+
+extern "C" int so_last_timing(so_ctx* ctx, double out[4]) {
     if (!ctx || !out) return SO_E_INVALID;
+    if (ctx->timing_pending) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->timing[0] = ms;
+        double me = 0, tq = 0;
+        for (auto& p : ctx->ev_me) { float t = 0; cudaEventElapsedTime(&t, p.first, p.second); me += t; }
+        for (auto& p : ctx->ev_tq) { float t = 0; cudaEventElapsedTime(&t, p.first, p.second); tq += t; }
+        ctx->timing[1] = me; ctx->timing[2] = tq; ctx->timing[3] = (double)ctx->launches;
+        ctx->timing[4] = (double)ctx->ev_me.size();
+        ctx->timing_pending = false;
+    }
     for (int i = 0; i < 4; ++i) out[i] = ctx->timing[i];
     return SO_OK;
+}
+
+// number of exhaustive-search kernel launches covered by timing [1] of the last run
+extern "C" int so_last_me_launches(so_ctx* ctx) {
+    double t[4];
+    if (!ctx) return SO_E_INVALID;
+    int rc = so_last_timing(ctx, t);
+    return rc ? rc : (int)ctx->timing[4];
 }
 
 // ---------------------------------------------------------------------------------------------------------
