@@ -7,6 +7,8 @@
 #include <vector>
 
 #include "so_kernels.cuh"
+#include "so_me_tma.cuh"
+#include <cstdlib>
 
 #define CU(expr)                                                                                  \
     do {                                                                                          \
@@ -304,9 +306,143 @@ static cudaError_t launch_me_full_n(int NDX, int G, const MeFullArgs& a, dim3 gr
     }
 }
 
+// ---- TMA: one 3-D tensor map {W, H, planes} over the whole reference ring, box = one search window --------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_ring_map(so_ctx* ctx, int box_w, int box_h, CUtensorMap* map) {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_err(ctx, "cuTensorMapEncodeTiled not available"); return SO_E_CUDA; }
+        fn = (PFN_tmapEncodeTiled)p;
+    }
+    const FrameGeom& g = ctx->g;
+    cuuint64_t gdim[3] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)ctx->batch * ctx->nslots * 4};
+    cuuint64_t gstr[2] = {(cuuint64_t)g.pitch, (cuuint64_t)ctx->plane_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->ring, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_err(ctx, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return SO_E_CUDA; }
+    return SO_OK;
+}
+
+template <int BS, int NDX, int G>
+static cudaError_t launch_me_tma(const CUtensorMap& map, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+    static bool attr_done[16] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (!attr_done[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(me_tma_kernel<BS, NDX, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done[dev & 15] = true;
+    }
+    me_tma_kernel<BS, NDX, G><<<grid, threads, smem, st>>>(map, a);
+    return cudaGetLastError();
+}
+template <int BS, int NDX>
+static cudaError_t launch_me_tma_g(int G, const CUtensorMap& map, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+    return G == 3 ? launch_me_tma<BS, NDX, 3>(map, a, grid, threads, smem, st) : launch_me_tma<BS, NDX, 1>(map, a, grid, threads, smem, st);
+}
+template <int BS>
+static cudaError_t launch_me_tma_n(int NDX, int G, const CUtensorMap& map, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+    switch (NDX) {
+        case 1: return launch_me_tma_g<BS, 1>(G, map, a, grid, threads, smem, st);
+        case 2: return launch_me_tma_g<BS, 2>(G, map, a, grid, threads, smem, st);
+        case 3: return launch_me_tma_g<BS, 3>(G, map, a, grid, threads, smem, st);
+        case 5: return launch_me_tma_g<BS, 5>(G, map, a, grid, threads, smem, st);
+        default: return launch_me_tma_g<BS, 9>(G, map, a, grid, threads, smem, st);
+    }
+}
+
+static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
+                      size_t out_stride, cudaStream_t st) {
+    MeTmaArgs a{};
+    a.g = ctx->g;
+    a.g.bs = bs; a.g.nbx = ctx->g.W / bs; a.g.nby = ctx->g.H / bs;
+    a.g.nref = (int)ctx->list.size();
+    a.cur = cur + (size_t)unit0 * cur_stride;
+    a.cur_unit_stride = cur_stride;
+    a.out = reinterpret_cast<unsigned long long*>(out + (size_t)unit0 * out_stride);
+    a.out_unit_stride = out_stride;
+    a.units = units;
+    a.nph = a.g.fme ? 4 : 1;
+    const int nb = a.g.nbx * a.g.nby;
+    a.items_per_unit = nb * a.g.nref * a.nph;
+    const int r = a.g.r;
+    const int ndx = (2 * r) / 4 + 1;
+    const int avail[5] = {1, 2, 3, 5, 9};
+    int NDX = 9;
+    for (int v : avail) if (v >= ndx) { NDX = v; break; }
+    const int G = ((2 * r + 1) % 3 == 0 || r >= 8) ? 3 : 1;
+    a.NG = (2 * r + 1 + G - 1) / G;
+    a.rows = bs + 2 * r;
+    const int NW = NDX + bs / 4 - 1;
+    int wp16 = (NW * 4 + 15) / 16;
+    if (wp16 % 2 == 0) wp16 += 1;
+    a.wpitch = wp16 * 16;
+    a.copy_stride = (a.rows * a.wpitch + 127) / 128 * 128;
+    a.item_stride = 4 * a.copy_stride;
+    const int tasks_per_item = 4 * a.NG;
+    int SI = (352 + tasks_per_item - 1) / tasks_per_item;
+    if (SI > 32) SI = 32;
+    a.aligned16 = (bs % 16 == 0 && r % 16 == 0) ? 1 : 0;
+    {   // raw TMA box: aligned -> 3 + 4*NW bytes needed (power-of-two chunk count); otherwise up to 15 + 3 more
+        const int need = (a.aligned16 ? 3 : 18) + 4 * NW;
+        int chunks = (need + 15) / 16;
+        if (a.aligned16) { int p2 = 1; while (p2 < chunks) p2 *= 2; chunks = p2; }
+        a.raw_w = chunks * 16;
+    }
+    a.raw_item_stride = (a.rows * a.raw_w + 127) / 128 * 128;
+    auto smem_for = [&](int si) { return (size_t)ME_TMA_STAGES * si * (a.item_stride + a.raw_item_stride + bs * bs + 8) + 64; };
+    while (SI > 1 && smem_for(SI) > 220 * 1024) --SI;
+    a.SI = SI;
+    a.stage_bytes = SI * a.item_stride;
+    a.raw_stage_bytes = SI * a.raw_item_stride;
+    a.stages_per_unit = (a.items_per_unit + SI - 1) / SI;
+    a.z_per_unit = ctx->nslots * 4;
+    for (int i = 0; i < SO_MAX_REF; ++i) a.slot[i] = i < (int)ctx->list.size() ? ctx->list[i] : 0;
+    int ncw = (SI * tasks_per_item + 31) / 32;
+    if (ncw > 11) ncw = 11;
+    if (ncw < 1) ncw = 1;
+    const int threads = 32 * (ncw + 1);
+    CUtensorMap map;
+    int rc = make_ring_map(ctx, a.raw_w, a.rows, &map);
+    if (rc) return rc;
+    // the map addresses the whole ring; unit0 offsets the z coordinate through a.units / unit index in the kernel
+    if (unit0 != 0) {      // kernels index units from 0: shift the plane index instead of the base pointer
+        for (int i = 0; i < SO_MAX_REF; ++i) a.slot[i] += unit0 * ctx->nslots;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int total_stages = units * a.stages_per_unit;
+    const int grid = total_stages < sms ? total_stages : sms;
+    CU(cudaMemsetAsync(out + (size_t)unit0 * out_stride, 0xFF, sizeof(MeResult) * out_stride * (units - 1) + sizeof(MeResult) * nb, st));
+    ev_pair(ctx, ctx->ev_me, st, true);
+    cudaError_t e;
+    const size_t smem = smem_for(SI);
+    if (bs == 16) e = launch_me_tma_n<16>(NDX, G, map, a, grid, threads, smem, st);
+    else if (bs == 8) e = launch_me_tma_n<8>(NDX, G, map, a, grid, threads, smem, st);
+    else e = launch_me_tma_n<4>(NDX, G, map, a, grid, threads, smem, st);
+    ev_pair(ctx, ctx->ev_me, st, false);
+    if (e != cudaSuccess) { set_err(ctx, std::string("me_tma_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
+    for (int u = 0; u < units; ++u) {
+        me_unpack_kernel<<<(nb + 255) / 256, 256, 0, st>>>(out + (size_t)(unit0 + u) * out_stride, nb, a.g.R);
+        ctx->launches++;
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SO_OK;
+}
+
 // exhaustive search of every bs x bs block of the frame (bs = parent or sub-block size) -> out[unit][nblocks]
 static int run_me_full(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
                        size_t out_stride, cudaStream_t st) {
+    static const bool use_simt = std::getenv("SO_ME_SIMT") != nullptr;      // development A/B switch
+    if (!use_simt) return run_me_tma(ctx, cur, cur_stride, unit0, units, bs, out, out_stride, st);
     MeFullArgs a{};
     a.g = ctx->g;
     a.g.bs = bs; a.g.nbx = ctx->g.W / bs; a.g.nby = ctx->g.H / bs;
