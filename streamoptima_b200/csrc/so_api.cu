@@ -384,7 +384,13 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     int wp16 = (NW * 4 + 15) / 16;
     if (wp16 % 2 == 0) wp16 += 1;
     a.wpitch = wp16 * 16;
-    a.copy_stride = (a.rows * a.wpitch + 127) / 128 * 128;
+    {   // copies are written by threads (16-B alignment is enough): pad so that consecutive tasks keep hitting
+        // consecutive 16-byte bank groups across the (item, shift) boundaries: copy_stride/16 == NG*G*wpitch/16 (mod 8)
+        int cs16 = a.rows * wp16;
+        const int want = (a.NG * G * wp16) % 8;
+        while (cs16 % 8 != want) ++cs16;
+        a.copy_stride = cs16 * 16;
+    }
     a.item_stride = 4 * a.copy_stride;
     const int tasks_per_item = 4 * a.NG;
     int SI = (352 + tasks_per_item - 1) / tasks_per_item;
@@ -408,7 +414,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     int ncw = (SI * tasks_per_item + 31) / 32;
     if (ncw > 11) ncw = 11;
     if (ncw < 1) ncw = 1;
-    const int threads = 32 * (ncw + 1);
+    const int threads = 32 * ncw;
     CUtensorMap map;
     int rc = make_ring_map(ctx, a.raw_w, a.rows, &map);
     if (rc) return rc;

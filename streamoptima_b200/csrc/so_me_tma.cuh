@@ -1,17 +1,17 @@
 // Exhaustive motion search, persistent + TMA + warp-specialised version (sm_100a).
 //
-//   grid  = one CTA per SM (persistent), block = 1 producer warp + NCW consumer warps
-//   stage = SI consecutive items (item = (block, reference, phase plane)); two stages are resident in shared memory
-//   producer: one TMA box load per item (cp.async.bulk.tensor.3d, SASS UTMALDG) brings the raw (bs+2r)-row search
+//   grid  = one CTA per SM (persistent); stage = SI consecutive items (item = (block, reference, phase plane))
+//   load    : one TMA box load per item (cp.async.bulk.tensor.3d, SASS UTMALDG) brings the raw (bs+2r)-row search
 //             window, 16-byte aligned in x (TMA faults on unaligned inner coordinates -- tools/tma_probe.cu), with the
 //             out-of-frame part zero-filled by the TMA unit (those candidates are invalid anyway, Encoder.py:695-698).
-//             While the consumers work on stage n the producer warp expands the raw window of stage n+1 into FOUR
-//             copies shifted by 0..3 bytes (funnel shifts), so that every candidate reads 32-bit aligned words, and
-//             stages the current blocks.  The raw load of stage n+2 is already in flight meanwhile.
-//   consumer: one task per thread = (item, byte shift c, group of G vertical offsets), NDX x G candidates accumulated
+//             Raw windows are double buffered; the load of stage n+2 is issued as soon as stage n has been expanded.
+//   expand  : all threads turn the raw window of stage n+1 into FOUR copies shifted by 0..3 bytes (funnel shifts, ~3 %
+//             of the integer-pipe work) so that every candidate reads 32-bit aligned words, and stage the current blocks
+//   search  : one task per thread = (item, byte shift c, group of G vertical offsets), NDX x G candidates accumulated
 //             with VABSDIFF4.U8.ACC from 128-bit shared loads; per-thread argmin on a packed 32-bit key, per-stage
 //             merge through warp shuffles / shared atomics, per-block merge through a global atomicMin on the 64-bit
 //             key (SAD, |dx|+|dy|, ref, dx, dy) that encodes the reference's replace rule (appendix A4).
+//   one bar.sync per stage separates expand(n+1)/search(n) from expand(n+2)/search(n+1) (copies are double buffered).
 // The whole reference ring is ONE 3-D tensor map {W, H, units*slots*4 planes}: plane index = z coordinate.
 #pragma once
 #include <cuda.h>
@@ -74,7 +74,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 constexpr int ME_TMA_STAGES = 2;
 
 template <int BS, int NDX, int G>
-__global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ CUtensorMap ring_map, const MeTmaArgs a) {
+__global__ void __launch_bounds__(352, 1) me_tma_kernel(const __grid_constant__ CUtensorMap ring_map, const MeTmaArgs a) {
     constexpr int WPR = BS / 4;
     constexpr int NW = NDX + WPR - 1;
     constexpr int NV = (NW + 3) / 4;
@@ -82,258 +82,248 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
     extern __shared__ __align__(1024) unsigned char smem_t[];
     unsigned char* const smem = smem_t;
     const FrameGeom& g = a.g;
-    // carve-up: [copies: 2 stages][raw: 2 stages][cur tiles: 2 x SI x BS*BS][keys: 2 x SI][mbarriers: rawfull, ready, empty]
-    unsigned char* wins = smem;
-    unsigned char* raws = smem + ME_TMA_STAGES * a.stage_bytes;
-    uint32_t* curs = reinterpret_cast<uint32_t*>(raws + ME_TMA_STAGES * a.raw_stage_bytes);
+    // carve-up: [raw: 2 stages (TMA destinations, 128-B aligned)][copies: 2 stages][cur tiles: 2 x SI x BS*BS][keys: 2 x SI][rawfull[2]]
+    unsigned char* raws = smem;
+    unsigned char* wins = smem + ME_TMA_STAGES * a.raw_stage_bytes;
+    uint32_t* curs = reinterpret_cast<uint32_t*>(wins + ME_TMA_STAGES * a.stage_bytes);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(curs) + ME_TMA_STAGES * a.SI * BS * BS);
     uint64_t* rawfull = reinterpret_cast<uint64_t*>(keys + ME_TMA_STAGES * a.SI);
-    uint64_t* ready = rawfull + ME_TMA_STAGES;
-    uint64_t* empty = ready + ME_TMA_STAGES;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncw = (blockDim.x >> 5) - 1;                    // consumer warps
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ME_TMA_STAGES; ++s) { mbar_init(&rawfull[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], ncw); }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthr = blockDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < ME_TMA_STAGES; ++s) mbar_init(&rawfull[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < ME_TMA_STAGES * a.SI; i += blockDim.x) keys[i] = ~0ull;
+    for (int i = tid; i < ME_TMA_STAGES * a.SI; i += nthr) keys[i] = ~0ull;
     __syncthreads();
 
     const int per_blk = g.nref * a.nph;
     const int total_stages = a.units * a.stages_per_unit;
+    const int nloc = (total_stages - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // stages of this CTA
+    auto stage_of = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
 
-    if (warp == 0) {
-        // ============================ producer ============================
-        auto issue_raw = [&](int itx, int sgx) {
-            const int rb = itx % ME_TMA_STAGES;
-            const int unit = sgx / a.stages_per_unit, sidx = sgx % a.stages_per_unit;
-            const int item0 = sidx * a.SI;
-            const int nitems = min(a.SI, a.items_per_unit - item0);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // raw buffer was read through the generic proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&rawfull[rb], (uint32_t)(nitems * a.rows * a.raw_w));
-            __syncwarp();
-            for (int li = lane; li < nitems; li += 32) {
-                const int item = item0 + li;
-                const int blk = item / per_blk, rp = item % per_blk;
-                const int ref = rp / a.nph, ph = rp % a.nph;
-                const int bx = blk % g.nbx, by = blk / g.nbx;
-                const int z = unit * a.z_per_unit + a.slot[ref] * 4 + ph;
-                const int X0 = bx * BS - g.r;
-                tma_load_3d(raws + rb * a.raw_stage_bytes + li * a.raw_item_stride, &ring_map, &rawfull[rb], X0 & ~15, by * BS - g.r, z);
-            }
-        };
-        int it = 0;
-        int sg = blockIdx.x;
-        if (sg < total_stages) issue_raw(0, sg);
-        for (; sg < total_stages; sg += gridDim.x, ++it) {
-            const int sb = it % ME_TMA_STAGES;
-            const uint32_t par = (it / ME_TMA_STAGES) & 1;
-            if (sg + (int)gridDim.x < total_stages) issue_raw(it + 1, sg + gridDim.x);   // raw[(it+1)%2] was consumed in iteration it-1
-            mbar_wait(&rawfull[sb], par);
-            mbar_wait(&empty[sb], par ^ 1);
-            const int unit = sg / a.stages_per_unit, sidx = sg % a.stages_per_unit;
-            const int item0 = sidx * a.SI;
-            const int nitems = min(a.SI, a.items_per_unit - item0);
-            // ---- current blocks
-            const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
-            uint32_t* cdst = curs + sb * a.SI * BS * WPR;
-            for (int i = lane; i < nitems * BS * WPR; i += 32) {
-                const int li = i / (BS * WPR), rem = i % (BS * WPR), row = rem / WPR, w = rem % WPR;
-                const int blk = (item0 + li) / per_blk;
-                const int bx = blk % g.nbx, by = blk / g.nbx;
-                cdst[i] = __ldg(reinterpret_cast<const uint32_t*>(cur + (size_t)(by * BS + row) * g.W + bx * BS + w * 4));
-            }
-            // ---- raw window -> four byte-shifted copies
-            if (a.aligned16) {
-                // lanes = (row, 16-byte chunk): one LDS.128 + one shuffle feed all four copies
-                const int lpr = a.raw_w >> 4;                 // chunks per raw row (power of two)
-                const int rpi = 32 / lpr;                     // rows per iteration
-                const int m = lane & (lpr - 1), rr = lane / lpr;
-                for (int li = 0; li < nitems; ++li) {
-                    const unsigned char* rsrc = raws + sb * a.raw_stage_bytes + li * a.raw_item_stride;
-                    unsigned char* wdst = wins + sb * a.stage_bytes + li * a.item_stride;
-                    for (int row0 = 0; row0 < a.rows; row0 += rpi) {
-                        const int row = row0 + rr;
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (row < a.rows) v = *reinterpret_cast<const uint4*>(rsrc + row * a.raw_w + m * 16);
-                        uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
-                        if (m == lpr - 1) nx = 0;
-                        if (row < a.rows && m < NCH) {
-                            unsigned char* o = wdst + row * a.wpitch + m * 16;
-                            *reinterpret_cast<uint4*>(o) = v;
-#pragma unroll
-                            for (int c = 1; c < 4; ++c) {
-                                uint4 w4;
-                                w4.x = __funnelshift_r(v.x, v.y, 8 * c); w4.y = __funnelshift_r(v.y, v.z, 8 * c);
-                                w4.z = __funnelshift_r(v.z, v.w, 8 * c); w4.w = __funnelshift_r(v.w, nx, 8 * c);
-                                *reinterpret_cast<uint4*>(o + c * a.copy_stride) = w4;
-                            }
-                        }
-                    }
-                }
-            } else {
-                // generic alignment: output chunk q of copy c = raw bytes [off + c + 16q, +16)
-                const int lpr = a.raw_w >> 4;
-                for (int li = 0; li < nitems; ++li) {
-                    const int blk = (item0 + li) / per_blk;
-                    const int X0 = (blk % g.nbx) * BS - g.r;
-                    const int off = X0 - (X0 & ~15);
-                    const unsigned char* rsrc = raws + sb * a.raw_stage_bytes + li * a.raw_item_stride;
-                    unsigned char* wdst = wins + sb * a.stage_bytes + li * a.item_stride;
-                    for (int c = 0; c < 4; ++c) {
-                        const int sbyte = off + c, cq = sbyte >> 4, wo = (sbyte & 15) >> 2, bits = (sbyte & 3) * 8;
-                        for (int u = lane; u < a.rows * NCH; u += 32) {
-                            const int row = u / NCH, q = u % NCH;
-                            const int m0 = q + cq;
-                            uint32_t W8[9];
-                            const uint4 A = m0 < lpr ? *reinterpret_cast<const uint4*>(rsrc + row * a.raw_w + m0 * 16) : make_uint4(0, 0, 0, 0);
-                            const uint4 B = m0 + 1 < lpr ? *reinterpret_cast<const uint4*>(rsrc + row * a.raw_w + (m0 + 1) * 16) : make_uint4(0, 0, 0, 0);
-                            W8[0] = A.x; W8[1] = A.y; W8[2] = A.z; W8[3] = A.w; W8[4] = B.x; W8[5] = B.y; W8[6] = B.z; W8[7] = B.w; W8[8] = 0;
-                            uint4 w4;
-                            switch (wo) {
-                                case 0: w4 = make_uint4(__funnelshift_r(W8[0], W8[1], bits), __funnelshift_r(W8[1], W8[2], bits),
-                                                        __funnelshift_r(W8[2], W8[3], bits), __funnelshift_r(W8[3], W8[4], bits)); break;
-                                case 1: w4 = make_uint4(__funnelshift_r(W8[1], W8[2], bits), __funnelshift_r(W8[2], W8[3], bits),
-                                                        __funnelshift_r(W8[3], W8[4], bits), __funnelshift_r(W8[4], W8[5], bits)); break;
-                                case 2: w4 = make_uint4(__funnelshift_r(W8[2], W8[3], bits), __funnelshift_r(W8[3], W8[4], bits),
-                                                        __funnelshift_r(W8[4], W8[5], bits), __funnelshift_r(W8[5], W8[6], bits)); break;
-                                default: w4 = make_uint4(__funnelshift_r(W8[3], W8[4], bits), __funnelshift_r(W8[4], W8[5], bits),
-                                                         __funnelshift_r(W8[5], W8[6], bits), __funnelshift_r(W8[6], W8[7], bits)); break;
-                            }
-                            *reinterpret_cast<uint4*>(wdst + c * a.copy_stride + row * a.wpitch + q * 16) = w4;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ready[sb]);
+    // ---- TMA issue of local stage j (one thread)
+    auto issue_raw = [&](int j) {
+        const int sg = stage_of(j), rb = j & 1;
+        const int unit = sg / a.stages_per_unit, sidx = sg % a.stages_per_unit;
+        const int item0 = sidx * a.SI;
+        const int nitems = min(a.SI, a.items_per_unit - item0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer was last read through the generic proxy
+        mbar_arrive_expect_tx(&rawfull[rb], (uint32_t)(nitems * a.rows * a.raw_w));
+        for (int li = 0; li < nitems; ++li) {
+            const int item = item0 + li;
+            const int blk = item / per_blk, rp = item % per_blk;
+            const int ref = rp / a.nph, ph = rp % a.nph;
+            const int bx = blk % g.nbx, by = blk / g.nbx;
+            const int z = unit * a.z_per_unit + a.slot[ref] * 4 + ph;
+            const int X0 = bx * BS - g.r;
+            tma_load_3d(raws + rb * a.raw_stage_bytes + li * a.raw_item_stride, &ring_map, &rawfull[rb], X0 & ~15, by * BS - g.r, z);
         }
-    } else {
-        // ============================ consumers ============================
-        const int ctid = threadIdx.x - 32;
-        const int tasks_per_item = 4 * a.NG;
-        int it = 0;
-        for (int sg = blockIdx.x; sg < total_stages; sg += gridDim.x, ++it) {
-            const int sb = it % ME_TMA_STAGES;
-            const uint32_t par = (it / ME_TMA_STAGES) & 1;
-            const int unit = sg / a.stages_per_unit, sidx = sg % a.stages_per_unit;
-            const int item0 = sidx * a.SI;
-            const int nitems = min(a.SI, a.items_per_unit - item0);
-            const int blk0 = item0 / per_blk;
-            unsigned long long* skeys = keys + sb * a.SI;
-            mbar_wait(&ready[sb], par);
+    };
 
-            for (int task = ctid; task < nitems * tasks_per_item; task += ncw * 32) {
-                const int li = task / tasks_per_item;
-                const int rem = task % tasks_per_item;
-                const int c = rem / a.NG, grp = rem % a.NG;
-                const int item = item0 + li;
-                const int blk = item / per_blk, rp = item % per_blk;
-                const int ref = rp / a.nph, ph = rp % a.nph;
-                const int px = ph & 1, py = ph >> 1;
-                const int lb = blk - blk0;
-                const int oy0 = grp * G;
-                const unsigned char* win = wins + sb * a.stage_bytes + li * a.item_stride + c * a.copy_stride + oy0 * a.wpitch;
-                const uint32_t* cb = curs + (sb * a.SI + li) * BS * WPR;
+    // ---- expand local stage j: raw window -> four byte-shifted copies, current blocks -> shared
+    auto expand = [&](int j) {
+        const int sg = stage_of(j), sb = j & 1;
+        const int unit = sg / a.stages_per_unit, sidx = sg % a.stages_per_unit;
+        const int item0 = sidx * a.SI;
+        const int nitems = min(a.SI, a.items_per_unit - item0);
+        const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
+        uint32_t* cdst = curs + sb * a.SI * BS * WPR;
+        for (int i = tid; i < nitems * BS * WPR; i += nthr) {
+            const int li = i / (BS * WPR), rem = i % (BS * WPR), row = rem / WPR, w = rem % WPR;
+            const int blk = (item0 + li) / per_blk;
+            const int bx = blk % g.nbx, by = blk / g.nbx;
+            cdst[i] = __ldg(reinterpret_cast<const uint32_t*>(cur + (size_t)(by * BS + row) * g.W + bx * BS + w * 4));
+        }
+        mbar_wait(&rawfull[sb], (uint32_t)((j >> 1) & 1));
+        const int lpr = a.raw_w >> 4;                         // 16-byte chunks per raw row
+        if (a.aligned16) {
+            // unit = (item, row, chunk m < NCH): one LDS.128 + the next word feed all four copies
+            const int per_item = a.rows * NCH;
+            for (int u = tid; u < nitems * per_item; u += nthr) {
+                const int li = u / per_item, rem = u % per_item, row = rem / NCH, m = rem % NCH;
+                const unsigned char* rsrc = raws + sb * a.raw_stage_bytes + li * a.raw_item_stride + row * a.raw_w + m * 16;
+                const uint4 v = *reinterpret_cast<const uint4*>(rsrc);
+                const uint32_t nx = (m + 1 < lpr) ? *reinterpret_cast<const uint32_t*>(rsrc + 16) : 0u;
+                unsigned char* o = wins + sb * a.stage_bytes + li * a.item_stride + row * a.wpitch + m * 16;
+                *reinterpret_cast<uint4*>(o) = v;
+#pragma unroll
+                for (int c = 1; c < 4; ++c) {
+                    uint4 w4;
+                    w4.x = __funnelshift_r(v.x, v.y, 8 * c); w4.y = __funnelshift_r(v.y, v.z, 8 * c);
+                    w4.z = __funnelshift_r(v.z, v.w, 8 * c); w4.w = __funnelshift_r(v.w, nx, 8 * c);
+                    *reinterpret_cast<uint4*>(o + c * a.copy_stride) = w4;
+                }
+            }
+        } else {
+            // generic alignment: output chunk q of copy c = raw bytes [off + c + 16q, +16)
+            const int per_item = 4 * a.rows * NCH;
+            for (int u = tid; u < nitems * per_item; u += nthr) {
+                const int li = u / per_item;
+                int rem = u % per_item;
+                const int c = rem / (a.rows * NCH);
+                rem %= a.rows * NCH;
+                const int row = rem / NCH, q = rem % NCH;
+                const int blk = (item0 + li) / per_blk;
+                const int X0 = (blk % g.nbx) * BS - g.r;
+                const int sbyte = X0 - (X0 & ~15) + c, cq = sbyte >> 4, wo = (sbyte & 15) >> 2, bits = (sbyte & 3) * 8;
+                const unsigned char* rsrc = raws + sb * a.raw_stage_bytes + li * a.raw_item_stride + row * a.raw_w;
+                const int m0 = q + cq;
+                const uint4 A = m0 < lpr ? *reinterpret_cast<const uint4*>(rsrc + m0 * 16) : make_uint4(0, 0, 0, 0);
+                const uint4 B = m0 + 1 < lpr ? *reinterpret_cast<const uint4*>(rsrc + (m0 + 1) * 16) : make_uint4(0, 0, 0, 0);
+                uint4 w4;
+                switch (wo) {
+                    case 0: w4 = make_uint4(__funnelshift_r(A.x, A.y, bits), __funnelshift_r(A.y, A.z, bits),
+                                            __funnelshift_r(A.z, A.w, bits), __funnelshift_r(A.w, B.x, bits)); break;
+                    case 1: w4 = make_uint4(__funnelshift_r(A.y, A.z, bits), __funnelshift_r(A.z, A.w, bits),
+                                            __funnelshift_r(A.w, B.x, bits), __funnelshift_r(B.x, B.y, bits)); break;
+                    case 2: w4 = make_uint4(__funnelshift_r(A.z, A.w, bits), __funnelshift_r(A.w, B.x, bits),
+                                            __funnelshift_r(B.x, B.y, bits), __funnelshift_r(B.y, B.z, bits)); break;
+                    default: w4 = make_uint4(__funnelshift_r(A.w, B.x, bits), __funnelshift_r(B.x, B.y, bits),
+                                             __funnelshift_r(B.y, B.z, bits), __funnelshift_r(B.z, B.w, bits)); break;
+                }
+                *reinterpret_cast<uint4*>(wins + sb * a.stage_bytes + li * a.item_stride + c * a.copy_stride + row * a.wpitch + q * 16) = w4;
+            }
+        }
+    };
 
-                uint32_t acc[G][NDX];
+    if (nloc <= 0) return;
+    if (tid == 0) { issue_raw(0); if (nloc > 1) issue_raw(1); }
+    expand(0);
+    __syncthreads();
+
+    const int tasks_per_item = 4 * a.NG;
+    for (int j = 0; j < nloc; ++j) {
+        const int sg = stage_of(j), sb = j & 1;
+        const int unit = sg / a.stages_per_unit, sidx = sg % a.stages_per_unit;
+        const int item0 = sidx * a.SI;
+        const int nitems = min(a.SI, a.items_per_unit - item0);
+        const int blk0 = item0 / per_blk;
+        unsigned long long* skeys = keys + sb * a.SI;
+        // raw[sb] has been expanded (barrier at the end of the previous iteration): refill it with stage j+2
+        if (tid == 0 && j + 2 < nloc) issue_raw(j + 2);
+        if (j + 1 < nloc) expand(j + 1);
+
+        for (int task = tid; task < nitems * tasks_per_item; task += nthr) {
+            const int li = task / tasks_per_item;
+            const int rem = task % tasks_per_item;
+            const int c = rem / a.NG, grp = rem % a.NG;
+            const int item = item0 + li;
+            const int blk = item / per_blk, rp = item % per_blk;
+            const int ref = rp / a.nph, ph = rp % a.nph;
+            const int px = ph & 1, py = ph >> 1;
+            const int lb = blk - blk0;
+            const int oy0 = grp * G;
+            const unsigned char* win = wins + sb * a.stage_bytes + li * a.item_stride + c * a.copy_stride + oy0 * a.wpitch;
+            const uint4* cb4 = reinterpret_cast<const uint4*>(curs + (sb * a.SI + li) * BS * WPR);
+            const uint32_t* cb = curs + (sb * a.SI + li) * BS * WPR;
+
+            uint32_t acc[G][NDX];
 #pragma unroll
-                for (int gg = 0; gg < G; ++gg)
+            for (int gg = 0; gg < G; ++gg)
 #pragma unroll
-                    for (int k = 0; k < NDX; ++k) acc[gg][k] = 0;
-                uint32_t curq[G][WPR];
+                for (int k = 0; k < NDX; ++k) acc[gg][k] = 0;
+            uint32_t curq[G][WPR];
 #pragma unroll
-                for (int rho = 0; rho < BS + G - 1; ++rho) {
-                    uint32_t refw[NV * 4];
-                    if (oy0 + rho < a.rows) {
+            for (int rho = 0; rho < BS + G - 1; ++rho) {
+                uint32_t refw[NV * 4];
+                if (oy0 + rho < a.rows) {
 #pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const uint4 q = *reinterpret_cast<const uint4*>(win + rho * a.wpitch + v * 16);
-                            refw[4 * v] = q.x; refw[4 * v + 1] = q.y; refw[4 * v + 2] = q.z; refw[4 * v + 3] = q.w;
-                        }
+                    for (int v = 0; v < NV; ++v) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(win + rho * a.wpitch + v * 16);
+                        refw[4 * v] = q.x; refw[4 * v + 1] = q.y; refw[4 * v + 2] = q.z; refw[4 * v + 3] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < NV * 4; ++v) refw[v] = 0;
+                }
+#pragma unroll
+                for (int gg = G - 1; gg > 0; --gg)
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) curq[gg][w] = curq[gg - 1][w];
+                if (rho < BS) {
+                    if constexpr (WPR == 4) {
+                        const uint4 q = cb4[rho];
+                        curq[0][0] = q.x; curq[0][1] = q.y; curq[0][2] = q.z; curq[0][3] = q.w;
+                    } else if constexpr (WPR == 2) {
+                        const uint2 q = reinterpret_cast<const uint2*>(cb)[rho];
+                        curq[0][0] = q.x; curq[0][1] = q.y;
                     } else {
-#pragma unroll
-                        for (int v = 0; v < NV * 4; ++v) refw[v] = 0;
-                    }
-#pragma unroll
-                    for (int gg = G - 1; gg > 0; --gg)
-#pragma unroll
-                        for (int w = 0; w < WPR; ++w) curq[gg][w] = curq[gg - 1][w];
-                    if (rho < BS) {
-#pragma unroll
-                        for (int w = 0; w < WPR; ++w) curq[0][w] = cb[rho * WPR + w];
-                    }
-#pragma unroll
-                    for (int gg = 0; gg < G; ++gg) {
-                        const int j = rho - gg;
-                        if (j >= 0 && j < BS) {
-#pragma unroll
-                            for (int k = 0; k < NDX; ++k)
-#pragma unroll
-                                for (int w = 0; w < WPR; ++w) acc[gg][k] = sad4_acc(refw[k + w], curq[gg][w], acc[gg][k]);
-                        }
+                        curq[0][0] = cb[rho];
                     }
                 }
+#pragma unroll
+                for (int gg = 0; gg < G; ++gg) {
+                    const int jr = rho - gg;
+                    if (jr >= 0 && jr < BS) {
+#pragma unroll
+                        for (int k = 0; k < NDX; ++k)
+#pragma unroll
+                            for (int w = 0; w < WPR; ++w) acc[gg][k] = sad4_acc(refw[k + w], curq[gg][w], acc[gg][k]);
+                    }
+                }
+            }
 
-                const int bx = blk % g.nbx, by = blk / g.nbx;
-                int xlo, xhi, ylo, yhi;
-                valid_range(bx * BS, g.W, BS, g.fme, g.fme, xlo, xhi);
-                valid_range(by * BS, g.H, BS, g.fme, g.fme, ylo, yhi);
-                xlo = max(xlo, -g.R); xhi = min(xhi, g.R);
-                ylo = max(ylo, -g.R); yhi = min(yhi, g.R);
-                uint32_t best = 0xFFFFFFFFu;
+            // ---- thread-local argmin.  key32 = sad<<16 | (|dx|+|dy|)<<8 | (k*G+g); invalid candidates are OR-ed to all ones.
+            const int bx = blk % g.nbx, by = blk / g.nbx;
+            int xlo, xhi, ylo, yhi;
+            valid_range(bx * BS, g.W, BS, g.fme, g.fme, xlo, xhi);
+            valid_range(by * BS, g.H, BS, g.fme, g.fme, ylo, yhi);
+            xlo = max(xlo, -g.R); xhi = min(xhi, g.R);
+            ylo = max(ylo, -g.R); yhi = min(yhi, g.R);
+            const int mul = g.fme ? 2 : 1;
+            uint32_t ly8[G], ybad[G];
 #pragma unroll
-                for (int k = 0; k < NDX; ++k) {
-                    const int ox = -g.r + c + 4 * k;
-                    const int dx = g.fme ? 2 * ox + px : ox;
-                    const bool vx = (ox <= g.r) && dx >= xlo && dx <= xhi;
+            for (int gg = 0; gg < G; ++gg) {
+                const int oy = -g.r + oy0 + gg, dy = mul * oy + (g.fme ? py : 0);
+                ly8[gg] = (uint32_t)(abs(dy) << 8) + gg;
+                ybad[gg] = (oy <= g.r && dy >= ylo && dy <= yhi) ? 0u : 0xFFFFFFFFu;
+            }
+            uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-                    for (int gg = 0; gg < G; ++gg) {
-                        const int oy = -g.r + oy0 + gg;
-                        const int dy = g.fme ? 2 * oy + py : oy;
-                        const bool v = vx && (oy <= g.r) && dy >= ylo && dy <= yhi;
-                        const uint32_t key = (acc[gg][k] << 16) | (uint32_t)((abs(dx) + abs(dy)) << 8) | (uint32_t)(k * G + gg);
-                        best = v ? min(best, key) : best;
-                    }
-                }
-                unsigned long long key = ~0ull;
-                if (best != 0xFFFFFFFFu) {
-                    const int idx = best & 0xFF, k = idx / G, gg = idx % G;
-                    const int ox = -g.r + c + 4 * k, oy = -g.r + oy0 + gg;
-                    const int dx = g.fme ? 2 * ox + px : ox;
-                    const int dy = g.fme ? 2 * oy + py : oy;
-                    key = ((unsigned long long)(best >> 16) << 40) | ((unsigned long long)((best >> 8) & 0xFF) << 24) |
-                          ((unsigned long long)ref << 16) | ((unsigned long long)(dx + g.R) << 8) | (unsigned long long)(dy + g.R);
-                }
-                // merge: warp shuffle when the whole warp works on the same block, shared atomics otherwise
-                const unsigned act = __activemask();
-                const int lb0 = __shfl_sync(act, lb, __ffs(act) - 1);
-                if (__all_sync(act, lb == lb0) && act == 0xFFFFFFFFu) {
+            for (int k = 0; k < NDX; ++k) {
+                const int ox = -g.r + c + 4 * k, dx = mul * ox + (g.fme ? px : 0);
+                const uint32_t lx8 = (uint32_t)(abs(dx) << 8) + k * G;
+                const uint32_t xbad = (ox <= g.r && dx >= xlo && dx <= xhi) ? 0u : 0xFFFFFFFFu;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
-                        key = other < key ? other : key;
-                    }
-                    if (lane == 0 && key < skeys[lb]) atomicMin(&skeys[lb], key);
-                } else if (key < skeys[lb]) {
-                    atomicMin(&skeys[lb], key);
+                for (int gg = 0; gg < G; ++gg) {
+                    const uint32_t key = ((acc[gg][k] << 16) + (lx8 + ly8[gg])) | xbad | ybad[gg];
+                    best = min(best, key);
                 }
             }
-            // all consumer warps done with this stage: flush the per-block keys, release the buffer
-            asm volatile("bar.sync 1, %0;" ::"r"(ncw * 32) : "memory");
-            if (warp == 1) {
-                const int blk_last = (item0 + nitems - 1) / per_blk;
-                for (int i = lane; i <= blk_last - blk0; i += 32) {
-                    const unsigned long long k = skeys[i];
-                    skeys[i] = ~0ull;
-                    if (k != ~0ull)
-                        atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + unit * a.out_unit_stride + blk0 + i), k);
-                }
+            unsigned long long key = ~0ull;
+            if (best != 0xFFFFFFFFu) {
+                const int idx = best & 0xFF, k = idx / G, gg = idx % G;
+                const int ox = -g.r + c + 4 * k, oy = -g.r + oy0 + gg;
+                const int dx = mul * ox + (g.fme ? px : 0);
+                const int dy = mul * oy + (g.fme ? py : 0);
+                key = ((unsigned long long)(best >> 16) << 40) | ((unsigned long long)((best >> 8) & 0xFF) << 24) |
+                      ((unsigned long long)ref << 16) | ((unsigned long long)(dx + g.R) << 8) | (unsigned long long)(dy + g.R);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[sb]);
+            // merge: warp shuffle when the whole warp works on the same block, shared atomics otherwise
+            const unsigned act = __activemask();
+            const int lb0 = __shfl_sync(act, lb, __ffs(act) - 1);
+            if (act == 0xFFFFFFFFu && __all_sync(act, lb == lb0)) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+                    key = other < key ? other : key;
+                }
+                if (lane == 0 && key < skeys[lb]) atomicMin(&skeys[lb], key);
+            } else if (key < skeys[lb]) {
+                atomicMin(&skeys[lb], key);
+            }
+        }
+        __syncthreads();        // search(j) and expand(j+1) complete
+        if (warp == 0) {        // flush the per-block keys of stage j (next written by search(j+2), after the next barrier)
+            const int blk_last = (item0 + nitems - 1) / per_blk;
+            for (int i = lane; i <= blk_last - blk0; i += 32) {
+                const unsigned long long k = skeys[i];
+                skeys[i] = ~0ull;
+                if (k != ~0ull)
+                    atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + unit * a.out_unit_stride + blk0 + i), k);
+            }
         }
     }
 }
