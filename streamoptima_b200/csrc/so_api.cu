@@ -30,7 +30,7 @@ struct so_ctx {
     FrameGeom g{};
     int nblk = 0, batch = 1;
     size_t frame_px = 0;
-    // reference ring: [unit][slot][phase][H][pitch]
+    // reference ring: [unit][slot][phase 4][shift 4][H][pitch]
     uint8_t* ring = nullptr;
     size_t plane_bytes = 0, slot_stride = 0, unit_stride = 0;
     int nslots = 0;
@@ -166,7 +166,7 @@ extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->nslots = p->n_ref_frames;
     ctx->plane_bytes = (size_t)g.pitch * g.H;
-    ctx->slot_stride = ctx->plane_bytes * 4;
+    ctx->slot_stride = ctx->plane_bytes * 16;
     ctx->unit_stride = ctx->slot_stride * ctx->nslots;
     CUC(cudaMalloc(&ctx->ring, ctx->unit_stride * ctx->batch));
     CUC(cudaMemset(ctx->ring, 0, ctx->unit_stride * ctx->batch));
@@ -255,7 +255,7 @@ extern "C" int so_ref_push(so_ctx* ctx, int /*unit*/, const uint8_t* recon_dev, 
 
 static RefRing make_ring(so_ctx* c) {
     RefRing r;
-    r.base = c->ring; r.unit_stride = c->unit_stride; r.slot_stride = c->slot_stride; r.plane_stride = c->plane_bytes;
+    r.base = c->ring; r.unit_stride = c->unit_stride; r.slot_stride = c->slot_stride; r.plane_stride = c->plane_bytes * 4;
     for (int i = 0; i < SO_MAX_REF; ++i) r.slot[i] = i < (int)c->list.size() ? c->list[i] : 0;
     return r;
 }
@@ -277,62 +277,48 @@ static void ev_pair(so_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>
 // ---------------------------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------------------
-template <int BS, int NDX, int G>
-static cudaError_t launch_me_full(const MeFullArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    static bool attr_done[16] = {};
-    int dev = 0; cudaGetDevice(&dev);
-    if (!attr_done[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(me_full_kernel<BS, NDX, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_done[dev & 15] = true;
-    }
-    me_full_kernel<BS, NDX, G><<<grid, threads, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-template <int BS, int NDX>
-static cudaError_t launch_me_full_g(int G, const MeFullArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    return G == 3 ? launch_me_full<BS, NDX, 3>(a, grid, threads, smem, st) : launch_me_full<BS, NDX, 1>(a, grid, threads, smem, st);
-}
-
-template <int BS>
-static cudaError_t launch_me_full_n(int NDX, int G, const MeFullArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    switch (NDX) {
-        case 1: return launch_me_full_g<BS, 1>(G, a, grid, threads, smem, st);
-        case 2: return launch_me_full_g<BS, 2>(G, a, grid, threads, smem, st);
-        case 3: return launch_me_full_g<BS, 3>(G, a, grid, threads, smem, st);
-        case 5: return launch_me_full_g<BS, 5>(G, a, grid, threads, smem, st);
-        default: return launch_me_full_g<BS, 9>(G, a, grid, threads, smem, st);
-    }
-}
-
 // ---- TMA: one 3-D tensor map {W, H, planes} over the whole reference ring, box = one search window --------------
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_ring_map(so_ctx* ctx, int box_w, int box_h, CUtensorMap* map) {
+static PFN_tmapEncodeTiled tmap_encoder(so_ctx* ctx) {
     static PFN_tmapEncodeTiled fn = nullptr;
     if (!fn) {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
-        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (!p || q != cudaDriverEntryPointSuccess) { set_err(ctx, "cuTensorMapEncodeTiled not available"); return SO_E_CUDA; }
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p ||
+            q != cudaDriverEntryPointSuccess) {
+            set_err(ctx, "cuTensorMapEncodeTiled not available");
+            return nullptr;
+        }
         fn = (PFN_tmapEncodeTiled)p;
     }
-    const FrameGeom& g = ctx->g;
-    cuuint64_t gdim[3] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)ctx->batch * ctx->nslots * 4};
-    cuuint64_t gstr[2] = {(cuuint64_t)g.pitch, (cuuint64_t)ctx->plane_bytes};
+    return fn;
+}
+
+static int make_map3d(so_ctx* ctx, const void* base, cuuint64_t w, cuuint64_t h, cuuint64_t z, cuuint64_t row_stride, cuuint64_t z_stride,
+                      int box_w, int box_h, CUtensorMap* map) {
+    PFN_tmapEncodeTiled fn = tmap_encoder(ctx);
+    if (!fn) return SO_E_CUDA;
+    cuuint64_t gdim[3] = {w, h, z};
+    cuuint64_t gstr[2] = {row_stride, z_stride};
     cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->ring, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_err(ctx, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return SO_E_CUDA; }
     return SO_OK;
 }
 
+// one 3-D tensor map {W, H, planes} over the whole reference ring, box = one search window
+static int make_ring_map(so_ctx* ctx, int box_w, int box_h, CUtensorMap* map) {
+    const FrameGeom& g = ctx->g;
+    return make_map3d(ctx, ctx->ring, g.W, g.H, (cuuint64_t)ctx->batch * ctx->nslots * 16, g.pitch, ctx->plane_bytes, box_w, box_h, map);
+}
+
 template <int BS, int NDX, int G>
-static cudaError_t launch_me_tma(const CUtensorMap& map, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+static cudaError_t launch_me_tma(const CUtensorMap& map, const CUtensorMap& cmap, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_done[16] = {};
     int dev = 0; cudaGetDevice(&dev);
     if (!attr_done[dev & 15]) {
@@ -340,21 +326,21 @@ static cudaError_t launch_me_tma(const CUtensorMap& map, const MeTmaArgs& a, int
         if (e != cudaSuccess) return e;
         attr_done[dev & 15] = true;
     }
-    me_tma_kernel<BS, NDX, G><<<grid, threads, smem, st>>>(map, a);
+    me_tma_kernel<BS, NDX, G><<<grid, threads, smem, st>>>(map, cmap, a);
     return cudaGetLastError();
 }
 template <int BS, int NDX>
-static cudaError_t launch_me_tma_g(int G, const CUtensorMap& map, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
-    return G == 3 ? launch_me_tma<BS, NDX, 3>(map, a, grid, threads, smem, st) : launch_me_tma<BS, NDX, 1>(map, a, grid, threads, smem, st);
+static cudaError_t launch_me_tma_g(int G, const CUtensorMap& map, const CUtensorMap& cmap, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+    return G == 3 ? launch_me_tma<BS, NDX, 3>(map, cmap, a, grid, threads, smem, st) : launch_me_tma<BS, NDX, 1>(map, cmap, a, grid, threads, smem, st);
 }
 template <int BS>
-static cudaError_t launch_me_tma_n(int NDX, int G, const CUtensorMap& map, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+static cudaError_t launch_me_tma_n(int NDX, int G, const CUtensorMap& map, const CUtensorMap& cmap, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
     switch (NDX) {
-        case 1: return launch_me_tma_g<BS, 1>(G, map, a, grid, threads, smem, st);
-        case 2: return launch_me_tma_g<BS, 2>(G, map, a, grid, threads, smem, st);
-        case 3: return launch_me_tma_g<BS, 3>(G, map, a, grid, threads, smem, st);
-        case 5: return launch_me_tma_g<BS, 5>(G, map, a, grid, threads, smem, st);
-        default: return launch_me_tma_g<BS, 9>(G, map, a, grid, threads, smem, st);
+        case 1: return launch_me_tma_g<BS, 1>(G, map, cmap, a, grid, threads, smem, st);
+        case 2: return launch_me_tma_g<BS, 2>(G, map, cmap, a, grid, threads, smem, st);
+        case 3: return launch_me_tma_g<BS, 3>(G, map, cmap, a, grid, threads, smem, st);
+        case 5: return launch_me_tma_g<BS, 5>(G, map, cmap, a, grid, threads, smem, st);
+        default: return launch_me_tma_g<BS, 9>(G, map, cmap, a, grid, threads, smem, st);
     }
 }
 
@@ -384,40 +370,64 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     int wp16 = (NW * 4 + 15) / 16;
     if (wp16 % 2 == 0) wp16 += 1;
     a.wpitch = wp16 * 16;
-    {   // copies are written by threads (16-B alignment is enough): pad so that consecutive tasks keep hitting
-        // consecutive 16-byte bank groups across the (item, shift) boundaries: copy_stride/16 == NG*G*wpitch/16 (mod 8)
-        int cs16 = a.rows * wp16;
-        const int want = (a.NG * G * wp16) % 8;
-        while (cs16 % 8 != want) ++cs16;
-        a.copy_stride = cs16 * 16;
-    }
-    a.item_stride = 4 * a.copy_stride;
     const int tasks_per_item = 4 * a.NG;
     int SI = (352 + tasks_per_item - 1) / tasks_per_item;
     if (SI > 32) SI = 32;
-    a.aligned16 = (bs % 16 == 0 && r % 16 == 0) ? 1 : 0;
-    {   // raw TMA box: aligned -> 3 + 4*NW bytes needed (power-of-two chunk count); otherwise up to 15 + 3 more
-        const int need = (a.aligned16 ? 3 : 18) + 4 * NW;
-        int chunks = (need + 15) / 16;
-        if (a.aligned16) { int p2 = 1; while (p2 < chunks) p2 *= 2; chunks = p2; }
-        a.raw_w = chunks * 16;
+    // DIRECT staging needs every window to start at a 16-byte aligned x (bs = 16, r multiple of 16), one group layout
+    // without over-read (NG*G == 2r+1) and a TMA-addressable current frame (16-byte aligned rows)
+    a.direct = (bs == 16 && r % 16 == 0 && r > 0 && a.NG * G == 2 * r + 1 && ctx->g.W % 16 == 0 &&
+                (reinterpret_cast<uintptr_t>(cur) % 16 == 0) && (cur_stride % 16 == 0)) ? 1 : 0;
+    size_t smem = 0;
+    if (a.direct) {
+        a.nstage = 3;
+        a.item_stride = (a.rows * a.wpitch + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
+        a.raw_w = a.wpitch; a.raw_item_stride = 0; a.aligned16 = 1;
+        auto smem_for = [&](int si, int ns) { return (size_t)ns * si * (4 * a.item_stride + bs * bs) + 256; };
+        while (SI > 1 && smem_for(SI, a.nstage) > 226 * 1024) --SI;
+        smem = smem_for(SI, a.nstage);
+    } else {
+        a.nstage = 2;
+        {   // copies are written by threads (16-B alignment is enough).  G-1 spare rows let the search read past the
+            // window without a guard (only invalid candidates see them); the stride is padded so that consecutive tasks
+            // keep hitting consecutive 16-byte bank groups across item boundaries: item_stride/16 == NG*G*wpitch/16 (mod 8)
+            int is16 = (a.rows + G - 1) * wp16;
+            const int want = (a.NG * G * wp16) % 8;
+            while (is16 % 8 != want) ++is16;
+            a.item_stride = is16 * 16;
+        }
+        {   // raw TMA box: aligned -> 64-byte rows (3 + 4*NW bytes needed); otherwise up to 15 + 3 more bytes
+            const int need_al = 3 + 4 * NW;
+            a.aligned16 = (bs % 16 == 0 && r % 16 == 0 && need_al <= 64) ? 1 : 0;
+            a.raw_w = a.aligned16 ? 64 : (18 + 4 * NW + 15) / 16 * 16;
+        }
+        a.raw_item_stride = (a.rows * a.raw_w + 127) / 128 * 128;
+        auto smem_for = [&](int si, int ns) {
+            // 128-byte alignment of the raw area: copies and cur tiles are multiples of 16 only
+            return (size_t)ns * si * (4 * a.item_stride + a.raw_item_stride + bs * bs) + 512;
+        };
+        while (SI > 1 && smem_for(SI, a.nstage) > 226 * 1024) --SI;
+        smem = smem_for(SI, a.nstage);
     }
-    a.raw_item_stride = (a.rows * a.raw_w + 127) / 128 * 128;
-    auto smem_for = [&](int si) { return (size_t)ME_TMA_STAGES * si * (a.item_stride + a.raw_item_stride + bs * bs + 8) + 64; };
-    while (SI > 1 && smem_for(SI) > 220 * 1024) --SI;
     a.SI = SI;
-    a.stage_bytes = SI * a.item_stride;
+    a.shift_stride = SI * a.item_stride;
+    a.stage_bytes = 4 * a.shift_stride;
     a.raw_stage_bytes = SI * a.raw_item_stride;
+    a.NB = (SI * tasks_per_item + 31) / 32;
     a.stages_per_unit = (a.items_per_unit + SI - 1) / SI;
-    a.z_per_unit = ctx->nslots * 4;
+    a.z_per_unit = ctx->nslots * 16;
     for (int i = 0; i < SO_MAX_REF; ++i) a.slot[i] = i < (int)ctx->list.size() ? ctx->list[i] : 0;
-    int ncw = (SI * tasks_per_item + 31) / 32;
-    if (ncw > 11) ncw = 11;
-    if (ncw < 1) ncw = 1;
-    const int threads = 32 * ncw;
-    CUtensorMap map;
+    // 1 producer warp + up to 11 search warps.  No more search warps than bundles per stage: a warp may then be at most one
+    // stage ahead of the slowest one, which is what the 1-bit mbarrier phase parity can distinguish.
+    const int threads = 32 * (1 + (a.NB < 11 ? a.NB : 11));
+    CUtensorMap map, cmap;
     int rc = make_ring_map(ctx, a.raw_w, a.rows, &map);
     if (rc) return rc;
+    if (a.direct) {     // current blocks: {W, H, units} view of the frames of this launch
+        rc = make_map3d(ctx, cur + (size_t)unit0 * cur_stride, ctx->g.W, ctx->g.H, units, ctx->g.W, cur_stride, bs, bs, &cmap);
+        if (rc) return rc;
+    } else {
+        cmap = map;     // unused
+    }
     // the map addresses the whole ring; unit0 offsets the z coordinate through a.units / unit index in the kernel
     if (unit0 != 0) {      // kernels index units from 0: shift the plane index instead of the base pointer
         for (int i = 0; i < SO_MAX_REF; ++i) a.slot[i] += unit0 * ctx->nslots;
@@ -429,10 +439,9 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     CU(cudaMemsetAsync(out + (size_t)unit0 * out_stride, 0xFF, sizeof(MeResult) * out_stride * (units - 1) + sizeof(MeResult) * nb, st));
     ev_pair(ctx, ctx->ev_me, st, true);
     cudaError_t e;
-    const size_t smem = smem_for(SI);
-    if (bs == 16) e = launch_me_tma_n<16>(NDX, G, map, a, grid, threads, smem, st);
-    else if (bs == 8) e = launch_me_tma_n<8>(NDX, G, map, a, grid, threads, smem, st);
-    else e = launch_me_tma_n<4>(NDX, G, map, a, grid, threads, smem, st);
+    if (bs == 16) e = launch_me_tma_n<16>(NDX, G, map, cmap, a, grid, threads, smem, st);
+    else if (bs == 8) e = launch_me_tma_n<8>(NDX, G, map, cmap, a, grid, threads, smem, st);
+    else e = launch_me_tma_n<4>(NDX, G, map, cmap, a, grid, threads, smem, st);
     ev_pair(ctx, ctx->ev_me, st, false);
     if (e != cudaSuccess) { set_err(ctx, std::string("me_tma_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
     for (int u = 0; u < units; ++u) {
@@ -447,63 +456,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
 // exhaustive search of every bs x bs block of the frame (bs = parent or sub-block size) -> out[unit][nblocks]
 static int run_me_full(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
                        size_t out_stride, cudaStream_t st) {
-    static const bool use_simt = std::getenv("SO_ME_SIMT") != nullptr;      // development A/B switch
-    if (!use_simt) return run_me_tma(ctx, cur, cur_stride, unit0, units, bs, out, out_stride, st);
-    MeFullArgs a{};
-    a.g = ctx->g;
-    a.g.bs = bs; a.g.nbx = ctx->g.W / bs; a.g.nby = ctx->g.H / bs;
-    a.g.nref = (int)ctx->list.size();
-    a.ring = make_ring(ctx);
-    a.ring.base += (size_t)unit0 * ctx->unit_stride;
-    a.cur = cur + (size_t)unit0 * cur_stride;
-    a.cur_unit_stride = cur_stride;
-    a.out = out + (size_t)unit0 * out_stride;
-    a.out_unit_stride = out_stride;
-    a.nph = a.g.fme ? 4 : 1;
-    const int nb = a.g.nbx * a.g.nby;
-    a.items_per_unit = nb * a.g.nref * a.nph;
-    const int r = a.g.r;
-    int ndx = (2 * r) / 4 + 1;
-    const int avail[5] = {1, 2, 3, 5, 9};
-    int NDX = 9;
-    for (int v : avail) if (v >= ndx) { NDX = v; break; }
-    const int G = ((2 * r + 1) % 3 == 0 || r >= 8) ? 3 : 1;
-    a.NG = (2 * r + 1 + G - 1) / G;
-    a.rows = bs + 2 * r;
-    const int NW = NDX + bs / 4 - 1;
-    int wp16 = (NW * 4 + 15) / 16;
-    if (wp16 % 2 == 0) wp16 += 1;
-    a.wpitch = wp16 * 16;
-    // bank-conflict-free continuation across the four shifted copies: copy_stride/16 == NG*G*wpitch/16 (mod 8)
-    int cs16 = a.rows * wp16;
-    const int want = (a.NG * G * wp16) % 8;
-    while (cs16 % 8 != want) ++cs16;
-    a.copy_stride = cs16 * 16;
-    a.item_stride = 4 * a.copy_stride;
-    a.WI = 16;
-    size_t smem = (size_t)a.WI * 8 + (size_t)a.WI * bs * bs + (size_t)a.WI * a.item_stride;
-    while (smem > 200 * 1024 && a.WI > 1) { a.WI /= 2; smem = (size_t)a.WI * 8 + (size_t)a.WI * bs * bs + (size_t)a.WI * a.item_stride; }
-    const int total = a.WI * 4 * a.NG;
-    const int rounds = (total + 383) / 384;
-    int threads = ((total + rounds - 1) / rounds + 31) / 32 * 32;
-    if (threads > 384) threads = 384;
-    a.tma = 0;
-    dim3 grid((a.items_per_unit + a.WI - 1) / a.WI, units);
-    CU(cudaMemsetAsync(a.out, 0xFF, sizeof(MeResult) * out_stride * (units - 1) + sizeof(MeResult) * nb, st));
-    cudaError_t e;
-    ev_pair(ctx, ctx->ev_me, st, true);
-    if (bs == 16) e = launch_me_full_n<16>(NDX, G, a, grid, threads, smem, st);
-    else if (bs == 8) e = launch_me_full_n<8>(NDX, G, a, grid, threads, smem, st);
-    else e = launch_me_full_n<4>(NDX, G, a, grid, threads, smem, st);
-    ev_pair(ctx, ctx->ev_me, st, false);
-    if (e != cudaSuccess) { set_err(ctx, std::string("me_full_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
-    for (int u = 0; u < units; ++u) {
-        me_unpack_kernel<<<(nb + 255) / 256, 256, 0, st>>>(a.out + (size_t)u * out_stride, nb, a.g.R);
-        ctx->launches++;
-    }
-    ctx->launches++;
-    CU(cudaGetLastError());
-    return SO_OK;
+    return run_me_tma(ctx, cur, cur_stride, unit0, units, bs, out, out_stride, st);
 }
 
 static FlowArgs make_flow(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, const so_frame_out* o, size_t out_frames_stride,
@@ -578,16 +531,15 @@ static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
 }
 
 static int ensure_planes(so_ctx* ctx, int units, cudaStream_t st) {
-    if (!ctx->g.fme) return SO_OK;
     bool all_u8 = true;
     for (int s : ctx->list) all_u8 = all_u8 && ctx->slot_u8[s];
-    const int wrap = all_u8 ? 1 : 0;                 // np.copy(list) is uint8 only if every frame is (quirk Q1)
     const FrameGeom& g = ctx->g;
+    const int wrap = (g.fme && all_u8) ? 1 : 0;      // np.copy(list) is uint8 only if every frame is (quirk Q1)
     for (int s : ctx->list) {
-        if (!ctx->slot_u8[s]) continue;              // the constant frame: planes were filled at reset
+        if (!ctx->slot_u8[s]) continue;              // the constant frame: every plane was filled at reset
         if (ctx->slot_wrap[s] == wrap) continue;
-        halfpel_planes_kernel<<<dim3((g.W + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, ctx->plane_bytes,
-                                                                                 g.W, g.H, g.pitch, wrap);
+        ring_planes_kernel<<<dim3((g.W / 4 + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, ctx->plane_bytes,
+                                                                                  g.W, g.H, g.pitch, g.fme, wrap);
         ctx->launches++;
         ctx->slot_wrap[s] = wrap;
     }
@@ -915,3 +867,7 @@ extern "C" int64_t so_format_residual_frame(const uint8_t* split, const int16_t*
     }
     return o.finish();
 }
+
+#ifdef SO_ME_DEBUG
+extern "C" int so_debug_read(long long* dst) { return (int)cudaMemcpyFromSymbol(dst, g_me_dbg, sizeof(long long) * 4096); }
+#endif

@@ -23,6 +23,18 @@ struct RefList {
     const uint8_t* plane[SO_MAX_REF][4];
 };
 
+// The reference ring as the kernels address it: [unit][slot][phase 0..3][byte shift 0..3][H][pitch].  Shift plane c of
+// a phase holds the phase plane moved left by c bytes (plane_c[x] = plane[x + c], zero past the frame edge): a TMA box
+// load at a 16-byte aligned x of plane c delivers a search window whose candidates at x = c (mod 4) are word aligned.
+struct RefRing {
+    const uint8_t* base;
+    size_t unit_stride, slot_stride, plane_stride;     // plane_stride: between phases (shift 0 of each)
+    int slot[SO_MAX_REF];                              // list index -> ring slot
+    __device__ __host__ const uint8_t* plane(int unit, int idx, int ph) const {
+        return base + unit * unit_stride + slot[idx] * slot_stride + ph * plane_stride;
+    }
+};
+
 // Result of a motion search for one (sub-)block.
 struct __align__(8) MeResult {
     int16_t dx, dy, ref;
@@ -104,4 +116,22 @@ __device__ __forceinline__ int quant_rhe(int tc, int s) {
     const int rem = tc - (q << s);
     const int half = 1 << (s - 1);
     return q + (rem > half ? 1 : (rem == half ? (q & 1) : 0));
+}
+
+// out[] holds packed 64-bit keys (SAD<<40 | L1<<24 | ref<<16 | dx+R<<8 | dy+R) after the search kernel; convert in place.
+__global__ void me_unpack_kernel(MeResult* out, int n, int R) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = *reinterpret_cast<unsigned long long*>(out + i);
+    MeResult r;
+    if (key == ~0ull) {
+        r.dx = 0; r.dy = 0; r.ref = 0; r.none = 1; r.sad = 0;      // best_mv = (0,0,0), MAE = inf (Encoder.py:684-685)
+    } else {
+        r.sad = (uint32_t)(key >> 40);
+        r.ref = (int16_t)((key >> 16) & 0xFF);
+        r.dx = (int16_t)((int)((key >> 8) & 0xFF) - R);
+        r.dy = (int16_t)((int)(key & 0xFF) - R);
+        r.none = 0;
+    }
+    out[i] = r;
 }

@@ -2,32 +2,67 @@
 // residual/transform/quant/RD/reconstruct "finish" kernels and the intra reconstruction chain.
 #pragma once
 #include "so_common.cuh"
-#include "so_me_full.cuh"
 #include "so_transform.cuh"
 #include "../../include/streamoptima_b200.h"
 
 // ------------------------------------------------------------------------------------------------------------
-// half-pel phase planes (frac_me_reference_frame, Encoder.py:388-406; appendix A1)
+// reference ring planes: half-pel phases (frac_me_reference_frame, Encoder.py:388-406; appendix A1) and the four
+// byte-shifted copies of every phase that the TMA search windows are loaded from
 // ------------------------------------------------------------------------------------------------------------
-// plane1 = ceil((a[x]+a[x+1])/2) with the uint8 wrap of the sum when `wrap` (quirk Q1), plane2 = vertical (never
-// wraps: the column pass is float), plane3 = ceil((sh[y]+sh[y+1])/4) on the (possibly wrapped) horizontal sums.
-__global__ void halfpel_planes_kernel(uint8_t* base, size_t unit_stride, size_t plane_stride, int W, int H, int pitch, int wrap) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+// slot layout [phase 0..3][shift 0..3][H][pitch]; input = phase 0 / shift 0 (the reconstruction).
+// phase 1 = ceil((a[x]+a[x+1])/2) with the uint8 wrap of the sum when `wrap` (quirk Q1), phase 2 = vertical (never
+// wraps: the column pass is float), phase 3 = ceil((sh[y]+sh[y+1])/4) on the (possibly wrapped) horizontal sums.
+// One thread per 4 output bytes; columns past the frame edge replicate the last column (only invalid candidates and
+// never-sampled half-pel positions see them).
+__global__ void ring_planes_kernel(uint8_t* slot0, size_t unit_stride, size_t plane_bytes, int W, int H, int pitch, int fme, int wrap) {
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
+    const int x = x4 * 4;
     if (x >= W) return;
-    uint8_t* p0 = base + blockIdx.z * unit_stride;
-    const uint8_t* a0 = p0 + (size_t)y * pitch;
-    const int xn = min(x + 1, W - 1), yn = min(y + 1, H - 1);
-    const uint8_t* a1 = p0 + (size_t)yn * pitch;
-    int sh0 = a0[x] + a0[xn], sh1 = a1[x] + a1[xn];
-    if (wrap) { sh0 &= 255; sh1 &= 255; }
+    uint8_t* base = slot0 + blockIdx.z * unit_stride;
+    const int yn = min(y + 1, H - 1);
+    int a0[9], a1[9];
+    {
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(base + (size_t)y * pitch);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(base + (size_t)yn * pitch);
+        uint32_t w0[3], w1[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const bool in = x + 4 * q < W;
+            w0[q] = in ? r0[x4 + q] : 0u;
+            w1[q] = in ? r1[x4 + q] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int col = min(x + i, W - 1) - x;            // replicate the last column
+            a0[i] = (w0[col >> 2] >> (8 * (col & 3))) & 255;
+            a1[i] = (w1[col >> 2] >> (8 * (col & 3))) & 255;
+        }
+    }
+    int ph[4][7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        int sh0 = a0[i] + a0[i + 1], sh1 = a1[i] + a1[i + 1];
+        if (wrap) { sh0 &= 255; sh1 &= 255; }
+        ph[0][i] = a0[i];
+        ph[1][i] = (sh0 + 1) >> 1;
+        ph[2][i] = (a0[i] + a1[i] + 1) >> 1;
+        ph[3][i] = (sh0 + sh1 + 3) >> 2;
+    }
     const size_t o = (size_t)y * pitch + x;
-    (p0 + plane_stride)[o] = (uint8_t)((sh0 + 1) >> 1);
-    (p0 + 2 * plane_stride)[o] = (uint8_t)((a0[x] + a1[x] + 1) >> 1);
-    (p0 + 3 * plane_stride)[o] = (uint8_t)((sh0 + sh1 + 3) >> 2);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (p > 0 && !fme) break;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (p == 0 && c == 0) continue;                   // the input plane
+            const uint32_t v = (uint32_t)ph[p][c] | ((uint32_t)ph[p][c + 1] << 8) | ((uint32_t)ph[p][c + 2] << 16) | ((uint32_t)ph[p][c + 3] << 24);
+            *reinterpret_cast<uint32_t*>(base + (size_t)(p * 4 + c) * plane_bytes + o) = v;
+        }
+    }
 }
 
-// dense [H][W] frame -> pitched plane 0 of a ring slot, all units
+// dense [H][W] frame -> pitched phase-0 / shift-0 plane of a ring slot, all units
 __global__ void ring_store_kernel(uint8_t* dst, size_t dst_unit_stride, int pitch, const uint8_t* src, size_t src_unit_stride, int W, int H) {
     const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
