@@ -375,7 +375,8 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     if (SI > 32) SI = 32;
     // DIRECT staging needs every window to start at a 16-byte aligned x (bs = 16, r multiple of 16), one group layout
     // without over-read (NG*G == 2r+1) and a TMA-addressable current frame (16-byte aligned rows)
-    a.direct = (bs == 16 && r % 16 == 0 && r > 0 && a.NG * G == 2 * r + 1 && ctx->g.W % 16 == 0 &&
+    static const bool no_direct = std::getenv("SO_ME_NO_DIRECT") != nullptr;     // tests: force the EXPAND staging mode
+    a.direct = (!no_direct && bs == 16 && r % 16 == 0 && r > 0 && a.NG * G == 2 * r + 1 && ctx->g.W % 16 == 0 &&
                 (reinterpret_cast<uintptr_t>(cur) % 16 == 0) && (cur_stride % 16 == 0)) ? 1 : 0;
     size_t smem = 0;
     if (a.direct) {

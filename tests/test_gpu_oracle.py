@@ -1,0 +1,117 @@
+"""GPU parity against the CPU oracle on seeded inputs, at configurations the goldens do not cover -- in particular
+search range 16 with 16x16 blocks, which is the DIRECT TMA staging path of the exhaustive search (BASELINE configs 2-5)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import codec_oracle as co
+from oracle.packing import package_to_arrays
+from streamoptima_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "r16_int": dict(gen=("translating", dict(F=3, H=96, W=128, seed=41)),
+                    enc=dict(block_size=16, search_range=16, Qp=3, intra_dur=8)),
+    "r16_fme_nref2": dict(gen=("zooming", dict(F=4, H=96, W=128, seed=42)),
+                          enc=dict(block_size=16, search_range=16, Qp=2, intra_dur=8, FMEEnable=True, nRefFrames=2)),
+    "r16_fme_nref4_ties": dict(gen=("flat_ties", dict(F=6, H=64, W=96, seed=43)),
+                               enc=dict(block_size=16, search_range=16, Qp=0, intra_dur=8, FMEEnable=True, nRefFrames=4)),
+    "r16_vbs_fme_bright": dict(gen=("translating", dict(F=3, H=96, W=128, seed=44, bright=True)),
+                               enc=dict(block_size=16, search_range=16, Qp=4, intra_dur=8, FMEEnable=True, nRefFrames=2,
+                                        VBSEnable=True, lam=0.02)),
+    "r8_i8_fme": dict(gen=("translating", dict(F=3, H=64, W=96, seed=45)),
+                      enc=dict(block_size=8, search_range=8, Qp=1, intra_dur=8, FMEEnable=True)),
+    "r5_i16": dict(gen=("zooming", dict(F=3, H=64, W=96, seed=46)),
+                   enc=dict(block_size=16, search_range=5, Qp=5, intra_dur=8, nRefFrames=2)),
+    "r7_i8_vbs": dict(gen=("translating", dict(F=3, H=64, W=96, seed=47)),
+                      enc=dict(block_size=8, search_range=7, Qp=2, intra_dur=8, VBSEnable=True, lam=0.03)),
+    "w_not_mult16": dict(gen=("translating", dict(F=3, H=48, W=72, seed=48)),
+                         enc=dict(block_size=8, search_range=3, Qp=2, intra_dur=8, FMEEnable=True, nRefFrames=2)),
+    "r0": dict(gen=("translating", dict(F=3, H=32, W=48, seed=49)),
+               enc=dict(block_size=8, search_range=0, Qp=2, intra_dur=8)),
+}
+
+
+def _encode_gpu(frames, enc):
+    from streamoptima_b200.Encoder import Y_Video_codec
+    Y_Video_codec.write_recon_yuv = False
+    F, H, W = frames.shape
+    e = dict(enc)
+    c = Y_Video_codec(H, W, F, e.pop("block_size"), e.pop("search_range"), e.pop("Qp"), e.pop("intra_dur"), 0,
+                      y_only_frame_arr=frames, **e)
+    psnr = c.encode()
+    return c, psnr
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matches_oracle(name):
+    kind, gkw = CASES[name]["gen"]
+    enc = CASES[name]["enc"]
+    frames = synth.make(kind, **gkw)
+    F, H, W = frames.shape
+    c, psnr = _encode_gpu(frames, enc)
+    p = c.encoded_package.packed
+    o = co.OracleCodec(H, W, F, y_only_frame_arr=frames, **enc).encode()
+    split, mv, lev = package_to_arrays(o["frame_types"], o["mvs"], o["levels"], H, W, enc["block_size"])
+    assert c.encoded_package["frame_type_seq"] == o["frame_types"]
+    np.testing.assert_array_equal(p["split"], split)
+    np.testing.assert_array_equal(p["mv"], mv)
+    np.testing.assert_array_equal(p["levels"], lev)
+    np.testing.assert_array_equal(p["recon"], o["recon"])
+    np.testing.assert_allclose(psnr, o["psnr"], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(p["qsize"], np.asarray(o["qsize"], np.uint32))
+    np.testing.assert_array_equal(p["row_sizes"], np.asarray(o["row_sizes"], np.uint32))
+
+
+_SCRIPT = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+from streamoptima_b200 import synth
+from streamoptima_b200.Encoder import Y_Video_codec
+Y_Video_codec.write_recon_yuv = False
+F, H, W = 4, 1088, 1920
+frames = synth.translating(F, H, W, seed=3)
+c = Y_Video_codec(H, W, F, 16, 16, 4, 30, 0, nRefFrames=4, FMEEnable=True, y_only_frame_arr=frames)
+c.encode()
+p = c.encoded_package.packed
+print(hashlib.sha256(p["mv"].tobytes() + p["levels"].tobytes() + p["recon"].tobytes()).hexdigest())
+"""
+
+
+def test_full_size_direct_equals_expand_staging():
+    """BASELINE config 2 geometry (1920x1088, i=16, r=16, half-pel, 4 refs): the DIRECT TMA staging used by the bench
+    and the EXPAND staging (the one the small goldens exercise) must produce identical MVs, levels and reconstruction."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {"SO_ME_NO_DIRECT": "1"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", _SCRIPT % root], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
+
+
+def test_full_size_crop_matches_oracle_interior():
+    """1080p P frame against the oracle on a crop: blocks whose whole search window lies inside the crop must get the
+    same motion vector when the crop is encoded on its own with the same reference pixels (integer search, 1 ref)."""
+    from streamoptima_b200.Encoder import Y_Video_codec
+    Y_Video_codec.write_recon_yuv = False
+    F, H, W = 2, 1088, 1920
+    frames = synth.translating(F, H, W, seed=5)
+    c = Y_Video_codec(H, W, F, 16, 16, 4, 30, 0, y_only_frame_arr=frames)
+    c.encode()
+    p = c.encoded_package.packed
+    recon0 = p["recon"][0]
+    # oracle full search of frame 1 against the GPU's reconstruction of frame 0 on a 256x160 crop at (512, 320)
+    y0, x0, ch, cw = 320, 512, 160, 256
+    mv, sad = co.full_search(frames[1, y0:y0 + ch, x0:x0 + cw].astype(np.int64), [recon0[y0:y0 + ch, x0:x0 + cw]], 16, 16, False)
+    nbx = W // 16
+    for by in range(1, ch // 16 - 2):
+        for bx in range(1, cw // 16 - 2):
+            gb = (y0 // 16 + by) * nbx + (x0 // 16 + bx)
+            got = tuple(int(v) for v in p["mv"][1, gb, 0])
+            assert got == tuple(int(v) for v in mv[by, bx]), (by, bx)
