@@ -20,6 +20,7 @@
 // The whole reference ring is ONE 3-D tensor map {W, H, units*slots*16 planes}: plane index = z coordinate.
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 
 #include "so_common.cuh"
 
@@ -320,37 +321,124 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 for (int gg = 0; gg < G; ++gg)
 #pragma unroll
                     for (int k = 0; k < NDX; ++k) acc[gg][k] = 0;
-                {
+                // One window row against the G candidate rows it belongs to.  curq[gg] holds current-block row (rho - gg).
+                // MASK bit gg = candidate group gg is active for this row (rho - gg inside 0..BS-1).
+                auto load_cur = [&](int row, uint32_t (&dst)[WPR]) {
+                    if constexpr (WPR == 4) {
+                        const uint4 q = reinterpret_cast<const uint4*>(cb)[row];
+                        dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+                    } else if constexpr (WPR == 2) {
+                        const uint2 q = reinterpret_cast<const uint2*>(cb)[row];
+                        dst[0] = q.x; dst[1] = q.y;
+                    } else {
+                        dst[0] = cb[row];
+                    }
+                };
+                constexpr int KM = EXTRA ? NM : NDX;
+                auto row_step = [&](const unsigned char* wrow, const uint32_t (&curq)[G][WPR], auto mask_c) {
+                    constexpr int MASK = decltype(mask_c)::value;
+                    uint32_t refw[NVM * 4];
+#pragma unroll
+                    for (int v = 0; v < NVM; ++v) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(wrow + v * 16);
+                        refw[4 * v] = q.x; refw[4 * v + 1] = q.y; refw[4 * v + 2] = q.z; refw[4 * v + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int gg = 0; gg < G; ++gg) {
+                        if ((MASK >> gg) & 1) {
+#pragma unroll
+                            for (int k = 0; k < KM; ++k)
+#pragma unroll
+                                for (int w = 0; w < WPR; ++w) acc[gg][k] = sad4_acc(refw[k + w], curq[gg][w], acc[gg][k]);
+                        }
+                    }
+                };
+                constexpr int WP = NCH * 16;                                  // == a.wpitch, as a compile-time constant
+                if constexpr (G == 3 && BS % 3 == 1) {
+                    // rows 0,1 ramp up, rows 2..BS-1 are steady (all three groups active) and are rolled in steps of three so
+                    // that the register rotation of curq is static while the loop body stays inside the instruction cache,
+                    // rows BS, BS+1 ramp down.  BS % 3 == 1 (bs 4, 16): BS-2 = 3*m steady rows exactly... handled generically:
+                    uint32_t cq[3][WPR];                                       // cq[i] = current row with (row % 3 == i)
+                    load_cur(0, cq[0]);
+                    { const uint32_t (&v)[3][WPR] = cq; uint32_t t[G][WPR];
+#pragma unroll
+                      for (int w = 0; w < WPR; ++w) { t[0][w] = v[0][w]; t[1][w] = 0; t[2][w] = 0; }
+                      row_step(win, t, std::integral_constant<int, 1>{}); }
+                    load_cur(1, cq[1]);
+                    { uint32_t t[G][WPR];
+#pragma unroll
+                      for (int w = 0; w < WPR; ++w) { t[0][w] = cq[1][w]; t[1][w] = cq[0][w]; t[2][w] = 0; }
+                      row_step(win + WP, t, std::integral_constant<int, 3>{}); }
+                    // steady rows rho = 2 .. BS-1: groups (rho, rho-1, rho-2) -> cq[(rho)%3], cq[(rho-1)%3], cq[(rho-2)%3]
+                    const unsigned char* wr = win + 2 * WP;
+                    constexpr int STEADY = BS - 2;                             // 14 for bs 16
+                    constexpr int TRIPLES = STEADY / 3;                        // 4 rolled iterations
+#pragma unroll 1
+                    for (int it3 = 0; it3 < TRIPLES; ++it3) {
+                        const int rho = 2 + 3 * it3;
+                        load_cur(rho, cq[2]);
+                        { uint32_t t[G][WPR];
+#pragma unroll
+                          for (int w = 0; w < WPR; ++w) { t[0][w] = cq[2][w]; t[1][w] = cq[1][w]; t[2][w] = cq[0][w]; }
+                          row_step(wr, t, std::integral_constant<int, 7>{}); }
+                        load_cur(rho + 1, cq[0]);
+                        { uint32_t t[G][WPR];
+#pragma unroll
+                          for (int w = 0; w < WPR; ++w) { t[0][w] = cq[0][w]; t[1][w] = cq[2][w]; t[2][w] = cq[1][w]; }
+                          row_step(wr + WP, t, std::integral_constant<int, 7>{}); }
+                        load_cur(rho + 2, cq[1]);
+                        { uint32_t t[G][WPR];
+#pragma unroll
+                          for (int w = 0; w < WPR; ++w) { t[0][w] = cq[1][w]; t[1][w] = cq[0][w]; t[2][w] = cq[2][w]; }
+                          row_step(wr + 2 * WP, t, std::integral_constant<int, 7>{}); }
+                        wr += 3 * WP;
+                    }
+                    // remaining steady rows (STEADY % 3 of them; 2 for bs 16: rho = 14, 15), then the two ramp-down rows
+                    constexpr int R0 = 2 + 3 * TRIPLES;                        // first row not yet processed; R0 % 3 == 2
+                    static_assert(STEADY % 3 == 2, "row schedule below assumes two trailing steady rows");
+                    load_cur(R0, cq[2]);
+                    { uint32_t t[G][WPR];
+#pragma unroll
+                      for (int w = 0; w < WPR; ++w) { t[0][w] = cq[2][w]; t[1][w] = cq[1][w]; t[2][w] = cq[0][w]; }
+                      row_step(wr, t, std::integral_constant<int, 7>{}); }
+                    load_cur(R0 + 1, cq[0]);
+                    { uint32_t t[G][WPR];
+#pragma unroll
+                      for (int w = 0; w < WPR; ++w) { t[0][w] = cq[0][w]; t[1][w] = cq[2][w]; t[2][w] = cq[1][w]; }
+                      row_step(wr + WP, t, std::integral_constant<int, 7>{}); }
+                    { uint32_t t[G][WPR];                                       // rho = BS: groups 1, 2 -> rows BS-1, BS-2
+#pragma unroll
+                      for (int w = 0; w < WPR; ++w) { t[0][w] = 0; t[1][w] = cq[0][w]; t[2][w] = cq[2][w]; }
+                      row_step(wr + 2 * WP, t, std::integral_constant<int, 6>{}); }
+                    { uint32_t t[G][WPR];                                       // rho = BS+1: group 2 -> row BS-1
+#pragma unroll
+                      for (int w = 0; w < WPR; ++w) { t[0][w] = 0; t[1][w] = 0; t[2][w] = cq[0][w]; }
+                      row_step(wr + 3 * WP, t, std::integral_constant<int, 4>{}); }
+                } else {
                     uint32_t curq[G][WPR];
 #pragma unroll
-                    for (int rho = 0; rho < BS + G - 1; ++rho) {
-                        uint32_t refw[NVM * 4];
+                    for (int gg = 0; gg < G; ++gg)
 #pragma unroll
-                        for (int v = 0; v < NVM; ++v) {
-                            const uint4 q = *reinterpret_cast<const uint4*>(win + rho * a.wpitch + v * 16);
-                            refw[4 * v] = q.x; refw[4 * v + 1] = q.y; refw[4 * v + 2] = q.z; refw[4 * v + 3] = q.w;
-                        }
+                        for (int w = 0; w < WPR; ++w) curq[gg][w] = 0;
+#pragma unroll
+                    for (int rho = 0; rho < BS + G - 1; ++rho) {
 #pragma unroll
                         for (int gg = G - 1; gg > 0; --gg)
 #pragma unroll
                             for (int w = 0; w < WPR; ++w) curq[gg][w] = curq[gg - 1][w];
-                        if (rho < BS) {
-                            if constexpr (WPR == 4) {
-                                const uint4 q = reinterpret_cast<const uint4*>(cb)[rho];
-                                curq[0][0] = q.x; curq[0][1] = q.y; curq[0][2] = q.z; curq[0][3] = q.w;
-                            } else if constexpr (WPR == 2) {
-                                const uint2 q = reinterpret_cast<const uint2*>(cb)[rho];
-                                curq[0][0] = q.x; curq[0][1] = q.y;
-                            } else {
-                                curq[0][0] = cb[rho];
-                            }
+                        if (rho < BS) load_cur(rho, curq[0]);
+                        uint32_t refw[NVM * 4];
+#pragma unroll
+                        for (int v = 0; v < NVM; ++v) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(win + rho * WP + v * 16);
+                            refw[4 * v] = q.x; refw[4 * v + 1] = q.y; refw[4 * v + 2] = q.z; refw[4 * v + 3] = q.w;
                         }
 #pragma unroll
                         for (int gg = 0; gg < G; ++gg) {
                             const int jr = rho - gg;
                             if (jr >= 0 && jr < BS) {
 #pragma unroll
-                                for (int k = 0; k < (EXTRA ? NM : NDX); ++k)
+                                for (int k = 0; k < KM; ++k)
 #pragma unroll
                                     for (int w = 0; w < WPR; ++w) acc[gg][k] = sad4_acc(refw[k + w], curq[gg][w], acc[gg][k]);
                             }
@@ -364,18 +452,19 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                         constexpr int W0 = (NDX - 1);                       // first window word of that candidate
                         uint32_t curq[G][WPR];
 #pragma unroll
+                        for (int gg = 0; gg < G; ++gg)
+#pragma unroll
+                            for (int w = 0; w < WPR; ++w) curq[gg][w] = 0;
+#pragma unroll
                         for (int rho = 0; rho < BS + G - 1; ++rho) {
                             uint32_t refw[WPR];
 #pragma unroll
-                            for (int w = 0; w < WPR; ++w) refw[w] = *reinterpret_cast<const uint32_t*>(win + rho * a.wpitch + (W0 + w) * 4);
+                            for (int w = 0; w < WPR; ++w) refw[w] = *reinterpret_cast<const uint32_t*>(win + rho * WP + (W0 + w) * 4);
 #pragma unroll
                             for (int gg = G - 1; gg > 0; --gg)
 #pragma unroll
                                 for (int w = 0; w < WPR; ++w) curq[gg][w] = curq[gg - 1][w];
-                            if (rho < BS) {
-#pragma unroll
-                                for (int w = 0; w < WPR; ++w) curq[0][w] = cb[rho * WPR + w];
-                            }
+                            if (rho < BS) load_cur(rho, curq[0]);
 #pragma unroll
                             for (int gg = 0; gg < G; ++gg) {
                                 const int jr = rho - gg;
@@ -411,8 +500,9 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                     const uint32_t xbad = (ox <= g.r && dx >= xlo && dx <= xhi) ? 0u : 0xFFFFFFFFu;
 #pragma unroll
                     for (int gg = 0; gg < G; ++gg) {
-                        const uint32_t key = ((acc[gg][k] << 16) + (lx8 + ly8[gg])) | xbad | ybad[gg];
-                        best = min(best, key);
+                        uint32_t key = acc[gg][k] * 65536u + (lx8 + ly8[gg]);
+                        asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(key) : "r"(xbad), "r"(ybad[gg]));      // key | xbad | ybad
+                        asm("min.u32 %0, %0, %1;" : "+r"(best) : "r"(key));
                     }
                 }
                 unsigned long long key = ~0ull;
