@@ -383,7 +383,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
         a.nstage = 3;
         a.item_stride = (a.rows * a.wpitch + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
         a.raw_w = a.wpitch; a.raw_item_stride = 0; a.aligned16 = 1;
-        auto smem_for = [&](int si, int ns) { return (size_t)ns * si * (4 * a.item_stride + bs * bs) + 256; };
+        auto smem_for = [&](int si, int ns) { return (size_t)ns * si * (4 * a.item_stride + bs * bs) + 256 + (size_t)ME_MAX_STAGES * si * 16 + (size_t)((si * tasks_per_item + 31) / 32) * 128; };
         while (SI > 1 && smem_for(SI, a.nstage) > 226 * 1024) --SI;
         smem = smem_for(SI, a.nstage);
     } else {
@@ -404,7 +404,8 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
         a.raw_item_stride = (a.rows * a.raw_w + 127) / 128 * 128;
         auto smem_for = [&](int si, int ns) {
             // 128-byte alignment of the raw area: copies and cur tiles are multiples of 16 only
-            return (size_t)ns * si * (4 * a.item_stride + a.raw_item_stride + bs * bs) + 512;
+            return (size_t)ns * si * (4 * a.item_stride + a.raw_item_stride + bs * bs) + 512 + (size_t)ME_MAX_STAGES * si * 16 +
+                   (size_t)((si * tasks_per_item + 31) / 32) * 128;
         };
         while (SI > 1 && smem_for(SI, a.nstage) > 226 * 1024) --SI;
         smem = smem_for(SI, a.nstage);
@@ -484,6 +485,7 @@ static FlowArgs make_flow(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, co
     a.frame_stride = out_frames_stride * ctx->frame_px;
     a.rows_stride = out_frames_stride * ctx->g.nby;
     a.stats_stride = out_frames_stride;
+    a.scratch_stride = ctx->frame_px;
     return a;
 }
 

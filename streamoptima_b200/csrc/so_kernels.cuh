@@ -99,6 +99,7 @@ struct FlowArgs {
     // outputs (dense per unit)
     uint8_t* split; int16_t* mv; int16_t* levels; uint8_t* recon; uint32_t* row_sizes; so_frame_stats* stats;
     size_t split_stride, mv_stride, frame_stride, rows_stride, stats_stride;   // per-unit strides in elements
+    size_t scratch_stride;       // per-unit stride of res_frame / band (one frame)
 };
 
 __device__ __forceinline__ double me_mae(const MeResult& m, int n, int fast) {
@@ -489,7 +490,7 @@ __global__ void intra_finish_kernel(const FlowArgs a) {
         ws[j * P + i] = (double)(level * (1 << shift));
     }
     if (split) transform2d<BS, S, true>(ws, t); else transform2d<BS, BS, true>(ws, t);
-    if (active) a.res_frame[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)rint(ws[j * P + i]);
+    if (active) a.res_frame[unit * a.scratch_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)rint(ws[j * P + i]);
     if (t == 0) {
         a.split[unit * a.split_stride + blk] = (uint8_t)split;
         int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
@@ -518,8 +519,8 @@ __global__ void intra_recon_kernel(const FlowArgs a) {
     const bool active = t < BS * BS;
     const int i = active ? t % BS : 0, j = active ? t / BS : 0;
     const int y = by * BS;
-    int32_t* band = a.band + unit * a.frame_stride + (size_t)(y + j) * g.W;
-    const int16_t* res = a.res_frame + unit * a.frame_stride + (size_t)(y + j) * g.W;
+    int32_t* band = a.band + unit * a.scratch_stride + (size_t)(y + j) * g.W;
+    const int16_t* res = a.res_frame + unit * a.scratch_stride + (size_t)(y + j) * g.W;
     const uint8_t* cur = a.cur + unit * a.cur_unit_stride + (size_t)(y + j) * g.W;
     uint8_t* rec = a.recon + unit * a.frame_stride + (size_t)(y + j) * g.W;
     if (active) for (int xx = i; xx < g.W; xx += BS) band[xx] = 128;

@@ -110,12 +110,20 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
     uint64_t* ready = rawfull + ME_MAX_STAGES;
     uint64_t* empty = ready + ME_MAX_STAGES;
     unsigned int* counter = reinterpret_cast<unsigned int*>(empty + ME_MAX_STAGES);
+    int4* meta = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(counter) + 16 + 15) & ~(uintptr_t)15);                      // [S][SI]: {blk, bx, by, ref | ph << 8} written by the producer
+    uint32_t* ttab = reinterpret_cast<uint32_t*>(meta + ME_MAX_STAGES * a.SI);   // [NB*32]: task -> c | li << 2 | grp << 10 (full stages)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < ME_MAX_STAGES; ++s) { mbar_init(&rawfull[s], 1); mbar_init(&ready[s], 1); mbar_init(&empty[s], a.NB); }
         *counter = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int t = tid; t < a.NB * 32; t += blockDim.x) {       // decode table of a full stage: no divisions in the search loop
+        const int tps = a.SI * a.NG;
+        uint32_t e = 0xFFFFFFFFu;
+        if (t < 4 * tps) { const int c = t / tps, rem = t % tps; e = (uint32_t)c | ((uint32_t)(rem / a.NG) << 2) | ((uint32_t)(rem % a.NG) << 10); }
+        ttab[t] = e;
     }
     __syncthreads();
 
@@ -137,6 +145,11 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 const int item0 = sidx * a.SI;
                 const int nitems = min(a.SI, a.items_per_unit - item0);
                 mbar_wait(&empty[sb], par ^ 1);
+                for (int li = lane; li < nitems; li += 32) {
+                    const int item = item0 + li;
+                    const int blk = item / per_blk, rp = item % per_blk;
+                    meta[sb * a.SI + li] = make_int4(blk, blk % g.nbx, blk / g.nbx, (rp / a.nph) | ((rp % a.nph) << 8));
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // buffer was read through the generic proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive_expect_tx(&ready[sb], (uint32_t)(nitems * (4 * a.rows * a.wpitch + BS * BS)));
@@ -278,6 +291,11 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                     *reinterpret_cast<uint4*>(wst + c * a.shift_stride + li * a.item_stride + row * a.wpitch + q * 16) = w4;
                 }
             }
+            for (int li = lane; li < nitems; li += 32) {
+                const int item = item0 + li;
+                const int blk = item / per_blk, rp = item % per_blk;
+                meta[sb * a.SI + li] = make_int4(blk, blk % g.nbx, blk / g.nbx, (rp / a.nph) | ((rp % a.nph) << 8));
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[sb]);
             ME_DBG(3, j);
@@ -303,14 +321,23 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
             if (kb == 10) ME_DBG(9, j);
             // task order inside a stage: shift-major, then item, then vertical group (keeps warps nearly uniform in c)
             const int task = kb * 32 + lane;
-            const int tasks_per_shift = nitems * a.NG;
-            if (task < 4 * tasks_per_shift) {
-                const int c = task / tasks_per_shift;
+            int c, li, grp;
+            bool has_task;
+            if (nitems == a.SI) {
+                const uint32_t e = ttab[task];
+                has_task = e != 0xFFFFFFFFu;
+                c = e & 3; li = (e >> 2) & 255; grp = (e >> 10) & 1023;
+            } else {
+                const int tasks_per_shift = nitems * a.NG;
+                has_task = task < 4 * tasks_per_shift;
+                c = task / tasks_per_shift;
                 const int rem = task % tasks_per_shift;
-                const int li = rem / a.NG, grp = rem % a.NG;
-                const int item = item0 + li;
-                const int blk = item / per_blk, rp = item % per_blk;
-                const int ref = rp / a.nph, ph = rp % a.nph;
+                li = rem / a.NG; grp = rem % a.NG;
+            }
+            if (has_task) {
+                const int4 mt = meta[sb * a.SI + li];
+                const int blk = mt.x, bx = mt.y, by = mt.z;
+                const int ref = mt.w & 255, ph = mt.w >> 8;
                 const int px = ph & 1, py = ph >> 1;
                 const int oy0 = grp * G;
                 const unsigned char* win = wins + sb * a.stage_bytes + c * a.shift_stride + li * a.item_stride + oy0 * a.wpitch;
@@ -478,7 +505,6 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 }
 
                 // ---- thread-local argmin.  key32 = sad<<16 | (|dx|+|dy|)<<8 | (k*G+g); invalid candidates are OR-ed to all ones.
-                const int bx = blk % g.nbx, by = blk / g.nbx;
                 int xlo, xhi, ylo, yhi;
                 valid_range(bx * BS, g.W, BS, g.fme, g.fme, xlo, xhi);
                 valid_range(by * BS, g.H, BS, g.fme, g.fme, ylo, yhi);
