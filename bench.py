@@ -170,6 +170,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from streamoptima_b200 import _native
     from streamoptima_b200.Encoder import Y_Video_codec
 
     if not torch.cuda.is_available():
@@ -180,7 +181,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     F, H, W = cfg["F"], cfg["H"], cfg["W"]
     frames_t = synth_frames_torch(F, H, W, seed=rank, device=dev)
-    frames = frames_t.cpu().numpy()
+    frames_pinned = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True)       # e2e inputs live in pinned host memory
+    frames_pinned.copy_(frames_t)
+    frames = frames_pinned.numpy()
     del frames_t
     torch.cuda.empty_cache()
 
@@ -190,22 +193,25 @@ def main():
     codec.device = local_rank
     ctx = codec._context(cfg["bs"], cfg["r"], cfg["intra_dur"], max_batch=1)
     lib = ctx.lib
-    from streamoptima_b200 import _native
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    stats_dev = torch.zeros((F, 8), dtype=torch.int32, device=dev)
+    stats_host = np.zeros((1, F), dtype=_native.STATS_DTYPE)
 
     def step_resident(k):
         ctx.set_qp(k % 12)
         _native.check(ctx.handle, lib.so_seq_run(ctx.handle))
         t = ctx.last_timing()                       # waits for the step's last event
-        if world > 1:                               # pass-1 statistics for two-pass rate control: tens of KB over NVLink
-            gathered = [torch.empty_like(stats_dev) for _ in range(world)]
-            dist.all_gather(gathered, stats_dev)
+        if world > 1:
+            # pass-1 statistics (quantized_sized, SSE, type per frame) that two-pass rate control consumes: all-gathered
+            # over NCCL/NVLink -- a few KB, the only collective of the path
+            _native.check(ctx.handle, lib.so_seq_download(ctx.handle, None, None, None, None, None, stats_host.ctypes.data))
+            mine = torch.from_numpy(np.stack([stats_host["qsize"][0].astype(np.int64), stats_host["sse"][0].astype(np.int64),
+                                              stats_host["frame_type"][0].astype(np.int64)], axis=1)).to(dev)
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
         return t
 
     # ---- kernel-only: inputs resident in HBM

@@ -231,15 +231,16 @@ class Y_Video_codec:
         # NOTE the returned arrays are views of these buffers and are overwritten by the next call.
         key = (U, F, H, W, nblk, rows)
         if getattr(self, "_pin_key", None) != key:
-            self._pin = dict(inp=_pinned_empty((U, F, H, W), np.uint8), split=_pinned_empty((U, F, nblk), np.uint8),
+            self._pin = dict(split=_pinned_empty((U, F, nblk), np.uint8),
                              mv=_pinned_empty((U, F, nblk, 4, 3), np.int16), rows=_pinned_empty((U, F, rows), np.uint32))
             self._pin_key = key
         if want_levels and "lev" not in self._pin:
             self._pin["lev"] = _pinned_empty((U, F, H, W), np.int16)
         if want_recon and "rec" not in self._pin:
             self._pin["rec"] = _pinned_empty((U, F, H, W), np.uint8)
-        a_in = self._pin["inp"][1]
-        np.copyto(a_in, arr)
+        # the input is handed to the library as is (pinned or pageable): its upload is chunked and overlapped with the
+        # encode of earlier chunks, so an extra staging copy would only add host time
+        a_in = np.ascontiguousarray(arr)
         split, mv, row_sizes = self._pin["split"][1], self._pin["mv"][1], self._pin["rows"][1]
         levels = self._pin["lev"][1] if want_levels else None
         recon = self._pin["rec"][1] if want_recon else None

@@ -9,6 +9,7 @@
 #include "so_kernels.cuh"
 #include "so_me_tma.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 #define CU(expr)                                                                                  \
     do {                                                                                          \
@@ -53,6 +54,19 @@ struct so_ctx {
     bool timing_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sq_units = 0, sq_nframes = 0;
+    // chunked copy/compute overlap of so_encode_sequence: H2D of chunk c+1 and D2H of chunk c-1 run on their own streams
+    // while chunk c is encoded
+    struct Pipe {
+        bool active = false;
+        int chunk = 8, nchunks = 0;
+        const uint8_t* h_frames = nullptr;
+        uint8_t *h_split = nullptr, *h_recon = nullptr;
+        int16_t *h_mv = nullptr, *h_levels = nullptr;
+        uint32_t* h_rows = nullptr;
+        so_frame_stats* h_stats = nullptr;
+        std::vector<cudaEvent_t> up, done;
+    } pipe;
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
     long launches = 0;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -115,6 +129,10 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->res_frame); cudaFree(c->band);
     cudaFree(c->qp_rows_dev);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (auto e : c->pipe.up) cudaEventDestroy(e);
+    for (auto e : c->pipe.done) cudaEventDestroy(e);
+    if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
+    if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -164,6 +182,8 @@ extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
 #define CUC(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return fail(SO_E_CUDA); } } while (0)
     CUC(cudaSetDevice(device));
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking));
     ctx->nslots = p->n_ref_frames;
     ctx->plane_bytes = (size_t)g.pitch * g.H;
     ctx->slot_stride = ctx->plane_bytes * 16;
@@ -627,6 +647,38 @@ static int ensure_seq(so_ctx* ctx, size_t nframes_total) {
     return SO_OK;
 }
 
+// ---- chunk pipeline helpers ------------------------------------------------------------------------------------
+static int pipe_upload_chunk(so_ctx* ctx, int c) {
+    auto& P = ctx->pipe;
+    const int U = ctx->sq_units, F = ctx->sq_nframes;
+    const int f0 = c * P.chunk, n = std::min(P.chunk, F - f0);
+    const size_t px = ctx->frame_px;
+    for (int u = 0; u < U; ++u)
+        CU(cudaMemcpyAsync(ctx->sq_frames + ((size_t)u * F + f0) * px, P.h_frames + ((size_t)u * F + f0) * px, (size_t)n * px,
+                           cudaMemcpyHostToDevice, ctx->st_h2d));
+    CU(cudaEventRecord(P.up[c], ctx->st_h2d));
+    return SO_OK;
+}
+
+static int pipe_download_chunk(so_ctx* ctx, int c) {
+    auto& P = ctx->pipe;
+    const int U = ctx->sq_units, F = ctx->sq_nframes;
+    const int f0 = c * P.chunk, n = std::min(P.chunk, F - f0);
+    const size_t px = ctx->frame_px, nblk = ctx->nblk, nby = ctx->g.nby;
+    cudaStream_t s = ctx->st_d2h;
+    CU(cudaStreamWaitEvent(s, P.done[c], 0));
+    for (int u = 0; u < U; ++u) {
+        const size_t o = (size_t)u * F + f0;
+        CU(cudaMemcpyAsync(P.h_split + o * nblk, ctx->sq_split + o * nblk, n * nblk, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(P.h_mv + o * nblk * 12, ctx->sq_mv + o * nblk * 12, n * nblk * 12 * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+        if (P.h_levels) CU(cudaMemcpyAsync(P.h_levels + o * px, ctx->sq_levels + o * px, n * px * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+        if (P.h_recon) CU(cudaMemcpyAsync(P.h_recon + o * px, ctx->sq_recon + o * px, n * px, cudaMemcpyDeviceToHost, s));
+        if (P.h_rows) CU(cudaMemcpyAsync(P.h_rows + o * nby, ctx->sq_rows + o * nby, n * nby * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(P.h_stats + o, ctx->sq_stats + o, n * sizeof(so_frame_stats), cudaMemcpyDeviceToHost, s));
+    }
+    return SO_OK;
+}
+
 // stage 1: host -> device copy of the input frames (async on the context stream)
 extern "C" int so_seq_upload(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames) {
     if (!ctx || !frames || n_units < 1 || n_frames < 1) return SO_E_INVALID;
@@ -661,6 +713,11 @@ extern "C" int so_seq_run(so_ctx* ctx) {
     if (rc) return rc;
     std::vector<so_frame_stats> hstats(n_units);
     for (int f = 0; f < n_frames; ++f) {
+        if (ctx->pipe.active && f % ctx->pipe.chunk == 0) {
+            const int c = f / ctx->pipe.chunk;
+            if (c + 2 < ctx->pipe.nchunks) { rc = pipe_upload_chunk(ctx, c + 2); if (rc) return rc; }   // two chunks ahead
+            CU(cudaStreamWaitEvent(st, ctx->pipe.up[c], 0));
+        }
         so_frame_out o;
         o.split = ctx->sq_split + (size_t)f * ctx->nblk;
         o.mv = ctx->sq_mv + (size_t)f * ctx->nblk * 12;
@@ -693,6 +750,12 @@ extern "C" int so_seq_run(so_ctx* ctx) {
         }
         if (f < n_frames - 1) {
             rc = ring_push(ctx, o.recon, (size_t)n_frames * px, n_units, st);
+            if (rc) return rc;
+        }
+        if (ctx->pipe.active && ((f + 1) % ctx->pipe.chunk == 0 || f == n_frames - 1)) {
+            const int c = f / ctx->pipe.chunk;
+            CU(cudaEventRecord(ctx->pipe.done[c], st));
+            rc = pipe_download_chunk(ctx, c);
             if (rc) return rc;
         }
     }
@@ -729,12 +792,31 @@ extern "C" int so_seq_sync(so_ctx* ctx) {
 
 extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames, uint8_t* split, int16_t* mv,
                                   int16_t* levels, uint8_t* recon, uint32_t* row_sizes, so_frame_stats* stats) {
-    if (!ctx || !frames || !split || !mv || !stats) return SO_E_INVALID;
-    int rc = so_seq_upload(ctx, frames, n_units, n_frames);
+    if (!ctx || !frames || !split || !mv || !stats || n_units < 1 || n_frames < 1) return SO_E_INVALID;
+    if (n_units > ctx->batch) { set_err(ctx, "n_units exceeds max_batch of the context"); return SO_E_INVALID; }
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_seq(ctx, (size_t)n_units * n_frames);
     if (rc) return rc;
-    rc = so_seq_run(ctx);
-    if (rc) return rc;
-    return so_seq_download(ctx, split, mv, levels, recon, row_sizes, stats);
+    ctx->sq_units = n_units; ctx->sq_nframes = n_frames;
+    auto& P = ctx->pipe;
+    P.chunk = 8;
+    P.nchunks = (n_frames + P.chunk - 1) / P.chunk;
+    while ((int)P.up.size() < P.nchunks) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        P.up.push_back(a); P.done.push_back(b);
+    }
+    P.h_frames = frames; P.h_split = split; P.h_mv = mv; P.h_levels = levels; P.h_recon = recon; P.h_rows = row_sizes; P.h_stats = stats;
+    P.active = true;
+    rc = pipe_upload_chunk(ctx, 0);
+    if (!rc && P.nchunks > 1) rc = pipe_upload_chunk(ctx, 1);
+    if (!rc) rc = so_seq_run(ctx);
+    P.active = false;
+    if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st_d2h); return rc; }
+    CU(cudaStreamSynchronize(ctx->st_d2h));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SO_OK;
 }
 
 extern "C" int so_last_timing(so_ctx* ctx, double out[4]) {
