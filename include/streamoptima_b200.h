@@ -142,6 +142,14 @@ int so_seq_download(so_ctx* ctx, uint8_t* split, int16_t* mv, int16_t* levels, u
                     uint32_t* row_sizes, so_frame_stats* stats);
 int so_seq_sync(so_ctx* ctx);
 
+/* Decoder (decoder.py:487-545 `decode` with decode_frame_inter :97 / decode_frame_intra :330) on packed arrays, host
+ * buffers in and out, one sequence (unit).  frame_types u8 [n_frames]; split / mv / levels as so_encode_sequence writes
+ * them; qp_rows_per_frame i32 [n_frames][height/block_size] or NULL (RCFlag off).  reset_at_intra != 0 clears the
+ * reference list at I frames like decoder.py:520 does; 0 keeps the ENCODER's list semantics (Encoder.py:1864-1867),
+ * which is what round-trips streams encoded with nRefFrames > 1 (quirk Q7).  out_frames u8 [n_frames][height][width]. */
+int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
+                       const int32_t* qp_rows_per_frame, int n_frames, int reset_at_intra, uint8_t* out_frames);
+
 /* Timing of the last so_seq_run, CUDA events on the context stream (ms): [0] whole device region, [1] motion-search
  * kernels only (exhaustive search: the me_full_kernel launches; fast ME: the chain kernel; intra frames: intra search),
  * [2] transform/quant/recon kernels, [3] number of kernel launches.  Waits for the run to finish. */

@@ -819,6 +819,64 @@ extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_unit
     return SO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// decoder: restates decoder.decode (decoder.py:487-545) on packed arrays, host buffers in and out
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
+                                  const int32_t* qp_rows_per_frame, int n_frames, int reset_at_intra, uint8_t* out_frames) {
+    if (!ctx || !frame_types || !split || !mv || !levels || !out_frames || n_frames < 1) return SO_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_seq(ctx, (size_t)n_frames);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const FrameGeom& g = ctx->g;
+    const size_t px = ctx->frame_px;
+    CU(cudaMemcpyAsync(ctx->sq_split, split, (size_t)n_frames * ctx->nblk, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->sq_mv, mv, (size_t)n_frames * ctx->nblk * 12 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->sq_levels, levels, (size_t)n_frames * px * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    rc = so_ref_reset(ctx, 0, st);
+    if (rc) return rc;
+    const int nt = nthreads_px(g.bs);
+    for (int f = 0; f < n_frames; ++f) {
+        so_frame_out o;
+        o.split = ctx->sq_split + (size_t)f * ctx->nblk;
+        o.mv = ctx->sq_mv + (size_t)f * ctx->nblk * 12;
+        o.levels = ctx->sq_levels + (size_t)f * px;
+        o.recon = ctx->sq_recon + (size_t)f * px;
+        o.row_sizes = ctx->sq_rows;
+        o.stats = ctx->sq_stats;
+        if (qp_rows_per_frame) CU(cudaMemcpyAsync(ctx->qp_rows_dev, qp_rows_per_frame + (size_t)f * g.nby, sizeof(int) * g.nby, cudaMemcpyHostToDevice, st));
+        const bool intra = frame_types[f] == 0 && ctx->p.parallel_mode != 1;
+        if (!intra && ctx->p.parallel_mode == 1) { rc = so_ref_reset(ctx, 0, st); if (rc) return rc; }     // decoder.py:504-509
+        if (!intra) {
+            if (ctx->list.empty()) { set_err(ctx, "inter frame with an empty reference list"); return SO_E_STATE; }
+            rc = ensure_planes(ctx, 1, st);
+            if (rc) return rc;
+        }
+        FlowArgs a = make_flow(ctx, o.recon, px, &o, n_frames, 0, ctx->p.qp);
+        a.qp_rows = qp_rows_per_frame ? ctx->qp_rows_dev : nullptr;
+        dim3 grid(ctx->nblk, 1);
+        if (g.bs == 16) decode_block_kernel<16><<<grid, nt, 0, st>>>(a, intra ? 1 : 0);
+        else if (g.bs == 8) decode_block_kernel<8><<<grid, nt, 0, st>>>(a, intra ? 1 : 0);
+        else decode_block_kernel<4><<<grid, nt, 0, st>>>(a, intra ? 1 : 0);
+        if (intra) {
+            dim3 grid2(g.nby, 1);
+            if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
+            else if (g.bs == 8) intra_recon_kernel<8><<<grid2, nt, 0, st>>>(a);
+            else intra_recon_kernel<4><<<grid2, nt, 0, st>>>(a);
+            if (reset_at_intra) ctx->list.clear();                                     // decoder.py:520 `ref_frames = []`
+        }
+        CU(cudaGetLastError());
+        if (f < n_frames - 1 && ctx->p.parallel_mode != 1) {
+            rc = ring_push(ctx, o.recon, px, 1, st);
+            if (rc) return rc;
+        }
+    }
+    CU(cudaMemcpyAsync(out_frames, ctx->sq_recon, (size_t)n_frames * px, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SO_OK;
+}
+
 extern "C" int so_last_timing(so_ctx* ctx, double out[4]) {
     if (!ctx || !out) return SO_E_INVALID;
     if (ctx->timing_pending) {

@@ -551,3 +551,53 @@ __global__ void intra_recon_kernel(const FlowArgs a) {
     se = block_sum_u64(se, sbuf);
     if (t == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&(a.stats + unit * a.stats_stride)->sse), se);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// decoder side (decoder.py:97-211 decode_frame_inter, :330-432 decode_frame_intra): levels + vectors -> frame.
+// Same arithmetic as the encoder's reconstruction (including the split-block bounds quirk Q5, decoder.py:185).
+// intra != 0: only the dequantised residual is produced (res_frame); intra_recon_kernel then runs the row chain.
+// ------------------------------------------------------------------------------------------------------------
+template <int BS>
+__global__ void decode_block_kernel(const FlowArgs a, int intra) {
+    constexpr int S = BS / 2;
+    constexpr int P = BS + 1;
+    __shared__ double ws[BS * P];
+    const FrameGeom& g = a.g;
+    const int blk = blockIdx.x, unit = a.unit0 + blockIdx.y;
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int t = threadIdx.x;
+    const bool active = t < BS * BS;
+    const int i = active ? t % BS : 0, j = active ? t / BS : 0;
+    const int x = bx * BS, y = by * BS;
+    const int split = a.split[unit * a.split_stride + blk];
+    const int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
+    const int qrow = a.qp_rows ? a.qp_rows[by] : a.qp_final;
+    const int k = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
+    const int si = i % S, sj = j % S;
+    const int level = a.levels[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i];
+    int shift;
+    if (!split) shift = q_shift(j, i, BS, qrow);
+    else { const int qs = qrow > 0 ? qrow - 1 : qrow; shift = q_shift(sj, si, S, qs); }
+    if (active) ws[j * P + i] = (double)(level * (1 << shift));
+    if (split) transform2d<BS, S, true>(ws, t); else transform2d<BS, BS, true>(ws, t);
+    if (!active) return;
+    const int r = (int)rint(ws[j * P + i]);
+    if (intra) {
+        a.res_frame[unit * a.scratch_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)r;
+        return;
+    }
+    RefList rl;
+    for (int q = 0; q < g.nref; ++q)
+        for (int ph = 0; ph < 4; ++ph) rl.plane[q][ph] = a.ring.plane(unit, q, ph);
+    const int mult = g.fme ? 2 : 1;
+    int pred;
+    if (!split) {
+        const PredSel sel = pred_select(g, x * mult, y * mult, mvo[0], mvo[1], BS, -1);
+        pred = pred_sample(g, rl, sel, mvo[2], i, j);
+    } else {
+        const int xs = x + (k & 1) * S, ys = y + (k >> 1) * S;
+        const PredSel sel = pred_select(g, xs * mult, ys * mult, mvo[k * 3], mvo[k * 3 + 1], S, BS);
+        pred = pred_sample(g, rl, sel, mvo[k * 3 + 2], si, sj);
+    }
+    a.recon[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (uint8_t)((pred + r) & 0xFF);
+}

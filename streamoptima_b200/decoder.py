@@ -1,0 +1,188 @@
+"""GPU decoder with the reference's ``decoder.decoder`` surface (``/root/reference/decoder.py``).
+
+``decode_bitstream(mv_file, residual_file, ...)`` parses the two text streams (decoder.py:590-690) into packed arrays on
+the host and reconstructs the frames on the GPU through ``so_decode_sequence`` (decoder.py:487-545, :97-211, :330-432).
+SURVEY.md 8(f)-2: it makes encode -> decode round trips cheap at full frame sizes.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+
+from . import _native
+
+_INT = re.compile(r"-?\d+")
+_LIST = re.compile(r"\[([^\]]*)\]")
+
+
+def scan_order(n):
+    """Row-major indices in the anti-diagonal scan of entropy_encoder_block (Encoder.py:1095-1123, decoder.py:573-586)."""
+    idx = []
+    for k in range(2 * n - 1):
+        i, j = (0, k) if k < n else (k - n + 1, n - 1)
+        while i < n and j >= 0:
+            idx.append(i * n + j)
+            i += 1
+            j -= 1
+    return np.array(idx, np.int64)
+
+
+def rle_decode(symbols, n, order):
+    """entropy_decoder_block (decoder.py:548-586): run-level list -> n x n block."""
+    flat = np.zeros(n * n, np.int16)
+    pos = 0
+    i = 0
+    L = len(symbols)
+    while i < L:
+        s = symbols[i]
+        if s < 0:
+            cnt = -s
+            flat[order[pos:pos + cnt]] = symbols[i + 1:i + 1 + cnt]
+            pos += cnt
+            i += cnt + 1
+        else:
+            if s == 0:
+                break
+            pos += s
+            i += 1
+    return flat.reshape(n, n)
+
+
+def parse_mv_line(line, nblk, blocks_per_row, rc_on):
+    """differential_decoder_frame (decoder.py:590-649) -> (frame_type, split u8 [nblk], mv i16 [nblk,4,3], qp rows)."""
+    ftype_s, body = line.rstrip("\n").split("|", 1)
+    ftype = int(ftype_s)
+    split = np.zeros(nblk, np.uint8)
+    mv = np.zeros((nblk, 4, 3), np.int16)
+    qps = []
+    ref_qp = 0
+    ref = [0, 0, 0]
+    for j, item in enumerate(body.split(";")):
+        if rc_on and j % blocks_per_row == 0:
+            q, item = item.split("@", 1)
+            ref_qp += int(q)
+            qps.append(ref_qp)
+        s, rest = item.split("'", 1)
+        vals = [int(v) for v in _INT.findall(rest)]
+        if ftype == 0:
+            if s == "0":
+                ref[0] += vals[0]
+                mv[j, 0, 0] = ref[0]
+            else:
+                split[j] = 1
+                for k in range(4):
+                    ref[0] += vals[k]
+                    mv[j, k, 0] = ref[0]
+        else:
+            if s == "0":
+                ref = [ref[0] + vals[0], ref[1] + vals[1], ref[2] + vals[2]]
+                mv[j, 0] = ref
+            else:
+                split[j] = 1
+                for k in range(4):
+                    ref = [ref[0] + vals[3 * k], ref[1] + vals[3 * k + 1], ref[2] + vals[3 * k + 2]]
+                    mv[j, k] = ref
+    return ftype, split, mv, qps
+
+
+def parse_residual_line(line, H, W, bs, split):
+    """entropy_decoder_frame (decoder.py:651-671) -> levels i16 [H, W] with each (sub-)block at its pixel position."""
+    lev = np.zeros((H, W), np.int16)
+    nbx = W // bs
+    sub = bs // 2
+    o_full, o_sub = scan_order(bs), scan_order(sub)
+    for b, item in enumerate(line.rstrip("\n").split(";")):
+        s, rest = item.split("'", 1)
+        lists = [np.array([int(v) for v in _INT.findall(m)], np.int64) for m in _LIST.findall(rest)]
+        y, x = (b // nbx) * bs, (b % nbx) * bs
+        if s == "0":
+            assert split[b] == 0
+            lev[y:y + bs, x:x + bs] = rle_decode(lists[0], bs, o_full)
+        else:
+            assert split[b] == 1
+            for k in range(4):
+                yy, xx = y + (k // 2) * sub, x + (k % 2) * sub
+                lev[yy:yy + sub, xx:xx + sub] = rle_decode(lists[k], sub, o_sub)
+    return lev
+
+
+class decoder:
+    """Same constructor as the reference (decoder.py:8)."""
+
+    device = 0
+
+    def __init__(self, intra_mode, intra_dur, block_size, frames, height, width, Qp, nRefFrames, FMEEnable, lam, VBSEnable,
+                 VBSoverlay=None, RCFlag=None, targetBR=None, frame_rate=30, qp_rate_tables=None, ParallelMode=0):
+        if intra_mode != 0:
+            raise NotImplementedError("intra_mode=1 is broken in the reference")
+        self.intra_mode, self.intra_dur, self.block_size = intra_mode, intra_dur, block_size
+        self.frames, self.h_pixels, self.w_pixels = frames, height, width
+        self.Qp, self.nRefFrames, self.FMEEnable, self.lam, self.VBSEnable = Qp, nRefFrames, FMEEnable, lam, VBSEnable
+        self.RCFlag, self.ParallelMode = RCFlag, ParallelMode
+        self.num_blocks_per_row = width / block_size
+        self.decoded_vid = None
+        self.decoded_vid_f = False
+        self._ctx = None
+
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = _native.Context(width=self.w_pixels, height=self.h_pixels, block_size=self.block_size, search_range=0,
+                                        qp=self.Qp, intra_dur=self.intra_dur, n_ref_frames=self.nRefFrames, fme=self.FMEEnable,
+                                        vbs=self.VBSEnable, rc_flag=0, parallel_mode=self.ParallelMode, lam=0.0, device=self.device)
+        return self._ctx
+
+    def decode_arrays(self, frame_types, split, mv, levels, qp_rows=None, reset_at_intra=True):
+        """Packed arrays (as ``Y_Video_codec.encoded_package.packed``) -> uint8 [F, H, W]."""
+        ctx = self._context()
+        F = len(frame_types)
+        ft = np.ascontiguousarray(frame_types, np.uint8)
+        split = np.ascontiguousarray(split, np.uint8)
+        mv = np.ascontiguousarray(mv, np.int16)
+        levels = np.ascontiguousarray(levels, np.int16)
+        qp = None
+        if qp_rows is not None and len(qp_rows) and len(qp_rows[0]):
+            qp = np.ascontiguousarray(qp_rows, np.int32).reshape(F, -1)
+            assert qp.shape[1] == self.h_pixels // self.block_size
+        out = np.empty((F, self.h_pixels, self.w_pixels), np.uint8)
+        rc = ctx.lib.so_decode_sequence(ctx.handle, ft.ctypes.data, split.ctypes.data, mv.ctypes.data, levels.ctypes.data,
+                                        qp.ctypes.data if qp is not None else None, F, 1 if reset_at_intra else 0, out.ctypes.data)
+        _native.check(ctx.handle, rc)
+        return out
+
+    def parse_bitstream(self, mv_file, residual_file, block_size=None):
+        """decode_differential_entropy (decoder.py:673-690)."""
+        bs = block_size or self.block_size
+        H, W = self.h_pixels, self.w_pixels
+        nblk = (H // bs) * (W // bs)
+        rc_on = self.RCFlag is not None and self.RCFlag > 0
+        fts, splits, mvs, qps, levs = [], [], [], [], []
+        with open(mv_file) as f:
+            for line in f:
+                if not line.strip():
+                    continue
+                t, s, m, q = parse_mv_line(line, nblk, W // bs, rc_on)
+                fts.append(t); splits.append(s); mvs.append(m); qps.append(q)
+        with open(residual_file) as f:
+            for i, line in enumerate(l for l in f if l.strip()):
+                levs.append(parse_residual_line(line, H, W, bs, splits[i]))
+        return np.array(fts, np.uint8), np.stack(splits), np.stack(mvs), np.stack(levs), qps
+
+    def decode_bitstream(self, mv_file, residual_file, intra_mode=None, intra_dur=None, block_size=None, frames=None, width=None,
+                         height=None, save_decoded_frames=True):
+        """decoder.py:692: returns the list of decoded frames."""
+        ft, split, mv, lev, qps = self.parse_bitstream(mv_file, residual_file, block_size)
+        out = self.decode_arrays(ft, split, mv, lev, qps if (self.RCFlag or 0) > 0 else None)
+        frames_list = [out[i] for i in range(out.shape[0])]
+        if save_decoded_frames:
+            self.decoded_vid_f = True
+            self.decoded_vid = frames_list
+        return frames_list
+
+    def save_decoded_frames(self, filename="yuv/decoded_bitstream_frames.yuv"):
+        if not self.decoded_vid_f:
+            print("[ERROR] No decoded frames available.")
+            return
+        with open(filename, "wb") as f:
+            for data in self.decoded_vid:
+                f.write(data.tobytes())
