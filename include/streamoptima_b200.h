@@ -142,6 +142,20 @@ int so_seq_download(so_ctx* ctx, uint8_t* split, int16_t* mv, int16_t* levels, u
                     uint32_t* row_sizes, so_frame_stats* stats);
 int so_seq_sync(so_ctx* ctx);
 
+/* Run-level symbols (entropy_encoder_block, Encoder.py:1086-1131) of the sequence resident after so_seq_run /
+ * so_encode_sequence, generated on the device: per-(sub-)block counts, a device-side exclusive prefix scan, then every
+ * symbol is written at its final position of a packed per-frame int16 stream.
+ *   so_seq_symbols           runs the three kernels (asynchronous)
+ *   so_seq_download_symbols  offsets u32 [units*frames][4*n_blocks + 1] (entry [b*4+k] = start of sub-block k of block b
+ *                            inside its frame, last entry = symbols in the frame); symbols i16 packed, frame f starting
+ *                            at sym_base[f] (u64 [units*frames + 1]); *needed = total symbols.  SO_E_NOMEM when
+ *                            sym_capacity is too small (call again with `*needed`).
+ *   so_format_residual_frame_symbols  the residual text of one frame from its symbols (same bytes as so_format_residual_frame) */
+int so_seq_symbols(so_ctx* ctx);
+int so_seq_download_symbols(so_ctx* ctx, uint32_t* offsets, int16_t* symbols, uint64_t sym_capacity, uint64_t* sym_base, uint64_t* needed);
+int64_t so_format_residual_frame_symbols(const uint8_t* split, const uint32_t* offsets, const int16_t* symbols, int n_blocks,
+                                         char* dst, int64_t cap);
+
 /* Decoder (decoder.py:487-545 `decode` with decode_frame_inter :97 / decode_frame_intra :330) on packed arrays, host
  * buffers in and out, one sequence (unit).  frame_types u8 [n_frames]; split / mv / levels as so_encode_sequence writes
  * them; qp_rows_per_frame i32 [n_frames][height/block_size] or NULL (RCFlag off).  reset_at_intra != 0 clears the

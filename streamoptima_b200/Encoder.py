@@ -250,6 +250,7 @@ class Y_Video_codec:
                                         recon.ctypes.data if want_recon else None, row_sizes.ctypes.data, stats.ctypes.data)
         _native.check(ctx.handle, rc)
         self.last_timing = ctx.last_timing()
+        self._last_shape = (U, F)
         return dict(split=split, mv=mv, levels=levels, recon=recon, row_sizes=row_sizes, stats=stats,
                     frame_types=stats["frame_type"].astype(np.uint8))
 
@@ -329,6 +330,43 @@ class Y_Video_codec:
             if n >= 0:
                 return bytes(buf[:n]).decode()
             cap = -n + 16
+
+    def symbol_streams(self):
+        """Run-level symbols of the last encode, generated on the GPU (count -> device prefix scan -> emit).
+
+        Returns ``(offsets u32 [U*F, 4*nblk+1], symbols i16 [total], sym_base u64 [U*F+1])``: the symbols of sub-block k of
+        block b of frame f are ``symbols[sym_base[f] + offsets[f, 4*b+k] : sym_base[f] + offsets[f, 4*b+k+1]]``."""
+        ctx = self._ctx
+        lib = ctx.lib
+        _native.check(ctx.handle, lib.so_seq_symbols(ctx.handle))
+        U, F = self._last_shape
+        n1 = ctx.nblk * 4 + 1
+        offsets = np.empty((U * F, n1), np.uint32)
+        base = np.empty(U * F + 1, np.uint64)
+        needed = _native.C.c_uint64(0)
+        rc = lib.so_seq_download_symbols(ctx.handle, offsets.ctypes.data, None, 0, base.ctypes.data, _native.C.byref(needed))
+        if rc not in (0, -3):
+            _native.check(ctx.handle, rc)
+        symbols = np.empty(max(int(needed.value), 1), np.int16)
+        _native.check(ctx.handle, lib.so_seq_download_symbols(ctx.handle, offsets.ctypes.data, symbols.ctypes.data, symbols.size,
+                                                              base.ctypes.data, _native.C.byref(needed)))
+        return offsets, symbols[:int(needed.value)], base
+
+    def residual_lines_from_symbols(self):
+        """Residual text of the last single-sequence encode formatted from the device-generated symbol streams."""
+        lib = _native.load()
+        offsets, symbols, base = self.symbol_streams()
+        pkg = self.encoded_package if self.encoded_package is not None else self._last_package
+        split = np.ascontiguousarray(pkg.packed["split"], np.uint8)
+        lines = []
+        for f in range(split.shape[0]):
+            sy = symbols[int(base[f]):int(base[f + 1])]
+            sy = np.ascontiguousarray(sy) if sy.size else np.zeros(1, np.int16)
+            off = np.ascontiguousarray(offsets[f])
+            sp = np.ascontiguousarray(split[f])
+            lines.append(self._fmt(lambda cbuf, cap: lib.so_format_residual_frame_symbols(sp.ctypes.data, off.ctypes.data, sy.ctypes.data,
+                                                                                         sp.shape[0], cbuf, cap), 1024 + sy.size * 8 + sp.shape[0] * 24))
+        return lines
 
     def bitstream_lines(self):
         """-> (mv_lines, residual_lines) of the last encode, one string per frame (no trailing newline)."""

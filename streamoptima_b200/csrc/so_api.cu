@@ -50,6 +50,10 @@ struct so_ctx {
     uint32_t* sq_rows = nullptr;
     so_frame_stats* sq_stats = nullptr;
     size_t sq_cap_frames = 0;               // capacity in (unit*frame) frames
+    // run-level symbol streams of the resident sequence (so_seq_symbols)
+    uint32_t *sym_lens = nullptr, *sym_offs = nullptr;
+    int16_t* sym_data = nullptr;
+    size_t sym_cap_frames = 0, sym_frame_stride = 0;
     double timing[5] = {0, 0, 0, 0, 0};
     bool timing_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -120,6 +124,8 @@ static void free_seq(so_ctx* c) {
     cudaFree(c->sq_levels); cudaFree(c->sq_rows); cudaFree(c->sq_stats);
     c->sq_frames = c->sq_split = c->sq_recon = nullptr; c->sq_mv = c->sq_levels = nullptr;
     c->sq_rows = nullptr; c->sq_stats = nullptr; c->sq_cap_frames = 0;
+    cudaFree(c->sym_lens); cudaFree(c->sym_offs); cudaFree(c->sym_data);
+    c->sym_lens = c->sym_offs = nullptr; c->sym_data = nullptr; c->sym_cap_frames = 0;
 }
 
 extern "C" void so_ctx_destroy(so_ctx* c) {
@@ -820,6 +826,64 @@ extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_unit
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// run-level symbols of the resident sequence: count -> device prefix scan -> emit (packed per frame)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int so_seq_symbols(so_ctx* ctx) {
+    if (!ctx) return SO_E_INVALID;
+    if (ctx->sq_units < 1) { set_err(ctx, "so_seq_symbols before a sequence was encoded"); return SO_E_STATE; }
+    CU(cudaSetDevice(ctx->device));
+    const size_t total = (size_t)ctx->sq_units * ctx->sq_nframes;
+    const FrameGeom& g = ctx->g;
+    const int nblk = ctx->nblk;
+    if (total > ctx->sym_cap_frames) {
+        cudaFree(ctx->sym_lens); cudaFree(ctx->sym_offs); cudaFree(ctx->sym_data);
+        ctx->sym_frame_stride = ctx->frame_px + ctx->frame_px / 2 + (size_t)4 * nblk;      // worst case: 1.5 symbols per coefficient + 1 per (sub-)block
+        CU(cudaMalloc(&ctx->sym_lens, total * nblk * 4 * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->sym_offs, total * (nblk * 4 + 1) * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->sym_data, total * ctx->sym_frame_stride * sizeof(int16_t)));
+        ctx->sym_cap_frames = total;
+    }
+    cudaStream_t st = ctx->stream;
+    dim3 grid(nblk, (unsigned)total);
+    const int nt = nthreads_px(g.bs);
+    for (int emit = 0; emit < 2; ++emit) {
+        if (g.bs == 16) rle_symbols_kernel<16><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit);
+        else if (g.bs == 8) rle_symbols_kernel<8><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit);
+        else rle_symbols_kernel<4><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit);
+        if (!emit) scan_lens_kernel<<<(unsigned)total, 1024, 0, st>>>(ctx->sym_lens, ctx->sym_offs, nblk * 4);
+    }
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return SO_OK;
+}
+
+// offsets u32 [units*frames][4*n_blocks + 1] (exclusive, per frame; the last entry is the frame's symbol count);
+// symbols i16: frame f of the packed output starts at sym_base[f] (u64 [units*frames + 1], filled here).  Returns
+// SO_E_NOMEM with the required symbol count in *needed when sym_capacity is too small.
+extern "C" int so_seq_download_symbols(so_ctx* ctx, uint32_t* offsets, int16_t* symbols, uint64_t sym_capacity, uint64_t* sym_base,
+                                       uint64_t* needed) {
+    if (!ctx || !offsets || !sym_base) return SO_E_INVALID;
+    if (!ctx->sym_offs) { set_err(ctx, "so_seq_download_symbols before so_seq_symbols"); return SO_E_STATE; }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t total = (size_t)ctx->sq_units * ctx->sq_nframes;
+    const size_t n1 = (size_t)ctx->nblk * 4 + 1;
+    CU(cudaMemcpyAsync(offsets, ctx->sym_offs, total * n1 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint64_t acc = 0;
+    for (size_t f = 0; f < total; ++f) { sym_base[f] = acc; acc += offsets[f * n1 + n1 - 1]; }
+    sym_base[total] = acc;
+    if (needed) *needed = acc;
+    if (!symbols || sym_capacity < acc) { set_err(ctx, "symbol buffer too small"); return SO_E_NOMEM; }
+    for (size_t f = 0; f < total; ++f) {
+        const uint64_t n = sym_base[f + 1] - sym_base[f];
+        if (n) CU(cudaMemcpyAsync(symbols + sym_base[f], ctx->sym_data + f * ctx->sym_frame_stride, n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return SO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // decoder: restates decoder.decode (decoder.py:487-545) on packed arrays, host buffers in and out
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
@@ -1014,3 +1078,22 @@ extern "C" int64_t so_format_residual_frame(const uint8_t* split, const int16_t*
 #ifdef SO_ME_DEBUG
 extern "C" int so_debug_read(long long* dst) { return (int)cudaMemcpyFromSymbol(dst, g_me_dbg, sizeof(long long) * 4096); }
 #endif
+
+extern "C" int64_t so_format_residual_frame_symbols(const uint8_t* split, const uint32_t* offsets, const int16_t* symbols, int n_blocks,
+                                                    char* dst, int64_t cap) {
+    Out o{dst, cap};
+    for (int b = 0; b < n_blocks; ++b) {
+        if (b) o.ch(';');
+        const int nseg = split[b] ? 4 : 1;
+        o.str(split[b] ? "1'(" : "0'(");
+        for (int k = 0; k < nseg; ++k) {
+            if (k) o.ch(',');
+            o.ch('[');
+            const uint32_t s0 = offsets[(size_t)b * 4 + k], s1 = offsets[(size_t)b * 4 + k + 1];
+            for (uint32_t i = s0; i < s1; ++i) { if (i > s0) o.str(", "); o.num(symbols[i]); }
+            o.ch(']');
+        }
+        o.ch(')');
+    }
+    return o.finish();
+}

@@ -601,3 +601,115 @@ __global__ void decode_block_kernel(const FlowArgs a, int intra) {
     }
     a.recon[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (uint8_t)((pred + r) & 0xFF);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// run-level symbol generation (entropy_encoder_block, Encoder.py:1086-1131) with a device-side prefix scan
+//   pass 1 (emit == 0): per (sub-)block symbol counts -> lens[frame][blk][4]
+//   scan              : exclusive prefix sum of lens per frame -> offs[frame][4*nblk + 1]
+//   pass 2 (emit == 1): symbols written at their final position of the packed per-frame stream (int16)
+// One CTA per block, one thread per coefficient in scan order.  A symbol stream is: for every maximal run, a header
+// (-count for non-zero runs followed by the values, +count for zero runs, a single 0 for a trailing zero run).
+// Every non-zero coefficient owns one slot, every run start owns one slot:
+//   slot(header of run starting at p) = #nonzeros before p + #run starts before p
+//   slot(value at p)                  = #nonzeros before p + #run starts up to and including p's run
+// ------------------------------------------------------------------------------------------------------------
+template <int BS>
+__global__ void rle_symbols_kernel(const int16_t* levels, const uint8_t* split, uint32_t* lens, const uint32_t* offs, int16_t* syms,
+                                   size_t sym_frame_stride, int W, int nbx, int nblk, int emit) {
+    constexpr int S = BS / 2;
+    constexpr int NT = BS * BS < 32 ? 32 : BS * BS;
+    __shared__ int16_t sv[BS * BS];         // coefficient at (segment, scan position)
+    __shared__ int snz[BS * BS + 1], sst[BS * BS + 1];     // inclusive prefix sums of non-zero / run-start flags
+    __shared__ int wsum[2][32];
+    const int blk = blockIdx.x, frame = blockIdx.y;
+    const int t = threadIdx.x;
+    const bool active = t < BS * BS;
+    const int bx = blk % nbx, by = blk / nbx;
+    const int sp = split[(size_t)frame * nblk + blk];
+    // element handled by this thread: pixel (i, j) -> (segment, scan position)
+    const int i = active ? t % BS : 0, j = active ? t / BS : 0;
+    const int n = sp ? S : BS;
+    const int seg = sp ? ((j >= S ? 2 : 0) + (i >= S ? 1 : 0)) : 0;
+    const int u = sp ? j % S : j, v = sp ? i % S : i;
+    const int p = c_scanpos[tbl_off(n) + u * n + v];
+    const int e = seg * n * n + p;                       // index in segment-major scan order
+    if (active) sv[e] = levels[(size_t)frame * W * (nblk / nbx) * BS + (size_t)(by * BS + j) * W + bx * BS + i];
+    __syncthreads();
+    // thread t now owns element t of the segment-major order
+    const int nseg_elems = n * n;
+    const int myseg = active ? t / nseg_elems : 0, myp = active ? t % nseg_elems : 0;
+    const int val = active ? sv[t] : 0;
+    const int nz = active && val != 0;
+    const int prev_nz = (active && myp > 0) ? (sv[t - 1] != 0) : 0;
+    const int st = active && (myp == 0 || nz != prev_nz);
+    // block-wide inclusive scans of nz and st
+    int a = nz, b = st;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xFFFFFFFFu, a, o), y = __shfl_up_sync(0xFFFFFFFFu, b, o);
+        if ((t & 31) >= o) { a += x; b += y; }
+    }
+    if ((t & 31) == 31) { wsum[0][t >> 5] = a; wsum[1][t >> 5] = b; }
+    __syncthreads();
+    int ba = 0, bb = 0;
+    for (int w = 0; w < (t >> 5); ++w) { ba += wsum[0][w]; bb += wsum[1][w]; }
+    a += ba; b += bb;
+    if (active) { snz[t + 1] = a; sst[t + 1] = b; }
+    if (t == 0) { snz[0] = 0; sst[0] = 0; }
+    __syncthreads();
+    const int nsegs = sp ? 4 : 1;
+    if (!emit) {
+        if (t < 4) {
+            uint32_t len = 0;
+            if (t < nsegs) {
+                const int lo = t * nseg_elems, hi = lo + nseg_elems;
+                len = (uint32_t)((snz[hi] - snz[lo]) + (sst[hi] - sst[lo]));
+            }
+            lens[((size_t)frame * nblk + blk) * 4 + t] = len;
+        }
+        return;
+    }
+    if (!active) return;
+    const int lo = myseg * nseg_elems;
+    const uint32_t base = offs[(size_t)frame * (4 * nblk + 1) + (size_t)blk * 4 + myseg];
+    int16_t* out = syms + (size_t)frame * sym_frame_stride + base;
+    const int nzb = snz[t] - snz[lo], stb = sst[t] - sst[lo];           // counts strictly before this element, within the segment
+    if (st) {
+        int len = 1;
+        while (myp + len < nseg_elems && ((sv[t + len] != 0) == nz)) ++len;
+        const bool trailing = (myp + len == nseg_elems);
+        out[nzb + stb] = (int16_t)(nz ? -len : (trailing ? 0 : len));
+    }
+    if (nz) out[nzb + (sst[t + 1] - sst[lo])] = (int16_t)val;
+}
+
+// exclusive prefix sum of n entries per frame (one CTA per frame): offs[frame][0..n], offs[frame][n] = total
+__global__ void scan_lens_kernel(const uint32_t* lens, uint32_t* offs, int n) {
+    __shared__ uint32_t wtot[32];
+    __shared__ uint32_t carry;
+    const int frame = blockIdx.x, t = threadIdx.x;
+    const uint32_t* in = lens + (size_t)frame * n;
+    uint32_t* out = offs + (size_t)frame * (n + 1);
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + t;
+        const uint32_t v = i < n ? in[i] : 0u;
+        uint32_t s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if ((t & 31) >= o) s += x;
+        }
+        if ((t & 31) == 31) wtot[t >> 5] = s;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < (t >> 5); ++w) wb += wtot[w];
+        const uint32_t c0 = carry;
+        if (i < n) out[i] = c0 + wb + s - v;
+        __syncthreads();
+        if (t == blockDim.x - 1) carry = c0 + wb + s;
+        __syncthreads();
+    }
+    if (t == 0) out[n] = carry;
+}
