@@ -343,16 +343,16 @@ static int make_ring_map(so_ctx* ctx, int box_w, int box_h, CUtensorMap* map) {
     return make_map3d(ctx, ctx->ring, g.W, g.H, (cuuint64_t)ctx->batch * ctx->nslots * 16, g.pitch, ctx->plane_bytes, box_w, box_h, map);
 }
 
-template <int BS, int NDX, int G>
+template <int BS, int NDX, int G, bool QUAD = false>
 static cudaError_t launch_me_tma(const CUtensorMap& map, const CUtensorMap& cmap, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_done[16] = {};
     int dev = 0; cudaGetDevice(&dev);
     if (!attr_done[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(me_tma_kernel<BS, NDX, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(me_tma_kernel<BS, NDX, G, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_done[dev & 15] = true;
     }
-    me_tma_kernel<BS, NDX, G><<<grid, threads, smem, st>>>(map, cmap, a);
+    me_tma_kernel<BS, NDX, G, QUAD><<<grid, threads, smem, st>>>(map, cmap, a);
     return cudaGetLastError();
 }
 template <int BS, int NDX>
@@ -370,8 +370,10 @@ static cudaError_t launch_me_tma_n(int NDX, int G, const CUtensorMap& map, const
     }
 }
 
+// out_sub != nullptr asks for the fused VBS search (sub-block results from quadrant sums); *used_quad tells whether the
+// geometry allowed it (16x16 blocks, DIRECT staging) -- otherwise the caller runs a second search on the sub-block grid
 static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
-                      size_t out_stride, cudaStream_t st) {
+                      size_t out_stride, cudaStream_t st, MeResult* out_sub = nullptr, size_t out_sub_stride = 0, bool* used_quad = nullptr) {
     MeTmaArgs a{};
     a.g = ctx->g;
     a.g.bs = bs; a.g.nbx = ctx->g.W / bs; a.g.nby = ctx->g.H / bs;
@@ -380,6 +382,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     a.cur_unit_stride = cur_stride;
     a.out = reinterpret_cast<unsigned long long*>(out + (size_t)unit0 * out_stride);
     a.out_unit_stride = out_stride;
+    a.out_sub = nullptr; a.out_sub_unit_stride = 0;
     a.units = units;
     a.nph = a.g.fme ? 4 : 1;
     const int nb = a.g.nbx * a.g.nby;
@@ -465,26 +468,29 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     const int total_stages = units * a.stages_per_unit;
     const int grid = total_stages < sms ? total_stages : sms;
     CU(cudaMemsetAsync(out + (size_t)unit0 * out_stride, 0xFF, sizeof(MeResult) * out_stride * (units - 1) + sizeof(MeResult) * nb, st));
+    const bool quad = out_sub && a.direct && bs == 16 && NDX == 9 && G == 3;
+    if (used_quad) *used_quad = quad;
+    if (quad) {
+        a.out_sub = reinterpret_cast<unsigned long long*>(out_sub + (size_t)unit0 * out_sub_stride);
+        a.out_sub_unit_stride = out_sub_stride;
+        CU(cudaMemsetAsync(out_sub + (size_t)unit0 * out_sub_stride, 0xFF, sizeof(MeResult) * out_sub_stride * (units - 1) + sizeof(MeResult) * nb * 4, st));
+    }
     ev_pair(ctx, ctx->ev_me, st, true);
     cudaError_t e;
-    if (bs == 16) e = launch_me_tma_n<16>(NDX, G, map, cmap, a, grid, threads, smem, st);
+    if (quad) e = launch_me_tma<16, 9, 3, true>(map, cmap, a, grid, threads, smem, st);
+    else if (bs == 16) e = launch_me_tma_n<16>(NDX, G, map, cmap, a, grid, threads, smem, st);
     else if (bs == 8) e = launch_me_tma_n<8>(NDX, G, map, cmap, a, grid, threads, smem, st);
     else e = launch_me_tma_n<4>(NDX, G, map, cmap, a, grid, threads, smem, st);
     ev_pair(ctx, ctx->ev_me, st, false);
     if (e != cudaSuccess) { set_err(ctx, std::string("me_tma_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
     for (int u = 0; u < units; ++u) {
         me_unpack_kernel<<<(nb + 255) / 256, 256, 0, st>>>(out + (size_t)(unit0 + u) * out_stride, nb, a.g.R);
-        ctx->launches++;
+        if (quad) me_unpack_kernel<<<(nb * 4 + 255) / 256, 256, 0, st>>>(out_sub + (size_t)(unit0 + u) * out_sub_stride, nb * 4, a.g.R);
+        ctx->launches += quad ? 2 : 1;
     }
     ctx->launches++;
     CU(cudaGetLastError());
     return SO_OK;
-}
-
-// exhaustive search of every bs x bs block of the frame (bs = parent or sub-block size) -> out[unit][nblocks]
-static int run_me_full(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
-                       size_t out_stride, cudaStream_t st) {
-    return run_me_tma(ctx, cur, cur_stride, unit0, units, bs, out, out_stride, st);
 }
 
 static FlowArgs make_flow(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, const so_frame_out* o, size_t out_frames_stride,
@@ -601,10 +607,12 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
         ev_pair(ctx, ctx->ev_me, st, false);
         ctx->launches++;
     } else {
-        rc = run_me_full(ctx, cur, cur_stride, unit0, units, g.bs, ctx->me_parent, ctx->nblk, st);
+        bool quad = false;
+        rc = run_me_tma(ctx, cur, cur_stride, unit0, units, g.bs, ctx->me_parent, ctx->nblk, st,
+                        a.vbs ? ctx->me_sub : nullptr, (size_t)ctx->nblk * 4, &quad);
         if (rc) return rc;
-        if (a.vbs) {
-            rc = run_me_full(ctx, cur, cur_stride, unit0, units, g.bs / 2, ctx->me_sub, (size_t)ctx->nblk * 4, st);
+        if (a.vbs && !quad) {       // generic geometry: second search on the sub-block grid
+            rc = run_me_tma(ctx, cur, cur_stride, unit0, units, g.bs / 2, ctx->me_sub, (size_t)ctx->nblk * 4, st);
             if (rc) return rc;
         }
     }

@@ -30,6 +30,8 @@ struct MeTmaArgs {
     size_t cur_unit_stride;
     unsigned long long* out;     // packed keys, stride of MeResult (16 B) per block
     size_t out_unit_stride;      // in MeResult elements
+    unsigned long long* out_sub; // QUAD mode: keys of the four bs/2 sub-blocks, grid (2nby x 2nbx), same packing
+    size_t out_sub_unit_stride;
     int units;
     int nph;                     // 4 (fme) or 1
     int items_per_unit;
@@ -79,6 +81,84 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                  : "memory");
 }
 
+
+// ---- G = 3 SAD pass over ROWS current-block rows (ROWS + 2 window rows) --------------------------------------------------
+// Window row rho meets current rows rho, rho-1, rho-2 (candidate groups 0, 1, 2).  cq[i] holds the current row r with
+// r % 3 == i, so group gg reads cq[(rho - gg) mod 3]: with rho mod 3 known at compile time the rotation costs nothing,
+// and the steady rows can be rolled in steps of three (keeps the loop body inside the instruction cache).
+// SPLIT: words of the left half of the block accumulate into accA, the right half into accB (quadrant SADs for VBS).
+template <int WPR, int NDX, int KM, int WP, bool SPLIT, int M, int MASK>
+__device__ __forceinline__ void sad_row_g3(const unsigned char* wrow, const uint32_t (&cq)[3][WPR], uint32_t (&accA)[3][NDX], uint32_t (&accB)[3][NDX]) {
+    constexpr int NWM = KM + WPR - 1;
+    constexpr int NVM = (NWM + 3) / 4;
+    uint32_t refw[NVM * 4];
+#pragma unroll
+    for (int v = 0; v < NVM; ++v) {
+        const uint4 q = *reinterpret_cast<const uint4*>(wrow + v * 16);
+        refw[4 * v] = q.x; refw[4 * v + 1] = q.y; refw[4 * v + 2] = q.z; refw[4 * v + 3] = q.w;
+    }
+#pragma unroll
+    for (int gg = 0; gg < 3; ++gg) {
+        if ((MASK >> gg) & 1) {
+            constexpr int dummy = 0; (void)dummy;
+            const int ci = (M - gg + 3) % 3;
+#pragma unroll
+            for (int k = 0; k < KM; ++k)
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) {
+                    if (SPLIT && w >= WPR / 2) accB[gg][k] = sad4_acc(refw[k + w], cq[ci][w], accB[gg][k]);
+                    else accA[gg][k] = sad4_acc(refw[k + w], cq[ci][w], accA[gg][k]);
+                }
+        }
+    }
+}
+
+template <int WPR>
+__device__ __forceinline__ void load_cur_row(const uint32_t* cb, int row, uint32_t (&dst)[WPR]) {
+    if constexpr (WPR == 4) {
+        const uint4 q = reinterpret_cast<const uint4*>(cb)[row];
+        dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+    } else if constexpr (WPR == 2) {
+        const uint2 q = reinterpret_cast<const uint2*>(cb)[row];
+        dst[0] = q.x; dst[1] = q.y;
+    } else {
+        dst[0] = cb[row];
+    }
+}
+
+template <int WPR, int NDX, int KM, int ROWS, int WP, bool SPLIT>
+__device__ __forceinline__ void sad_pass_g3(const unsigned char* win, const uint32_t* cb, uint32_t (&accA)[3][NDX], uint32_t (&accB)[3][NDX]) {
+    static_assert(ROWS >= 4, "needs two ramp rows on each side");
+    uint32_t cq[3][WPR];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) cq[i][w] = 0;
+    load_cur_row<WPR>(cb, 0, cq[0]);
+    sad_row_g3<WPR, NDX, KM, WP, SPLIT, 0, 1>(win, cq, accA, accB);
+    load_cur_row<WPR>(cb, 1, cq[1]);
+    sad_row_g3<WPR, NDX, KM, WP, SPLIT, 1, 3>(win + WP, cq, accA, accB);
+    constexpr int STEADY = ROWS - 2, TRIPLES = STEADY / 3, REM = STEADY % 3;
+    const unsigned char* wr = win + 2 * WP;
+#pragma unroll 1
+    for (int t3 = 0; t3 < TRIPLES; ++t3) {
+        const int rho = 2 + 3 * t3;
+        load_cur_row<WPR>(cb, rho, cq[2]);
+        sad_row_g3<WPR, NDX, KM, WP, SPLIT, 2, 7>(wr, cq, accA, accB);
+        load_cur_row<WPR>(cb, rho + 1, cq[0]);
+        sad_row_g3<WPR, NDX, KM, WP, SPLIT, 0, 7>(wr + WP, cq, accA, accB);
+        load_cur_row<WPR>(cb, rho + 2, cq[1]);
+        sad_row_g3<WPR, NDX, KM, WP, SPLIT, 1, 7>(wr + 2 * WP, cq, accA, accB);
+        wr += 3 * WP;
+    }
+    constexpr int R0 = 2 + 3 * TRIPLES;                 // R0 % 3 == 2
+    if constexpr (REM >= 1) { load_cur_row<WPR>(cb, R0, cq[2]); sad_row_g3<WPR, NDX, KM, WP, SPLIT, 2, 7>(wr, cq, accA, accB); }
+    if constexpr (REM >= 2) { load_cur_row<WPR>(cb, R0 + 1, cq[0]); sad_row_g3<WPR, NDX, KM, WP, SPLIT, 0, 7>(wr + WP, cq, accA, accB); }
+    // ramp down: window rows ROWS (groups 1, 2) and ROWS + 1 (group 2)
+    sad_row_g3<WPR, NDX, KM, WP, SPLIT, ROWS % 3, 6>(wr + REM * WP, cq, accA, accB);
+    sad_row_g3<WPR, NDX, KM, WP, SPLIT, (ROWS + 1) % 3, 4>(wr + (REM + 1) * WP, cq, accA, accB);
+}
+
 constexpr int ME_MAX_STAGES = 3;
 #ifdef SO_ME_DEBUG
 __device__ long long g_me_dbg[4096];
@@ -88,7 +168,7 @@ __device__ long long g_me_dbg[4096];
 #endif
 constexpr int ME_CUR_REGS = 16;          // per-lane staging of current-block words in the producer (SI*bs*bs/4 <= 32*16)
 
-template <int BS, int NDX, int G>
+template <int BS, int NDX, int G, bool QUAD>
 __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ CUtensorMap ring_map,
                                                         const __grid_constant__ CUtensorMap cur_map, const MeTmaArgs a) {
     constexpr int WPR = BS / 4;
@@ -343,104 +423,121 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 const unsigned char* win = wins + sb * a.stage_bytes + c * a.shift_stride + li * a.item_stride + oy0 * a.wpitch;
                 const uint32_t* cb = curs + (sb * a.SI + li) * BS * WPR;
 
+                constexpr int WP = NCH * 16;                                  // == a.wpitch, as a compile-time constant
+                constexpr int KM = EXTRA ? NM : NDX;
+                const int mul = g.fme ? 2 : 1;
+                if constexpr (QUAD) {
+                    // ---- VBS: the four bs/2 sub-blocks search the same offsets, so their SADs are the quadrant sums of the
+                    // parent's candidates (Encoder.py:517-536 vs :558).  Two half passes (top / bottom 8 rows), left and right
+                    // words in separate accumulators; quadrant minima are folded after each half, the parent sum is kept.
+                    static_assert(G == 3 && BS == 16, "QUAD is built for 16x16 blocks with G = 3");
+                    uint32_t par[3][NDX];
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+                        for (int k = 0; k < NDX; ++k) par[gg][k] = 0;
+                    int xlo, xhi, ylo, yhi;
+                    uint32_t lyk[3], lxk[NDX];
+                    uint32_t ybadP[3], ybadT[3], ybadB[3], xbadP[NDX], xbadL[NDX], xbadR[NDX];
+                    {
+                        int l0, h0, l1, h1, l2, h2;
+                        valid_range(by * BS, g.H, BS, g.fme, g.fme, l0, h0);
+                        valid_range(by * BS, g.H, BS / 2, g.fme, g.fme, l1, h1);
+                        valid_range(by * BS + BS / 2, g.H, BS / 2, g.fme, g.fme, l2, h2);
+#pragma unroll
+                        for (int gg = 0; gg < 3; ++gg) {
+                            const int oy = -g.r + oy0 + gg, dy = mul * oy + (g.fme ? py : 0);
+                            const bool in = oy <= g.r && dy >= -g.R && dy <= g.R;
+                            lyk[gg] = (uint32_t)(abs(dy) << 8) + gg;
+                            ybadP[gg] = (in && dy >= l0 && dy <= h0) ? 0u : 0xFFFFFFFFu;
+                            ybadT[gg] = (in && dy >= l1 && dy <= h1) ? 0u : 0xFFFFFFFFu;
+                            ybadB[gg] = (in && dy >= l2 && dy <= h2) ? 0u : 0xFFFFFFFFu;
+                        }
+                        valid_range(bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
+                        valid_range(bx * BS, g.W, BS / 2, g.fme, g.fme, l1, h1);
+                        valid_range(bx * BS + BS / 2, g.W, BS / 2, g.fme, g.fme, l2, h2);
+#pragma unroll
+                        for (int k = 0; k < NDX; ++k) {
+                            const int ox = -g.r + c + 4 * k, dx = mul * ox + (g.fme ? px : 0);
+                            const bool in = ox <= g.r && dx >= -g.R && dx <= g.R;
+                            lxk[k] = (uint32_t)(abs(dx) << 8) + k * 3;
+                            xbadP[k] = (in && dx >= l0 && dx <= h0) ? 0u : 0xFFFFFFFFu;
+                            xbadL[k] = (in && dx >= l1 && dx <= h1) ? 0u : 0xFFFFFFFFu;
+                            xbadR[k] = (in && dx >= l2 && dx <= h2) ? 0u : 0xFFFFFFFFu;
+                        }
+                        (void)xlo; (void)xhi; (void)ylo; (void)yhi;
+                    }
+                    uint32_t bq[5] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // parent, TL, TR, BL, BR
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t aL[3][NDX], aR[3][NDX];
+#pragma unroll
+                        for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+                            for (int k = 0; k < NDX; ++k) { aL[gg][k] = 0; aR[gg][k] = 0; }
+                        sad_pass_g3<WPR, NDX, NDX, BS / 2, WP, true>(win + half * (BS / 2) * WP, cb + half * (BS / 2) * WPR, aL, aR);
+#pragma unroll
+                        for (int k = 0; k < NDX; ++k)
+#pragma unroll
+                            for (int gg = 0; gg < 3; ++gg) {
+                                const uint32_t l1v = lxk[k] + lyk[gg];
+                                const uint32_t yb = half ? ybadB[gg] : ybadT[gg];
+                                uint32_t kl = aL[gg][k] * 65536u + l1v, kr = aR[gg][k] * 65536u + l1v;
+                                asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(kl) : "r"(xbadL[k]), "r"(yb));
+                                asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(kr) : "r"(xbadR[k]), "r"(yb));
+                                asm("min.u32 %0, %0, %1;" : "+r"(bq[1 + half * 2]) : "r"(kl));
+                                asm("min.u32 %0, %0, %1;" : "+r"(bq[2 + half * 2]) : "r"(kr));
+                                par[gg][k] += aL[gg][k] + aR[gg][k];
+                            }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NDX; ++k)
+#pragma unroll
+                        for (int gg = 0; gg < 3; ++gg) {
+                            uint32_t kp = par[gg][k] * 65536u + (lxk[k] + lyk[gg]);
+                            asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(kp) : "r"(xbadP[k]), "r"(ybadP[gg]));
+                            asm("min.u32 %0, %0, %1;" : "+r"(bq[0]) : "r"(kp));
+                        }
+                    // 64-bit keys, warp merge (a stage of SI = 8 items never spans two blocks when 16 items make a block)
+#pragma unroll
+                    for (int e = 0; e < 5; ++e) {
+                        unsigned long long key = ~0ull;
+                        if (bq[e] != 0xFFFFFFFFu) {
+                            const int idx = bq[e] & 0xFF, k = idx / 3, gg = idx % 3;
+                            const int ox = -g.r + c + 4 * k, oy = -g.r + oy0 + gg;
+                            const int dx = mul * ox + (g.fme ? px : 0), dy = mul * oy + (g.fme ? py : 0);
+                            key = ((unsigned long long)(bq[e] >> 16) << 40) | ((unsigned long long)((bq[e] >> 8) & 0xFF) << 24) |
+                                  ((unsigned long long)ref << 16) | ((unsigned long long)(dx + g.R) << 8) | (unsigned long long)(dy + g.R);
+                        }
+                        unsigned long long* okey;
+                        if (e == 0) okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + unit * a.out_unit_stride + blk);
+                        else {
+                            const int kx = (e - 1) & 1, ky = (e - 1) >> 1;
+                            okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out_sub) + unit * a.out_sub_unit_stride +
+                                                                         (size_t)(by * 2 + ky) * (g.nbx * 2) + bx * 2 + kx);
+                        }
+                        const unsigned act = __activemask();
+                        const int blk_first = __shfl_sync(act, blk, __ffs(act) - 1);
+                        if (act == 0xFFFFFFFFu && __all_sync(act, blk == blk_first)) {
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+                                key = other < key ? other : key;
+                            }
+                            if (lane == 0 && key != ~0ull) atomicMin(okey, key);
+                        } else if (key != ~0ull) {
+                            atomicMin(okey, key);
+                        }
+                    }
+                } else {
                 uint32_t acc[G][NDX];
 #pragma unroll
                 for (int gg = 0; gg < G; ++gg)
 #pragma unroll
                     for (int k = 0; k < NDX; ++k) acc[gg][k] = 0;
-                // One window row against the G candidate rows it belongs to.  curq[gg] holds current-block row (rho - gg).
-                // MASK bit gg = candidate group gg is active for this row (rho - gg inside 0..BS-1).
-                auto load_cur = [&](int row, uint32_t (&dst)[WPR]) {
-                    if constexpr (WPR == 4) {
-                        const uint4 q = reinterpret_cast<const uint4*>(cb)[row];
-                        dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
-                    } else if constexpr (WPR == 2) {
-                        const uint2 q = reinterpret_cast<const uint2*>(cb)[row];
-                        dst[0] = q.x; dst[1] = q.y;
-                    } else {
-                        dst[0] = cb[row];
-                    }
-                };
-                constexpr int KM = EXTRA ? NM : NDX;
-                auto row_step = [&](const unsigned char* wrow, const uint32_t (&curq)[G][WPR], auto mask_c) {
-                    constexpr int MASK = decltype(mask_c)::value;
-                    uint32_t refw[NVM * 4];
-#pragma unroll
-                    for (int v = 0; v < NVM; ++v) {
-                        const uint4 q = *reinterpret_cast<const uint4*>(wrow + v * 16);
-                        refw[4 * v] = q.x; refw[4 * v + 1] = q.y; refw[4 * v + 2] = q.z; refw[4 * v + 3] = q.w;
-                    }
-#pragma unroll
-                    for (int gg = 0; gg < G; ++gg) {
-                        if ((MASK >> gg) & 1) {
-#pragma unroll
-                            for (int k = 0; k < KM; ++k)
-#pragma unroll
-                                for (int w = 0; w < WPR; ++w) acc[gg][k] = sad4_acc(refw[k + w], curq[gg][w], acc[gg][k]);
-                        }
-                    }
-                };
-                constexpr int WP = NCH * 16;                                  // == a.wpitch, as a compile-time constant
-                if constexpr (G == 3 && BS % 3 == 1) {
-                    // rows 0,1 ramp up, rows 2..BS-1 are steady (all three groups active) and are rolled in steps of three so
-                    // that the register rotation of curq is static while the loop body stays inside the instruction cache,
-                    // rows BS, BS+1 ramp down.  BS % 3 == 1 (bs 4, 16): BS-2 = 3*m steady rows exactly... handled generically:
-                    uint32_t cq[3][WPR];                                       // cq[i] = current row with (row % 3 == i)
-                    load_cur(0, cq[0]);
-                    { const uint32_t (&v)[3][WPR] = cq; uint32_t t[G][WPR];
-#pragma unroll
-                      for (int w = 0; w < WPR; ++w) { t[0][w] = v[0][w]; t[1][w] = 0; t[2][w] = 0; }
-                      row_step(win, t, std::integral_constant<int, 1>{}); }
-                    load_cur(1, cq[1]);
-                    { uint32_t t[G][WPR];
-#pragma unroll
-                      for (int w = 0; w < WPR; ++w) { t[0][w] = cq[1][w]; t[1][w] = cq[0][w]; t[2][w] = 0; }
-                      row_step(win + WP, t, std::integral_constant<int, 3>{}); }
-                    // steady rows rho = 2 .. BS-1: groups (rho, rho-1, rho-2) -> cq[(rho)%3], cq[(rho-1)%3], cq[(rho-2)%3]
-                    const unsigned char* wr = win + 2 * WP;
-                    constexpr int STEADY = BS - 2;                             // 14 for bs 16
-                    constexpr int TRIPLES = STEADY / 3;                        // 4 rolled iterations
-#pragma unroll 1
-                    for (int it3 = 0; it3 < TRIPLES; ++it3) {
-                        const int rho = 2 + 3 * it3;
-                        load_cur(rho, cq[2]);
-                        { uint32_t t[G][WPR];
-#pragma unroll
-                          for (int w = 0; w < WPR; ++w) { t[0][w] = cq[2][w]; t[1][w] = cq[1][w]; t[2][w] = cq[0][w]; }
-                          row_step(wr, t, std::integral_constant<int, 7>{}); }
-                        load_cur(rho + 1, cq[0]);
-                        { uint32_t t[G][WPR];
-#pragma unroll
-                          for (int w = 0; w < WPR; ++w) { t[0][w] = cq[0][w]; t[1][w] = cq[2][w]; t[2][w] = cq[1][w]; }
-                          row_step(wr + WP, t, std::integral_constant<int, 7>{}); }
-                        load_cur(rho + 2, cq[1]);
-                        { uint32_t t[G][WPR];
-#pragma unroll
-                          for (int w = 0; w < WPR; ++w) { t[0][w] = cq[1][w]; t[1][w] = cq[0][w]; t[2][w] = cq[2][w]; }
-                          row_step(wr + 2 * WP, t, std::integral_constant<int, 7>{}); }
-                        wr += 3 * WP;
-                    }
-                    // remaining steady rows (STEADY % 3 of them; 2 for bs 16: rho = 14, 15), then the two ramp-down rows
-                    constexpr int R0 = 2 + 3 * TRIPLES;                        // first row not yet processed; R0 % 3 == 2
-                    static_assert(STEADY % 3 == 2, "row schedule below assumes two trailing steady rows");
-                    load_cur(R0, cq[2]);
-                    { uint32_t t[G][WPR];
-#pragma unroll
-                      for (int w = 0; w < WPR; ++w) { t[0][w] = cq[2][w]; t[1][w] = cq[1][w]; t[2][w] = cq[0][w]; }
-                      row_step(wr, t, std::integral_constant<int, 7>{}); }
-                    load_cur(R0 + 1, cq[0]);
-                    { uint32_t t[G][WPR];
-#pragma unroll
-                      for (int w = 0; w < WPR; ++w) { t[0][w] = cq[0][w]; t[1][w] = cq[2][w]; t[2][w] = cq[1][w]; }
-                      row_step(wr + WP, t, std::integral_constant<int, 7>{}); }
-                    { uint32_t t[G][WPR];                                       // rho = BS: groups 1, 2 -> rows BS-1, BS-2
-#pragma unroll
-                      for (int w = 0; w < WPR; ++w) { t[0][w] = 0; t[1][w] = cq[0][w]; t[2][w] = cq[2][w]; }
-                      row_step(wr + 2 * WP, t, std::integral_constant<int, 6>{}); }
-                    { uint32_t t[G][WPR];                                       // rho = BS+1: group 2 -> row BS-1
-#pragma unroll
-                      for (int w = 0; w < WPR; ++w) { t[0][w] = 0; t[1][w] = 0; t[2][w] = cq[0][w]; }
-                      row_step(wr + 3 * WP, t, std::integral_constant<int, 4>{}); }
+                if constexpr (G == 3 && BS >= 4) {
+                    uint32_t unused[3][NDX];
+                    sad_pass_g3<WPR, NDX, KM, BS, WP, false>(win, cb, acc, unused);
                 } else {
                     uint32_t curq[G][WPR];
 #pragma unroll
@@ -453,7 +550,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                         for (int gg = G - 1; gg > 0; --gg)
 #pragma unroll
                             for (int w = 0; w < WPR; ++w) curq[gg][w] = curq[gg - 1][w];
-                        if (rho < BS) load_cur(rho, curq[0]);
+                        if (rho < BS) load_cur_row<WPR>(cb, rho, curq[0]);
                         uint32_t refw[NVM * 4];
 #pragma unroll
                         for (int v = 0; v < NVM; ++v) {
@@ -491,7 +588,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                             for (int gg = G - 1; gg > 0; --gg)
 #pragma unroll
                                 for (int w = 0; w < WPR; ++w) curq[gg][w] = curq[gg - 1][w];
-                            if (rho < BS) load_cur(rho, curq[0]);
+                            if (rho < BS) load_cur_row<WPR>(cb, rho, curq[0]);
 #pragma unroll
                             for (int gg = 0; gg < G; ++gg) {
                                 const int jr = rho - gg;
@@ -510,7 +607,6 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 valid_range(by * BS, g.H, BS, g.fme, g.fme, ylo, yhi);
                 xlo = max(xlo, -g.R); xhi = min(xhi, g.R);
                 ylo = max(ylo, -g.R); yhi = min(yhi, g.R);
-                const int mul = g.fme ? 2 : 1;
                 uint32_t ly8[G], ybad[G];
 #pragma unroll
                 for (int gg = 0; gg < G; ++gg) {
@@ -554,6 +650,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 } else if (key != ~0ull) {
                     atomicMin(okey, key);
                 }
+                }   // !QUAD
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[sb]);

@@ -23,6 +23,15 @@ CASES = {
     "r16_vbs_fme_bright": dict(gen=("translating", dict(F=3, H=96, W=128, seed=44, bright=True)),
                                enc=dict(block_size=16, search_range=16, Qp=4, intra_dur=8, FMEEnable=True, nRefFrames=2,
                                         VBSEnable=True, lam=0.02)),
+    "r16_vbs_int": dict(gen=("zooming", dict(F=3, H=96, W=128, seed=50)),
+                        enc=dict(block_size=16, search_range=16, Qp=2, intra_dur=8, VBSEnable=True, lam=0.01)),
+    "r16_vbs_fme_nref1_ties": dict(gen=("flat_ties", dict(F=3, H=96, W=128, seed=51)),
+                                   enc=dict(block_size=16, search_range=16, Qp=1, intra_dur=8, VBSEnable=True, lam=0.05, FMEEnable=True)),
+    "r16_vbs_fme_nref3_rc": dict(gen=("translating", dict(F=5, H=96, W=128, seed=52)),
+                                 enc=dict(block_size=16, search_range=16, Qp=3, intra_dur=8, VBSEnable=True, lam=0.02, FMEEnable=True,
+                                          nRefFrames=3, RCFlag=1, targetBR="900 kbps",
+                                          qp_rate_tables=[[9000, 7000, 5200, 3900, 2800, 1900, 1300, 900, 600, 400, 250, 100],
+                                                          [6000, 4600, 3400, 2500, 1800, 1200, 800, 560, 380, 250, 160, 60]])),
     "r8_i8_fme": dict(gen=("translating", dict(F=3, H=64, W=96, seed=45)),
                       enc=dict(block_size=8, search_range=8, Qp=1, intra_dur=8, FMEEnable=True)),
     "r5_i16": dict(gen=("zooming", dict(F=3, H=64, W=96, seed=46)),
