@@ -228,7 +228,14 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 for (int li = lane; li < nitems; li += 32) {
                     const int item = item0 + li;
                     const int blk = item / per_blk, rp = item % per_blk;
-                    meta[sb * a.SI + li] = make_int4(blk, blk % g.nbx, blk / g.nbx, (rp / a.nph) | ((rp % a.nph) << 8));
+                    {
+                        const int mbx = blk % g.nbx, mby = blk / g.nbx;
+                        int l0, h0, l1, h1;
+                        valid_range(mbx * BS, g.W, BS, g.fme, g.fme, l0, h0);
+                        valid_range(mby * BS, g.H, BS, g.fme, g.fme, l1, h1);
+                        const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
+                        meta[sb * a.SI + li] = make_int4(blk, mbx, mby, (rp / a.nph) | ((rp % a.nph) << 8) | (interior << 16));
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // buffer was read through the generic proxy
                 __syncwarp();
@@ -374,7 +381,14 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
             for (int li = lane; li < nitems; li += 32) {
                 const int item = item0 + li;
                 const int blk = item / per_blk, rp = item % per_blk;
-                meta[sb * a.SI + li] = make_int4(blk, blk % g.nbx, blk / g.nbx, (rp / a.nph) | ((rp % a.nph) << 8));
+                {
+                        const int mbx = blk % g.nbx, mby = blk / g.nbx;
+                        int l0, h0, l1, h1;
+                        valid_range(mbx * BS, g.W, BS, g.fme, g.fme, l0, h0);
+                        valid_range(mby * BS, g.H, BS, g.fme, g.fme, l1, h1);
+                        const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
+                        meta[sb * a.SI + li] = make_int4(blk, mbx, mby, (rp / a.nph) | ((rp % a.nph) << 8) | (interior << 16));
+                    }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[sb]);
@@ -417,7 +431,10 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
             if (has_task) {
                 const int4 mt = meta[sb * a.SI + li];
                 const int blk = mt.x, bx = mt.y, by = mt.z;
-                const int ref = mt.w & 255, ph = mt.w >> 8;
+                const int ref = mt.w & 255, ph = (mt.w >> 8) & 255;
+                // DIRECT geometry + interior block: the only invalid candidates are ox = r on odd horizontal phases and oy = r on
+                // odd vertical phases (dx, dy = 2r + 1 > R), plus the unused NDX-th slot of shifts 1..3
+                const bool fast_valid = a.direct && __all_sync(__activemask(), (mt.w >> 16) & 1);
                 const int px = ph & 1, py = ph >> 1;
                 const int oy0 = grp * G;
                 const unsigned char* win = wins + sb * a.stage_bytes + c * a.shift_stride + li * a.item_stride + oy0 * a.wpitch;
@@ -602,6 +619,27 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 }
 
                 // ---- thread-local argmin.  key32 = sad<<16 | (|dx|+|dy|)<<8 | (k*G+g); invalid candidates are OR-ed to all ones.
+                uint32_t best = 0xFFFFFFFFu;
+                if (fast_valid) {
+                    const int pxe = g.fme ? px : 0, pye = g.fme ? py : 0;
+                    const uint32_t xbl = (c == 0 && !pxe) ? 0u : 0xFFFFFFFFu;             // candidate k = NDX-1
+                    const uint32_t ybl = (grp == a.NG - 1 && pye) ? 0xFFFFFFFFu : 0u;      // candidate g = G-1 of the last group
+                    uint32_t ly8[G];
+#pragma unroll
+                    for (int gg = 0; gg < G; ++gg) ly8[gg] = (uint32_t)(abs(mul * (-g.r + oy0 + gg) + pye) << 8) + gg;
+#pragma unroll
+                    for (int k = 0; k < NDX; ++k) {
+                        const uint32_t lx8 = (uint32_t)(abs(mul * (-g.r + c + 4 * k) + pxe) << 8) + k * G;
+#pragma unroll
+                        for (int gg = 0; gg < G; ++gg) {
+                            uint32_t key = acc[gg][k] * 65536u + (lx8 + ly8[gg]);
+                            if (k == NDX - 1 && gg == G - 1) asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(key) : "r"(xbl), "r"(ybl));
+                            else if (k == NDX - 1) key |= xbl;
+                            else if (gg == G - 1) key |= ybl;
+                            asm("min.u32 %0, %0, %1;" : "+r"(best) : "r"(key));
+                        }
+                    }
+                } else {
                 int xlo, xhi, ylo, yhi;
                 valid_range(bx * BS, g.W, BS, g.fme, g.fme, xlo, xhi);
                 valid_range(by * BS, g.H, BS, g.fme, g.fme, ylo, yhi);
@@ -614,7 +652,6 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                     ly8[gg] = (uint32_t)(abs(dy) << 8) + gg;
                     ybad[gg] = (oy <= g.r && dy >= ylo && dy <= yhi) ? 0u : 0xFFFFFFFFu;
                 }
-                uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
                 for (int k = 0; k < NDX; ++k) {
                     const int ox = -g.r + c + 4 * k, dx = mul * ox + (g.fme ? px : 0);
@@ -626,6 +663,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                         asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(key) : "r"(xbad), "r"(ybad[gg]));      // key | xbad | ybad
                         asm("min.u32 %0, %0, %1;" : "+r"(best) : "r"(key));
                     }
+                }
                 }
                 unsigned long long key = ~0ull;
                 if (best != 0xFFFFFFFFu) {
