@@ -240,10 +240,12 @@ def main():
         codec.encode_arrays(frames)
     barrier()
     t1 = time.perf_counter()
+    e2e_dev_ms = 0.0
     for k in range(args.steps):
         codec.const_init_Qp = k % 12
         out = codec.encode_arrays(frames)
         _ = int(out["stats"]["sse"][0, -1])
+        e2e_dev_ms += codec.last_timing["device_ms"]
     barrier()
     e2e_wall = time.perf_counter() - t1
     nblk = (H // cfg["bs"]) * (W // cfg["bs"])
@@ -275,7 +277,8 @@ def main():
                                        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
                                        "unit": "GB/s", "note": "5*H*W algorithmic bytes per frame (SURVEY §8d); launch-bound at one 1080p frame per launch"},
                 "e2e": {"value": total_frames / (e2e_ms_max / 1e3), "unit": "frames/s", "h2d_bytes_per_step": F * H * W,
-                        "d2h_bytes_per_step": d2h},
+                        "d2h_bytes_per_step": d2h, "wall_ms_per_step": e2e_ms_max / args.steps,
+                        "device_ms_per_step_rank0": e2e_dev_ms / args.steps},
                 "gpu_launches": launches, "clocks": sampler.summary()}
         line["roofline_transform"]["frac"] = line["roofline_transform"]["achieved"] / line["roofline_transform"]["peak"]
         if world == 1 and not args.no_cpu_baseline:

@@ -232,7 +232,8 @@ class Y_Video_codec:
         key = (U, F, H, W, nblk, rows)
         if getattr(self, "_pin_key", None) != key:
             self._pin = dict(split=_pinned_empty((U, F, nblk), np.uint8),
-                             mv=_pinned_empty((U, F, nblk, 4, 3), np.int16), rows=_pinned_empty((U, F, rows), np.uint32))
+                             mv=_pinned_empty((U, F, nblk, 4, 3), np.int16), rows=_pinned_empty((U, F, rows), np.uint32),
+                             stats=_pinned_empty((U, F, 32), np.uint8))
             self._pin_key = key
         if want_levels and "lev" not in self._pin:
             self._pin["lev"] = _pinned_empty((U, F, H, W), np.int16)
@@ -244,7 +245,8 @@ class Y_Video_codec:
         split, mv, row_sizes = self._pin["split"][1], self._pin["mv"][1], self._pin["rows"][1]
         levels = self._pin["lev"][1] if want_levels else None
         recon = self._pin["rec"][1] if want_recon else None
-        stats = np.zeros((U, F), dtype=_native.STATS_DTYPE)
+        # pinned too: a pageable target makes the per-chunk D2H synchronous and stalls the host behind the GPU
+        stats = self._pin["stats"][1].view(_native.STATS_DTYPE).reshape(U, F)
         rc = ctx.lib.so_encode_sequence(ctx.handle, a_in.ctypes.data, U, F, split.ctypes.data, mv.ctypes.data,
                                         levels.ctypes.data if want_levels else None,
                                         recon.ctypes.data if want_recon else None, row_sizes.ctypes.data, stats.ctypes.data)
