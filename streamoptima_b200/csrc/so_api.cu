@@ -39,7 +39,8 @@ struct so_ctx {
     std::vector<char> slot_u8;              // slot holds a uint8 reconstruction (false: the float 128 frame)
     std::vector<int> slot_wrap;             // wrap mode the half-pel planes of the slot were built with (-1 none)
     // scratch
-    MeResult *me_parent = nullptr, *me_sub = nullptr;
+    MeResult *me_parent = nullptr, *me_sub = nullptr;       // exhaustive search: packed keys (all ones between frames); fast ME: records
+    MeResult *in_parent = nullptr, *in_sub = nullptr;       // intra search results (separate: they must not disturb the keys)
     int16_t* res_frame = nullptr;
     int32_t* band = nullptr;
     int* qp_rows_dev = nullptr;
@@ -132,7 +133,8 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     free_seq(c);
-    cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->res_frame); cudaFree(c->band);
+    cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->in_parent); cudaFree(c->in_sub);
+    cudaFree(c->res_frame); cudaFree(c->band);
     cudaFree(c->qp_rows_dev);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto e : c->pipe.up) cudaEventDestroy(e);
@@ -198,6 +200,8 @@ extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
     CUC(cudaMemset(ctx->ring, 0, ctx->unit_stride * ctx->batch));
     CUC(cudaMalloc(&ctx->me_parent, sizeof(MeResult) * ctx->nblk * ctx->batch));
     CUC(cudaMalloc(&ctx->me_sub, sizeof(MeResult) * ctx->nblk * 4 * ctx->batch));
+    CUC(cudaMalloc(&ctx->in_parent, sizeof(MeResult) * ctx->nblk * ctx->batch));
+    CUC(cudaMalloc(&ctx->in_sub, sizeof(MeResult) * ctx->nblk * 4 * ctx->batch));
     CUC(cudaMalloc(&ctx->res_frame, sizeof(int16_t) * ctx->frame_px * ctx->batch));
     CUC(cudaMalloc(&ctx->band, sizeof(int32_t) * ctx->frame_px * ctx->batch));
     CUC(cudaMalloc(&ctx->qp_rows_dev, sizeof(int) * g.nby));
@@ -241,11 +245,27 @@ static int take_free_slot(so_ctx* c) {
     return -1;
 }
 
+// exhaustive-search key arrays := all ones (the identity of the atomicMin merge)
+static int keys_reset(so_ctx* ctx, cudaStream_t st) {
+    CU(cudaMemsetAsync(ctx->me_parent, 0xFF, sizeof(MeResult) * ctx->nblk * ctx->batch, st));
+    CU(cudaMemsetAsync(ctx->me_sub, 0xFF, sizeof(MeResult) * ctx->nblk * 4 * ctx->batch, st));
+    return SO_OK;
+}
+
+static int ref_reset_impl(so_ctx* ctx, cudaStream_t st, bool reset_keys);
+
 extern "C" int so_ref_reset(so_ctx* ctx, int /*unit*/, void* stream) {
     if (!ctx) return SO_E_INVALID;
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    return ref_reset_impl(ctx, (cudaStream_t)stream, true);
+}
+
+static int ref_reset_impl(so_ctx* ctx, cudaStream_t st, bool reset_keys) {
     ctx->list.clear();
+    if (reset_keys) {
+        const int rc = keys_reset(ctx, st);
+        if (rc) return rc;
+    }
     const int s = 0;
     // ref_frames = [np.ones((h, w)) * 128]  (Encoder.py:1798): a float frame -> never triggers the uint8 wrap
     const size_t n16 = ctx->slot_stride / 16;
@@ -467,13 +487,12 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const int total_stages = units * a.stages_per_unit;
     const int grid = total_stages < sms ? total_stages : sms;
-    CU(cudaMemsetAsync(out + (size_t)unit0 * out_stride, 0xFF, sizeof(MeResult) * out_stride * (units - 1) + sizeof(MeResult) * nb, st));
+    // the key arrays are all-ones here: initialised by keys_reset() and restored by the finish kernel after it decodes them
     const bool quad = out_sub && a.direct && bs == 16 && NDX == 9 && G == 3;
     if (used_quad) *used_quad = quad;
     if (quad) {
         a.out_sub = reinterpret_cast<unsigned long long*>(out_sub + (size_t)unit0 * out_sub_stride);
         a.out_sub_unit_stride = out_sub_stride;
-        CU(cudaMemsetAsync(out_sub + (size_t)unit0 * out_sub_stride, 0xFF, sizeof(MeResult) * out_sub_stride * (units - 1) + sizeof(MeResult) * nb * 4, st));
     }
     ev_pair(ctx, ctx->ev_me, st, true);
     cudaError_t e;
@@ -483,11 +502,6 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     else e = launch_me_tma_n<4>(NDX, G, map, cmap, a, grid, threads, smem, st);
     ev_pair(ctx, ctx->ev_me, st, false);
     if (e != cudaSuccess) { set_err(ctx, std::string("me_tma_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
-    for (int u = 0; u < units; ++u) {
-        me_unpack_kernel<<<(nb + 255) / 256, 256, 0, st>>>(out + (size_t)(unit0 + u) * out_stride, nb, a.g.R);
-        if (quad) me_unpack_kernel<<<(nb * 4 + 255) / 256, 256, 0, st>>>(out_sub + (size_t)(unit0 + u) * out_sub_stride, nb * 4, a.g.R);
-        ctx->launches += quad ? 2 : 1;
-    }
     ctx->launches++;
     CU(cudaGetLastError());
     return SO_OK;
@@ -541,6 +555,7 @@ static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
                              int unit0, int units, int qp_rd, cudaStream_t st) {
     const FrameGeom& g = ctx->g;
     FlowArgs a = make_flow(ctx, cur, cur_stride, o, ofs, unit0, qp_rd);
+    a.me_parent = ctx->in_parent; a.me_sub = ctx->in_sub;
     stats_init_kernel<<<units, 64, 0, st>>>(o->stats + unit0 * a.stats_stride, a.stats_stride, o->row_sizes + unit0 * a.rows_stride,
                                             a.rows_stride, g.nby, (uint32_t)(g.bs * g.bs), 0u);
     dim3 grid(ctx->nblk, units);
@@ -592,6 +607,7 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     const bool parallel = ctx->p.parallel_mode != 0;
     const bool use_fast = (ctx->p.flags & SO_FLAG_FAST_ME) && ctx->p.parallel_mode != 1;      // Encoder.py:641
     a.fast = use_fast ? 1 : 0;
+    a.me_packed = use_fast ? 0 : 1;
     a.chain = parallel ? 0 : 1;
     a.nref_fast = parallel ? 1 : ctx->p.n_ref_frames;                                        // Encoder.py:590
     stats_init_kernel<<<units, 64, 0, st>>>(o->stats + unit0 * a.stats_stride, a.stats_stride, o->row_sizes + unit0 * a.rows_stride,
@@ -746,7 +762,7 @@ extern "C" int so_seq_run(so_ctx* ctx) {
             rc = encode_intra_impl(ctx, cur, cur_stride, &o, n_frames, 0, n_units, ctx->p.qp, st);
             if (rc) return rc;
         } else {
-            if (ctx->p.parallel_mode == 1) { rc = so_ref_reset(ctx, 0, st); if (rc) return rc; }   // Encoder.py:1846
+            if (ctx->p.parallel_mode == 1) { rc = ref_reset_impl(ctx, st, false); if (rc) return rc; }   // Encoder.py:1846
             rc = encode_inter_impl(ctx, cur, cur_stride, &o, n_frames, 0, n_units, st);
             if (rc) return rc;
             if (ctx->p.rc_flag > 1) {                                                     // scene cut, Encoder.py:1851-1856
@@ -919,7 +935,7 @@ extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const
         o.stats = ctx->sq_stats;
         if (qp_rows_per_frame) CU(cudaMemcpyAsync(ctx->qp_rows_dev, qp_rows_per_frame + (size_t)f * g.nby, sizeof(int) * g.nby, cudaMemcpyHostToDevice, st));
         const bool intra = frame_types[f] == 0 && ctx->p.parallel_mode != 1;
-        if (!intra && ctx->p.parallel_mode == 1) { rc = so_ref_reset(ctx, 0, st); if (rc) return rc; }     // decoder.py:504-509
+        if (!intra && ctx->p.parallel_mode == 1) { rc = ref_reset_impl(ctx, st, false); if (rc) return rc; }     // decoder.py:504-509
         if (!intra) {
             if (ctx->list.empty()) { set_err(ctx, "inter frame with an empty reference list"); return SO_E_STATE; }
             rc = ensure_planes(ctx, 1, st);

@@ -86,6 +86,7 @@ struct FlowArgs {
     size_t cur_unit_stride;
     int unit0;                   // first unit processed by this launch (grid.y / grid.x index is added)
     int vbs, fast, chain;        // chain: fast ME carries mvp across blocks (ParallelMode 0)
+    int me_packed;               // me_parent / me_sub hold packed search keys; the finish kernel decodes and resets them
     int nref_fast;               // refs[:nRefFrames] of fast ME (1 in ParallelMode 2, Encoder.py:590)
     int qp_final;                // QP when no rate control
     int qp_rd;                   // QP of self.Q during prediction (RD cost)
@@ -101,6 +102,20 @@ struct FlowArgs {
     size_t split_stride, mv_stride, frame_stride, rows_stride, stats_stride;   // per-unit strides in elements
     size_t scratch_stride;       // per-unit stride of res_frame / band (one frame)
 };
+
+// ME results are either plain MeResult records (fast ME, intra search) or the packed 64-bit keys the exhaustive search
+// merges with atomicMin (decoded like me_unpack_kernel does).
+__device__ __forceinline__ MeResult me_get(const MeResult* p, int packed, int R) {
+    if (!packed) return *p;
+    const unsigned long long key = *reinterpret_cast<const unsigned long long*>(p);
+    MeResult r;
+    if (key == ~0ull) { r.dx = 0; r.dy = 0; r.ref = 0; r.none = 1; r.sad = 0; }          // (0,0,0), MAE = inf (Encoder.py:684-685)
+    else {
+        r.sad = (uint32_t)(key >> 40); r.ref = (int16_t)((key >> 16) & 0xFF);
+        r.dx = (int16_t)((int)((key >> 8) & 0xFF) - R); r.dy = (int16_t)((int)(key & 0xFF) - R); r.none = 0;
+    }
+    return r;
+}
 
 __device__ __forceinline__ double me_mae(const MeResult& m, int n, int fast) {
     if (fast) return (double)m.sad;                         // quirk Q4: the "MAE" is the reference index
@@ -160,7 +175,20 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
         for (int ph = 0; ph < 4; ++ph) rl.plane[r][ph] = a.ring.plane(unit, r, ph);
 
     const int c = a.cur[unit * a.cur_unit_stride + (size_t)(y + j) * g.W + x + i];
-    const MeResult mp = a.me_parent[unit * a.me_parent_stride + blk];
+    MeResult* pme = a.me_parent + unit * a.me_parent_stride + blk;
+    const MeResult mp = me_get(pme, a.me_packed, g.R);
+    MeResult msub[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        msub[kk] = mp;
+        if (a.vbs) msub[kk] = me_get(a.me_sub + unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1), a.me_packed, g.R);
+    }
+    if (a.me_packed) {          // every thread holds its copy: reset the keys for the next frame's atomicMin merge
+        __syncthreads();
+        if (t == 0) *reinterpret_cast<unsigned long long*>(pme) = ~0ull;
+        if (a.vbs && t < 4)
+            *reinterpret_cast<unsigned long long*>(a.me_sub + unit * a.me_sub_stride + (by * 2 + (t >> 1)) * (g.nbx * 2) + bx * 2 + (t & 1)) = ~0ull;
+    }
     const PredSel selp = pred_select(g, x * mult, y * mult, mp.dx, mp.dy, BS, -1);
     const int predp = pred_sample(g, rl, selp, mp.ref, i, j);
     const int resp = c - predp;
@@ -179,8 +207,7 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
     int tcs = 0, preds_q5 = 0;
     MeResult ms = mp;
     if (eligible) {
-        const int sblk = (by * 2 + (k >> 1)) * (g.nbx * 2) + bx * 2 + (k & 1);
-        ms = a.me_sub[unit * a.me_sub_stride + sblk];
+        ms = k == 0 ? msub[0] : (k == 1 ? msub[1] : (k == 2 ? msub[2] : msub[3]));
         const int xs = x + (k & 1) * S, ys = y + (k >> 1) * S;
         const PredSel sels = pred_select(g, xs * mult, ys * mult, ms.dx, ms.dy, S, -1);
         const int preds = pred_sample(g, rl, sels, ms.ref, si, sj);
@@ -195,10 +222,8 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
         const int lens = rle_len_cta<BS, S>(quant_rhe(tcs, q_shift(sj, si, S, qs)), sj, si, k, nzbuf, active);
         // vbs_mae = (sum of the four sub MAEs) / 4, accumulated in Z order
         double vm = 0.0;
-        for (int kk = 0; kk < 4; ++kk) {
-            const int sb = (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1);
-            vm = __dadd_rn(vm, me_mae(a.me_sub[unit * a.me_sub_stride + sb], S, a.fast));
-        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) vm = __dadd_rn(vm, me_mae(msub[kk], S, a.fast));
         vm = vm / 4.0;
         const double rd_bs = __dadd_rn(__dmul_rn(a.lam, (double)(16 + 8 * lenp)), mae_blk);
         const double rd_vbs = __dadd_rn(__dmul_rn(a.lam, (double)(64 + 8 * lens)), vm);
@@ -236,9 +261,9 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
     if (t == 0) {
         a.split[unit * a.split_stride + blk] = (uint8_t)split;
         int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
+#pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            MeResult m = mp;
-            if (split) m = a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)];
+            const MeResult m = split ? msub[kk] : mp;
             const bool on = split || kk == 0;
             mvo[kk * 3 + 0] = on ? m.dx : 0; mvo[kk * 3 + 1] = on ? m.dy : 0; mvo[kk * 3 + 2] = on ? m.ref : 0;
         }
@@ -252,8 +277,8 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
             unsigned long long n = (unsigned long long)mp.sad * 4ull;
             if (eligible) {
                 n = 0;
-                for (int kk = 0; kk < 4; ++kk)
-                    n += a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)].sad;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) n += msub[kk].sad;
             }
             atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), n);
         } else {
@@ -261,10 +286,8 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
             bool inf = mp.none;
             if (eligible) {
                 n = 0; inf = false;
-                for (int kk = 0; kk < 4; ++kk) {
-                    const MeResult m = a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)];
-                    n += m.sad; inf = inf || m.none;
-                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) { n += msub[kk].sad; inf = inf || msub[kk].none; }
             }
             if (inf) atomicOr(&st->mae_inf, 1u); else atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), n);
         }
