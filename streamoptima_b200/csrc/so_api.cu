@@ -77,6 +77,7 @@ struct so_ctx {
     size_t ev_used = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_me, ev_tq;
     bool timing_on = false;
+    bool stats_prezeroed = false;           // so_seq_run zeroes the statistics of the whole sequence with one memset
 };
 
 static void set_err(so_ctx* ctx, const std::string& s) {
@@ -284,12 +285,19 @@ static int ring_push(so_ctx* ctx, const uint8_t* recon_dev, size_t src_unit_stri
     const int s = take_free_slot(ctx);
     if (s < 0) { set_err(ctx, "reference ring has no free slot"); return SO_E_STATE; }
     const FrameGeom& g = ctx->g;
-    ring_store_kernel<<<dim3((g.W / 4 + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, g.pitch, recon_dev, src_unit_stride, g.W, g.H);
-    ctx->launches++;
-    CU(cudaGetLastError());
     ctx->list.push_back(s);
     ctx->slot_u8[s] = 1;
-    ctx->slot_wrap[s] = -1;
+    // One kernel stores the frame and derives its half-pel phases and byte-shifted copies.  The uint8-wrap mode (quirk
+    // Q1) of the next inter frame is already known: the list does not change before it (ensure_planes re-derives the
+    // planes from the stored frame in the one case it does: ParallelMode 1 resets the list every frame).
+    bool all_u8 = true;
+    for (int l : ctx->list) all_u8 = all_u8 && ctx->slot_u8[l];
+    const int wrap = (g.fme && all_u8) ? 1 : 0;
+    ring_planes_kernel<<<dim3((g.W / 4 + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, ctx->plane_bytes, recon_dev,
+                                                                              src_unit_stride, g.W, g.W, g.H, g.pitch, g.fme, wrap, 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    ctx->slot_wrap[s] = wrap;
     return SO_OK;
 }
 
@@ -556,8 +564,12 @@ static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     const FrameGeom& g = ctx->g;
     FlowArgs a = make_flow(ctx, cur, cur_stride, o, ofs, unit0, qp_rd);
     a.me_parent = ctx->in_parent; a.me_sub = ctx->in_sub;
-    stats_init_kernel<<<units, 64, 0, st>>>(o->stats + unit0 * a.stats_stride, a.stats_stride, o->row_sizes + unit0 * a.rows_stride,
-                                            a.rows_stride, g.nby, (uint32_t)(g.bs * g.bs), 0u);
+    a.mae_den = (uint32_t)(g.bs * g.bs); a.frame_type = 0;
+    if (!ctx->stats_prezeroed) {
+        stats_init_kernel<<<units, 64, 0, st>>>(o->stats + unit0 * a.stats_stride, a.stats_stride, o->row_sizes + unit0 * a.rows_stride,
+                                                a.rows_stride, g.nby, a.mae_den, 0u);
+        ctx->launches++;
+    }
     dim3 grid(ctx->nblk, units);
     const int nt = nthreads_px(g.bs);
     const size_t ism = sizeof(unsigned) * 4 * (2 * g.r + 1);
@@ -575,7 +587,7 @@ static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     else if (g.bs == 8) intra_recon_kernel<8><<<grid2, nt, 0, st>>>(a);
     else intra_recon_kernel<4><<<grid2, nt, 0, st>>>(a);
     ev_pair(ctx, ctx->ev_tq, st, false);
-    ctx->launches += 4;
+    ctx->launches += 3;
     CU(cudaGetLastError());
     return SO_OK;
 }
@@ -589,7 +601,8 @@ static int ensure_planes(so_ctx* ctx, int units, cudaStream_t st) {
         if (!ctx->slot_u8[s]) continue;              // the constant frame: every plane was filled at reset
         if (ctx->slot_wrap[s] == wrap) continue;
         ring_planes_kernel<<<dim3((g.W / 4 + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, ctx->plane_bytes,
-                                                                                  g.W, g.H, g.pitch, g.fme, wrap);
+                                                                                  slot_ptr(ctx, s), ctx->unit_stride, g.pitch,
+                                                                                  g.W, g.H, g.pitch, g.fme, wrap, 0);
         ctx->launches++;
         ctx->slot_wrap[s] = wrap;
     }
@@ -610,9 +623,12 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     a.me_packed = use_fast ? 0 : 1;
     a.chain = parallel ? 0 : 1;
     a.nref_fast = parallel ? 1 : ctx->p.n_ref_frames;                                        // Encoder.py:590
-    stats_init_kernel<<<units, 64, 0, st>>>(o->stats + unit0 * a.stats_stride, a.stats_stride, o->row_sizes + unit0 * a.rows_stride,
-                                            a.rows_stride, g.nby, use_fast ? 4u : (uint32_t)(g.bs * g.bs), 1u);
-    ctx->launches++;
+    a.mae_den = use_fast ? 4u : (uint32_t)(g.bs * g.bs); a.frame_type = 1;
+    if (!ctx->stats_prezeroed) {
+        stats_init_kernel<<<units, 64, 0, st>>>(o->stats + unit0 * a.stats_stride, a.stats_stride, o->row_sizes + unit0 * a.rows_stride,
+                                                a.rows_stride, g.nby, a.mae_den, 1u);
+        ctx->launches++;
+    }
     const int nt = nthreads_px(g.bs);
     if (use_fast) {
         ev_pair(ctx, ctx->ev_me, st, true);
@@ -741,6 +757,10 @@ extern "C" int so_seq_run(so_ctx* ctx) {
     CU(cudaEventRecord(ctx->ev0, st));
     int rc = so_ref_reset(ctx, 0, st);
     if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->sq_stats, 0, (size_t)n_units * n_frames * sizeof(so_frame_stats), st));
+    CU(cudaMemsetAsync(ctx->sq_rows, 0, (size_t)n_units * n_frames * nby * sizeof(uint32_t), st));
+    ctx->stats_prezeroed = true;
+    struct Unflag { so_ctx* c; ~Unflag() { c->stats_prezeroed = false; } } unflag{ctx};
     std::vector<so_frame_stats> hstats(n_units);
     for (int f = 0; f < n_frames; ++f) {
         if (ctx->pipe.active && f % ctx->pipe.chunk == 0) {
@@ -772,7 +792,9 @@ extern "C" int so_seq_run(so_ctx* ctx) {
                 for (int u = 0; u < n_units; ++u) {
                     if ((int64_t)hstats[u].qsize > ctx->p.intra_thresh) {
                         // self.Qp still holds the last row QP of the inter flow: it is the RD QP of this intra pass
+                        ctx->stats_prezeroed = false;        // the frame's statistics hold the inter attempt: re-initialise
                         rc = encode_intra_impl(ctx, cur, cur_stride, &o, n_frames, u, 1, ctx->qp_rows.back(), st);
+                        ctx->stats_prezeroed = true;
                         if (rc) return rc;
                     }
                 }

@@ -14,17 +14,21 @@
 // wraps: the column pass is float), phase 3 = ceil((sh[y]+sh[y+1])/4) on the (possibly wrapped) horizontal sums.
 // One thread per 4 output bytes; columns past the frame edge replicate the last column (only invalid candidates and
 // never-sampled half-pel positions see them).
-__global__ void ring_planes_kernel(uint8_t* slot0, size_t unit_stride, size_t plane_bytes, int W, int H, int pitch, int fme, int wrap) {
+// src: the frame the planes are derived from -- the dense reconstruction at push time (write_p0 = 1: it is also stored as
+// phase 0 / shift 0), or the slot's own phase-0 plane when only the wrap mode changed (write_p0 = 0).
+__global__ void ring_planes_kernel(uint8_t* slot0, size_t unit_stride, size_t plane_bytes, const uint8_t* src, size_t src_unit_stride,
+                                   int src_pitch, int W, int H, int pitch, int fme, int wrap, int write_p0) {
     const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int x = x4 * 4;
     if (x >= W) return;
     uint8_t* base = slot0 + blockIdx.z * unit_stride;
+    const uint8_t* sbase = src + blockIdx.z * src_unit_stride;
     const int yn = min(y + 1, H - 1);
     int a0[9], a1[9];
     {
-        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(base + (size_t)y * pitch);
-        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(base + (size_t)yn * pitch);
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(sbase + (size_t)y * src_pitch);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(sbase + (size_t)yn * src_pitch);
         uint32_t w0[3], w1[3];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
@@ -55,7 +59,7 @@ __global__ void ring_planes_kernel(uint8_t* slot0, size_t unit_stride, size_t pl
         if (p > 0 && !fme) break;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            if (p == 0 && c == 0) continue;                   // the input plane
+            if (p == 0 && c == 0 && !write_p0) continue;      // the input plane itself
             const uint32_t v = (uint32_t)ph[p][c] | ((uint32_t)ph[p][c + 1] << 8) | ((uint32_t)ph[p][c + 2] << 16) | ((uint32_t)ph[p][c + 3] << 24);
             *reinterpret_cast<uint32_t*>(base + (size_t)(p * 4 + c) * plane_bytes + o) = v;
         }
@@ -86,6 +90,7 @@ struct FlowArgs {
     size_t cur_unit_stride;
     int unit0;                   // first unit processed by this launch (grid.y / grid.x index is added)
     int vbs, fast, chain;        // chain: fast ME carries mvp across blocks (ParallelMode 0)
+    uint32_t mae_den, frame_type; // written into the frame's statistics by block 0 of the finish kernels
     int me_packed;               // me_parent / me_sub hold packed search keys; the finish kernel decodes and resets them
     int nref_fast;               // refs[:nRefFrames] of fast ME (1 in ParallelMode 2, Encoder.py:590)
     int qp_final;                // QP when no rate control
@@ -268,6 +273,7 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
             mvo[kk * 3 + 0] = on ? m.dx : 0; mvo[kk * 3 + 1] = on ? m.dy : 0; mvo[kk * 3 + 2] = on ? m.ref : 0;
         }
         so_frame_stats* st = a.stats + unit * a.stats_stride;
+        if (blk == 0) { st->mae_den = a.mae_den; st->frame_type = a.frame_type; }
         atomicAdd(reinterpret_cast<unsigned long long*>(&st->sse), se);
         atomicAdd(&st->qsize, (unsigned)len);
         atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
@@ -524,6 +530,7 @@ __global__ void intra_finish_kernel(const FlowArgs a) {
             mvo[kk * 3 + 0] = on ? m.dx : 0; mvo[kk * 3 + 1] = 0; mvo[kk * 3 + 2] = 0;
         }
         so_frame_stats* st = a.stats + unit * a.stats_stride;
+        if (blk == 0) { st->mae_den = a.mae_den; st->frame_type = a.frame_type; }
         atomicAdd(&st->qsize, (unsigned)len);
         atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
         if (mae_inf) atomicOr(&st->mae_inf, 1u); else atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), mae_n);
