@@ -301,6 +301,245 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// inter finish for 16x16 blocks, warp-synchronous: one half-warp per block (lane = block row), two blocks per warp, no
+// block-wide barriers.  Same arithmetic as inter_finish_kernel<16> (which stays the generic version for 8x8 / 4x4).
+//   * a lane owns one row of 16 pixels: 128-bit loads/stores of cur, levels and recon
+//   * 2-D transforms through a per-warp shared tile: column pass (lane = column), row pass (lane = row)
+//   * RLE symbol count from 16-bit non-zero row masks: the scan predecessor of (i, j) is (i-1, j+1) inside the block,
+//     (k-1, 0) for the first-row element (0, k) and (n-1, i-1) for the last-column element (i, n-1); a run starts where
+//     the non-zero flag differs from the predecessor's, so  len = #nonzeros + #starts  needs only shifts, XORs and
+//     popcounts of row masks exchanged by shuffles / ballots (see the closed form in oracle/codec_oracle.py:rle_length)
+// ------------------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ int rle_rows_partial(uint32_t m, int rr, uint32_t m_prev, uint32_t c0, uint32_t cl, uint32_t m_last) {
+    constexpr uint32_t MASK = (1u << (N - 1)) - 1u;
+    int v = __popc(m);
+    if (rr > 0) v += __popc((m ^ (m_prev >> 1)) & MASK);
+    else v += 1 + __popc(((m >> 1) ^ c0) & MASK) + __popc(((cl >> 1) ^ m_last) & MASK);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
+    constexpr int BS = 16, S = 8, P = 17;
+    __shared__ double tiles[4][2][BS * P];
+    const FrameGeom& g = a.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = lane >> 4, r = lane & 15;
+    const int nblk = g.nbx * g.nby;
+    const int unit = a.unit0 + blockIdx.y;
+    int blk = (blockIdx.x * 4 + warp) * 2 + h;
+    const bool live = blk < nblk;
+    if (!live) blk = nblk - 1;                        // keep the lanes in the warp-synchronous flow; results are not stored
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int x = bx * BS, y = by * BS;
+    const int mult = g.fme ? 2 : 1;
+    double* ws = tiles[warp][h];
+    const unsigned FULL = 0xFFFFFFFFu;
+    RefList rl;
+    for (int q = 0; q < g.nref; ++q)
+        for (int ph = 0; ph < 4; ++ph) rl.plane[q][ph] = a.ring.plane(unit, q, ph);
+
+    // ---- current row, motion results (decoded from the packed keys, which are reset for the next frame)
+    int c[BS];
+    {
+        const uint4 v = *reinterpret_cast<const uint4*>(a.cur + unit * a.cur_unit_stride + (size_t)(y + r) * g.W + x);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < BS; ++i) c[i] = (w[i >> 2] >> (8 * (i & 3))) & 255;
+    }
+    MeResult* pme = a.me_parent + unit * a.me_parent_stride + blk;
+    const MeResult mp = me_get(pme, a.me_packed, g.R);
+    MeResult msub[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        msub[kk] = mp;
+        if (a.vbs) msub[kk] = me_get(a.me_sub + unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1), a.me_packed, g.R);
+    }
+    __syncwarp();
+    if (a.me_packed && live) {
+        if (r == 0) *reinterpret_cast<unsigned long long*>(pme) = ~0ull;
+        if (a.vbs && r < 4)
+            *reinterpret_cast<unsigned long long*>(a.me_sub + unit * a.me_sub_stride + (by * 2 + (r >> 1)) * (g.nbx * 2) + bx * 2 + (r & 1)) = ~0ull;
+    }
+
+    // ---- whole-block predictor row and residual -> forward transform
+    int predp[BS];
+    {
+        const PredSel sel = pred_select(g, x * mult, y * mult, mp.dx, mp.dy, BS, -1);
+#pragma unroll
+        for (int i = 0; i < BS; ++i) predp[i] = pred_sample(g, rl, sel, mp.ref, i, r);
+    }
+#pragma unroll
+    for (int i = 0; i < BS; ++i) ws[r * P + i] = (double)(c[i] - predp[i]);
+    __syncwarp();
+    dct1d<BS>(ws + r, P);                      // column r
+    __syncwarp();
+    dct1d<BS>(ws + r * P, 1);                  // row r
+    int tcp[BS];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) tcp[i] = (int)rint(ws[r * P + i]);
+    __syncwarp();
+
+    const bool eligible = a.vbs && bx != 0 && by != 0;
+    const int qrow = a.qp_rows ? a.qp_rows[by] : a.qp_final;
+    const int ky = r >> 3, sr = r & 7;        // sub-block row group of this lane
+    int split = 0;
+    int tcs[BS], predq5[BS];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) { tcs[i] = 0; predq5[i] = 0; }
+    const bool any_elig = __any_sync(FULL, eligible);
+    if (any_elig) {
+        // sub-block residuals: columns 0..7 belong to sub-block (ky, 0), columns 8..15 to (ky, 1)
+        if (eligible) {
+#pragma unroll
+            for (int kx = 0; kx < 2; ++kx) {
+                const MeResult ms = ky ? (kx ? msub[3] : msub[2]) : (kx ? msub[1] : msub[0]);
+                const int xs = x + kx * S, ys = y + ky * S;
+                const PredSel sels = pred_select(g, xs * mult, ys * mult, ms.dx, ms.dy, S, -1);
+                const PredSel selq = pred_select(g, xs * mult, ys * mult, ms.dx, ms.dy, S, BS);      // quirk Q5
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    ws[r * P + kx * S + i] = (double)(c[kx * S + i] - pred_sample(g, rl, sels, ms.ref, i, sr));
+                    predq5[kx * S + i] = pred_sample(g, rl, selq, ms.ref, i, sr);
+                }
+            }
+        }
+        __syncwarp();
+        if (eligible) { dct1d<S>(ws + r, P); dct1d<S>(ws + S * P + r, P); }          // column r of the top and bottom sub-blocks
+        __syncwarp();
+        if (eligible) { dct1d<S>(ws + r * P, 1); dct1d<S>(ws + r * P + S, 1); }      // row r of the left and right sub-blocks
+        if (eligible) {
+#pragma unroll
+            for (int i = 0; i < BS; ++i) tcs[i] = (int)rint(ws[r * P + i]);
+        }
+        __syncwarp();
+        // RD costs at the prediction-time QP (calculate_RD_cost, Encoder.py:1133-1158)
+        uint32_t mP = 0, mL = 0, mR = 0;
+        {
+            const int qs = a.qp_rd > 0 ? a.qp_rd - 1 : a.qp_rd;
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+                if (quant_rhe(tcp[i], q_shift(r, i, BS, a.qp_rd)) != 0) mP |= 1u << i;
+                if (quant_rhe(tcs[i], q_shift(sr, i & 7, S, qs)) != 0) { if (i < S) mL |= 1u << i; else mR |= 1u << (i - S); }
+            }
+        }
+        // whole block: group = half-warp
+        int lenp, lens;
+        {
+            const uint32_t prev = __shfl_up_sync(FULL, mP, 1);
+            const uint32_t c0 = (__ballot_sync(FULL, mP & 1u) >> (16 * h)) & 0xFFFFu;
+            const uint32_t cl = (__ballot_sync(FULL, (mP >> 15) & 1u) >> (16 * h)) & 0xFFFFu;
+            const uint32_t last = __shfl_sync(FULL, mP, 16 * h + 15);
+            int v = rle_rows_partial<BS>(mP, r, prev, c0, cl, last);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+            lenp = v;
+        }
+        {   // four sub-blocks: groups of 8 lanes, two masks per lane
+            const int q8 = lane >> 3;
+            const uint32_t prevL = __shfl_up_sync(FULL, mL, 1), prevR = __shfl_up_sync(FULL, mR, 1);
+            const uint32_t c0L = (__ballot_sync(FULL, mL & 1u) >> (8 * q8)) & 0xFFu, clL = (__ballot_sync(FULL, (mL >> 7) & 1u) >> (8 * q8)) & 0xFFu;
+            const uint32_t c0R = (__ballot_sync(FULL, mR & 1u) >> (8 * q8)) & 0xFFu, clR = (__ballot_sync(FULL, (mR >> 7) & 1u) >> (8 * q8)) & 0xFFu;
+            const uint32_t lastL = __shfl_sync(FULL, mL, 8 * q8 + 7), lastR = __shfl_sync(FULL, mR, 8 * q8 + 7);
+            int v = rle_rows_partial<S>(mL, sr, prevL, c0L, clL, lastL) + rle_rows_partial<S>(mR, sr, prevR, c0R, clR, lastR);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+            lens = v;
+        }
+        if (eligible) {
+            double vm = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) vm = __dadd_rn(vm, me_mae(msub[kk], S, a.fast));
+            vm = vm / 4.0;
+            const double rd_bs = __dadd_rn(__dmul_rn(a.lam, (double)(16 + 8 * lenp)), me_mae(mp, BS, a.fast));
+            const double rd_vbs = __dadd_rn(__dmul_rn(a.lam, (double)(64 + 8 * lens)), vm);
+            split = (rd_bs < rd_vbs) ? 0 : 1;
+        }
+    }
+
+    // ---- final quantisation with the row QP, RLE size, dequantisation, inverse transform, reconstruction
+    int level[BS];
+    uint32_t m0 = 0, m1 = 0;                  // non-zero masks: whole row (no split) or left / right sub-block rows (split)
+    {
+        const int qs = qrow > 0 ? qrow - 1 : qrow;
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            const int shift = split ? q_shift(sr, i & 7, S, qs) : q_shift(r, i, BS, qrow);
+            level[i] = quant_rhe(split ? tcs[i] : tcp[i], shift);
+            ws[r * P + i] = (double)(level[i] * (1 << shift));
+            if (level[i] != 0) { if (!split) m0 |= 1u << i; else if (i < S) m0 |= 1u << i; else m1 |= 1u << (i - S); }
+        }
+    }
+    int len;
+    {
+        const int q8 = lane >> 3;
+        const uint32_t prev0 = __shfl_up_sync(FULL, m0, 1), prev1 = __shfl_up_sync(FULL, m1, 1);
+        const unsigned b0lo = __ballot_sync(FULL, m0 & 1u), b0hi16 = __ballot_sync(FULL, (m0 >> 15) & 1u), b0hi8 = __ballot_sync(FULL, (m0 >> 7) & 1u);
+        const unsigned b1lo = __ballot_sync(FULL, m1 & 1u), b1hi8 = __ballot_sync(FULL, (m1 >> 7) & 1u);
+        const uint32_t last16 = __shfl_sync(FULL, m0, 16 * h + 15);
+        const uint32_t last0 = __shfl_sync(FULL, m0, 8 * q8 + 7), last1 = __shfl_sync(FULL, m1, 8 * q8 + 7);
+        int v;
+        if (!split) v = rle_rows_partial<BS>(m0, r, prev0, (b0lo >> (16 * h)) & 0xFFFFu, (b0hi16 >> (16 * h)) & 0xFFFFu, last16);
+        else v = rle_rows_partial<S>(m0, sr, prev0, (b0lo >> (8 * q8)) & 0xFFu, (b0hi8 >> (8 * q8)) & 0xFFu, last0) +
+                 rle_rows_partial<S>(m1, sr, prev1, (b1lo >> (8 * q8)) & 0xFFu, (b1hi8 >> (8 * q8)) & 0xFFu, last1);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        len = v;
+    }
+    if (live) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = ((uint32_t)(uint16_t)(int16_t)level[2 * i]) | ((uint32_t)(uint16_t)(int16_t)level[2 * i + 1] << 16);
+        uint4* lp = reinterpret_cast<uint4*>(a.levels + unit * a.frame_stride + (size_t)(y + r) * g.W + x);
+        lp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        lp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    __syncwarp();
+    if (split) { idct1d<S>(ws + r, P); idct1d<S>(ws + S * P + r, P); } else idct1d<BS>(ws + r, P);
+    __syncwarp();
+    if (split) { idct1d<S>(ws + r * P, 1); idct1d<S>(ws + r * P + S, 1); } else idct1d<BS>(ws + r * P, 1);
+    unsigned long long se = 0;
+    {
+        uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+            const int rec = ((split ? predq5[i] : predp[i]) + (int)rint(ws[r * P + i])) & 0xFF;      // astype(np.uint8) wraps (A5)
+            pk[i >> 2] |= (uint32_t)rec << (8 * (i & 3));
+            const int d = rec - c[i];
+            se += (unsigned long long)(d * d);
+        }
+        if (live) *reinterpret_cast<uint4*>(a.recon + unit * a.frame_stride + (size_t)(y + r) * g.W + x) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) se += __shfl_xor_sync(FULL, se, o);
+    if (r == 0 && live) {
+        a.split[unit * a.split_stride + blk] = (uint8_t)split;
+        int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const MeResult m = split ? msub[kk] : mp;
+            const bool on = split || kk == 0;
+            mvo[kk * 3 + 0] = on ? m.dx : 0; mvo[kk * 3 + 1] = on ? m.dy : 0; mvo[kk * 3 + 2] = on ? m.ref : 0;
+        }
+        so_frame_stats* st = a.stats + unit * a.stats_stride;
+        if (blk == 0) { st->mae_den = a.mae_den; st->frame_type = a.frame_type; }
+        atomicAdd(reinterpret_cast<unsigned long long*>(&st->sse), se);
+        atomicAdd(&st->qsize, (unsigned)len);
+        atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
+        if (a.fast) {
+            unsigned long long n = (unsigned long long)mp.sad * 4ull;
+            if (eligible) { n = 0; for (int kk = 0; kk < 4; ++kk) n += msub[kk].sad; }
+            atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), n);
+        } else {
+            unsigned long long n = mp.sad;
+            bool inf = mp.none;
+            if (eligible) { n = 0; inf = false; for (int kk = 0; kk < 4; ++kk) { n += msub[kk].sad; inf = inf || msub[kk].none; } }
+            if (inf) atomicOr(&st->mae_inf, 1u); else atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), n);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // fast motion estimation (fast_motion_estimation, Encoder.py:719-742; chained by inter_prediction :581)
 // grid.x = 1 (chain over all blocks) or nblk (ParallelMode 2: mvp = (0,0,0) for every block), grid.y = units
 // The four sub-blocks search the same nine offsets around the same predictor, so their SADs are the quadrant
