@@ -112,9 +112,9 @@ class ClockSampler(threading.Thread):
 
 def cpu_sample(frames_np, cfg, steps=1):
     """Oracle port of the reference's algorithm on a bounded crop of the same workload: 3 frames (I, P, P) of a
-    480x128 window, same i / r / nRef / half-pel.  Returns (frames/s extrapolated to the full frame, description)."""
+    640x256 window, same i / r / nRef / half-pel.  Returns (frames/s extrapolated to the full frame, description)."""
     from oracle import codec_oracle as co
-    ch, cw, cf = 128, 480, 3
+    ch, cw, cf = 256, 640, 3
     crop = np.ascontiguousarray(frames_np[:cf, :ch, :cw])
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -262,16 +262,22 @@ def main():
         peaks = json.load(open(INT_PEAK_FILE)) if os.path.exists(INT_PEAK_FILE) else {}
         peak = peaks.get("vabsdiff4_lane_Tops", 18.33)
         achieved = (w_me / 4) * args.steps / (me_ms / 1e3) / 1e12       # rank 0's own kernels
+        traffic = None                                                  # DRAM bytes per ME launch from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "r01_me_traffic.json")
+        if os.path.exists(tpath) and F >= 30:
+            tj = json.load(open(tpath))
+            traffic = {"dram_bytes_per_launch": tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"], "unit": "B",
+                       "source": tj["source"], "note": "the kernel is integer-ALU bound; DRAM traffic = every ring plane once"}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "wall_ms_per_step": wall_ms_max / args.steps,
-                "roofline": {"bound": "int32-alu (VABSDIFF4 pipe)", "kernel": "me_full_kernel<16,9,3>", "achieved": achieved,
+                "roofline": {"bound": "int32-alu (VABSDIFF4 pipe)", "kernel": "me_tma_kernel<16,9,3>", "achieved": achieved,
                              "peak": peak, "unit": "T lane-instr/s (1 instr = 4 pixel SADs)", "frac": achieved / peak,
                              "peak_source": "measured: tools/int_peak.cu vabsdiff4.add, profiles/int_peak_r01.json (MEASURED_PEAKS.json has no integer figure)",
                              "algorithmic_sad_pixel_ops_per_step": w_me, "launches_per_step": me_l,
                              "avg_launch_ms": me_ms / max(1, me_launches), "me_share_of_step": me_ms / dev_ms,
-                             "traffic": None},
+                             "traffic": traffic},
                 "roofline_transform": {"bound": "hbm", "achieved": 5.0 * H * W * F * args.steps / (tq_ms / 1e3) / 1e9,
                                        "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                                        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,

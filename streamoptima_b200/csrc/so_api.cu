@@ -436,9 +436,13 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     a.direct = (!no_direct && bs == 16 && r % 16 == 0 && r > 0 && a.NG * G == 2 * r + 1 && ctx->g.W % 16 == 0 &&
                 (reinterpret_cast<uintptr_t>(cur) % 16 == 0) && (cur_stride % 16 == 0)) ? 1 : 0;
     size_t smem = 0;
+    static const bool want_pad = std::getenv("SO_ME_NO_ROW_PAD") == nullptr;    // on by default; the switch is for A/B measurements
+    a.row_pad = 0;
     if (a.direct) {
         a.nstage = 3;
-        a.item_stride = (a.rows * a.wpitch + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
+        a.row_pad = want_pad ? 1 : 0;
+        if (a.row_pad) a.nstage = 2;
+        a.item_stride = ((a.rows + (a.row_pad ? 7 : 0)) * a.wpitch + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
         a.raw_w = a.wpitch; a.raw_item_stride = 0; a.aligned16 = 1;
         auto smem_for = [&](int si, int ns) { return (size_t)ns * si * (4 * a.item_stride + bs * bs) + 256 + (size_t)ME_MAX_STAGES * si * 16 + (size_t)((si * tasks_per_item + 31) / 32) * 128; };
         while (SI > 1 && smem_for(SI, a.nstage) > 226 * 1024) --SI;
@@ -479,7 +483,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     // stage ahead of the slowest one, which is what the 1-bit mbarrier phase parity can distinguish.
     const int threads = 32 * (1 + (a.NB < 11 ? a.NB : 11));
     CUtensorMap map, cmap;
-    int rc = make_ring_map(ctx, a.raw_w, a.rows, &map);
+    int rc = make_ring_map(ctx, a.raw_w, a.rows + (a.row_pad ? 7 : 0), &map);
     if (rc) return rc;
     if (a.direct) {     // current blocks: {W, H, units} view of the frames of this launch
         rc = make_map3d(ctx, cur + (size_t)unit0 * cur_stride, ctx->g.W, ctx->g.H, units, ctx->g.W, cur_stride, bs, bs, &cmap);

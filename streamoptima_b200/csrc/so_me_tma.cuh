@@ -49,6 +49,7 @@ struct MeTmaArgs {
     int raw_stage_bytes;         // SI * raw_item_stride
     int aligned16;               // bx*bs - r is a multiple of 16 for every block and raw_w == 64
     int direct;                  // DIRECT staging (see the header comment)
+    int row_pad;                 // DIRECT: item li is loaded (li & 7) rows lower in its buffer -> conflict-free LDS.128 (0 = off)
     int nstage;                  // shared-memory stages: 3 (direct) or 2 (expand)
     int z_per_unit;              // planes per unit in the ring tensor = nslots * 16
     int slot[SO_MAX_REF];        // list index -> ring slot
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // buffer was read through the generic proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive_expect_tx(&ready[sb], (uint32_t)(nitems * (4 * a.rows * a.wpitch + BS * BS)));
+                if (lane == 0) mbar_arrive_expect_tx(&ready[sb], (uint32_t)(nitems * (4 * (a.rows + (a.row_pad ? 7 : 0)) * a.wpitch + BS * BS)));
                 __syncwarp();
                 for (int q = lane; q < nitems * 5; q += 32) {
                     const int li = q / 5, c = q % 5;
@@ -249,8 +250,10 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                     const int bx = blk % g.nbx, by = blk / g.nbx;
                     if (c < 4) {
                         const int z = unit * a.z_per_unit + a.slot[ref] * 16 + ph * 4 + c;
+                        // row_pad: the box starts (li & 7) rows above the window, so window row 0 lands (li & 7) rows into the
+                        // buffer: consecutive tasks then keep hitting consecutive 16-byte bank groups across item boundaries
                         tma_load_3d(wins + sb * a.stage_bytes + c * a.shift_stride + li * a.item_stride, &ring_map, &ready[sb],
-                                    bx * BS - g.r, by * BS - g.r, z);
+                                    bx * BS - g.r, by * BS - g.r - (a.row_pad ? (li & 7) : 0), z);
                     } else {
                         tma_load_3d(reinterpret_cast<unsigned char*>(curs) + (sb * a.SI + li) * BS * BS, &cur_map, &ready[sb],
                                     bx * BS, by * BS, unit);
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 const bool fast_valid = a.direct && __all_sync(__activemask(), (mt.w >> 16) & 1);
                 const int px = ph & 1, py = ph >> 1;
                 const int oy0 = grp * G;
-                const unsigned char* win = wins + sb * a.stage_bytes + c * a.shift_stride + li * a.item_stride + oy0 * a.wpitch;
+                const unsigned char* win = wins + sb * a.stage_bytes + c * a.shift_stride + li * a.item_stride + (oy0 + (a.row_pad ? (li & 7) : 0)) * a.wpitch;
                 const uint32_t* cb = curs + (sb * a.SI + li) * BS * WPR;
 
                 constexpr int WP = NCH * 16;                                  // == a.wpitch, as a compile-time constant
