@@ -50,7 +50,7 @@ typedef struct so_params {
     int32_t width;          /* w_pixels, multiple of block_size (Encoder.py:1382)              */
     int32_t height;         /* h_pixels, multiple of block_size                                */
     int32_t block_size;     /* i : 4, 8 or 16                                                  */
-    int32_t search_range;   /* r : integer-pel range; half-pel search covers +-2r (Encoder.py:1649) */
+    int32_t search_range;   /* r : integer-pel range 0..63; half-pel search covers +-2r (Encoder.py:1649) */
     int32_t qp;             /* Qp (const_init_Qp); 0 .. log2(block_size)+7                      */
     int32_t intra_dur;      /* I_Period                                                        */
     int32_t n_ref_frames;   /* nRefFrames, 1 .. SO_MAX_REF                                     */

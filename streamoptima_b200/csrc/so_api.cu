@@ -154,7 +154,7 @@ extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
     if (p->block_size != 4 && p->block_size != 8 && p->block_size != 16) return bad("block_size must be 4, 8 or 16");
     if (p->width <= 0 || p->height <= 0 || p->width % p->block_size || p->height % p->block_size)
         return bad("width/height must be positive multiples of block_size (Encoder.py:1382)");
-    if (p->search_range < 0 || p->search_range > 16) return bad("search_range must be 0..16");
+    if (p->search_range < 0 || p->search_range > 63) return bad("search_range must be 0..63");
     if (p->n_ref_frames < 1 || p->n_ref_frames > SO_MAX_REF) return bad("n_ref_frames must be 1..8");
     if (p->qp < 0 || p->qp > 15) return bad("qp out of range");
     if (p->parallel_mode < 0 || p->parallel_mode > 2) return bad("parallel_mode must be 0, 1 or 2 (3 is broken in the reference)");
@@ -414,8 +414,13 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     a.units = units;
     a.nph = a.g.fme ? 4 : 1;
     const int nb = a.g.nbx * a.g.nby;
-    a.items_per_unit = nb * a.g.nref * a.nph;
-    const int r = a.g.r;
+    // ranges above 16 are tiled into chunks of 32 offsets per axis (the last chunk also takes offset +r): every chunk is
+    // an r = 16 search with its own window origin, so the kernel geometry (9 x 3 candidates per task, 48-row windows) is shared
+    const int r_real = a.g.r;
+    const int r = r_real > 16 ? 16 : r_real;            // chunk half-range used for all geometry below
+    a.cw = 2 * r;
+    a.nxc = a.nyc = r_real > 16 ? (r_real + 15) / 16 : 1;
+    a.items_per_unit = nb * a.g.nref * a.nph * a.nxc * a.nyc;
     const int ndx = (2 * r) / 4 + 1;
     const int avail[5] = {1, 2, 3, 5, 9};
     int NDX = 9;
@@ -433,7 +438,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     // DIRECT staging needs every window to start at a 16-byte aligned x (bs = 16, r multiple of 16), one group layout
     // without over-read (NG*G == 2r+1) and a TMA-addressable current frame (16-byte aligned rows)
     static const bool no_direct = std::getenv("SO_ME_NO_DIRECT") != nullptr;     // tests: force the EXPAND staging mode
-    a.direct = (!no_direct && bs == 16 && r % 16 == 0 && r > 0 && a.NG * G == 2 * r + 1 && ctx->g.W % 16 == 0 &&
+    a.direct = (!no_direct && bs == 16 && r_real % 16 == 0 && r > 0 && a.NG * G == 2 * r + 1 && ctx->g.W % 16 == 0 &&
                 (reinterpret_cast<uintptr_t>(cur) % 16 == 0) && (cur_stride % 16 == 0)) ? 1 : 0;
     size_t smem = 0;
     static const bool want_pad = std::getenv("SO_ME_NO_ROW_PAD") == nullptr;    // on by default; the switch is for A/B measurements
@@ -444,7 +449,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
         if (a.row_pad) a.nstage = 2;
         a.item_stride = ((a.rows + (a.row_pad ? 7 : 0)) * a.wpitch + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
         a.raw_w = a.wpitch; a.raw_item_stride = 0; a.aligned16 = 1;
-        auto smem_for = [&](int si, int ns) { return (size_t)ns * si * (4 * a.item_stride + bs * bs) + 256 + (size_t)ME_MAX_STAGES * si * 16 + (size_t)((si * tasks_per_item + 31) / 32) * 128; };
+        auto smem_for = [&](int si, int ns) { return (size_t)ns * si * (4 * a.item_stride + bs * bs) + 256 + (size_t)ME_MAX_STAGES * si * 32 + (size_t)((si * tasks_per_item + 31) / 32) * 128; };
         while (SI > 1 && smem_for(SI, a.nstage) > 226 * 1024) --SI;
         smem = smem_for(SI, a.nstage);
     } else {
@@ -459,13 +464,13 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
         }
         {   // raw TMA box: aligned -> 64-byte rows (3 + 4*NW bytes needed); otherwise up to 15 + 3 more bytes
             const int need_al = 3 + 4 * NW;
-            a.aligned16 = (bs % 16 == 0 && r % 16 == 0 && need_al <= 64) ? 1 : 0;
+            a.aligned16 = (bs % 16 == 0 && r_real % 16 == 0 && need_al <= 64) ? 1 : 0;
             a.raw_w = a.aligned16 ? 64 : (18 + 4 * NW + 15) / 16 * 16;
         }
         a.raw_item_stride = (a.rows * a.raw_w + 127) / 128 * 128;
         auto smem_for = [&](int si, int ns) {
             // 128-byte alignment of the raw area: copies and cur tiles are multiples of 16 only
-            return (size_t)ns * si * (4 * a.item_stride + a.raw_item_stride + bs * bs) + 512 + (size_t)ME_MAX_STAGES * si * 16 +
+            return (size_t)ns * si * (4 * a.item_stride + a.raw_item_stride + bs * bs) + 512 + (size_t)ME_MAX_STAGES * si * 32 +
                    (size_t)((si * tasks_per_item + 31) / 32) * 128;
         };
         while (SI > 1 && smem_for(SI, a.nstage) > 226 * 1024) --SI;

@@ -48,6 +48,8 @@ struct MeTmaArgs {
     int raw_item_stride;         // bytes between raw windows (multiple of 128)
     int raw_stage_bytes;         // SI * raw_item_stride
     int aligned16;               // bx*bs - r is a multiple of 16 for every block and raw_w == 64
+    int cw;                      // offsets covered by one search chunk per axis: 2 * min(r, 16); larger ranges are tiled
+    int nxc, nyc;                // chunks per axis (1 when r <= 16): item = (block, ref, phase, y chunk, x chunk)
     int direct;                  // DIRECT staging (see the header comment)
     int row_pad;                 // DIRECT: item li is loaded (li & 7) rows lower in its buffer -> conflict-free LDS.128 (0 = off)
     int nstage;                  // shared-memory stages: 3 (direct) or 2 (expand)
@@ -192,7 +194,8 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
     uint64_t* empty = ready + ME_MAX_STAGES;
     unsigned int* counter = reinterpret_cast<unsigned int*>(empty + ME_MAX_STAGES);
     int4* meta = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(counter) + 16 + 15) & ~(uintptr_t)15);                      // [S][SI]: {blk, bx, by, ref | ph << 8} written by the producer
-    uint32_t* ttab = reinterpret_cast<uint32_t*>(meta + ME_MAX_STAGES * a.SI);   // [NB*32]: task -> c | li << 2 | grp << 10 (full stages)
+    int4* meta2 = meta + ME_MAX_STAGES * a.SI;                                 // [S][SI]: {chunk x origin, chunk y origin, max ox, max oy}
+    uint32_t* ttab = reinterpret_cast<uint32_t*>(meta2 + ME_MAX_STAGES * a.SI);  // [NB*32]: task -> c | li << 2 | grp << 10 (full stages)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -208,8 +211,25 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
     }
     __syncthreads();
 
-    const int per_blk = g.nref * a.nph;
+    const int nch = a.nxc * a.nyc;
+    const int per_blk = g.nref * a.nph * nch;
     const int total_stages = a.units * a.stages_per_unit;
+    // item -> (block, reference, phase, search chunk); chunk (xc, yc) covers offsets [-r + cw*xc, ...] (the last chunk of
+    // an axis also takes the final offset +r)
+    struct ItemInfo { int blk, ref, ph, oxb, oyb, xlim, ylim; };
+    auto item_info = [&](int item) {
+        ItemInfo t;
+        t.blk = item / per_blk;
+        const int rp = item % per_blk;
+        t.ref = rp / (a.nph * nch);
+        const int rem = rp % (a.nph * nch);
+        t.ph = rem / nch;
+        const int ch = rem % nch, yc = ch / a.nxc, xc = ch % a.nxc;
+        t.oxb = -g.r + a.cw * xc; t.oyb = -g.r + a.cw * yc;
+        t.xlim = (xc == a.nxc - 1) ? g.r : t.oxb + a.cw - 1;
+        t.ylim = (yc == a.nyc - 1) ? g.r : t.oyb + a.cw - 1;
+        return t;
+    };
     const int nloc = (total_stages - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // stages of this CTA
     auto stage_of = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
 
@@ -227,16 +247,14 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 const int nitems = min(a.SI, a.items_per_unit - item0);
                 mbar_wait(&empty[sb], par ^ 1);
                 for (int li = lane; li < nitems; li += 32) {
-                    const int item = item0 + li;
-                    const int blk = item / per_blk, rp = item % per_blk;
-                    {
-                        const int mbx = blk % g.nbx, mby = blk / g.nbx;
-                        int l0, h0, l1, h1;
-                        valid_range(mbx * BS, g.W, BS, g.fme, g.fme, l0, h0);
-                        valid_range(mby * BS, g.H, BS, g.fme, g.fme, l1, h1);
-                        const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
-                        meta[sb * a.SI + li] = make_int4(blk, mbx, mby, (rp / a.nph) | ((rp % a.nph) << 8) | (interior << 16));
-                    }
+                    const ItemInfo it = item_info(item0 + li);
+                    const int mbx = it.blk % g.nbx, mby = it.blk / g.nbx;
+                    int l0, h0, l1, h1;
+                    valid_range(mbx * BS, g.W, BS, g.fme, g.fme, l0, h0);
+                    valid_range(mby * BS, g.H, BS, g.fme, g.fme, l1, h1);
+                    const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
+                    meta[sb * a.SI + li] = make_int4(it.blk, mbx, mby, it.ref | (it.ph << 8) | (interior << 16));
+                    meta2[sb * a.SI + li] = make_int4(it.oxb, it.oyb, it.xlim, it.ylim);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // buffer was read through the generic proxy
                 __syncwarp();
@@ -244,16 +262,14 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 __syncwarp();
                 for (int q = lane; q < nitems * 5; q += 32) {
                     const int li = q / 5, c = q % 5;
-                    const int item = item0 + li;
-                    const int blk = item / per_blk, rp = item % per_blk;
-                    const int ref = rp / a.nph, ph = rp % a.nph;
-                    const int bx = blk % g.nbx, by = blk / g.nbx;
+                    const ItemInfo it = item_info(item0 + li);
+                    const int bx = it.blk % g.nbx, by = it.blk / g.nbx;
                     if (c < 4) {
-                        const int z = unit * a.z_per_unit + a.slot[ref] * 16 + ph * 4 + c;
+                        const int z = unit * a.z_per_unit + a.slot[it.ref] * 16 + it.ph * 4 + c;
                         // row_pad: the box starts (li & 7) rows above the window, so window row 0 lands (li & 7) rows into the
                         // buffer: consecutive tasks then keep hitting consecutive 16-byte bank groups across item boundaries
                         tma_load_3d(wins + sb * a.stage_bytes + c * a.shift_stride + li * a.item_stride, &ring_map, &ready[sb],
-                                    bx * BS - g.r, by * BS - g.r - (a.row_pad ? (li & 7) : 0), z);
+                                    bx * BS + it.oxb, by * BS + it.oyb - (a.row_pad ? (li & 7) : 0), z);
                     } else {
                         tma_load_3d(reinterpret_cast<unsigned char*>(curs) + (sb * a.SI + li) * BS * BS, &cur_map, &ready[sb],
                                     bx * BS, by * BS, unit);
@@ -272,13 +288,11 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
             if (lane == 0) mbar_arrive_expect_tx(&rawfull[rb], (uint32_t)(nitems * a.rows * a.raw_w));
             __syncwarp();
             for (int li = lane; li < nitems; li += 32) {
-                const int item = item0 + li;
-                const int blk = item / per_blk, rp = item % per_blk;
-                const int ref = rp / a.nph, ph = rp % a.nph;
-                const int bx = blk % g.nbx, by = blk / g.nbx;
-                const int z = unit * a.z_per_unit + a.slot[ref] * 16 + ph * 4;
-                const int X0 = bx * BS - g.r;
-                tma_load_3d(raws + rb * a.raw_stage_bytes + li * a.raw_item_stride, &ring_map, &rawfull[rb], X0 & ~15, by * BS - g.r, z);
+                const ItemInfo it = item_info(item0 + li);
+                const int bx = it.blk % g.nbx, by = it.blk / g.nbx;
+                const int z = unit * a.z_per_unit + a.slot[it.ref] * 16 + it.ph * 4;
+                const int X0 = bx * BS + it.oxb;
+                tma_load_3d(raws + rb * a.raw_stage_bytes + li * a.raw_item_stride, &ring_map, &rawfull[rb], X0 & ~15, by * BS + it.oyb, z);
             }
         };
         if (nloc > 0) issue_raw(0);
@@ -360,8 +374,8 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                     const int c = rem / (a.rows * NCH);
                     rem %= a.rows * NCH;
                     const int row = rem / NCH, q = rem % NCH;
-                    const int blk = (item0 + li) / per_blk;
-                    const int X0 = (blk % g.nbx) * BS - g.r;
+                    const ItemInfo it = item_info(item0 + li);
+                    const int X0 = (it.blk % g.nbx) * BS + it.oxb;
                     const int sbyte = X0 - (X0 & ~15) + c, cq = sbyte >> 4, wo = (sbyte & 15) >> 2, bits = (sbyte & 3) * 8;
                     const unsigned char* rsrc = rst + li * a.raw_item_stride + row * a.raw_w;
                     const int m0 = q + cq;
@@ -382,16 +396,10 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 }
             }
             for (int li = lane; li < nitems; li += 32) {
-                const int item = item0 + li;
-                const int blk = item / per_blk, rp = item % per_blk;
-                {
-                        const int mbx = blk % g.nbx, mby = blk / g.nbx;
-                        int l0, h0, l1, h1;
-                        valid_range(mbx * BS, g.W, BS, g.fme, g.fme, l0, h0);
-                        valid_range(mby * BS, g.H, BS, g.fme, g.fme, l1, h1);
-                        const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
-                        meta[sb * a.SI + li] = make_int4(blk, mbx, mby, (rp / a.nph) | ((rp % a.nph) << 8) | (interior << 16));
-                    }
+                const ItemInfo it = item_info(item0 + li);
+                const int mbx = it.blk % g.nbx, mby = it.blk / g.nbx;
+                meta[sb * a.SI + li] = make_int4(it.blk, mbx, mby, it.ref | (it.ph << 8));
+                meta2[sb * a.SI + li] = make_int4(it.oxb, it.oyb, it.xlim, it.ylim);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[sb]);
@@ -433,11 +441,13 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
             }
             if (has_task) {
                 const int4 mt = meta[sb * a.SI + li];
+                const int4 m2 = meta2[sb * a.SI + li];
+                const int oxb = m2.x, oyb = m2.y, xlim = m2.z, ylim = m2.w;
                 const int blk = mt.x, bx = mt.y, by = mt.z;
                 const int ref = mt.w & 255, ph = (mt.w >> 8) & 255;
                 // DIRECT geometry + interior block: the only invalid candidates are ox = r on odd horizontal phases and oy = r on
                 // odd vertical phases (dx, dy = 2r + 1 > R), plus the unused NDX-th slot of shifts 1..3
-                const bool fast_valid = a.direct && __all_sync(__activemask(), (mt.w >> 16) & 1);
+                const bool fast_valid = a.direct && nch == 1 && __all_sync(__activemask(), (mt.w >> 16) & 1);
                 const int px = ph & 1, py = ph >> 1;
                 const int oy0 = grp * G;
                 const unsigned char* win = wins + sb * a.stage_bytes + c * a.shift_stride + li * a.item_stride + (oy0 + (a.row_pad ? (li & 7) : 0)) * a.wpitch;
@@ -466,8 +476,8 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                         valid_range(by * BS + BS / 2, g.H, BS / 2, g.fme, g.fme, l2, h2);
 #pragma unroll
                         for (int gg = 0; gg < 3; ++gg) {
-                            const int oy = -g.r + oy0 + gg, dy = mul * oy + (g.fme ? py : 0);
-                            const bool in = oy <= g.r && dy >= -g.R && dy <= g.R;
+                            const int oy = oyb + oy0 + gg, dy = mul * oy + (g.fme ? py : 0);
+                            const bool in = oy <= ylim && dy >= -g.R && dy <= g.R;
                             lyk[gg] = (uint32_t)(abs(dy) << 8) + gg;
                             ybadP[gg] = (in && dy >= l0 && dy <= h0) ? 0u : 0xFFFFFFFFu;
                             ybadT[gg] = (in && dy >= l1 && dy <= h1) ? 0u : 0xFFFFFFFFu;
@@ -478,8 +488,8 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                         valid_range(bx * BS + BS / 2, g.W, BS / 2, g.fme, g.fme, l2, h2);
 #pragma unroll
                         for (int k = 0; k < NDX; ++k) {
-                            const int ox = -g.r + c + 4 * k, dx = mul * ox + (g.fme ? px : 0);
-                            const bool in = ox <= g.r && dx >= -g.R && dx <= g.R;
+                            const int ox = oxb + c + 4 * k, dx = mul * ox + (g.fme ? px : 0);
+                            const bool in = ox <= xlim && dx >= -g.R && dx <= g.R;
                             lxk[k] = (uint32_t)(abs(dx) << 8) + k * 3;
                             xbadP[k] = (in && dx >= l0 && dx <= h0) ? 0u : 0xFFFFFFFFu;
                             xbadL[k] = (in && dx >= l1 && dx <= h1) ? 0u : 0xFFFFFFFFu;
@@ -524,7 +534,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                         unsigned long long key = ~0ull;
                         if (bq[e] != 0xFFFFFFFFu) {
                             const int idx = bq[e] & 0xFF, k = idx / 3, gg = idx % 3;
-                            const int ox = -g.r + c + 4 * k, oy = -g.r + oy0 + gg;
+                            const int ox = oxb + c + 4 * k, oy = oyb + oy0 + gg;
                             const int dx = mul * ox + (g.fme ? px : 0), dy = mul * oy + (g.fme ? py : 0);
                             key = ((unsigned long long)(bq[e] >> 16) << 40) | ((unsigned long long)((bq[e] >> 8) & 0xFF) << 24) |
                                   ((unsigned long long)ref << 16) | ((unsigned long long)(dx + g.R) << 8) | (unsigned long long)(dy + g.R);
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 }
                 if constexpr (EXTRA) {
                     // second pass: candidate k = NDX-1 exists only for shifts whose last offset is still <= r
-                    const bool need = (-g.r + c + 4 * (NDX - 1)) <= g.r;
+                    const bool need = (oxb + c + 4 * (NDX - 1)) <= xlim;
                     if (__any_sync(__activemask(), need)) {
                         constexpr int W0 = (NDX - 1);                       // first window word of that candidate
                         uint32_t curq[G][WPR];
@@ -629,10 +639,10 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                     const uint32_t ybl = (grp == a.NG - 1 && pye) ? 0xFFFFFFFFu : 0u;      // candidate g = G-1 of the last group
                     uint32_t ly8[G];
 #pragma unroll
-                    for (int gg = 0; gg < G; ++gg) ly8[gg] = (uint32_t)(abs(mul * (-g.r + oy0 + gg) + pye) << 8) + gg;
+                    for (int gg = 0; gg < G; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oyb + oy0 + gg) + pye) << 8) + gg;
 #pragma unroll
                     for (int k = 0; k < NDX; ++k) {
-                        const uint32_t lx8 = (uint32_t)(abs(mul * (-g.r + c + 4 * k) + pxe) << 8) + k * G;
+                        const uint32_t lx8 = (uint32_t)(abs(mul * (oxb + c + 4 * k) + pxe) << 8) + k * G;
 #pragma unroll
                         for (int gg = 0; gg < G; ++gg) {
                             uint32_t key = acc[gg][k] * 65536u + (lx8 + ly8[gg]);
@@ -651,15 +661,15 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 uint32_t ly8[G], ybad[G];
 #pragma unroll
                 for (int gg = 0; gg < G; ++gg) {
-                    const int oy = -g.r + oy0 + gg, dy = mul * oy + (g.fme ? py : 0);
+                    const int oy = oyb + oy0 + gg, dy = mul * oy + (g.fme ? py : 0);
                     ly8[gg] = (uint32_t)(abs(dy) << 8) + gg;
-                    ybad[gg] = (oy <= g.r && dy >= ylo && dy <= yhi) ? 0u : 0xFFFFFFFFu;
+                    ybad[gg] = (oy <= ylim && dy >= ylo && dy <= yhi) ? 0u : 0xFFFFFFFFu;
                 }
 #pragma unroll
                 for (int k = 0; k < NDX; ++k) {
-                    const int ox = -g.r + c + 4 * k, dx = mul * ox + (g.fme ? px : 0);
+                    const int ox = oxb + c + 4 * k, dx = mul * ox + (g.fme ? px : 0);
                     const uint32_t lx8 = (uint32_t)(abs(dx) << 8) + k * G;
-                    const uint32_t xbad = (ox <= g.r && dx >= xlo && dx <= xhi) ? 0u : 0xFFFFFFFFu;
+                    const uint32_t xbad = (ox <= xlim && dx >= xlo && dx <= xhi) ? 0u : 0xFFFFFFFFu;
 #pragma unroll
                     for (int gg = 0; gg < G; ++gg) {
                         uint32_t key = acc[gg][k] * 65536u + (lx8 + ly8[gg]);
@@ -671,7 +681,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                 unsigned long long key = ~0ull;
                 if (best != 0xFFFFFFFFu) {
                     const int idx = best & 0xFF, k = idx / G, gg = idx % G;
-                    const int ox = -g.r + c + 4 * k, oy = -g.r + oy0 + gg;
+                    const int ox = oxb + c + 4 * k, oy = oyb + oy0 + gg;
                     const int dx = mul * ox + (g.fme ? px : 0);
                     const int dy = mul * oy + (g.fme ? py : 0);
                     key = ((unsigned long long)(best >> 16) << 40) | ((unsigned long long)((best >> 8) & 0xFF) << 24) |

@@ -32,6 +32,15 @@ CASES = {
                                           nRefFrames=3, RCFlag=1, targetBR="900 kbps",
                                           qp_rate_tables=[[9000, 7000, 5200, 3900, 2800, 1900, 1300, 900, 600, 400, 250, 100],
                                                           [6000, 4600, 3400, 2500, 1800, 1200, 800, 560, 380, 250, 160, 60]])),
+    "r32_fme_vbs_chunked": dict(gen=("translating", dict(F=3, H=96, W=128, seed=53)),
+                                enc=dict(block_size=16, search_range=32, Qp=2, intra_dur=8, FMEEnable=True, nRefFrames=2,
+                                         VBSEnable=True, lam=0.02)),
+    "r48_int_chunked": dict(gen=("flat_ties", dict(F=3, H=96, W=160, seed=54)),
+                            enc=dict(block_size=16, search_range=48, Qp=1, intra_dur=8)),
+    "r20_i8_chunked": dict(gen=("zooming", dict(F=3, H=64, W=96, seed=55)),
+                           enc=dict(block_size=8, search_range=20, Qp=3, intra_dur=8, FMEEnable=True)),
+    "r17_i16_vbs_chunked": dict(gen=("translating", dict(F=3, H=64, W=96, seed=56)),
+                                enc=dict(block_size=16, search_range=17, Qp=2, intra_dur=8, VBSEnable=True, lam=0.02)),
     "r8_i8_fme": dict(gen=("translating", dict(F=3, H=64, W=96, seed=45)),
                       enc=dict(block_size=8, search_range=8, Qp=1, intra_dur=8, FMEEnable=True)),
     "r5_i16": dict(gen=("zooming", dict(F=3, H=64, W=96, seed=46)),
