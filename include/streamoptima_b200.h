@@ -105,6 +105,12 @@ int so_set_qp(so_ctx* ctx, int qp);
  * shared by every frame.  n must equal height/block_size. */
 int so_set_row_qps(so_ctx* ctx, const int32_t* qp_rows, int n);
 
+/* ROI extension -- NOT part of the reference (its README advertises ROI, its code has none): per-block QPs
+ * for the final quantisation of the next so_encode_sequence / so_seq_run / so_decode_sequence calls, i32
+ * [n_frames][n_blocks], shared by all units; NULL clears.  The reference text format carries a QP only at block-row
+ * starts, so a per-block map is side information the unchanged decoder.py cannot read. */
+int so_set_block_qps(so_ctx* ctx, const int32_t* qp_blocks, int n_frames);
+
 /* Reference ring (Encoder.py:1798, :1864-1867).  unit selects one of max_batch independent chains. */
 int so_ref_reset(so_ctx* ctx, int unit, void* stream);                 /* ring := [constant-128 float frame] */
 int so_ref_push(so_ctx* ctx, int unit, const uint8_t* recon_dev, void* stream);   /* FIFO append of a uint8 frame [height][width] */

@@ -115,6 +115,7 @@ class Y_Video_codec:
     """Same constructor as the reference (Encoder.py:24)."""
 
     write_recon_yuv = True      # encode() writes yuv/y_only_reconstructed.yuv like the reference (Encoder.py:1894)
+    roi_qp_map = None           # EXTENSION (not in the reference): int [F, n_blocks] per-block QPs for the final quantisation
     device = 0                  # CUDA device ordinal used by encode()
 
     def __init__(self, h_pixels, w_pixels, frames, block_size, search_range, Qp, intra_dur, intra_mode, lam=None,
@@ -206,7 +207,8 @@ class Y_Video_codec:
             self._ctx.set_row_qps(self._rc_row_qps(self.h_pixels // block_size))
         return self._ctx
 
-    def encode_arrays(self, frames_u8, block_size=None, search_range=None, intra_dur=None, want_levels=True, want_recon=True):
+    def encode_arrays(self, frames_u8, block_size=None, search_range=None, intra_dur=None, want_levels=True, want_recon=True,
+                      qp_map=None):
         """Encode ``frames_u8`` ([F,H,W] or [U,F,H,W] for U independent sequences) and return the packed outputs.
 
         This is the call the reference-facing ``encode()`` is built on; inputs and outputs are HOST arrays and the
@@ -227,6 +229,8 @@ class Y_Video_codec:
             raise ValueError("frame dimensions must be multiples of the block size (Encoder.py:1382)")
         ctx = self._context(block_size, search_range, intra_dur, max_batch=U)
         nblk, rows = ctx.nblk, ctx.rows
+        qp_map = self.roi_qp_map if qp_map is None else qp_map
+        ctx.set_block_qps(qp_map)            # ROI extension; None clears
         # pinned staging buffers are cached per shape: cudaHostAlloc of GBs costs more than the encode itself.
         # NOTE the returned arrays are views of these buffers and are overwritten by the next call.
         key = (U, F, H, W, nblk, rows)

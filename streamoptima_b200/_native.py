@@ -42,7 +42,7 @@ STATS_DTYPE = [("sse", "<u8"), ("mae_num", "<u8"), ("mae_den", "<u4"), ("mae_inf
                ("frame_type", "<u4")]
 
 # every symbol declared in include/streamoptima_b200.h
-EXPORTS = ["so_abi_version", "so_last_error", "so_device_count", "so_ctx_create", "so_ctx_destroy", "so_set_qp", "so_set_row_qps",
+EXPORTS = ["so_abi_version", "so_last_error", "so_device_count", "so_ctx_create", "so_ctx_destroy", "so_set_qp", "so_set_row_qps", "so_set_block_qps",
            "so_ref_reset", "so_ref_push", "so_encode_intra", "so_encode_inter", "so_encode_sequence", "so_seq_upload", "so_seq_run", "so_seq_download", "so_seq_sync", "so_decode_sequence", "so_seq_symbols", "so_seq_download_symbols",
            "so_format_residual_frame_symbols",
            "so_last_timing", "so_last_me_launches",
@@ -73,6 +73,7 @@ def load():
     lib.so_ctx_destroy.argtypes = [vp]
     lib.so_ctx_destroy.restype = None
     lib.so_set_qp.argtypes = [vp, i32]
+    lib.so_set_block_qps.argtypes = [vp, vp, i32]
     lib.so_set_row_qps.argtypes = [vp, C.POINTER(C.c_int32), i32]
     lib.so_ref_reset.argtypes = [vp, i32, vp]
     lib.so_ref_push.argtypes = [vp, i32, vp, vp]
@@ -143,6 +144,16 @@ class Context:
     def set_row_qps(self, qps):
         arr = (C.c_int32 * len(qps))(*[int(q) for q in qps])
         check(self.handle, self.lib.so_set_row_qps(self.handle, arr, len(qps)))
+
+    def set_block_qps(self, qp_blocks):
+        """ROI extension: per-block QPs [F, nblk] for the next sequence, or None to clear."""
+        if qp_blocks is None:
+            check(self.handle, self.lib.so_set_block_qps(self.handle, None, 0))
+            return
+        import numpy as np
+        a = np.ascontiguousarray(qp_blocks, np.int32)
+        assert a.ndim == 2 and a.shape[1] == self.nblk
+        check(self.handle, self.lib.so_set_block_qps(self.handle, a.ctypes.data, a.shape[0]))
 
     def last_timing(self):
         out = (C.c_double * 4)()

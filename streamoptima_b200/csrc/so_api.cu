@@ -45,6 +45,8 @@ struct so_ctx {
     int32_t* band = nullptr;
     int* qp_rows_dev = nullptr;
     std::vector<int> qp_rows;
+    int* qp_blocks_dev = nullptr;           // ROI extension: [frames][nblk] per-block QPs of the next sequence, or nullptr
+    int qp_blocks_frames = 0;
     // sequence buffers
     uint8_t *sq_frames = nullptr, *sq_split = nullptr, *sq_recon = nullptr;
     int16_t *sq_mv = nullptr, *sq_levels = nullptr;
@@ -77,6 +79,7 @@ struct so_ctx {
     size_t ev_used = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_me, ev_tq;
     bool timing_on = false;
+    const int* cur_qp_blocks = nullptr;     // per-block QPs of the frame being encoded (ROI extension)
     bool stats_prezeroed = false;           // so_seq_run zeroes the statistics of the whole sequence with one memset
 };
 
@@ -136,7 +139,7 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     free_seq(c);
     cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->in_parent); cudaFree(c->in_sub);
     cudaFree(c->res_frame); cudaFree(c->band);
-    cudaFree(c->qp_rows_dev);
+    cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto e : c->pipe.up) cudaEventDestroy(e);
     for (auto e : c->pipe.done) cudaEventDestroy(e);
@@ -218,6 +221,23 @@ extern "C" int so_set_qp(so_ctx* ctx, int qp) {
     if (!ctx) return SO_E_INVALID;
     if (qp < 0 || qp > 15) { set_err(ctx, "qp out of range"); return SO_E_INVALID; }
     ctx->p.qp = qp;
+    return SO_OK;
+}
+
+// ROI extension (no counterpart in the reference, whose bitstream carries a QP only at block-row starts): per-block QPs
+// for the final quantisation of the next sequence(s), qp_blocks i32 [n_frames][n_blocks] (shared by all units); NULL clears.
+extern "C" int so_set_block_qps(so_ctx* ctx, const int32_t* qp_blocks, int n_frames) {
+    if (!ctx) return SO_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaFree(ctx->qp_blocks_dev);
+    ctx->qp_blocks_dev = nullptr; ctx->qp_blocks_frames = 0;
+    if (!qp_blocks || n_frames < 1) return SO_OK;
+    const size_t n = (size_t)n_frames * ctx->nblk;
+    for (size_t i = 0; i < n; ++i)
+        if (qp_blocks[i] < 0 || qp_blocks[i] > 15) { set_err(ctx, "block qp out of range"); return SO_E_INVALID; }
+    CU(cudaMalloc(&ctx->qp_blocks_dev, n * sizeof(int)));
+    CU(cudaMemcpy(ctx->qp_blocks_dev, qp_blocks, n * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->qp_blocks_frames = n_frames;
     return SO_OK;
 }
 
@@ -538,6 +558,7 @@ static FlowArgs make_flow(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, co
     a.qp_final = ctx->p.qp;
     a.qp_rd = qp_rd;
     a.qp_rows = (ctx->p.rc_flag > 0) ? ctx->qp_rows_dev : nullptr;
+    a.qp_blocks = ctx->cur_qp_blocks;
     a.lam = ctx->p.lam;
     a.me_parent = ctx->me_parent; a.me_sub = ctx->me_sub;
     a.me_parent_stride = ctx->nblk; a.me_sub_stride = (size_t)ctx->nblk * 4;
@@ -789,6 +810,8 @@ extern "C" int so_seq_run(so_ctx* ctx) {
         const uint8_t* cur = ctx->sq_frames + (size_t)f * px;
         const size_t cur_stride = (size_t)n_frames * px;
         const bool intra = (f % ctx->p.intra_dur == 0) && ctx->p.parallel_mode != 1;       // Encoder.py:1839
+        ctx->cur_qp_blocks = (ctx->qp_blocks_dev && f < ctx->qp_blocks_frames) ? ctx->qp_blocks_dev + (size_t)f * ctx->nblk : nullptr;
+        struct ClearQ { so_ctx* c; ~ClearQ() { c->cur_qp_blocks = nullptr; } } clearq{ctx};
         if (intra) {
             rc = encode_intra_impl(ctx, cur, cur_stride, &o, n_frames, 0, n_units, ctx->p.qp, st);
             if (rc) return rc;
@@ -976,6 +999,7 @@ extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const
         }
         FlowArgs a = make_flow(ctx, o.recon, px, &o, n_frames, 0, ctx->p.qp);
         a.qp_rows = qp_rows_per_frame ? ctx->qp_rows_dev : nullptr;
+        a.qp_blocks = (ctx->qp_blocks_dev && f < ctx->qp_blocks_frames) ? ctx->qp_blocks_dev + (size_t)f * ctx->nblk : nullptr;
         dim3 grid(ctx->nblk, 1);
         if (g.bs == 16) decode_block_kernel<16><<<grid, nt, 0, st>>>(a, intra ? 1 : 0);
         else if (g.bs == 8) decode_block_kernel<8><<<grid, nt, 0, st>>>(a, intra ? 1 : 0);

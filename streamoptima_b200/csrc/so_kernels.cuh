@@ -96,6 +96,7 @@ struct FlowArgs {
     int qp_final;                // QP when no rate control
     int qp_rd;                   // QP of self.Q during prediction (RD cost)
     const int* qp_rows;          // device, per block row, or nullptr
+    const int* qp_blocks;        // device, per block (ROI extension, overrides qp_rows / qp_final), or nullptr
     double lam;
     MeResult* me_parent;         // [unit][nblk]
     MeResult* me_sub;            // [unit][4*nblk], sub grid (2nby x 2nbx)
@@ -203,7 +204,7 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
     const int tcp = active ? (int)rint(ws[j * P + i]) : 0;
 
     const bool eligible = a.vbs && bx != 0 && by != 0;
-    const int qrow = a.qp_rows ? a.qp_rows[by] : a.qp_final;
+    const int qrow = a.qp_blocks ? a.qp_blocks[blk] : (a.qp_rows ? a.qp_rows[by] : a.qp_final);
     int split = 0;
     double mae_blk = me_mae(mp, BS, a.fast);
     // sub-block data (computed only when eligible; eligibility is CTA-uniform)
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
     __syncwarp();
 
     const bool eligible = a.vbs && bx != 0 && by != 0;
-    const int qrow = a.qp_rows ? a.qp_rows[by] : a.qp_final;
+    const int qrow = a.qp_blocks ? a.qp_blocks[blk] : (a.qp_rows ? a.qp_rows[by] : a.qp_final);
     const int ky = r >> 3, sr = r & 7;        // sub-block row group of this lane
     int split = 0;
     int tcs[BS], predq5[BS];
@@ -717,7 +718,7 @@ __global__ void intra_finish_kernel(const FlowArgs a) {
     const int tcp = active ? (int)rint(ws[j * P + i]) : 0;
 
     const bool eligible = a.vbs && bx != 0 && by != 0;
-    const int qrow = a.qp_rows ? a.qp_rows[by] : a.qp_final;
+    const int qrow = a.qp_blocks ? a.qp_blocks[blk] : (a.qp_rows ? a.qp_rows[by] : a.qp_final);
     int split = 0;
     const int k = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
     const int si = i % S, sj = j % S;
@@ -840,7 +841,7 @@ __global__ void decode_block_kernel(const FlowArgs a, int intra) {
     const int x = bx * BS, y = by * BS;
     const int split = a.split[unit * a.split_stride + blk];
     const int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
-    const int qrow = a.qp_rows ? a.qp_rows[by] : a.qp_final;
+    const int qrow = a.qp_blocks ? a.qp_blocks[blk] : (a.qp_rows ? a.qp_rows[by] : a.qp_final);
     const int k = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
     const int si = i % S, sj = j % S;
     const int level = a.levels[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i];

@@ -132,9 +132,12 @@ class decoder:
                                         vbs=self.VBSEnable, rc_flag=0, parallel_mode=self.ParallelMode, lam=0.0, device=self.device)
         return self._ctx
 
-    def decode_arrays(self, frame_types, split, mv, levels, qp_rows=None, reset_at_intra=True):
-        """Packed arrays (as ``Y_Video_codec.encoded_package.packed``) -> uint8 [F, H, W]."""
+    def decode_arrays(self, frame_types, split, mv, levels, qp_rows=None, reset_at_intra=True, qp_map=None):
+        """Packed arrays (as ``Y_Video_codec.encoded_package.packed``) -> uint8 [F, H, W].
+
+        ``qp_map`` (extension): the per-block QPs an ROI encode used -- side information the text streams cannot carry."""
         ctx = self._context()
+        ctx.set_block_qps(qp_map)
         F = len(frame_types)
         ft = np.ascontiguousarray(frame_types, np.uint8)
         split = np.ascontiguousarray(split, np.uint8)
