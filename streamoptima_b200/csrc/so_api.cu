@@ -8,6 +8,7 @@
 
 #include "so_kernels.cuh"
 #include "so_me_tma.cuh"
+#include "so_me_ring.cuh"
 #include <cstdlib>
 #include <algorithm>
 
@@ -418,6 +419,44 @@ static cudaError_t launch_me_tma_n(int NDX, int G, const CUtensorMap& map, const
     }
 }
 
+// Item-ring search kernel (so_me_ring.cuh): 16x16 blocks, r = 16, DIRECT staging
+static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, MeResult* out, size_t out_stride,
+                       cudaStream_t st) {
+    MeRingArgs a{};
+    a.g = ctx->g;
+    a.g.bs = 16; a.g.nbx = ctx->g.W / 16; a.g.nby = ctx->g.H / 16;
+    a.g.nref = (int)ctx->list.size();
+    a.out = reinterpret_cast<unsigned long long*>(out + (size_t)unit0 * out_stride);
+    a.out_unit_stride = out_stride;
+    a.units = units;
+    a.nph = a.g.fme ? 4 : 1;
+    a.items_per_unit = a.g.nbx * a.g.nby * a.g.nref * a.nph;
+    a.z_per_unit = ctx->nslots * 16;
+    a.z_unit0 = unit0 * a.z_per_unit;
+    for (int i = 0; i < SO_MAX_REF; ++i) a.slot[i] = i < (int)ctx->list.size() ? ctx->list[i] : 0;
+    CUtensorMap map, cmap;
+    int rc = make_ring_map(ctx, MR_WP, MR_BOXROWS, &map);
+    if (rc) return rc;
+    rc = make_map3d(ctx, cur + (size_t)unit0 * cur_stride, ctx->g.W, ctx->g.H, units, ctx->g.W, cur_stride, 16, 16, &cmap);
+    if (rc) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const long long total = (long long)units * a.items_per_unit;
+    const int grid = total < sms ? (int)total : sms;
+    static bool attr_done[16] = {};
+    if (!attr_done[ctx->device & 15]) {
+        CU(cudaFuncSetAttribute(me_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
+        attr_done[ctx->device & 15] = true;
+    }
+    ev_pair(ctx, ctx->ev_me, st, true);
+    me_ring_kernel<false><<<grid, 512, MR_SMEM, st>>>(map, cmap, a);
+    cudaError_t e = cudaGetLastError();
+    ev_pair(ctx, ctx->ev_me, st, false);
+    if (e != cudaSuccess) { set_err(ctx, std::string("me_ring_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
+    ctx->launches++;
+    return SO_OK;
+}
+
 // out_sub != nullptr asks for the fused VBS search (sub-block results from quadrant sums); *used_quad tells whether the
 // geometry allowed it (16x16 blocks, DIRECT staging) -- otherwise the caller runs a second search on the sub-block grid
 static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
@@ -460,6 +499,11 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     static const bool no_direct = std::getenv("SO_ME_NO_DIRECT") != nullptr;     // tests: force the EXPAND staging mode
     a.direct = (!no_direct && bs == 16 && r_real % 16 == 0 && r > 0 && a.NG * G == 2 * r + 1 && ctx->g.W % 16 == 0 &&
                 (reinterpret_cast<uintptr_t>(cur) % 16 == 0) && (cur_stride % 16 == 0)) ? 1 : 0;
+    static const bool no_ring = std::getenv("SO_ME_NO_RING") != nullptr;        // A/B switch: stage-based kernel of so_me_tma.cuh
+    if (a.direct && r_real == 16 && !out_sub && !no_ring) {
+        if (used_quad) *used_quad = false;
+        return run_me_ring(ctx, cur, cur_stride, unit0, units, out, out_stride, st);
+    }
     size_t smem = 0;
     static const bool want_pad = std::getenv("SO_ME_NO_ROW_PAD") == nullptr;    // on by default; the switch is for A/B measurements
     a.row_pad = 0;

@@ -1,0 +1,283 @@
+// Exhaustive motion search for 16x16 blocks at r = 16 (BASELINE configs 2-5), item-ring version (sm_100a).
+//
+// Same arithmetic and the same reference ring as so_me_tma.cuh (four byte-shifted copies of every phase plane, TMA box
+// loads straight into shared memory); what changes is the pipeline around the VABSDIFF4 loop:
+//   * every CTA owns a CONTIGUOUS range of items (item = (block, reference, phase plane)) and keeps a ring of MR_NS = 20
+//     item slots in shared memory.  A slot is refilled as soon as the 44 tasks of its item have finished (per-item
+//     mbarriers), so up to 20 items are in flight instead of two 8-item stages;
+//   * tasks are ordered [item][vertical group][byte shift]; a bundle = 32 consecutive tasks (it spans at most two items),
+//     fetched from a CTA-wide counter by 15 search warps (one producer warp issues the TMA loads);
+//   * all four shifts of an (item, group) sit in adjacent lanes.  The 33rd horizontal offset (ox = +16, shift 0 only) is
+//     no longer a separate warp-divergent pass: its 16 rows are split over the four lanes (4 rows each, partial SADs
+//     combined with two shuffles), so every lane of every bundle runs the same code;
+//   * per-bundle bookkeeping is cut down: no divisions by run-time values, REDUX-based argmin merge per item, one
+//     global atomicMin per (bundle, item).
+// Bank conflicts: the box of shift c of an item in slot s is loaded ((8 - 2c) & 7) + (s & 1) rows above the window, so
+// the eight lanes of a quarter warp (two (item, group) pairs x four shifts) hit eight distinct 16-byte bank groups.
+#pragma once
+#include "so_me_tma.cuh"
+
+constexpr int MR_NS = 20;                       // item slots (even: the slot parity alternates across the wrap)
+constexpr int MR_NG = 11;                       // vertical groups of 3 offsets: 33 = 2r + 1
+constexpr int MR_TPI = 4 * MR_NG;               // tasks per item
+constexpr int MR_WP = 48;                       // window row pitch (bytes): 12 words = offsets -16..16 plus 15 block pixels
+constexpr int MR_BOXROWS = 48 + 7;              // window rows + the largest row offset
+constexpr int MR_PLANE = (MR_BOXROWS * MR_WP + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
+constexpr int MR_SLOT = 4 * MR_PLANE;
+constexpr int MR_CUR = 256;
+constexpr int MR_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 1024;
+
+struct MeRingArgs {
+    FrameGeom g;                 // g.bs == 16, g.r == 16
+    unsigned long long* out;     // packed keys, stride of MeResult (16 B) per block
+    size_t out_unit_stride;      // in MeResult elements
+    unsigned long long* out_sub; // QUAD: keys of the four 8x8 sub-blocks, grid (2nby x 2nbx)
+    size_t out_sub_unit_stride;
+    int units;
+    int nph;                     // 4 (fme) or 1
+    int items_per_unit;          // blocks * nref * nph
+    int z_per_unit;              // planes per unit in the ring tensor = nslots * 16
+    int z_unit0;                 // plane offset of unit 0 of this launch
+    int slot[SO_MAX_REF];        // list index -> ring slot
+};
+
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <bool QUAD>
+__global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __grid_constant__ CUtensorMap ring_map,
+                                                                      const __grid_constant__ CUtensorMap cur_map, const MeRingArgs a) {
+    constexpr int BS = 16, WPR = 4, G = 3;
+    extern __shared__ __align__(1024) unsigned char smem_r[];
+    unsigned char* const wins = smem_r;                                        // [NS][4][MR_PLANE]
+    unsigned char* const curs = wins + MR_NS * MR_SLOT;                        // [NS][256]
+    uint64_t* const ready = reinterpret_cast<uint64_t*>(curs + MR_NS * MR_CUR);
+    uint64_t* const empty = ready + MR_NS;
+    int4* const meta = reinterpret_cast<int4*>(empty + MR_NS);                  // [NS]: {out index, bx, by, ref | ph << 8 | interior << 16}
+    unsigned int* const counter = reinterpret_cast<unsigned int*>(meta + MR_NS);
+    volatile int* const issued = reinterpret_cast<volatile int*>(counter + 1);  // items whose loads have been issued
+
+    const FrameGeom& g = a.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (int)(blockDim.x >> 5);
+    if (tid == 0) {
+        for (int s = 0; s < MR_NS; ++s) { mbar_init(&ready[s], 1); mbar_init(&empty[s], MR_TPI); }
+        *counter = 0;
+        *issued = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long total = (long long)a.units * a.items_per_unit;
+    const int i0 = (int)(total * blockIdx.x / gridDim.x), i1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    const int cnt = i1 - i0;
+    const int per_blk = g.nref * a.nph;
+    const int mul = g.fme ? 2 : 1;
+
+    if (warp == nwarps - 1) {
+        // ================================= producer =================================
+        int unit = i0 / a.items_per_unit;
+        int rem = i0 - unit * a.items_per_unit;
+        int blk = rem / per_blk;
+        int rp = rem - blk * per_blk;
+        int ref = rp / a.nph, ph = rp - ref * a.nph;
+        int by = blk / g.nbx, bx = blk - by * g.nbx;
+        int slot = 0;
+        uint32_t par = 1;                       // parity of (use - 1) for the wait on `empty`
+        bool first_round = true;
+        for (int n = 0; n < cnt; ++n) {
+            if (!first_round) {
+                while (!mbar_try(&empty[slot], par)) __nanosleep(40);
+            }
+            if (lane == 0) {
+                int l0, h0, l1, h1;
+                valid_range(bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
+                valid_range(by * BS, g.H, BS, g.fme, g.fme, l1, h1);
+                const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
+                meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (ph << 8) | (interior << 16));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(&ready[slot], (uint32_t)(4 * MR_BOXROWS * MR_WP + BS * BS));
+            __syncwarp();
+            if (lane < 4) {
+                const int c = lane;
+                const int ro = ((8 - 2 * c) & 7) + (slot & 1);
+                const int z = a.z_unit0 + unit * a.z_per_unit + a.slot[ref] * 16 + ph * 4 + c;
+                tma_load_3d(wins + slot * MR_SLOT + c * MR_PLANE, &ring_map, &ready[slot], bx * BS - 16, by * BS - 16 - ro, z);
+            } else if (lane == 4) {
+                tma_load_3d(curs + slot * MR_CUR, &cur_map, &ready[slot], bx * BS, by * BS, unit);
+            }
+            if (lane == 0) *issued = n + 1;
+            // next item
+            if (++ph == a.nph) {
+                ph = 0;
+                if (++ref == g.nref) {
+                    ref = 0; ++blk;
+                    if (++bx == g.nbx) { bx = 0; if (++by == g.nby) { by = 0; blk = 0; ++unit; } }
+                }
+            }
+            if (++slot == MR_NS) { slot = 0; par ^= 1; first_round = false; }
+        }
+        return;
+    }
+
+    // ================================= search warps =================================
+    const unsigned NBt = ((unsigned)cnt * MR_TPI + 31u) >> 5;
+    unsigned b = 0;
+    if (lane == 0) b = atomicAdd(counter, 1u);
+    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+    while (b < NBt) {
+        const unsigned t0 = b * 32u;
+        const unsigned first = t0 / (unsigned)MR_TPI;
+        const unsigned r0 = t0 - first * MR_TPI;
+        unsigned rem = r0 + lane;
+        const unsigned second = rem >= (unsigned)MR_TPI ? 1u : 0u;
+        rem -= second * MR_TPI;
+        const bool two = (r0 + 31u >= (unsigned)MR_TPI) && (first + 1u < (unsigned)cnt);    // warp-uniform
+        const bool has = second == 0u || two;
+        const unsigned n = has ? first + second : first;
+        const int grp = (int)(rem >> 2), c = (int)(rem & 3u);
+        unsigned nb = 0;
+        if (lane == 0) nb = atomicAdd(counter, 1u);         // next bundle index: consumed at the end of this iteration
+        const unsigned use0 = __umulhi(first, 0xCCCCCCCDu) >> 4, slot0 = first - use0 * MR_NS;       // first / 20
+        const unsigned slot1 = slot0 + 1 == MR_NS ? 0u : slot0 + 1, use1 = slot1 == 0 ? use0 + 1 : use0;
+        // `issued` makes the parity test unambiguous: once the loads of item n have been issued, ready[slot] is in phase
+        // `use` (pending or complete), never an older one
+        {
+            const int need = (int)first + (two ? 2 : 1);
+            while (*issued < need) { }
+            mbar_wait(&ready[slot0], use0 & 1u);
+            if (two) mbar_wait(&ready[slot1], use1 & 1u);
+        }
+        const unsigned slot = (second && two) ? slot1 : slot0;
+        const int4 mt = meta[slot];
+        const int bx = mt.y, by = mt.z;
+        const int ph = (mt.w >> 8) & 255;
+        const int px = g.fme ? (ph & 1) : 0, py = g.fme ? (ph >> 1) : 0;
+        const int p = (int)(slot & 1u);
+        const unsigned char* wslot = wins + slot * MR_SLOT;
+        const unsigned char* win = wslot + c * MR_PLANE + (((8 - 2 * c) & 7) + p + G * grp) * MR_WP;
+        const uint32_t* cb = reinterpret_cast<const uint32_t*>(curs + slot * MR_CUR);
+        const int oy0 = -16 + G * grp;
+
+        // ---- main pass: 8 horizontal x 3 vertical offsets
+        uint32_t acc[3][8];
+#pragma unroll
+        for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[gg][k] = 0;
+        {
+            uint32_t unused[3][8];
+            sad_pass_g3<WPR, 8, 8, BS, MR_WP, false>(win, cb, acc, unused);
+        }
+        // ---- 33rd horizontal offset (ox = +16: words 8..11 of the shift-0 copy): lane c of the four takes block rows 4c..4c+3
+        uint32_t ex[3] = {0u, 0u, 0u};
+        if (__any_sync(0xFFFFFFFFu, px == 0)) {
+            const unsigned char* w0 = wslot + (p + G * grp + 4 * c) * MR_WP + 32;
+            uint4 cr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cr[i] = reinterpret_cast<const uint4*>(cb)[4 * c + i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const uint4 w = *reinterpret_cast<const uint4*>(w0 + i * MR_WP);
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    const int r = i - gg;
+                    if (r >= 0 && r < 4) {
+                        ex[gg] = sad4_acc(w.x, cr[r].x, ex[gg]); ex[gg] = sad4_acc(w.y, cr[r].y, ex[gg]);
+                        ex[gg] = sad4_acc(w.z, cr[r].z, ex[gg]); ex[gg] = sad4_acc(w.w, cr[r].w, ex[gg]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) {
+                ex[gg] += __shfl_xor_sync(0xFFFFFFFFu, ex[gg], 1);
+                ex[gg] += __shfl_xor_sync(0xFFFFFFFFu, ex[gg], 2);
+            }
+        }
+
+        // ---- thread-local argmin.  key32 = sad << 16 | (|dx| + |dy|) << 8 | (k * 3 + g); invalid candidates are OR-ed to all ones.
+        uint32_t best = 0xFFFFFFFFu;
+        const bool fast_valid = __all_sync(0xFFFFFFFFu, (mt.w >> 16) & 1);
+        if (fast_valid) {
+            // interior block: the only invalid candidates are ox = 16 on odd horizontal phases and oy = 16 on odd vertical ones
+            const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;          // candidate k = 8
+            const uint32_t ybl = (grp == MR_NG - 1 && py) ? 0xFFFFFFFFu : 0u;     // candidate g = 2 of the last group
+            uint32_t ly8[3];
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const uint32_t lx8 = (uint32_t)(abs(mul * (-16 + c + 4 * k) + px) << 8) + k * 3;
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    uint32_t key = (k < 8 ? acc[gg][k < 8 ? k : 0] : ex[gg]) * 65536u + (lx8 + ly8[gg]);
+                    if (k == 8) key |= xbl;
+                    if (gg == 2) key |= ybl;
+                    best = min(best, key);
+                }
+            }
+        } else {
+            int xlo, xhi, ylo, yhi;
+            valid_range(bx * BS, g.W, BS, g.fme, g.fme, xlo, xhi);
+            valid_range(by * BS, g.H, BS, g.fme, g.fme, ylo, yhi);
+            xlo = max(xlo, -g.R); xhi = min(xhi, g.R);
+            ylo = max(ylo, -g.R); yhi = min(yhi, g.R);
+            uint32_t ly8[3], ybad[3];
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) {
+                const int dy = mul * (oy0 + gg) + py;
+                ly8[gg] = (uint32_t)(abs(dy) << 8) + gg;
+                ybad[gg] = (dy >= ylo && dy <= yhi) ? 0u : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int dx = mul * (-16 + c + 4 * k) + px;
+                const uint32_t lx8 = (uint32_t)(abs(dx) << 8) + k * 3;
+                const uint32_t xbad = ((k < 8 || c == 0) && dx >= xlo && dx <= xhi) ? 0u : 0xFFFFFFFFu;
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    const uint32_t key = ((k < 8 ? acc[gg][k < 8 ? k : 0] : ex[gg]) * 65536u + (lx8 + ly8[gg])) | xbad | ybad[gg];
+                    best = min(best, key);
+                }
+            }
+        }
+        // ---- merge per item: order (SAD, |dx|+|dy|, ref, dx, dy); all lanes of a segment share ref, so two REDUX steps
+        //      ((SAD, L1), then (dx, dy) among the lanes that tie) give the winner of the segment
+        uint32_t xy;
+        {
+            const int idx = (int)(best & 0xFFu), k = (idx * 11) >> 5, gg = idx - 3 * k;
+            const int dx = mul * (-16 + c + 4 * k) + px, dy = mul * (oy0 + gg) + py;
+            xy = ((uint32_t)(dx + g.R) << 8) | (uint32_t)(dy + g.R);
+        }
+        const uint32_t v1 = (has && best != 0xFFFFFFFFu) ? (best >> 8) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (s == 1 && !two) break;
+            const bool mine = second == (unsigned)s;
+            const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, mine ? v1 : 0xFFFFFFFFu);
+            const uint32_t m2 = __reduce_min_sync(0xFFFFFFFFu, (mine && v1 == m1) ? xy : 0xFFFFFFFFu);
+            if (lane == 0 && m1 != 0xFFFFFFFFu) {
+                const int4 ms = meta[s ? slot1 : slot0];
+                const unsigned long long key = ((unsigned long long)(m1 >> 8) << 40) | ((unsigned long long)(m1 & 0xFFu) << 24) |
+                                               ((unsigned long long)(ms.w & 255) << 16) | (unsigned long long)m2;
+                atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + ms.x), key);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t c0 = min(32u, (unsigned)MR_TPI - r0);
+            mbar_arrive_cnt(&empty[slot0], c0);
+            if (two) mbar_arrive_cnt(&empty[slot1], 32u - c0);
+        }
+        b = __shfl_sync(0xFFFFFFFFu, nb, 0);
+    }
+}
