@@ -373,12 +373,12 @@ static PFN_tmapEncodeTiled tmap_encoder(so_ctx* ctx) {
 }
 
 static int make_map3d(so_ctx* ctx, const void* base, cuuint64_t w, cuuint64_t h, cuuint64_t z, cuuint64_t row_stride, cuuint64_t z_stride,
-                      int box_w, int box_h, CUtensorMap* map) {
+                      int box_w, int box_h, CUtensorMap* map, int box_z = 1) {
     PFN_tmapEncodeTiled fn = tmap_encoder(ctx);
     if (!fn) return SO_E_CUDA;
     cuuint64_t gdim[3] = {w, h, z};
     cuuint64_t gstr[2] = {row_stride, z_stride};
-    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_z};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -387,9 +387,9 @@ static int make_map3d(so_ctx* ctx, const void* base, cuuint64_t w, cuuint64_t h,
 }
 
 // one 3-D tensor map {W, H, planes} over the whole reference ring, box = one search window
-static int make_ring_map(so_ctx* ctx, int box_w, int box_h, CUtensorMap* map) {
+static int make_ring_map(so_ctx* ctx, int box_w, int box_h, CUtensorMap* map, int box_z = 1) {
     const FrameGeom& g = ctx->g;
-    return make_map3d(ctx, ctx->ring, g.W, g.H, (cuuint64_t)ctx->batch * ctx->nslots * 16, g.pitch, ctx->plane_bytes, box_w, box_h, map);
+    return make_map3d(ctx, ctx->ring, g.W, g.H, (cuuint64_t)ctx->batch * ctx->nslots * 16, g.pitch, ctx->plane_bytes, box_w, box_h, map, box_z);
 }
 
 template <int BS, int NDX, int G, bool QUAD = false>
@@ -433,9 +433,10 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
     a.items_per_unit = a.g.nbx * a.g.nby * a.g.nref * a.nph;
     a.z_per_unit = ctx->nslots * 16;
     a.z_unit0 = unit0 * a.z_per_unit;
-    for (int i = 0; i < SO_MAX_REF; ++i) a.slot[i] = i < (int)ctx->list.size() ? ctx->list[i] : 0;
+    a.slot_packed = 0;
+    for (int i = 0; i < SO_MAX_REF && i < (int)ctx->list.size(); ++i) a.slot_packed |= (unsigned)(ctx->list[i] & 15) << (4 * i);
     CUtensorMap map, cmap;
-    int rc = make_ring_map(ctx, MR_WP, MR_BOXROWS, &map);
+    int rc = make_ring_map(ctx, MR_WP, MR_BOXROWS, &map, 4);      // one box = the four shift planes of a phase
     if (rc) return rc;
     rc = make_map3d(ctx, cur + (size_t)unit0 * cur_stride, ctx->g.W, ctx->g.H, units, ctx->g.W, cur_stride, 16, 16, &cmap);
     if (rc) return rc;

@@ -2,9 +2,9 @@
 //
 // Same arithmetic and the same reference ring as so_me_tma.cuh (four byte-shifted copies of every phase plane, TMA box
 // loads straight into shared memory); what changes is the pipeline around the VABSDIFF4 loop:
-//   * every CTA owns a CONTIGUOUS range of items (item = (block, reference, phase plane)) and keeps a ring of MR_NS = 20
+//   * every CTA owns a CONTIGUOUS range of items (item = (block, reference, phase plane)) and keeps a ring of MR_NS = 22
 //     item slots in shared memory.  A slot is refilled as soon as the 44 tasks of its item have finished (per-item
-//     mbarriers), so up to 20 items are in flight instead of two 8-item stages;
+//     mbarriers), so up to 22 items are in flight instead of two 8-item stages;
 //   * tasks are ordered [item][vertical group][byte shift]; a bundle = 32 consecutive tasks (it spans at most two items),
 //     fetched from a CTA-wide counter by 15 search warps (one producer warp issues the TMA loads);
 //   * all four shifts of an (item, group) sit in adjacent lanes.  The 33rd horizontal offset (ox = +16, shift 0 only) is
@@ -12,18 +12,20 @@
 //     combined with two shuffles), so every lane of every bundle runs the same code;
 //   * per-bundle bookkeeping is cut down: no divisions by run-time values, REDUX-based argmin merge per item, one
 //     global atomicMin per (bundle, item).
-// Bank conflicts: the box of shift c of an item in slot s is loaded ((8 - 2c) & 7) + (s & 1) rows above the window, so
+// Bank conflicts: the four shift planes of an item are 2400 B apart (6 bank groups of 16 B mod 8), consecutive vertical
+// groups are 144 B apart (1 mod 8) and the box of an item in an odd slot is loaded one row above the window (3 mod 8):
 // the eight lanes of a quarter warp (two (item, group) pairs x four shifts) hit eight distinct 16-byte bank groups.
 #pragma once
 #include "so_me_tma.cuh"
 
-constexpr int MR_NS = 20;                       // item slots (even: the slot parity alternates across the wrap)
+constexpr int MR_NS = 22;                       // item slots (even: the slot parity alternates across the wrap)
 constexpr int MR_NG = 11;                       // vertical groups of 3 offsets: 33 = 2r + 1
 constexpr int MR_TPI = 4 * MR_NG;               // tasks per item
 constexpr int MR_WP = 48;                       // window row pitch (bytes): 12 words = offsets -16..16 plus 15 block pixels
-constexpr int MR_BOXROWS = 48 + 7;              // window rows + the largest row offset
-constexpr int MR_PLANE = (MR_BOXROWS * MR_WP + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
-constexpr int MR_SLOT = 4 * MR_PLANE;
+constexpr int MR_BOXROWS = 50;                  // window rows + row offset (0 | 1); 50 * 48 B = 150 x 16 B = 6 (mod 8) bank groups
+constexpr int MR_PLANE = MR_BOXROWS * MR_WP;    // the four shift planes of an item come in ONE box of depth 4 (consecutive z)
+constexpr int MR_SLOT = 4 * MR_PLANE;           // 9600 B: a multiple of 128 (TMA destination alignment)
+static_assert(MR_SLOT % 128 == 0 && (MR_PLANE / 16) % 8 == 6, "slot alignment / bank-group stride of the shift planes");
 constexpr int MR_CUR = 256;
 constexpr int MR_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 1024;
 
@@ -38,7 +40,7 @@ struct MeRingArgs {
     int items_per_unit;          // blocks * nref * nph
     int z_per_unit;              // planes per unit in the ring tensor = nslots * 16
     int z_unit0;                 // plane offset of unit 0 of this launch
-    int slot[SO_MAX_REF];        // list index -> ring slot
+    unsigned int slot_packed;    // list index -> ring slot, 4 bits each
 };
 
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
@@ -107,12 +109,10 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive_expect_tx(&ready[slot], (uint32_t)(4 * MR_BOXROWS * MR_WP + BS * BS));
             __syncwarp();
-            if (lane < 4) {
-                const int c = lane;
-                const int ro = ((8 - 2 * c) & 7) + (slot & 1);
-                const int z = a.z_unit0 + unit * a.z_per_unit + a.slot[ref] * 16 + ph * 4 + c;
-                tma_load_3d(wins + slot * MR_SLOT + c * MR_PLANE, &ring_map, &ready[slot], bx * BS - 16, by * BS - 16 - ro, z);
-            } else if (lane == 4) {
+            if (lane == 0) {
+                const int z = a.z_unit0 + unit * a.z_per_unit + (int)((a.slot_packed >> (4 * ref)) & 15u) * 16 + ph * 4;
+                tma_load_3d(wins + slot * MR_SLOT, &ring_map, &ready[slot], bx * BS - 16, by * BS - 16 - (slot & 1), z);
+            } else if (lane == 1) {
                 tma_load_3d(curs + slot * MR_CUR, &cur_map, &ready[slot], bx * BS, by * BS, unit);
             }
             if (lane == 0) *issued = n + 1;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
         const int grp = (int)(rem >> 2), c = (int)(rem & 3u);
         unsigned nb = 0;
         if (lane == 0) nb = atomicAdd(counter, 1u);         // next bundle index: consumed at the end of this iteration
-        const unsigned use0 = __umulhi(first, 0xCCCCCCCDu) >> 4, slot0 = first - use0 * MR_NS;       // first / 20
+        const unsigned use0 = __umulhi(first, 0xBA2E8BA3u) >> 4, slot0 = first - use0 * MR_NS;       // first / 22
         const unsigned slot1 = slot0 + 1 == MR_NS ? 0u : slot0 + 1, use1 = slot1 == 0 ? use0 + 1 : use0;
         // `issued` makes the parity test unambiguous: once the loads of item n have been issued, ready[slot] is in phase
         // `use` (pending or complete), never an older one
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
         const int px = g.fme ? (ph & 1) : 0, py = g.fme ? (ph >> 1) : 0;
         const int p = (int)(slot & 1u);
         const unsigned char* wslot = wins + slot * MR_SLOT;
-        const unsigned char* win = wslot + c * MR_PLANE + (((8 - 2 * c) & 7) + p + G * grp) * MR_WP;
+        const unsigned char* win = wslot + c * MR_PLANE + (p + G * grp) * MR_WP;
         const uint32_t* cb = reinterpret_cast<const uint32_t*>(curs + slot * MR_CUR);
         const int oy0 = -16 + G * grp;
 
@@ -214,17 +214,20 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
             uint32_t ly8[3];
 #pragma unroll
             for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
+            // min over the three vertical offsets first (their keys differ by SAD and ly8 only), then add the horizontal part:
+            // 3 IMAD (FMA pipe) + one 3-input min + one add per column instead of 3 adds + 3 mins on the ALU pipe
+            uint32_t kk[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                const uint32_t lx8 = (uint32_t)(abs(mul * (-16 + c + 4 * k) + px) << 8) + k * 3;
-#pragma unroll
-                for (int gg = 0; gg < 3; ++gg) {
-                    uint32_t key = (k < 8 ? acc[gg][k < 8 ? k : 0] : ex[gg]) * 65536u + (lx8 + ly8[gg]);
-                    if (k == 8) key |= xbl;
-                    if (gg == 2) key |= ybl;
-                    best = min(best, key);
-                }
+                const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative (c <= 3)
+                const uint32_t lx8 = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
+                const uint32_t t0 = (k < 8 ? acc[0][k < 8 ? k : 0] : ex[0]) * 65536u + ly8[0];
+                const uint32_t t1 = (k < 8 ? acc[1][k < 8 ? k : 0] : ex[1]) * 65536u + ly8[1];
+                const uint32_t t2 = ((k < 8 ? acc[2][k < 8 ? k : 0] : ex[2]) * 65536u + ly8[2]) | ybl;
+                kk[k] = min(min(t0, t1), t2) + lx8;
             }
+            kk[8] |= xbl;
+            best = min(min(min(kk[0], kk[1]), min(kk[2], kk[3])), min(min(kk[4], kk[5]), min(kk[6], min(kk[7], kk[8]))));
         } else {
             int xlo, xhi, ylo, yhi;
             valid_range(bx * BS, g.W, BS, g.fme, g.fme, xlo, xhi);
