@@ -726,7 +726,10 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     ev_pair(ctx, ctx->ev_tq, st, true);
     dim3 grid(ctx->nblk, units);
     static const bool generic16 = std::getenv("SO_FINISH_GENERIC") != nullptr;      // tests: force the generic kernel
-    if (g.bs == 16 && g.W % 16 == 0 && !generic16) inter_finish16_kernel<<<dim3((ctx->nblk + 7) / 8, units), 128, 0, st>>>(a);
+    if (g.bs == 16 && g.W % 16 == 0 && !generic16) {
+        if (a.vbs) inter_finish16_kernel<true><<<dim3((ctx->nblk + 7) / 8, units), 128, 0, st>>>(a);
+        else inter_finish16_kernel<false><<<dim3((ctx->nblk + 7) / 8, units), 128, 0, st>>>(a);
+    }
     else if (g.bs == 16) inter_finish_kernel<16><<<grid, nt, 0, st>>>(a);
     else if (g.bs == 8) inter_finish_kernel<8><<<grid, nt, 0, st>>>(a);
     else inter_finish_kernel<4><<<grid, nt, 0, st>>>(a);

@@ -25,6 +25,32 @@ __global__ void ring_planes_kernel(uint8_t* slot0, size_t unit_stride, size_t pl
     uint8_t* base = slot0 + blockIdx.z * unit_stride;
     const uint8_t* sbase = src + blockIdx.z * src_unit_stride;
     const int yn = min(y + 1, H - 1);
+    if (wrap && fme) {
+        // uint8-wrap variant (quirk Q1; every frame after the first nRefFrames): all four pixels at once with packed byte
+        // arithmetic.  (s + 1) >> 1 = vavgu4(s, 0); (s0 + s1 + 3) >> 2 = ceil(ceil((s0 + s1) / 2) / 2) = vavgu4(vavgu4(s0, s1), 0)
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(sbase + (size_t)y * src_pitch);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(sbase + (size_t)yn * src_pitch);
+        const bool in1 = x + 4 < W;
+        const uint32_t w00 = r0[x4], w10 = r1[x4];
+        const uint32_t w01 = in1 ? r0[x4 + 1] : (w00 >> 24) * 0x01010101u;      // replicate the last column
+        const uint32_t w11 = in1 ? r1[x4 + 1] : (w10 >> 24) * 0x01010101u;
+        const uint32_t s0l = __vadd4(w00, __funnelshift_r(w00, w01, 8)), s0h = __vadd4(w01, w01 >> 8);
+        const uint32_t s1l = __vadd4(w10, __funnelshift_r(w10, w11, 8)), s1h = __vadd4(w11, w11 >> 8);
+        uint32_t lo[4], hi[4];
+        lo[0] = w00; hi[0] = w01;
+        lo[1] = __vavgu4(s0l, 0u); hi[1] = __vavgu4(s0h, 0u);
+        lo[2] = __vavgu4(w00, w10); hi[2] = __vavgu4(w01, w11);
+        lo[3] = __vavgu4(__vavgu4(s0l, s1l), 0u); hi[3] = __vavgu4(__vavgu4(s0h, s1h), 0u);
+        const size_t o = (size_t)y * pitch + x;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (p == 0 && c == 0 && !write_p0) continue;
+                *reinterpret_cast<uint32_t*>(base + (size_t)(p * 4 + c) * plane_bytes + o) = c ? __funnelshift_r(lo[p], hi[p], 8 * c) : lo[p];
+            }
+        return;
+    }
     int a0[9], a1[9];
     {
         const uint32_t* r0 = reinterpret_cast<const uint32_t*>(sbase + (size_t)y * src_pitch);
@@ -320,6 +346,7 @@ __device__ __forceinline__ int rle_rows_partial(uint32_t m, int rr, uint32_t m_p
     return v;
 }
 
+template <bool VBS>
 __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
     constexpr int BS = 16, S = 8, P = 17;
     __shared__ double tiles[4][2][BS * P];
@@ -354,12 +381,12 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
         msub[kk] = mp;
-        if (a.vbs) msub[kk] = me_get(a.me_sub + unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1), a.me_packed, g.R);
+        if (VBS && a.vbs) msub[kk] = me_get(a.me_sub + unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1), a.me_packed, g.R);
     }
     __syncwarp();
     if (a.me_packed && live) {
         if (r == 0) *reinterpret_cast<unsigned long long*>(pme) = ~0ull;
-        if (a.vbs && r < 4)
+        if (VBS && a.vbs && r < 4)
             *reinterpret_cast<unsigned long long*>(a.me_sub + unit * a.me_sub_stride + (by * 2 + (r >> 1)) * (g.nbx * 2) + bx * 2 + (r & 1)) = ~0ull;
     }
 
@@ -367,8 +394,21 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
     int predp[BS];
     {
         const PredSel sel = pred_select(g, x * mult, y * mult, mp.dx, mp.dy, BS, -1);
+        if (sel.mode == 0) {
+            // in-bounds predictor = 16 contiguous bytes of one phase plane (appendix A1); the copy shifted by X & 3 bytes
+            // holds them at a word-aligned address: four 32-bit loads instead of sixteen byte gathers
+            const int X = g.fme ? (sel.PX >> 1) : sel.PX, Y = (g.fme ? (sel.PY >> 1) : sel.PY) + r;
+            const int ph = g.fme ? (((sel.PY & 1) << 1) | (sel.PX & 1)) : 0;
+            const int cs = X & 3;
+            const uint32_t* pw = reinterpret_cast<const uint32_t*>(a.ring.plane(unit, mp.ref, ph) + (size_t)cs * (a.ring.plane_stride >> 2) +
+                                                                   (size_t)Y * g.pitch + (X - cs));
+            const uint32_t w[4] = {__ldg(pw), __ldg(pw + 1), __ldg(pw + 2), __ldg(pw + 3)};
 #pragma unroll
-        for (int i = 0; i < BS; ++i) predp[i] = pred_sample(g, rl, sel, mp.ref, i, r);
+            for (int i = 0; i < BS; ++i) predp[i] = (w[i >> 2] >> (8 * (i & 3))) & 255;
+        } else {
+#pragma unroll
+            for (int i = 0; i < BS; ++i) predp[i] = pred_sample(g, rl, sel, mp.ref, i, r);
+        }
     }
 #pragma unroll
     for (int i = 0; i < BS; ++i) ws[r * P + i] = (double)(c[i] - predp[i]);
@@ -381,14 +421,14 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
     for (int i = 0; i < BS; ++i) tcp[i] = (int)rint(ws[r * P + i]);
     __syncwarp();
 
-    const bool eligible = a.vbs && bx != 0 && by != 0;
+    const bool eligible = VBS && a.vbs && bx != 0 && by != 0;
     const int qrow = a.qp_blocks ? a.qp_blocks[blk] : (a.qp_rows ? a.qp_rows[by] : a.qp_final);
     const int ky = r >> 3, sr = r & 7;        // sub-block row group of this lane
     int split = 0;
     int tcs[BS], predq5[BS];
 #pragma unroll
     for (int i = 0; i < BS; ++i) { tcs[i] = 0; predq5[i] = 0; }
-    const bool any_elig = __any_sync(FULL, eligible);
+    const bool any_elig = VBS ? __any_sync(FULL, eligible) : false;
     if (any_elig) {
         // sub-block residuals: columns 0..7 belong to sub-block (ky, 0), columns 8..15 to (ky, 1)
         if (eligible) {
