@@ -175,6 +175,9 @@ int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const uint8_t* s
  * [2] transform/quant/recon kernels, [3] number of kernel launches.  Waits for the run to finish. */
 int so_last_timing(so_ctx* ctx, double out[4]);
 int so_last_me_launches(so_ctx* ctx);    /* number of launches covered by timing [1] */
+/* The exhaustive-search kernel alone (me_ring_kernel / me_tma_kernel) in the last so_seq_run: out[0] = summed CUDA-event
+ * time of its launches (ms), out[1] = number of launches.  This is the per-launch duration bench.py's roofline uses. */
+int so_last_search_timing(so_ctx* ctx, double out[2]);
 
 /* Host-side text formatters, byte-identical to the reference's (Encoder.py:1419-1542 with canonical integers).
  * Return the number of bytes written (excluding the terminating NUL), or the required size (negative) when cap

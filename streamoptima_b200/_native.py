@@ -45,7 +45,7 @@ STATS_DTYPE = [("sse", "<u8"), ("mae_num", "<u8"), ("mae_den", "<u4"), ("mae_inf
 EXPORTS = ["so_abi_version", "so_last_error", "so_device_count", "so_ctx_create", "so_ctx_destroy", "so_set_qp", "so_set_row_qps", "so_set_block_qps",
            "so_ref_reset", "so_ref_push", "so_encode_intra", "so_encode_inter", "so_encode_sequence", "so_seq_upload", "so_seq_run", "so_seq_download", "so_seq_sync", "so_decode_sequence", "so_seq_symbols", "so_seq_download_symbols",
            "so_format_residual_frame_symbols",
-           "so_last_timing", "so_last_me_launches",
+           "so_last_timing", "so_last_me_launches", "so_last_search_timing",
            "so_format_mv_frame", "so_format_residual_frame"]
 
 _lib = None
@@ -89,6 +89,7 @@ def load():
     lib.so_format_residual_frame_symbols.restype = i64
     lib.so_format_residual_frame_symbols.argtypes = [vp, vp, vp, i32, C.c_char_p, i64]
     lib.so_decode_sequence.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.so_last_search_timing.argtypes = [vp, C.POINTER(C.c_double)]
     lib.so_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
     lib.so_last_me_launches.argtypes = [vp]
     lib.so_format_mv_frame.restype = i64
@@ -158,5 +159,7 @@ class Context:
     def last_timing(self):
         out = (C.c_double * 4)()
         check(self.handle, self.lib.so_last_timing(self.handle, out))
+        xs = (C.c_double * 2)()
+        check(self.handle, self.lib.so_last_search_timing(self.handle, xs))
         return dict(device_ms=out[0], me_ms=out[1], tq_ms=out[2], launches=int(out[3]),
-                    me_launches=int(self.lib.so_last_me_launches(self.handle)))
+                    me_launches=int(self.lib.so_last_me_launches(self.handle)), search_ms=xs[0], search_launches=int(xs[1]))

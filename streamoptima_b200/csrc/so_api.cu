@@ -46,6 +46,7 @@ struct so_ctx {
     int32_t* band = nullptr;
     int* qp_rows_dev = nullptr;
     std::vector<int> qp_rows;
+    unsigned int* me_work = nullptr;        // chunk counter of the item-ring search kernel
     int* qp_blocks_dev = nullptr;           // ROI extension: [frames][nblk] per-block QPs of the next sequence, or nullptr
     int qp_blocks_frames = 0;
     // sequence buffers
@@ -58,7 +59,7 @@ struct so_ctx {
     uint32_t *sym_lens = nullptr, *sym_offs = nullptr;
     int16_t* sym_data = nullptr;
     size_t sym_cap_frames = 0, sym_frame_stride = 0;
-    double timing[5] = {0, 0, 0, 0, 0};
+    double timing[7] = {0, 0, 0, 0, 0, 0, 0};
     bool timing_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sq_units = 0, sq_nframes = 0;
@@ -79,6 +80,7 @@ struct so_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_me, ev_tq;
+    std::vector<size_t> ev_xs;              // indices into ev_me of the exhaustive-search kernel launches
     bool timing_on = false;
     const int* cur_qp_blocks = nullptr;     // per-block QPs of the frame being encoded (ROI extension)
     bool stats_prezeroed = false;           // so_seq_run zeroes the statistics of the whole sequence with one memset
@@ -140,7 +142,7 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     free_seq(c);
     cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->in_parent); cudaFree(c->in_sub);
     cudaFree(c->res_frame); cudaFree(c->band);
-    cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev);
+    cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev); cudaFree(c->me_work);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto e : c->pipe.up) cudaEventDestroy(e);
     for (auto e : c->pipe.done) cudaEventDestroy(e);
@@ -443,13 +445,18 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const long long total = (long long)units * a.items_per_unit;
-    const int grid = total < sms ? (int)total : sms;
+    const long long nchunks = (total + MR_CHUNK - 1) / MR_CHUNK;
+    const int grid = nchunks < sms ? (int)nchunks : sms;
     static bool attr_done[16] = {};
     if (!attr_done[ctx->device & 15]) {
         CU(cudaFuncSetAttribute(me_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
         attr_done[ctx->device & 15] = true;
     }
+    if (!ctx->me_work) CU(cudaMalloc(&ctx->me_work, 256));
+    a.work = ctx->me_work;
+    CU(cudaMemsetAsync(ctx->me_work, 0, sizeof(unsigned int), st));
     ev_pair(ctx, ctx->ev_me, st, true);
+    if (ctx->timing_on) ctx->ev_xs.push_back(ctx->ev_me.size() - 1);
     me_ring_kernel<false><<<grid, 512, MR_SMEM, st>>>(map, cmap, a);
     cudaError_t e = cudaGetLastError();
     ev_pair(ctx, ctx->ev_me, st, false);
@@ -577,6 +584,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
         a.out_sub_unit_stride = out_sub_stride;
     }
     ev_pair(ctx, ctx->ev_me, st, true);
+    if (ctx->timing_on) ctx->ev_xs.push_back(ctx->ev_me.size() - 1);
     cudaError_t e;
     if (quad) e = launch_me_tma<16, 9, 3, true>(map, cmap, a, grid, threads, smem, st);
     else if (bs == 16) e = launch_me_tma_n<16>(NDX, G, map, cmap, a, grid, threads, smem, st);
@@ -830,7 +838,7 @@ extern "C" int so_seq_run(so_ctx* ctx) {
     const size_t px = ctx->frame_px;
     const int nby = ctx->g.nby;
     ctx->launches = 0;
-    ctx->ev_used = 0; ctx->ev_me.clear(); ctx->ev_tq.clear();
+    ctx->ev_used = 0; ctx->ev_me.clear(); ctx->ev_tq.clear(); ctx->ev_xs.clear();
     ctx->timing_on = true;
     if (ctx->ev_pool.size() < 2) { for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); } }
     ctx->ev0 = ctx->ev_pool[ctx->ev_used++]; ctx->ev1 = ctx->ev_pool[ctx->ev_used++];
@@ -1083,6 +1091,9 @@ extern "C" int so_last_timing(so_ctx* ctx, double out[4]) {
         for (auto& p : ctx->ev_tq) { float t = 0; cudaEventElapsedTime(&t, p.first, p.second); tq += t; }
         ctx->timing[1] = me; ctx->timing[2] = tq; ctx->timing[3] = (double)ctx->launches;
         ctx->timing[4] = (double)ctx->ev_me.size();
+        double xs = 0;
+        for (size_t i : ctx->ev_xs) { float t = 0; cudaEventElapsedTime(&t, ctx->ev_me[i].first, ctx->ev_me[i].second); xs += t; }
+        ctx->timing[5] = xs; ctx->timing[6] = (double)ctx->ev_xs.size();
         ctx->timing_pending = false;
     }
     for (int i = 0; i < 4; ++i) out[i] = ctx->timing[i];
@@ -1095,6 +1106,16 @@ extern "C" int so_last_me_launches(so_ctx* ctx) {
     if (!ctx) return SO_E_INVALID;
     int rc = so_last_timing(ctx, t);
     return rc ? rc : (int)ctx->timing[4];
+}
+
+// exhaustive-search kernels alone (me_ring_kernel / me_tma_kernel): out[0] = summed CUDA-event time (ms), out[1] = launches
+extern "C" int so_last_search_timing(so_ctx* ctx, double out[2]) {
+    double t[4];
+    if (!ctx || !out) return SO_E_INVALID;
+    int rc = so_last_timing(ctx, t);
+    if (rc) return rc;
+    out[0] = ctx->timing[5]; out[1] = ctx->timing[6];
+    return SO_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -27,6 +27,7 @@ constexpr int MR_PLANE = MR_BOXROWS * MR_WP;    // the four shift planes of an i
 constexpr int MR_SLOT = 4 * MR_PLANE;           // 9600 B: a multiple of 128 (TMA destination alignment)
 static_assert(MR_SLOT % 128 == 0 && (MR_PLANE / 16) % 8 == 6, "slot alignment / bank-group stride of the shift planes");
 constexpr int MR_CUR = 256;
+constexpr int MR_CHUNK = 8;                     // items per work chunk handed out by the device-wide counter
 constexpr int MR_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 1024;
 
 struct MeRingArgs {
@@ -41,6 +42,7 @@ struct MeRingArgs {
     int z_per_unit;              // planes per unit in the ring tensor = nslots * 16
     int z_unit0;                 // plane offset of unit 0 of this launch
     unsigned int slot_packed;    // list index -> ring slot, 4 bits each
+    unsigned int* work;          // device-wide chunk counter, zero at launch
 };
 
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
     int4* const meta = reinterpret_cast<int4*>(empty + MR_NS);                  // [NS]: {out index, bx, by, ref | ph << 8 | interior << 16}
     unsigned int* const counter = reinterpret_cast<unsigned int*>(meta + MR_NS);
     volatile int* const issued = reinterpret_cast<volatile int*>(counter + 1);  // items whose loads have been issued
+    volatile int* const final_cnt = issued + 1;                                 // number of items of this CTA, once known
 
     const FrameGeom& g = a.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -73,90 +76,115 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
         for (int s = 0; s < MR_NS; ++s) { mbar_init(&ready[s], 1); mbar_init(&empty[s], MR_TPI); }
         *counter = 0;
         *issued = 0;
+        *final_cnt = 0x7FFFFFFF;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const long long total = (long long)a.units * a.items_per_unit;
-    const int i0 = (int)(total * blockIdx.x / gridDim.x), i1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
-    const int cnt = i1 - i0;
+    const int nchunks = (int)((total + MR_CHUNK - 1) / MR_CHUNK);
     const int per_blk = g.nref * a.nph;
     const int mul = g.fme ? 2 : 1;
 
     if (warp == nwarps - 1) {
         // ================================= producer =================================
-        int unit = i0 / a.items_per_unit;
-        int rem = i0 - unit * a.items_per_unit;
-        int blk = rem / per_blk;
-        int rp = rem - blk * per_blk;
-        int ref = rp / a.nph, ph = rp - ref * a.nph;
-        int by = blk / g.nbx, bx = blk - by * g.nbx;
-        int slot = 0;
+        // work is handed out in chunks of MR_CHUNK consecutive items from a device-wide counter: all CTAs stay in the same
+        // neighbourhood of the frame (window rows are re-read from L2, not DRAM) and the tail balances itself
+        int q = 0, qn = 0;
+        if (lane == 0) q = (int)atomicAdd(a.work, 1u);
+        q = __shfl_sync(0xFFFFFFFFu, q, 0);
+        int slot = 0, n = 0;
         uint32_t par = 1;                       // parity of (use - 1) for the wait on `empty`
         bool first_round = true;
-        for (int n = 0; n < cnt; ++n) {
-            if (!first_round) {
-                while (!mbar_try(&empty[slot], par)) __nanosleep(40);
-            }
-            if (lane == 0) {
-                int l0, h0, l1, h1;
-                valid_range(bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
-                valid_range(by * BS, g.H, BS, g.fme, g.fme, l1, h1);
-                const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
-                meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (ph << 8) | (interior << 16));
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&ready[slot], (uint32_t)(4 * MR_BOXROWS * MR_WP + BS * BS));
-            __syncwarp();
-            if (lane == 0) {
-                const int z = a.z_unit0 + unit * a.z_per_unit + (int)((a.slot_packed >> (4 * ref)) & 15u) * 16 + ph * 4;
-                tma_load_3d(wins + slot * MR_SLOT, &ring_map, &ready[slot], bx * BS - 16, by * BS - 16 - (slot & 1), z);
-            } else if (lane == 1) {
-                tma_load_3d(curs + slot * MR_CUR, &cur_map, &ready[slot], bx * BS, by * BS, unit);
-            }
-            if (lane == 0) *issued = n + 1;
-            // next item
-            if (++ph == a.nph) {
-                ph = 0;
-                if (++ref == g.nref) {
-                    ref = 0; ++blk;
-                    if (++bx == g.nbx) { bx = 0; if (++by == g.nby) { by = 0; blk = 0; ++unit; } }
+        while (q < nchunks) {
+            if (lane == 0) qn = (int)atomicAdd(a.work, 1u);             // next chunk: the latency hides behind this one
+            const long long it0 = (long long)q * MR_CHUNK;
+            const int nit = (int)min((long long)MR_CHUNK, total - it0);
+            int unit = (int)(it0 / a.items_per_unit);
+            int rem = (int)(it0 - (long long)unit * a.items_per_unit);
+            int blk = rem / per_blk;
+            int rp = rem - blk * per_blk;
+            int ref = rp / a.nph, ph = rp - ref * a.nph;
+            int by = blk / g.nbx, bx = blk - by * g.nbx;
+            for (int k = 0; k < nit; ++k) {
+                if (!first_round) {
+                    while (!mbar_try(&empty[slot], par)) __nanosleep(40);
                 }
+                if (lane == 0) {
+                    int l0, h0, l1, h1;
+                    valid_range(bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
+                    valid_range(by * BS, g.H, BS, g.fme, g.fme, l1, h1);
+                    const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
+                    meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (ph << 8) | (interior << 16));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive_expect_tx(&ready[slot], (uint32_t)(4 * MR_BOXROWS * MR_WP + BS * BS));
+                __syncwarp();
+                if (lane == 0) {
+                    const int z = a.z_unit0 + unit * a.z_per_unit + (int)((a.slot_packed >> (4 * ref)) & 15u) * 16 + ph * 4;
+                    tma_load_3d(wins + slot * MR_SLOT, &ring_map, &ready[slot], bx * BS - 16, by * BS - 16 - (slot & 1), z);
+                } else if (lane == 1) {
+                    tma_load_3d(curs + slot * MR_CUR, &cur_map, &ready[slot], bx * BS, by * BS, unit);
+                }
+                ++n;
+                if (lane == 0) *issued = n;
+                // next item
+                if (++ph == a.nph) {
+                    ph = 0;
+                    if (++ref == g.nref) {
+                        ref = 0; ++blk;
+                        if (++bx == g.nbx) { bx = 0; if (++by == g.nby) { by = 0; blk = 0; ++unit; } }
+                    }
+                }
+                if (++slot == MR_NS) { slot = 0; par ^= 1; first_round = false; }
             }
-            if (++slot == MR_NS) { slot = 0; par ^= 1; first_round = false; }
+            q = __shfl_sync(0xFFFFFFFFu, qn, 0);
         }
+        if (lane == 0) *final_cnt = n;          // no item with local index >= n will ever exist
         return;
     }
 
     // ================================= search warps =================================
-    const unsigned NBt = ((unsigned)cnt * MR_TPI + 31u) >> 5;
     unsigned b = 0;
     if (lane == 0) b = atomicAdd(counter, 1u);
     b = __shfl_sync(0xFFFFFFFFu, b, 0);
-    while (b < NBt) {
+    while (true) {
         const unsigned t0 = b * 32u;
         const unsigned first = t0 / (unsigned)MR_TPI;
         const unsigned r0 = t0 - first * MR_TPI;
         unsigned rem = r0 + lane;
         const unsigned second = rem >= (unsigned)MR_TPI ? 1u : 0u;
         rem -= second * MR_TPI;
-        const bool two = (r0 + 31u >= (unsigned)MR_TPI) && (first + 1u < (unsigned)cnt);    // warp-uniform
+        // does item `first` (and `first + 1` when the bundle runs into it) exist?  `issued` counts the items whose loads
+        // have been issued; `final_cnt` is set once the producer has run out of chunks.  Waiting for `issued` also makes
+        // the parity test below unambiguous: ready[slot] is then in phase `use` (pending or complete), never an older one.
+        bool two = r0 + 31u >= (unsigned)MR_TPI;
+        {
+            bool exists = true;
+            unsigned long long spins = 0;
+            while (true) {
+                const int iss = *issued, fin = *final_cnt;
+                if (iss > (int)first) break;
+                if (fin <= (int)first) { exists = false; break; }
+                if (++spins > (1ull << 26)) __trap();
+            }
+            if (!exists) break;
+            while (two) {
+                const int iss = *issued, fin = *final_cnt;
+                if (iss > (int)first + 1) break;
+                if (fin <= (int)first + 1) two = false;
+                if (++spins > (1ull << 26)) __trap();
+            }
+        }
         const bool has = second == 0u || two;
-        const unsigned n = has ? first + second : first;
         const int grp = (int)(rem >> 2), c = (int)(rem & 3u);
         unsigned nb = 0;
         if (lane == 0) nb = atomicAdd(counter, 1u);         // next bundle index: consumed at the end of this iteration
         const unsigned use0 = __umulhi(first, 0xBA2E8BA3u) >> 4, slot0 = first - use0 * MR_NS;       // first / 22
         const unsigned slot1 = slot0 + 1 == MR_NS ? 0u : slot0 + 1, use1 = slot1 == 0 ? use0 + 1 : use0;
-        // `issued` makes the parity test unambiguous: once the loads of item n have been issued, ready[slot] is in phase
-        // `use` (pending or complete), never an older one
-        {
-            const int need = (int)first + (two ? 2 : 1);
-            while (*issued < need) { }
-            mbar_wait(&ready[slot0], use0 & 1u);
-            if (two) mbar_wait(&ready[slot1], use1 & 1u);
-        }
+        mbar_wait(&ready[slot0], use0 & 1u);
+        if (two) mbar_wait(&ready[slot1], use1 & 1u);
         const unsigned slot = (second && two) ? slot1 : slot0;
         const int4 mt = meta[slot];
         const int bx = mt.y, by = mt.z;
