@@ -133,3 +133,21 @@ def test_full_size_crop_matches_oracle_interior():
             gb = (y0 // 16 + by) * nbx + (x0 // 16 + bx)
             got = tuple(int(v) for v in p["mv"][1, gb, 0])
             assert got == tuple(int(v) for v in mv[by, bx]), (by, bx)
+
+
+def test_batched_units_equal_single_sequences_r16():
+    """Three independent sequences in one context (batched launches: the item-ring search kernel indexes units through
+    the plane / output offsets) must equal the three sequences encoded one by one; half-pel and integer search."""
+    from streamoptima_b200.Encoder import Y_Video_codec
+    Y_Video_codec.write_recon_yuv = False
+    U, F, H, W = 3, 4, 96, 128
+    seqs = np.stack([synth.make(k, F=F, H=H, W=W, seed=70 + i) for i, k in enumerate(("translating", "zooming", "flat_ties"))])
+    for kw in (dict(FMEEnable=True, nRefFrames=3), dict(nRefFrames=2)):
+        cb = Y_Video_codec(H, W, F, 16, 16, 2, 8, 0, **kw)
+        ob = cb.encode_arrays(seqs)
+        got = {k: np.array(ob[k]) for k in ("split", "mv", "levels", "recon", "row_sizes")}
+        for u in range(U):
+            cs = Y_Video_codec(H, W, F, 16, 16, 2, 8, 0, **kw)
+            o1 = cs.encode_arrays(seqs[u])
+            for k in got:
+                np.testing.assert_array_equal(got[k][u], o1[k][0], err_msg=f"{k} unit {u} {kw}")
