@@ -423,13 +423,15 @@ static cudaError_t launch_me_tma_n(int NDX, int G, const CUtensorMap& map, const
 
 // Item-ring search kernel (so_me_ring.cuh): 16x16 blocks, r = 16, DIRECT staging
 static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, MeResult* out, size_t out_stride,
-                       cudaStream_t st) {
+                       cudaStream_t st, MeResult* out_sub = nullptr, size_t out_sub_stride = 0) {
     MeRingArgs a{};
     a.g = ctx->g;
     a.g.bs = 16; a.g.nbx = ctx->g.W / 16; a.g.nby = ctx->g.H / 16;
     a.g.nref = (int)ctx->list.size();
     a.out = reinterpret_cast<unsigned long long*>(out + (size_t)unit0 * out_stride);
     a.out_unit_stride = out_stride;
+    a.out_sub = out_sub ? reinterpret_cast<unsigned long long*>(out_sub + (size_t)unit0 * out_sub_stride) : nullptr;   // fused VBS search
+    a.out_sub_unit_stride = out_sub_stride;
     a.units = units;
     a.nph = a.g.fme ? 4 : 1;
     a.items_per_unit = a.g.nbx * a.g.nby * a.g.nref * a.nph;
@@ -450,6 +452,7 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
     static bool attr_done[16] = {};
     if (!attr_done[ctx->device & 15]) {
         CU(cudaFuncSetAttribute(me_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
+        CU(cudaFuncSetAttribute(me_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
         attr_done[ctx->device & 15] = true;
     }
     if (!ctx->me_work) CU(cudaMalloc(&ctx->me_work, 256));
@@ -457,7 +460,8 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
     CU(cudaMemsetAsync(ctx->me_work, 0, sizeof(unsigned int), st));
     ev_pair(ctx, ctx->ev_me, st, true);
     if (ctx->timing_on) ctx->ev_xs.push_back(ctx->ev_me.size() - 1);
-    me_ring_kernel<false><<<grid, 512, MR_SMEM, st>>>(map, cmap, a);
+    if (out_sub) me_ring_kernel<true><<<grid, 384, MR_SMEM, st>>>(map, cmap, a);
+    else me_ring_kernel<false><<<grid, 512, MR_SMEM, st>>>(map, cmap, a);
     cudaError_t e = cudaGetLastError();
     ev_pair(ctx, ctx->ev_me, st, false);
     if (e != cudaSuccess) { set_err(ctx, std::string("me_ring_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
@@ -508,9 +512,9 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     a.direct = (!no_direct && bs == 16 && r_real % 16 == 0 && r > 0 && a.NG * G == 2 * r + 1 && ctx->g.W % 16 == 0 &&
                 (reinterpret_cast<uintptr_t>(cur) % 16 == 0) && (cur_stride % 16 == 0)) ? 1 : 0;
     static const bool no_ring = std::getenv("SO_ME_NO_RING") != nullptr;        // A/B switch: stage-based kernel of so_me_tma.cuh
-    if (a.direct && r_real == 16 && !out_sub && !no_ring) {
-        if (used_quad) *used_quad = false;
-        return run_me_ring(ctx, cur, cur_stride, unit0, units, out, out_stride, st);
+    if (a.direct && r_real == 16 && !no_ring) {
+        if (used_quad) *used_quad = out_sub != nullptr;
+        return run_me_ring(ctx, cur, cur_stride, unit0, units, out, out_stride, st, out_sub, out_sub_stride);
     }
     size_t smem = 0;
     static const bool want_pad = std::getenv("SO_ME_NO_ROW_PAD") == nullptr;    // on by default; the switch is for A/B measurements

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
                     valid_range(bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
                     valid_range(by * BS, g.H, BS, g.fme, g.fme, l1, h1);
                     const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
-                    meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (ph << 8) | (interior << 16));
+                    meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (ph << 8) | (interior << 16) | (unit << 17));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
                 __syncwarp();
@@ -196,6 +196,180 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
         const uint32_t* cb = reinterpret_cast<const uint32_t*>(curs + slot * MR_CUR);
         const int oy0 = -16 + G * grp;
 
+        if constexpr (QUAD) {
+            // ---- VBS: the four 8x8 sub-blocks search the same offsets, so their SADs are the quadrant sums of the parent's
+            // candidates (Encoder.py:517-536 vs :558).  Two half passes (top / bottom 8 rows), left and right words in
+            // separate accumulators; quadrant minima are folded after each half, the parent sums are kept.
+            uint32_t par[3][8];
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) par[gg][k] = 0;
+            // 33rd horizontal offset first: lane c takes block rows 4c..4c+3 (c = 0, 1: top half; 2, 3: bottom half)
+            uint32_t exq[5][3];                      // parent, TL, TR, BL, BR sums of candidate k = 8, complete on every lane
+            {
+                uint32_t eL[3] = {0u, 0u, 0u}, eR[3] = {0u, 0u, 0u};
+                const unsigned char* w0 = wslot + (p + G * grp + 4 * c) * MR_WP + 32;
+                uint4 cr[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cr[i] = reinterpret_cast<const uint4*>(cb)[4 * c + i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(w0 + i * MR_WP);
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg) {
+                        const int r = i - gg;
+                        if (r >= 0 && r < 4) {
+                            eL[gg] = sad4_acc(w.x, cr[r].x, eL[gg]); eL[gg] = sad4_acc(w.y, cr[r].y, eL[gg]);
+                            eR[gg] = sad4_acc(w.z, cr[r].z, eR[gg]); eR[gg] = sad4_acc(w.w, cr[r].w, eR[gg]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    const uint32_t hl = eL[gg] + __shfl_xor_sync(0xFFFFFFFFu, eL[gg], 1);      // my half (top for c < 2)
+                    const uint32_t hr = eR[gg] + __shfl_xor_sync(0xFFFFFFFFu, eR[gg], 1);
+                    const uint32_t ol = __shfl_xor_sync(0xFFFFFFFFu, hl, 2), orr = __shfl_xor_sync(0xFFFFFFFFu, hr, 2);   // the other half
+                    const bool top = c < 2;
+                    exq[1][gg] = top ? hl : ol; exq[2][gg] = top ? hr : orr;
+                    exq[3][gg] = top ? ol : hl; exq[4][gg] = top ? orr : hr;
+                    exq[0][gg] = hl + hr + ol + orr;
+                }
+            }
+            uint32_t bq[5] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // parent, TL, TR, BL, BR
+            const bool fast_valid = __all_sync(0xFFFFFFFFu, (mt.w >> 16) & 1);
+            if (fast_valid) {
+                // interior block: parent and sub-blocks share the two special cases (ox = 16 on odd horizontal phases, oy = 16
+                // on odd vertical ones); keys are folded rows-first like in the plain search (3 IMAD + min3 + add per column)
+                const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;
+                const uint32_t ybl = (grp == MR_NG - 1 && py) ? 0xFFFFFFFFu : 0u;
+                uint32_t ly8[3], lx8[9];
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative
+                    lx8[k] = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
+                }
+                auto fold = [&](uint32_t s0, uint32_t s1, uint32_t s2, int k) {
+                    const uint32_t t0 = s0 * 65536u + ly8[0], t1 = s1 * 65536u + ly8[1], t2 = (s2 * 65536u + ly8[2]) | ybl;
+                    uint32_t v = min(min(t0, t1), t2) + lx8[k];
+                    if (k == 8) v |= xbl;
+                    return v;
+                };
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t aL[3][8], aR[3][8];
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { aL[gg][k] = 0; aR[gg][k] = 0; }
+                    sad_pass_g3<WPR, 8, 8, BS / 2, MR_WP, true>(win + half * (BS / 2) * MR_WP, cb + half * (BS / 2) * WPR, aL, aR);
+                    uint32_t bl = fold(exq[1 + 2 * half][0], exq[1 + 2 * half][1], exq[1 + 2 * half][2], 8);
+                    uint32_t br = fold(exq[2 + 2 * half][0], exq[2 + 2 * half][1], exq[2 + 2 * half][2], 8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        bl = min(bl, fold(aL[0][k], aL[1][k], aL[2][k], k));
+                        br = min(br, fold(aR[0][k], aR[1][k], aR[2][k], k));
+#pragma unroll
+                        for (int gg = 0; gg < 3; ++gg) par[gg][k] += aL[gg][k] + aR[gg][k];
+                    }
+                    bq[1 + half * 2] = bl; bq[2 + half * 2] = br;
+                }
+                uint32_t bp = fold(exq[0][0], exq[0][1], exq[0][2], 8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bp = min(bp, fold(par[0][k], par[1][k], par[2][k], k));
+                bq[0] = bp;
+            } else {
+            // validity masks: parent and sub-blocks have different rectangles (Encoder.py:695-698 with their own size / position)
+            uint32_t lyk[3], lxk[9];
+            uint32_t ybadP[3], ybadT[3], ybadB[3], xbadP[9], xbadL[9], xbadR[9];
+            {
+                int l0, h0, l1, h1, l2, h2;
+                valid_range(by * BS, g.H, BS, g.fme, g.fme, l0, h0);
+                valid_range(by * BS, g.H, BS / 2, g.fme, g.fme, l1, h1);
+                valid_range(by * BS + BS / 2, g.H, BS / 2, g.fme, g.fme, l2, h2);
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    const int dy = mul * (oy0 + gg) + py;
+                    const bool in = dy >= -g.R && dy <= g.R;
+                    lyk[gg] = (uint32_t)(abs(dy) << 8) + gg;
+                    ybadP[gg] = (in && dy >= l0 && dy <= h0) ? 0u : 0xFFFFFFFFu;
+                    ybadT[gg] = (in && dy >= l1 && dy <= h1) ? 0u : 0xFFFFFFFFu;
+                    ybadB[gg] = (in && dy >= l2 && dy <= h2) ? 0u : 0xFFFFFFFFu;
+                }
+                valid_range(bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
+                valid_range(bx * BS, g.W, BS / 2, g.fme, g.fme, l1, h1);
+                valid_range(bx * BS + BS / 2, g.W, BS / 2, g.fme, g.fme, l2, h2);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const int dx = mul * (-16 + c + 4 * k) + px;
+                    const bool in = (k < 8 || c == 0) && dx >= -g.R && dx <= g.R;
+                    lxk[k] = (uint32_t)(abs(dx) << 8) + k * 3;
+                    xbadP[k] = (in && dx >= l0 && dx <= h0) ? 0u : 0xFFFFFFFFu;
+                    xbadL[k] = (in && dx >= l1 && dx <= h1) ? 0u : 0xFFFFFFFFu;
+                    xbadR[k] = (in && dx >= l2 && dx <= h2) ? 0u : 0xFFFFFFFFu;
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t aL[3][8], aR[3][8];
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { aL[gg][k] = 0; aR[gg][k] = 0; }
+                sad_pass_g3<WPR, 8, 8, BS / 2, MR_WP, true>(win + half * (BS / 2) * MR_WP, cb + half * (BS / 2) * WPR, aL, aR);
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg) {
+                        const uint32_t l1v = lxk[k] + lyk[gg];
+                        const uint32_t yb = half ? ybadB[gg] : ybadT[gg];
+                        const uint32_t sl = k < 8 ? aL[gg][k < 8 ? k : 0] : exq[1 + 2 * half][gg];
+                        const uint32_t sr = k < 8 ? aR[gg][k < 8 ? k : 0] : exq[2 + 2 * half][gg];
+                        bq[1 + half * 2] = min(bq[1 + half * 2], (sl * 65536u + l1v) | xbadL[k] | yb);
+                        bq[2 + half * 2] = min(bq[2 + half * 2], (sr * 65536u + l1v) | xbadR[k] | yb);
+                        if (k < 8) par[gg][k < 8 ? k : 0] += sl + sr;
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    const uint32_t sp = k < 8 ? par[gg][k < 8 ? k : 0] : exq[0][gg];
+                    bq[0] = min(bq[0], (sp * 65536u + (lxk[k] + lyk[gg])) | xbadP[k] | ybadP[gg]);
+                }
+            }   // generic validity
+            // ---- merge: five keys per segment
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                const uint32_t best = bq[e];
+                const int idx = (int)(best & 0xFFu), k = (idx * 11) >> 5, gg = idx - 3 * k;
+                const int dx = mul * (-16 + c + 4 * k) + px, dy = mul * (oy0 + gg) + py;
+                const uint32_t xy = ((uint32_t)(dx + g.R) << 8) | (uint32_t)(dy + g.R);
+                const uint32_t v1 = (has && best != 0xFFFFFFFFu) ? (best >> 8) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    if (s2 == 1 && !two) break;
+                    const bool mine = second == (unsigned)s2;
+                    const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, mine ? v1 : 0xFFFFFFFFu);
+                    const uint32_t m2 = __reduce_min_sync(0xFFFFFFFFu, (mine && v1 == m1) ? xy : 0xFFFFFFFFu);
+                    if (lane == 0 && m1 != 0xFFFFFFFFu) {
+                        const int4 ms = meta[s2 ? slot1 : slot0];
+                        const unsigned long long key = ((unsigned long long)(m1 >> 8) << 40) | ((unsigned long long)(m1 & 0xFFu) << 24) |
+                                                       ((unsigned long long)(ms.w & 255) << 16) | (unsigned long long)m2;
+                        unsigned long long* okey;
+                        if (e == 0) okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + ms.x);
+                        else {
+                            const int kx = (e - 1) & 1, ky = (e - 1) >> 1, un = ms.w >> 17;
+                            okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out_sub) + un * a.out_sub_unit_stride +
+                                                                         (size_t)(ms.z * 2 + ky) * (g.nbx * 2) + ms.y * 2 + kx);
+                        }
+                        atomicMin(okey, key);
+                    }
+                }
+            }
+        } else {
         // ---- main pass: 8 horizontal x 3 vertical offsets
         uint32_t acc[3][8];
 #pragma unroll
@@ -303,6 +477,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
                 atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + ms.x), key);
             }
         }
+        }   // !QUAD
         __syncwarp();
         if (lane == 0) {
             const uint32_t c0 = min(32u, (unsigned)MR_TPI - r0);
