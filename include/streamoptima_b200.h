@@ -136,6 +136,15 @@ int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_fr
                        uint8_t* split, int16_t* mv, int16_t* levels, uint8_t* recon,
                        uint32_t* row_sizes, so_frame_stats* stats);
 
+/* Frame ingest fused with the encode of ONE sequence (read_yuv Encoder.py:110-126, pad_hw :140-155): frames
+ * first_frame .. first_frame + n_frames - 1 of a planar YUV 4:2:0 file whose luma is src_width x src_height (<= the coded
+ * size of the context; the missing rows / columns are padded with 128 like pad_hw does).  Only the luma planes are read,
+ * in chunks of 8 frames into rotating pinned buffers: disk reads, H2D copies, the encode and the D2H copies of different
+ * chunks overlap.  Outputs as so_encode_sequence with n_units = 1.  Synchronous. */
+int so_encode_yuv420_file(so_ctx* ctx, const char* path, int src_width, int src_height, int first_frame, int n_frames,
+                          uint8_t* split, int16_t* mv, int16_t* levels, uint8_t* recon, uint32_t* row_sizes,
+                          so_frame_stats* stats);
+
 /* The three stages of so_encode_sequence, separately callable (bench.py times so_seq_run alone with the inputs
  * already resident in HBM, and the whole so_encode_sequence for the end-to-end figure):
  *   so_seq_upload   H2D copy of the frames, asynchronous on the context stream

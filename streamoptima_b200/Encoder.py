@@ -153,13 +153,24 @@ class Y_Video_codec:
             else:
                 self.target_bitrate = num
             self.bitrate_per_row = (self.target_bitrate // self.frame_rate) / (self.h_pixels / self.block_size)
-        if yuv_file is not None:
-            self.y_only_f_arr = self.read_yuv(yuv_file, h_pixels, w_pixels, frames)
-        else:
-            self.y_only_f_arr = y_only_frame_arr
+        # Encoder.py:103-106.  With a file the luma planes are NOT read here: encode() hands the path to the library, which
+        # reads them chunk by chunk while earlier chunks are being encoded (so_encode_yuv420_file); touching
+        # ``y_only_f_arr`` still gives the array the reference would hold.
+        self._yuv_file = yuv_file
+        self._y_arr = None if yuv_file is not None else y_only_frame_arr
         self._ctx = None
         self._ctx_key = None
         self.last_timing = None
+
+    @property
+    def y_only_f_arr(self):
+        if self._y_arr is None and self._yuv_file is not None:
+            self._y_arr = self.read_yuv(self._yuv_file, self.h_pixels, self.w_pixels, self.frames)
+        return self._y_arr
+
+    @y_only_f_arr.setter
+    def y_only_f_arr(self, value):
+        self._y_arr = value
 
     # Encoder.py:110-126
     @staticmethod
@@ -228,9 +239,37 @@ class Y_Video_codec:
         if H % block_size or W % block_size:
             raise ValueError("frame dimensions must be multiples of the block size (Encoder.py:1382)")
         ctx = self._context(block_size, search_range, intra_dur, max_batch=U)
-        nblk, rows = ctx.nblk, ctx.rows
         qp_map = self.roi_qp_map if qp_map is None else qp_map
         ctx.set_block_qps(qp_map)            # ROI extension; None clears
+        # the input is handed to the library as is (pinned or pageable): its upload is chunked and overlapped with the
+        # encode of earlier chunks, so an extra staging copy would only add host time
+        a_in = np.ascontiguousarray(arr)
+        return self._run(ctx, U, F, want_levels, want_recon,
+                         lambda o: ctx.lib.so_encode_sequence(ctx.handle, a_in.ctypes.data, U, F, *o))
+
+    def encode_yuv_file(self, path, src_height=None, src_width=None, first_frame=0, n_frames=None, block_size=None,
+                        search_range=None, intra_dur=None, want_levels=True, want_recon=True, qp_map=None):
+        """Encode frames of a planar YUV 4:2:0 file without materialising them on the Python side (read_yuv + pad_hw,
+        Encoder.py:110-126 / :140-155, fused with the encode: ``so_encode_yuv420_file``).  ``src_height`` / ``src_width``: luma
+        size in the file (default: the codec's size); smaller sources are padded with 128 to the codec's size."""
+        block_size = block_size or self.block_size
+        search_range = self.search_range if search_range is None else search_range
+        intra_dur = intra_dur or self.intra_dur
+        F = self.frames if n_frames is None else n_frames
+        sh = self.h_pixels if src_height is None else src_height
+        sw = self.w_pixels if src_width is None else src_width
+        if self.h_pixels % block_size or self.w_pixels % block_size:
+            raise ValueError("frame dimensions must be multiples of the block size (Encoder.py:1382)")
+        ctx = self._context(block_size, search_range, intra_dur, max_batch=1)
+        ctx.set_block_qps(self.roi_qp_map if qp_map is None else qp_map)
+        bpath = os.fsencode(path)
+        return self._run(ctx, 1, F, want_levels, want_recon,
+                         lambda o: ctx.lib.so_encode_yuv420_file(ctx.handle, bpath, sw, sh, first_frame, F, *o))
+
+    def _run(self, ctx, U, F, want_levels, want_recon, call):
+        """Pinned output buffers (cached per shape) + one library call ``call(output pointers)`` + result dict."""
+        H, W = self.h_pixels, self.w_pixels
+        nblk, rows = ctx.nblk, ctx.rows
         # pinned staging buffers are cached per shape: cudaHostAlloc of GBs costs more than the encode itself.
         # NOTE the returned arrays are views of these buffers and are overwritten by the next call.
         key = (U, F, H, W, nblk, rows)
@@ -243,17 +282,13 @@ class Y_Video_codec:
             self._pin["lev"] = _pinned_empty((U, F, H, W), np.int16)
         if want_recon and "rec" not in self._pin:
             self._pin["rec"] = _pinned_empty((U, F, H, W), np.uint8)
-        # the input is handed to the library as is (pinned or pageable): its upload is chunked and overlapped with the
-        # encode of earlier chunks, so an extra staging copy would only add host time
-        a_in = np.ascontiguousarray(arr)
         split, mv, row_sizes = self._pin["split"][1], self._pin["mv"][1], self._pin["rows"][1]
         levels = self._pin["lev"][1] if want_levels else None
         recon = self._pin["rec"][1] if want_recon else None
         # pinned too: a pageable target makes the per-chunk D2H synchronous and stalls the host behind the GPU
         stats = self._pin["stats"][1].view(_native.STATS_DTYPE).reshape(U, F)
-        rc = ctx.lib.so_encode_sequence(ctx.handle, a_in.ctypes.data, U, F, split.ctypes.data, mv.ctypes.data,
-                                        levels.ctypes.data if want_levels else None,
-                                        recon.ctypes.data if want_recon else None, row_sizes.ctypes.data, stats.ctypes.data)
+        rc = call((split.ctypes.data, mv.ctypes.data, levels.ctypes.data if want_levels else None,
+                   recon.ctypes.data if want_recon else None, row_sizes.ctypes.data, stats.ctypes.data))
         _native.check(ctx.handle, rc)
         self.last_timing = ctx.last_timing()
         self._last_shape = (U, F)
@@ -277,8 +312,11 @@ class Y_Video_codec:
             raise NotImplementedError("intra_mode=1 raises TypeError in the reference (Encoder.py:1399-1407)")
         if self.ParallelMode == 3:
             raise NotImplementedError("ParallelMode=3 is racy / crashes in the reference (Encoder.py:1712-1787)")
-        frames = np.ascontiguousarray(self.y_only_f_arr[:self.frames])
-        out = self.encode_arrays(frames, block_size, search_range, intra_dur)
+        if self._yuv_file is not None and self._y_arr is None:
+            out = self.encode_yuv_file(self._yuv_file, block_size=block_size, search_range=search_range, intra_dur=intra_dur)
+        else:
+            frames = np.ascontiguousarray(self.y_only_f_arr[:self.frames])
+            out = self.encode_arrays(frames, block_size, search_range, intra_dur)
         st = out["stats"][0]
         H, W = self.h_pixels, self.w_pixels
         nblk = (H // block_size) * (W // block_size)

@@ -10,6 +10,8 @@
 #include "so_me_tma.cuh"
 #include "so_me_ring.cuh"
 #include <cstdlib>
+#include <fcntl.h>
+#include <unistd.h>
 #include <algorithm>
 
 #define CU(expr)                                                                                  \
@@ -74,6 +76,11 @@ struct so_ctx {
         uint32_t* h_rows = nullptr;
         so_frame_stats* h_stats = nullptr;
         std::vector<cudaEvent_t> up, done;
+        // file ingest (so_encode_yuv420_file): luma planes are pread() chunk by chunk into three rotating pinned buffers
+        int fd = -1;
+        int src_w = 0, src_h = 0, first_frame = 0;
+        uint8_t* stage[3] = {nullptr, nullptr, nullptr};
+        size_t stage_bytes = 0;
     } pipe;
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
     long launches = 0;
@@ -144,6 +151,7 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     cudaFree(c->res_frame); cudaFree(c->band);
     cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev); cudaFree(c->me_work);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (auto b : c->pipe.stage) if (b) cudaFreeHost(b);
     for (auto e : c->pipe.up) cudaEventDestroy(e);
     for (auto e : c->pipe.done) cudaEventDestroy(e);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
@@ -791,6 +799,41 @@ static int pipe_upload_chunk(so_ctx* ctx, int c) {
     const int U = ctx->sq_units, F = ctx->sq_nframes;
     const int f0 = c * P.chunk, n = std::min(P.chunk, F - f0);
     const size_t px = ctx->frame_px;
+    if (P.fd >= 0) {
+        // Y extraction + padding (read_yuv Encoder.py:110-126, pad_hw :140-155): the chroma planes are skipped on disk, rows and
+        // columns beyond the source size are 128.  The host blocks in pread() here while the GPU works through the two chunks
+        // that are already queued.
+        uint8_t* dst = P.stage[c % 3];
+        if (c >= 3) CU(cudaEventSynchronize(P.up[c - 3]));            // the H2D copy that last read this staging buffer
+        const int W = ctx->g.W, H = ctx->g.H;
+        const size_t ysz = (size_t)P.src_w * P.src_h, fsz = ysz + 2 * (ysz / 4);
+        const bool padded = P.src_w != W || P.src_h != H;
+        if (padded) memset(dst, 128, (size_t)n * px);
+        for (int i = 0; i < n; ++i) {
+            const off_t base = (off_t)((size_t)(P.first_frame + f0 + i) * fsz);
+            if (!padded) {
+                size_t got = 0;
+                while (got < ysz) {
+                    const ssize_t r = pread(P.fd, dst + (size_t)i * px + got, ysz - got, base + (off_t)got);
+                    if (r <= 0) { set_err(ctx, "yuv file is too short for the requested frames"); return SO_E_INVALID; }
+                    got += (size_t)r;
+                }
+            } else {
+                for (int y = 0; y < P.src_h; ++y) {
+                    size_t got = 0;
+                    while (got < (size_t)P.src_w) {
+                        const ssize_t r = pread(P.fd, dst + (size_t)i * px + (size_t)y * W + got, (size_t)P.src_w - got,
+                                                base + (off_t)((size_t)y * P.src_w + got));
+                        if (r <= 0) { set_err(ctx, "yuv file is too short for the requested frames"); return SO_E_INVALID; }
+                        got += (size_t)r;
+                    }
+                }
+            }
+        }
+        CU(cudaMemcpyAsync(ctx->sq_frames + (size_t)f0 * px, dst, (size_t)n * px, cudaMemcpyHostToDevice, ctx->st_h2d));
+        CU(cudaEventRecord(P.up[c], ctx->st_h2d));
+        return SO_OK;
+    }
     for (int u = 0; u < U; ++u)
         CU(cudaMemcpyAsync(ctx->sq_frames + ((size_t)u * F + f0) * px, P.h_frames + ((size_t)u * F + f0) * px, (size_t)n * px,
                            cudaMemcpyHostToDevice, ctx->st_h2d));
@@ -954,6 +997,52 @@ extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_unit
         P.up.push_back(a); P.done.push_back(b);
     }
     P.h_frames = frames; P.h_split = split; P.h_mv = mv; P.h_levels = levels; P.h_recon = recon; P.h_rows = row_sizes; P.h_stats = stats;
+    P.active = true;
+    rc = pipe_upload_chunk(ctx, 0);
+    if (!rc && P.nchunks > 1) rc = pipe_upload_chunk(ctx, 1);
+    if (!rc) rc = so_seq_run(ctx);
+    P.active = false;
+    if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st_d2h); return rc; }
+    CU(cudaStreamSynchronize(ctx->st_d2h));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SO_OK;
+}
+
+// Frame ingest from a planar YUV 4:2:0 file (Encoder.py:110-126 read_yuv + :140-155 pad_hw) fused with the encode of one
+// sequence: only the luma planes are read, chunk by chunk, into rotating pinned buffers; file reads, H2D copies, the
+// encode and the D2H copies of different chunks overlap.
+extern "C" int so_encode_yuv420_file(so_ctx* ctx, const char* path, int src_width, int src_height, int first_frame, int n_frames,
+                                     uint8_t* split, int16_t* mv, int16_t* levels, uint8_t* recon, uint32_t* row_sizes,
+                                     so_frame_stats* stats) {
+    if (!ctx || !path || !split || !mv || !stats || n_frames < 1 || first_frame < 0) return SO_E_INVALID;
+    if (src_width < 1 || src_height < 1 || src_width > ctx->g.W || src_height > ctx->g.H) {
+        set_err(ctx, "source size must be positive and not larger than the coded size of the context");
+        return SO_E_INVALID;
+    }
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_seq(ctx, (size_t)n_frames);
+    if (rc) return rc;
+    auto& P = ctx->pipe;
+    P.fd = open(path, O_RDONLY);
+    if (P.fd < 0) { set_err(ctx, std::string("cannot open ") + path); return SO_E_INVALID; }
+    struct Closer { so_ctx::Pipe& p; ~Closer() { if (p.fd >= 0) close(p.fd); p.fd = -1; p.active = false; } } closer{P};
+    ctx->sq_units = 1; ctx->sq_nframes = n_frames;
+    P.chunk = 8;
+    P.nchunks = (n_frames + P.chunk - 1) / P.chunk;
+    P.src_w = src_width; P.src_h = src_height; P.first_frame = first_frame;
+    const size_t need = (size_t)P.chunk * ctx->frame_px;
+    if (P.stage_bytes < need) {
+        for (auto& b : P.stage) { if (b) cudaFreeHost(b); b = nullptr; }
+        for (auto& b : P.stage) CU(cudaHostAlloc(&b, need, cudaHostAllocDefault));
+        P.stage_bytes = need;
+    }
+    while ((int)P.up.size() < P.nchunks) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        P.up.push_back(a); P.done.push_back(b);
+    }
+    P.h_frames = nullptr; P.h_split = split; P.h_mv = mv; P.h_levels = levels; P.h_recon = recon; P.h_rows = row_sizes; P.h_stats = stats;
     P.active = true;
     rc = pipe_upload_chunk(ctx, 0);
     if (!rc && P.nchunks > 1) rc = pipe_upload_chunk(ctx, 1);
