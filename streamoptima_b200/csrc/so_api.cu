@@ -669,7 +669,10 @@ static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     const int nt = nthreads_px(g.bs);
     const size_t ism = sizeof(unsigned) * 4 * (2 * g.r + 1);
     ev_pair(ctx, ctx->ev_me, st, true);
-    if (g.bs == 16) intra_search_kernel<16><<<grid, 256, ism, st>>>(a);
+    static const bool intra_generic = std::getenv("SO_INTRA_GENERIC") != nullptr;     // tests: force the generic intra kernels
+    const bool fast16 = g.bs == 16 && g.W % 16 == 0 && !intra_generic;
+    if (fast16) intra_search16_kernel<<<dim3((ctx->nblk + 3) / 4, units), 128, 0, st>>>(a);
+    else if (g.bs == 16) intra_search_kernel<16><<<grid, 256, ism, st>>>(a);
     else if (g.bs == 8) intra_search_kernel<8><<<grid, 128, ism, st>>>(a);
     else intra_search_kernel<4><<<grid, 64, ism, st>>>(a);
     ev_pair(ctx, ctx->ev_me, st, false);
@@ -678,7 +681,8 @@ static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     else if (g.bs == 8) intra_finish_kernel<8><<<grid, nt, 0, st>>>(a);
     else intra_finish_kernel<4><<<grid, nt, 0, st>>>(a);
     dim3 grid2(g.nby, units);
-    if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
+    if (fast16) intra_recon16_kernel<<<grid2, 256, 0, st>>>(a);
+    else if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
     else if (g.bs == 8) intra_recon_kernel<8><<<grid2, nt, 0, st>>>(a);
     else intra_recon_kernel<4><<<grid2, nt, 0, st>>>(a);
     ev_pair(ctx, ctx->ev_tq, st, false);
@@ -1155,7 +1159,8 @@ extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const
         else decode_block_kernel<4><<<grid, nt, 0, st>>>(a, intra ? 1 : 0);
         if (intra) {
             dim3 grid2(g.nby, 1);
-            if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
+            if (g.bs == 16 && g.W % 16 == 0 && std::getenv("SO_INTRA_GENERIC") == nullptr) intra_recon16_kernel<<<grid2, 256, 0, st>>>(a);
+            else if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
             else if (g.bs == 8) intra_recon_kernel<8><<<grid2, nt, 0, st>>>(a);
             else intra_recon_kernel<4><<<grid2, nt, 0, st>>>(a);
             if (reset_at_intra) ctx->list.clear();                                     // decoder.py:520 `ref_frames = []`

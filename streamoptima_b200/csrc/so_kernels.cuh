@@ -727,6 +727,83 @@ __global__ void intra_search_kernel(const FlowArgs a) {
     }
 }
 
+// 16x16 blocks, one warp per block, lane = candidate.  The search frame holds original pixels LEFT of the parent block and
+// 128 from the parent's first column on (Encoder.py:1248, :1329-1338), so every offset dx >= 0 predicts a flat 128 block:
+// their SADs all equal SAD(dx = 0) and the replace rule (SAD, |dx|, -dx) (appendix A4) keeps dx = 0.  Only dx = -t,
+// t = 0..r, has to be evaluated: predictor byte i = row[x - t + i] for i < t, else 128.  Each lane builds its 16 predictor
+// bytes per row from aligned 32-bit loads + funnel shifts + a byte mask and accumulates the four quadrant SADs with
+// VABSDIFF4; the five argmins (parent + four 8x8 sub-blocks = quadrant sums, same pixels) are REDUX reductions.
+__global__ void __launch_bounds__(128) intra_search16_kernel(const FlowArgs a) {
+    constexpr int BS = 16;
+    const FrameGeom& g = a.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * 4 + warp, unit = a.unit0 + blockIdx.y;
+    if (blk >= g.nbx * g.nby) return;
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int x = bx * BS, y = by * BS;
+    const uint8_t* cur = a.cur + unit * a.cur_unit_stride + (size_t)y * g.W;
+    const bool eligible = a.vbs && bx != 0 && by != 0;
+    uint32_t bestk[5] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};     // SAD << 8 | t: parent, TL, TR, BL, BR
+    const int tmax = bx == 0 ? 0 : g.r;
+    for (int t0 = 0; t0 <= tmax; t0 += 32) {
+        const int t = t0 + lane;
+        const bool cand = t <= tmax;
+        const int start = x - t;                                  // first predictor column
+        // start may be negative by up to 8 columns: the candidate is then invalid for the parent and the left sub-blocks but
+        // still valid for the right ones, whose eight predictor columns start at x + 8 - t >= 0 (words wholly left of the
+        // frame are skipped; they only feed bytes of the invalid half)
+        const bool readable = cand && t > 0;
+        const int b0 = start & ~3, sh = (start & 3) * 8;
+        uint32_t m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cnt = min(max(t - 4 * k, 0), 4);            // real pixels in word k
+            m[k] = cnt == 4 ? 0xFFFFFFFFu : ((1u << (8 * cnt)) - 1u);
+        }
+        uint32_t q4[4] = {0u, 0u, 0u, 0u};                        // TL, TR, BL, BR
+#pragma unroll 4
+        for (int j = 0; j < BS; ++j) {
+            const uint8_t* row = cur + (size_t)j * g.W;
+            const uint4 cw = *reinterpret_cast<const uint4*>(row + x);       // same address for all lanes: one broadcast load
+            uint32_t q[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                q[k] = (readable && b0 + 4 * k >= 0 && b0 + 4 * k < x) ? __ldg(reinterpret_cast<const uint32_t*>(row + b0 + 4 * k)) : 0u;
+            const uint32_t cwv[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t pw = (__funnelshift_r(q[k], q[k + 1], sh) & m[k]) | (0x80808080u & ~m[k]);
+                const int qi = (j >= 8 ? 2 : 0) + (k >= 2 ? 1 : 0);
+                q4[qi] = sad4_acc(cwv[k], pw, q4[qi]);
+            }
+        }
+        // validity (Encoder.py:1026: x + dx >= 0 and x + dx + bs <= W; the second holds for dx <= 0)
+        const uint32_t par = q4[0] + q4[1] + q4[2] + q4[3];
+        if (cand && x - t >= 0) bestk[0] = min(bestk[0], (par << 8) | (uint32_t)t);
+        if (eligible) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ex = x + (e & 1) * 8;
+                if (cand && ex - t >= 0) bestk[1 + e] = min(bestk[1 + e], (q4[e] << 8) | (uint32_t)t);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+        if (e > 0 && !eligible) break;
+        const uint32_t k = __reduce_min_sync(0xFFFFFFFFu, bestk[e]);
+        if (lane == 0) {
+            MeResult r;
+            r.dy = 0; r.ref = 0; r.none = 0;
+            r.sad = k >> 8;
+            r.dx = (int16_t)(-(int)(k & 0xFFu));
+            if (e == 0 && bx == 0) r.dx = -1;                     // x == 0: mode -1, predictor 128 (Encoder.py:1016-1019)
+            if (e == 0) a.me_parent[unit * a.me_parent_stride + blk] = r;
+            else a.me_sub[unit * a.me_sub_stride + (by * 2 + ((e - 1) >> 1)) * (g.nbx * 2) + bx * 2 + ((e - 1) & 1)] = r;
+        }
+    }
+}
+
 // intra predictor sample for a (sub-)block at column ex with offset mv, parent block starting at column xpar
 __device__ __forceinline__ int intra_pred(const uint8_t* row, int ex, int mv, int i, int xpar, bool first_col) {
     if (first_col) return 128;
@@ -857,6 +934,54 @@ __global__ void intra_recon_kernel(const FlowArgs a) {
             se += (unsigned long long)(d * d);
         }
         __syncthreads();
+    }
+    se = block_sum_u64(se, sbuf);
+    if (t == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&(a.stats + unit * a.stats_stride)->sse), se);
+}
+
+// 16x16 variant of the row chain: a pixel row only ever reads its own row (the predictor is horizontal), so the 16 lanes
+// of a half warp carry one row on their own -- no CTA barrier, no global read-after-write.  The reconstructed row lives in
+// a 128-column shared-memory ring (a predictor reaches at most r <= 63 columns back); columns at or right of the block
+// being built read as 128 like the unwritten frame does.  Residuals, split flags and vectors of the next block are
+// fetched while the current one is computed.
+__global__ void __launch_bounds__(256) intra_recon16_kernel(const FlowArgs a) {
+    constexpr int BS = 16, S = 8, RING = 128;
+    __shared__ int ring[BS][RING];
+    __shared__ unsigned long long sbuf[32];
+    const FrameGeom& g = a.g;
+    const int by = blockIdx.x, unit = a.unit0 + blockIdx.y;
+    const int t = threadIdx.x, i = t & 15, j = t >> 4;
+    const int y = by * BS;
+    const int16_t* res = a.res_frame + unit * a.scratch_stride + (size_t)(y + j) * g.W;
+    const uint8_t* cur = a.cur + unit * a.cur_unit_stride + (size_t)(y + j) * g.W;
+    uint8_t* rec = a.recon + unit * a.frame_stride + (size_t)(y + j) * g.W;
+    const uint8_t* splitp = a.split + unit * a.split_stride + (size_t)by * g.nbx;
+    const int16_t* mvp = a.mv + unit * a.mv_stride + (size_t)by * g.nbx * 12;
+    const int k = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
+    unsigned long long se = 0;
+    int r_n = res[i], c_n = cur[i], sp_n = splitp[0], mv_n = 0;
+    for (int bx = 0; bx < g.nbx; ++bx) {
+        const int x = bx * BS;
+        const int r = r_n, c = c_n, split = sp_n, mv = mv_n;
+        if (bx + 1 < g.nbx) {                       // prefetch the next block
+            r_n = res[x + BS + i]; c_n = cur[x + BS + i];
+            sp_n = splitp[bx + 1];
+            mv_n = mvp[(size_t)(bx + 1) * 12 + (sp_n ? k * 3 : 0)];
+        }
+        int val;
+        if (bx == 0) val = 128 + r;
+        else {
+            const int col = split ? x + (k & 1) * S + mv + (i & (S - 1)) : x + mv + i;
+            const int pv = (col >= x || col < 0) ? 128 : ring[j][col & (RING - 1)];
+            val = pv + r;
+        }
+        __syncwarp();                               // everybody has read the ring before anybody overwrites it
+        ring[j][(x + i) & (RING - 1)] = val;
+        const int rv = val & 0xFF;                  // astype(np.uint8) of the whole frame wraps (appendix A5)
+        rec[x + i] = (uint8_t)rv;
+        const int d = rv - c;
+        se += (unsigned long long)(d * d);
+        __syncwarp();
     }
     se = block_sum_u64(se, sbuf);
     if (t == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&(a.stats + unit * a.stats_stride)->sse), se);

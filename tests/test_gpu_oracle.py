@@ -151,3 +151,35 @@ def test_batched_units_equal_single_sequences_r16():
             o1 = cs.encode_arrays(seqs[u])
             for k in got:
                 np.testing.assert_array_equal(got[k][u], o1[k][0], err_msg=f"{k} unit {u} {kw}")
+
+
+_INTRA_SCRIPT = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+from streamoptima_b200 import synth
+from streamoptima_b200.Encoder import Y_Video_codec
+Y_Video_codec.write_recon_yuv = False
+h = hashlib.sha256()
+for (F, H, W, r, kw) in ((3, 272, 480, 16, dict(VBSEnable=True, lam=0.02)), (2, 96, 256, 40, dict(VBSEnable=True, lam=0.01)), (2, 1088, 1920, 16, {})):
+    frames = synth.zooming(F, H, W, seed=9)
+    c = Y_Video_codec(H, W, F, 16, r, 3, 1, 0, y_only_frame_arr=frames, **kw)      # I_Period 1: every frame is intra
+    c.encode()
+    p = c.encoded_package.packed
+    for k in ("split", "mv", "levels", "recon"):
+        h.update(np.ascontiguousarray(p[k]).tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_intra_fast16_kernels_equal_generic():
+    """The warp-per-block intra search / shared-memory row chain for 16x16 blocks against the generic intra kernels
+    (which the goldens pin at every block size): all-intra sequences with VBS, a range above 32 (two candidate chunks) and a
+    full 1080p frame."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {"SO_INTRA_GENERIC": "1"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", _INTRA_SCRIPT % root], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
