@@ -681,7 +681,7 @@ static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     else if (g.bs == 8) intra_finish_kernel<8><<<grid, nt, 0, st>>>(a);
     else intra_finish_kernel<4><<<grid, nt, 0, st>>>(a);
     dim3 grid2(g.nby, units);
-    if (fast16) intra_recon16_kernel<<<grid2, 256, 0, st>>>(a);
+    if (fast16) intra_recon16_kernel<<<grid2, 256, (size_t)g.nbx * 9 + 16, st>>>(a);
     else if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
     else if (g.bs == 8) intra_recon_kernel<8><<<grid2, nt, 0, st>>>(a);
     else intra_recon_kernel<4><<<grid2, nt, 0, st>>>(a);
@@ -1159,7 +1159,7 @@ extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const
         else decode_block_kernel<4><<<grid, nt, 0, st>>>(a, intra ? 1 : 0);
         if (intra) {
             dim3 grid2(g.nby, 1);
-            if (g.bs == 16 && g.W % 16 == 0 && std::getenv("SO_INTRA_GENERIC") == nullptr) intra_recon16_kernel<<<grid2, 256, 0, st>>>(a);
+            if (g.bs == 16 && g.W % 16 == 0 && std::getenv("SO_INTRA_GENERIC") == nullptr) intra_recon16_kernel<<<grid2, 256, (size_t)g.nbx * 9 + 16, st>>>(a);
             else if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
             else if (g.bs == 8) intra_recon_kernel<8><<<grid2, nt, 0, st>>>(a);
             else intra_recon_kernel<4><<<grid2, nt, 0, st>>>(a);

@@ -945,9 +945,10 @@ __global__ void intra_recon_kernel(const FlowArgs a) {
 // being built read as 128 like the unwritten frame does.  Residuals, split flags and vectors of the next block are
 // fetched while the current one is computed.
 __global__ void __launch_bounds__(256) intra_recon16_kernel(const FlowArgs a) {
-    constexpr int BS = 16, S = 8, RING = 128;
+    constexpr int BS = 16, S = 8, RING = 128, PF = 8;
     __shared__ int ring[BS][RING];
     __shared__ unsigned long long sbuf[32];
+    extern __shared__ int16_t s_mv[];                 // [nbx][4] horizontal offsets (slot 0 only when not split), then [nbx] split flags
     const FrameGeom& g = a.g;
     const int by = blockIdx.x, unit = a.unit0 + blockIdx.y;
     const int t = threadIdx.x, i = t & 15, j = t >> 4;
@@ -955,33 +956,56 @@ __global__ void __launch_bounds__(256) intra_recon16_kernel(const FlowArgs a) {
     const int16_t* res = a.res_frame + unit * a.scratch_stride + (size_t)(y + j) * g.W;
     const uint8_t* cur = a.cur + unit * a.cur_unit_stride + (size_t)(y + j) * g.W;
     uint8_t* rec = a.recon + unit * a.frame_stride + (size_t)(y + j) * g.W;
-    const uint8_t* splitp = a.split + unit * a.split_stride + (size_t)by * g.nbx;
-    const int16_t* mvp = a.mv + unit * a.mv_stride + (size_t)by * g.nbx * 12;
+    uint8_t* s_split = reinterpret_cast<uint8_t*>(s_mv + (size_t)g.nbx * 4);
+    {   // vectors and split flags of the whole block row: one parallel load, the chain below never waits on them
+        const uint8_t* splitp = a.split + unit * a.split_stride + (size_t)by * g.nbx;
+        const int16_t* mvp = a.mv + unit * a.mv_stride + (size_t)by * g.nbx * 12;
+        for (int e = t; e < g.nbx * 4; e += blockDim.x) s_mv[e] = mvp[(size_t)(e >> 2) * 12 + (e & 3) * 3];
+        for (int e = t; e < g.nbx; e += blockDim.x) s_split[e] = splitp[e];
+    }
     const int k = (j >= S ? 2 : 0) + (i >= S ? 1 : 0);
     unsigned long long se = 0;
-    int r_n = res[i], c_n = cur[i], sp_n = splitp[0], mv_n = 0;
-    for (int bx = 0; bx < g.nbx; ++bx) {
-        const int x = bx * BS;
-        const int r = r_n, c = c_n, split = sp_n, mv = mv_n;
-        if (bx + 1 < g.nbx) {                       // prefetch the next block
-            r_n = res[x + BS + i]; c_n = cur[x + BS + i];
-            sp_n = splitp[bx + 1];
-            mv_n = mvp[(size_t)(bx + 1) * 12 + (sp_n ? k * 3 : 0)];
+    int rq[PF], cq[PF];                               // residual / current pixel of the next PF blocks
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        rq[p] = p < g.nbx ? res[p * BS + i] : 0;
+        cq[p] = p < g.nbx ? cur[p * BS + i] : 0;
+    }
+    __syncthreads();
+    for (int bx0 = 0; bx0 < g.nbx; bx0 += PF) {
+        int rn[PF], cn[PF];                           // the whole next group is requested before this one is worked through
+#pragma unroll
+        for (int p = 0; p < PF; ++p) {
+            const int bn = bx0 + PF + p;
+            rn[p] = bn < g.nbx ? res[bn * BS + i] : 0;
+            cn[p] = bn < g.nbx ? cur[bn * BS + i] : 0;
         }
-        int val;
-        if (bx == 0) val = 128 + r;
-        else {
-            const int col = split ? x + (k & 1) * S + mv + (i & (S - 1)) : x + mv + i;
-            const int pv = (col >= x || col < 0) ? 128 : ring[j][col & (RING - 1)];
-            val = pv + r;
+#pragma unroll
+        for (int p = 0; p < PF; ++p) {
+            const int bx = bx0 + p;
+            if (bx < g.nbx) {
+                const int x = bx * BS;
+                const int r = rq[p], c = cq[p];
+                const int split = s_split[bx];
+                const int mv = s_mv[bx * 4 + (split ? k : 0)];
+                int val;
+                if (bx == 0) val = 128 + r;
+                else {
+                    const int col = split ? x + (k & 1) * S + mv + (i & (S - 1)) : x + mv + i;
+                    const int pv = (col >= x || col < 0) ? 128 : ring[j][col & (RING - 1)];
+                    val = pv + r;
+                }
+                __syncwarp();                       // everybody has read the ring before anybody overwrites it
+                ring[j][(x + i) & (RING - 1)] = val;
+                const int rv = val & 0xFF;          // astype(np.uint8) of the whole frame wraps (appendix A5)
+                rec[x + i] = (uint8_t)rv;
+                const int d = rv - c;
+                se += (unsigned long long)(d * d);
+                __syncwarp();
+            }
         }
-        __syncwarp();                               // everybody has read the ring before anybody overwrites it
-        ring[j][(x + i) & (RING - 1)] = val;
-        const int rv = val & 0xFF;                  // astype(np.uint8) of the whole frame wraps (appendix A5)
-        rec[x + i] = (uint8_t)rv;
-        const int d = rv - c;
-        se += (unsigned long long)(d * d);
-        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < PF; ++p) { rq[p] = rn[p]; cq[p] = cn[p]; }
     }
     se = block_sum_u64(se, sbuf);
     if (t == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&(a.stats + unit * a.stats_stride)->sse), se);
