@@ -732,7 +732,9 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     if (use_fast) {
         ev_pair(ctx, ctx->ev_me, st, true);
         dim3 grid(a.chain ? 1 : ctx->nblk, units);
-        if (g.bs == 16) fast_me_kernel<16><<<grid, nt, 0, st>>>(a);
+        static const bool fast_generic = std::getenv("SO_FAST_GENERIC") != nullptr;      // tests: force the generic kernel
+        if (g.bs == 16 && g.W % 16 == 0 && !fast_generic) fast_me16_kernel<<<grid, 576, 0, st>>>(a);
+        else if (g.bs == 16) fast_me_kernel<16><<<grid, nt, 0, st>>>(a);
         else if (g.bs == 8) fast_me_kernel<8><<<grid, nt, 0, st>>>(a);
         else fast_me_kernel<4><<<grid, nt, 0, st>>>(a);
         ev_pair(ctx, ctx->ev_me, st, false);

@@ -663,6 +663,122 @@ __global__ void fast_me_kernel(const FlowArgs a) {
     }
 }
 
+// 16x16 variant of the fast search.  The chain is serial (block b needs the vector of block b - 1), so what counts is
+// the latency of one step.  Thread = (candidate, block row): 36 candidates x 16 rows = 576 threads issue all loads of a
+// step at once -- a candidate row is 16 contiguous bytes of ONE phase plane (appendix A1), read as four aligned words
+// from the copy shifted by (column & 3) bytes -- then 4 VABSDIFF4 per thread, three shuffles to the quadrant sums, and
+// one warp per entity (whole block + four sub-blocks) picks the winner with a REDUX on (SAD, scan index): strict '<' in
+// scan order (ref, dx, dy) (Encoder.py:726-740) == lexicographic minimum.  The current block of the next step is
+// fetched during this one.
+__global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
+    constexpr int BS = 16, S = 8, CPP = 36;           // candidates per pass
+    __shared__ unsigned int sadq[SO_MAX_REF * 9][4];
+    __shared__ __align__(16) uint32_t s_cur[BS][4];
+    __shared__ int s_mvp[3];
+    const FrameGeom& g = a.g;
+    const int unit = a.unit0 + blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int cl = t >> 4, row = t & 15;
+    const int mult = g.fme ? 2 : 1;
+    const int nref = min(a.nref_fast, g.nref);
+    const int ncand = nref * 9;
+    const int nblk = g.nbx * g.nby;
+    const int b0 = a.chain ? 0 : blockIdx.x, b1 = a.chain ? nblk : blockIdx.x + 1;
+    const int Wr = g.fme ? 2 * g.W - 1 : g.W, Hr = g.fme ? 2 * g.H - 1 : g.H;
+    const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
+    const size_t shift_stride = a.ring.plane_stride >> 2;
+    if (t < 3) s_mvp[t] = 0;
+    if (t < 64) s_cur[t >> 2][t & 3] = *reinterpret_cast<const uint32_t*>(cur + (size_t)((b0 / g.nbx) * BS + (t >> 2)) * g.W + (b0 % g.nbx) * BS + (t & 3) * 4);
+    __syncthreads();
+    for (int blk = b0; blk < b1; ++blk) {
+        const int bx = blk % g.nbx, by = blk / g.nbx;
+        const int x = bx * BS, y = by * BS;
+        const int mvx = s_mvp[0], mvy = s_mvp[1], mvr = s_mvp[2];
+        uint32_t cnext = 0;
+        if (t < 64 && blk + 1 < b1) {
+            const int nb = blk + 1;
+            cnext = *reinterpret_cast<const uint32_t*>(cur + (size_t)((nb / g.nbx) * BS + (t >> 2)) * g.W + (nb % g.nbx) * BS + (t & 3) * 4);
+        }
+        const uint4 cw = *reinterpret_cast<const uint4*>(&s_cur[row][0]);
+        for (int c0 = 0; c0 < ncand; c0 += CPP) {
+            const int cand = c0 + cl;
+            uint32_t sl = 0, sr = 0;
+            if (cand < ncand) {
+                const int ref = cand / 9, dx = mvx - 1 + (cand % 9) / 3, dy = mvy - 1 + (cand % 3);
+                const int Xh = x * mult + dx, Yh = y * mult + dy;
+                const int ph = g.fme ? (((Yh & 1) << 1) | (Xh & 1)) : 0;
+                const int col0 = g.fme ? (Xh >> 1) : Xh, Y = (g.fme ? (Yh >> 1) : Yh) + row;
+                uint32_t pw[4] = {0u, 0u, 0u, 0u};
+                if (Y >= 0 && Y < g.H) {
+                    const uint8_t* pl = a.ring.plane(unit, ref, ph);
+                    const int cs = col0 & 3, colA = col0 - cs;
+                    const uint8_t* rowp = pl + (size_t)Y * g.pitch;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const int cA = colA + 4 * w;
+                        if (cA >= 0 && col0 + 4 * w + 3 < g.W) {
+                            pw[w] = __ldg(reinterpret_cast<const uint32_t*>(rowp + (size_t)cs * shift_stride + cA));
+                        } else {                        // straddles the frame edge: only invalid (sub-)candidates see these bytes
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const int col = col0 + 4 * w + b;
+                                if (col >= 0 && col < g.W) pw[w] |= (uint32_t)rowp[col] << (8 * b);
+                            }
+                        }
+                    }
+                }
+                sl = sad4_acc(cw.x, pw[0], 0u); sl = sad4_acc(cw.y, pw[1], sl);
+                sr = sad4_acc(cw.z, pw[2], 0u); sr = sad4_acc(cw.w, pw[3], sr);
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                sl += __shfl_xor_sync(0xFFFFFFFFu, sl, o);
+                sr += __shfl_xor_sync(0xFFFFFFFFu, sr, o);
+            }
+            if (cand < ncand && (row & 7) == 0) {
+                sadq[cand][(row >> 3) * 2] = sl;
+                sadq[cand][(row >> 3) * 2 + 1] = sr;
+            }
+        }
+        __syncthreads();
+        if (t < 64 && blk + 1 < b1) s_cur[t >> 2][t & 3] = cnext;
+        const bool eligible = a.vbs && bx != 0 && by != 0;
+        if (warp < 5 && (warp == 0 || eligible)) {
+            const int e = warp;
+            const int n = e == 0 ? BS : S;
+            const int ex = (e == 0 ? x : x + ((e - 1) & 1) * S) * mult, ey = (e == 0 ? y : y + ((e - 1) >> 1) * S) * mult;
+            uint32_t best = 0xFFFFFFFFu;
+            for (int cand = lane; cand < ncand; cand += 32) {
+                const int dx = mvx - 1 + (cand % 9) / 3, dy = mvy - 1 + (cand % 3);
+                const int px = ex + dx, py = ey + dy;
+                const bool ok = px >= 0 && px < Wr - n && py >= 0 && py < Hr - n &&
+                                px + 2 * n >= 0 && px + 2 * n < Wr - n && py + 2 * n >= 0 && py + 2 * n < Hr - n;
+                if (ok) {
+                    const unsigned sv = e == 0 ? sadq[cand][0] + sadq[cand][1] + sadq[cand][2] + sadq[cand][3] : sadq[cand][e - 1];
+                    best = min(best, (sv << 7) | (uint32_t)cand);
+                }
+            }
+            best = __reduce_min_sync(0xFFFFFFFFu, best);
+            if (lane == 0) {
+                int bdx = mvx, bdy = mvy, bref = mvr, best_ref_idx = 0;        // no valid candidate: best_mv = mvp (Encoder.py:722)
+                if (best != 0xFFFFFFFFu) {
+                    const int cand = (int)(best & 127u);
+                    bref = cand / 9; bdx = mvx - 1 + (cand % 9) / 3; bdy = mvy - 1 + (cand % 3); best_ref_idx = bref;
+                }
+                MeResult r;
+                r.dx = (int16_t)bdx; r.dy = (int16_t)bdy; r.ref = (int16_t)bref; r.none = 0; r.sad = (uint32_t)best_ref_idx;   // quirk Q4
+                if (e == 0) a.me_parent[unit * a.me_parent_stride + blk] = r;
+                else {
+                    const int kk = e - 1;
+                    a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)] = r;
+                }
+                if (e == 0 && a.chain) { s_mvp[0] = bdx; s_mvp[1] = bdy; s_mvp[2] = bref; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // intra search (intra_find_best_match_horizontal, Encoder.py:1010-1045; intra_prediction :1272-1338)
 // The search frame holds ORIGINAL pixels left of the current parent block and 128 elsewhere, so all blocks are

@@ -183,3 +183,37 @@ def test_intra_fast16_kernels_equal_generic():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1]
+
+
+_FAST_SCRIPT = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+from streamoptima_b200 import synth
+from streamoptima_b200.Encoder import Y_Video_codec
+Y_Video_codec.write_recon_yuv = False
+h = hashlib.sha256()
+for (F, H, W, kw) in ((4, 272, 480, dict(fast_me=True, FMEEnable=True, nRefFrames=4, VBSEnable=True, lam=0.015)),
+                      (3, 144, 176, dict(fast_me=True, nRefFrames=2)),
+                      (3, 272, 480, dict(fast_me=True, FMEEnable=True, ParallelMode=2)),
+                      (3, 1088, 1920, dict(fast_me=True, FMEEnable=True, nRefFrames=2))):
+    frames = synth.zooming(F, H, W, seed=12)
+    c = Y_Video_codec(H, W, F, 16, 16, 4, 8, 0, y_only_frame_arr=frames, **kw)
+    c.encode()
+    p = c.encoded_package.packed
+    for k in ("split", "mv", "levels", "recon"):
+        h.update(np.ascontiguousarray(p[k]).tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_fast_me16_kernel_equals_generic():
+    """Latency-oriented fast-ME kernel for 16x16 blocks (thread = candidate x row, REDUX decision) against the generic
+    chain kernel that the goldens pin: half-pel + 4 refs + VBS, integer, ParallelMode 2 and a 1080p chain."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {"SO_FAST_GENERIC": "1"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", _FAST_SCRIPT % root], capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
