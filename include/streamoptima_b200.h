@@ -181,12 +181,16 @@ int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const uint8_t* s
 
 /* Timing of the last so_seq_run, CUDA events on the context stream (ms): [0] whole device region, [1] motion-search
  * kernels only (exhaustive search: the me_full_kernel launches; fast ME: the chain kernel; intra frames: intra search),
- * [2] transform/quant/recon kernels, [3] number of kernel launches.  Waits for the run to finish. */
+ * [2] transform/quant/recon kernels, [3] number of kernel launches.  Waits for the run to finish.  [1] and [2] cover the
+ * frames that carry per-kernel events (see so_last_search_timing). */
 int so_last_timing(so_ctx* ctx, double out[4]);
 int so_last_me_launches(so_ctx* ctx);    /* number of launches covered by timing [1] */
-/* The exhaustive-search kernel alone (me_ring_kernel / me_tma_kernel) in the last so_seq_run: out[0] = summed CUDA-event
- * time of its launches (ms), out[1] = number of launches.  This is the per-launch duration bench.py's roofline uses. */
-int so_last_search_timing(so_ctx* ctx, double out[2]);
+/* Per-kernel CUDA events are recorded on every 8th frame of a sequence only (they serialise the stream: ~10 us per frame;
+ * SO_TIMING_STRIDE=n in the environment changes the stride), so timing [1] and [2] above are sums over those frames.
+ * The exhaustive-search kernel alone (me_ring_kernel / me_tma_kernel) in the last so_seq_run: out[0] = summed event time of
+ * its timed launches (ms), out[1] = number of timed launches, out[2] = frames with per-kernel events, out[3] = frames of
+ * the run.  out[0] / out[1] is the per-launch duration bench.py's roofline uses. */
+int so_last_search_timing(so_ctx* ctx, double out[4]);
 
 /* Host-side text formatters, byte-identical to the reference's (Encoder.py:1419-1542 with canonical integers).
  * Return the number of bytes written (excluding the terminating NUL), or the required size (negative) when cap

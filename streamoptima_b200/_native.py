@@ -160,7 +160,9 @@ class Context:
     def last_timing(self):
         out = (C.c_double * 4)()
         check(self.handle, self.lib.so_last_timing(self.handle, out))
-        xs = (C.c_double * 2)()
+        xs = (C.c_double * 4)()
         check(self.handle, self.lib.so_last_search_timing(self.handle, xs))
+        # me_ms / tq_ms / search_ms are sums over the frames that carry per-kernel events (timed_frames of frames)
         return dict(device_ms=out[0], me_ms=out[1], tq_ms=out[2], launches=int(out[3]),
-                    me_launches=int(self.lib.so_last_me_launches(self.handle)), search_ms=xs[0], search_launches=int(xs[1]))
+                    me_launches=int(self.lib.so_last_me_launches(self.handle)), search_ms=xs[0], search_launches=int(xs[1]),
+                    timed_frames=int(xs[2]), frames=int(xs[3]))

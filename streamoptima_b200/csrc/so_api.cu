@@ -26,6 +26,20 @@
 static_assert(sizeof(so_params) == 64 && sizeof(so_frame_stats) == 32, "ABI struct layout (mirrored in _native.py)");
 static std::string g_create_err;
 
+// Launch with programmatic dependent launch (PDL): the grid may be scheduled while its predecessor in the stream is still
+// draining; the kernel itself waits (griddepcontrol.wait) before it touches anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool no_pdl = std::getenv("SO_NO_PDL") != nullptr;      // A/B switch
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 struct so_ctx {
     so_params p{};
     int device = 0;
@@ -89,6 +103,7 @@ struct so_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_me, ev_tq;
     std::vector<size_t> ev_xs;              // indices into ev_me of the exhaustive-search kernel launches
     bool timing_on = false;
+    int timed_frames = 0, total_frames = 0;    // frames of the last so_seq_run with / without per-kernel events
     const int* cur_qp_blocks = nullptr;     // per-block QPs of the frame being encoded (ROI extension)
     bool stats_prezeroed = false;           // so_seq_run zeroes the statistics of the whole sequence with one memset
 };
@@ -324,8 +339,8 @@ static int ring_push(so_ctx* ctx, const uint8_t* recon_dev, size_t src_unit_stri
     bool all_u8 = true;
     for (int l : ctx->list) all_u8 = all_u8 && ctx->slot_u8[l];
     const int wrap = (g.fme && all_u8) ? 1 : 0;
-    ring_planes_kernel<<<dim3((g.W / 4 + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, ctx->plane_bytes, recon_dev,
-                                                                              src_unit_stride, g.W, g.W, g.H, g.pitch, g.fme, wrap, 1);
+    CU(launch_pdl(ring_planes_kernel, dim3((g.W / 4 + 127) / 128, g.H, units), dim3(128), 0, st, slot_ptr(ctx, s), ctx->unit_stride,
+                  ctx->plane_bytes, recon_dev, src_unit_stride, g.W, g.W, g.H, g.pitch, g.fme, wrap, 1));
     ctx->launches++;
     CU(cudaGetLastError());
     ctx->slot_wrap[s] = wrap;
@@ -463,14 +478,17 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
         CU(cudaFuncSetAttribute(me_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
         attr_done[ctx->device & 15] = true;
     }
-    if (!ctx->me_work) CU(cudaMalloc(&ctx->me_work, 256));
+    if (!ctx->me_work) {      // {chunk counter, finished CTAs}: zero at every launch -- the last CTA of a launch resets both
+        CU(cudaMalloc(&ctx->me_work, 256));
+        CU(cudaMemsetAsync(ctx->me_work, 0, 256, st));
+    }
     a.work = ctx->me_work;
-    CU(cudaMemsetAsync(ctx->me_work, 0, sizeof(unsigned int), st));
     ev_pair(ctx, ctx->ev_me, st, true);
     if (ctx->timing_on) ctx->ev_xs.push_back(ctx->ev_me.size() - 1);
-    if (out_sub) me_ring_kernel<true><<<grid, 384, MR_SMEM, st>>>(map, cmap, a);
-    else me_ring_kernel<false><<<grid, 512, MR_SMEM, st>>>(map, cmap, a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (out_sub) e = launch_pdl(me_ring_kernel<true>, dim3(grid), dim3(384), MR_SMEM, st, map, cmap, a);
+    else e = launch_pdl(me_ring_kernel<false>, dim3(grid), dim3(512), MR_SMEM, st, map, cmap, a);
+    if (e == cudaSuccess) e = cudaGetLastError();
     ev_pair(ctx, ctx->ev_me, st, false);
     if (e != cudaSuccess) { set_err(ctx, std::string("me_ring_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
     ctx->launches++;
@@ -753,8 +771,8 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     dim3 grid(ctx->nblk, units);
     static const bool generic16 = std::getenv("SO_FINISH_GENERIC") != nullptr;      // tests: force the generic kernel
     if (g.bs == 16 && g.W % 16 == 0 && !generic16) {
-        if (a.vbs) inter_finish16_kernel<true><<<dim3((ctx->nblk + 7) / 8, units), 128, 0, st>>>(a);
-        else inter_finish16_kernel<false><<<dim3((ctx->nblk + 7) / 8, units), 128, 0, st>>>(a);
+        if (a.vbs) CU(launch_pdl(inter_finish16_kernel<true>, dim3((ctx->nblk + 7) / 8, units), dim3(128), 0, st, a));
+        else CU(launch_pdl(inter_finish16_kernel<false>, dim3((ctx->nblk + 7) / 8, units), dim3(128), 0, st, a));
     }
     else if (g.bs == 16) inter_finish_kernel<16><<<grid, nt, 0, st>>>(a);
     else if (g.bs == 8) inter_finish_kernel<8><<<grid, nt, 0, st>>>(a);
@@ -903,7 +921,13 @@ extern "C" int so_seq_run(so_ctx* ctx) {
     ctx->stats_prezeroed = true;
     struct Unflag { so_ctx* c; ~Unflag() { c->stats_prezeroed = false; } } unflag{ctx};
     std::vector<so_frame_stats> hstats(n_units);
+    // per-kernel CUDA events cost ~10 us of stream serialisation per frame (1.8 % of a 1080p P frame), so they are recorded on
+    // every timing_stride-th frame only (default 8; SO_TIMING_STRIDE=1 times every launch)
+    static const int timing_stride = std::getenv("SO_TIMING_STRIDE") ? std::max(1, atoi(std::getenv("SO_TIMING_STRIDE"))) : 8;
+    ctx->timed_frames = 0; ctx->total_frames = n_frames;
     for (int f = 0; f < n_frames; ++f) {
+        ctx->timing_on = (f % timing_stride) == 0;
+        if (ctx->timing_on) ctx->timed_frames++;
         if (ctx->pipe.active && f % ctx->pipe.chunk == 0) {
             const int c = f / ctx->pipe.chunk;
             if (c + 2 < ctx->pipe.nchunks) { rc = pipe_upload_chunk(ctx, c + 2); if (rc) return rc; }   // two chunks ahead
@@ -1208,13 +1232,14 @@ extern "C" int so_last_me_launches(so_ctx* ctx) {
     return rc ? rc : (int)ctx->timing[4];
 }
 
-// exhaustive-search kernels alone (me_ring_kernel / me_tma_kernel): out[0] = summed CUDA-event time (ms), out[1] = launches
-extern "C" int so_last_search_timing(so_ctx* ctx, double out[2]) {
+// exhaustive-search kernels alone (me_ring_kernel / me_tma_kernel): out[0] = summed CUDA-event time (ms) of the timed
+// launches, out[1] = timed launches, out[2] = frames with per-kernel events, out[3] = frames of the run
+extern "C" int so_last_search_timing(so_ctx* ctx, double out[4]) {
     double t[4];
     if (!ctx || !out) return SO_E_INVALID;
     int rc = so_last_timing(ctx, t);
     if (rc) return rc;
-    out[0] = ctx->timing[5]; out[1] = ctx->timing[6];
+    out[0] = ctx->timing[5]; out[1] = ctx->timing[6]; out[2] = (double)ctx->timed_frames; out[3] = (double)ctx->total_frames;
     return SO_OK;
 }
 

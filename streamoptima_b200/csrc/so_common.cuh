@@ -42,6 +42,12 @@ struct __align__(8) MeResult {
     uint32_t sad;      // SAD of the winner; for fast ME the reference returns the ref index as "MAE" (quirk Q4)
 };
 
+// Programmatic dependent launch: pdl_trigger() lets the next kernel of the stream be scheduled once every CTA of this grid
+// has called it (or exited); pdl_wait() blocks until the previous kernel of the stream has completed and its writes are
+// visible.  Both are no-ops for a grid launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t acc) {
     uint32_t d;
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));

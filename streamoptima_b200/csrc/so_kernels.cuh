@@ -18,6 +18,8 @@
 // phase 0 / shift 0), or the slot's own phase-0 plane when only the wrap mode changed (write_p0 = 0).
 __global__ void ring_planes_kernel(uint8_t* slot0, size_t unit_stride, size_t plane_bytes, const uint8_t* src, size_t src_unit_stride,
                                    int src_pitch, int W, int H, int pitch, int fme, int wrap, int write_p0) {
+    pdl_trigger();
+    pdl_wait();
     const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int x = x4 * 4;
@@ -350,6 +352,8 @@ template <bool VBS>
 __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
     constexpr int BS = 16, S = 8, P = 17;
     __shared__ double tiles[4][2][BS * P];
+    pdl_trigger();
+    pdl_wait();
     const FrameGeom& g = a.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = lane >> 4, r = lane & 15;
@@ -412,10 +416,13 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
     }
 #pragma unroll
     for (int i = 0; i < BS; ++i) ws[r * P + i] = (double)(c[i] - predp[i]);
-    __syncwarp();
-    dct1d<BS>(ws + r, P);                      // column r
-    __syncwarp();
-    dct1d<BS>(ws + r * P, 1);                  // row r
+    // column r, then row r: one copy of the straight-line transform in the instruction stream (the kernel is latency-bound
+    // and its code does not fit the instruction cache when every pass is inlined separately)
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncwarp();
+        dct1d<BS>(pass ? ws + r * P : ws + r, pass ? 1 : P);
+    }
     int tcp[BS];
 #pragma unroll
     for (int i = 0; i < BS; ++i) tcp[i] = (int)rint(ws[r * P + i]);
@@ -535,10 +542,13 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
         lp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         lp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
-    __syncwarp();
-    if (split) { idct1d<S>(ws + r, P); idct1d<S>(ws + S * P + r, P); } else idct1d<BS>(ws + r, P);
-    __syncwarp();
-    if (split) { idct1d<S>(ws + r * P, 1); idct1d<S>(ws + r * P + S, 1); } else idct1d<BS>(ws + r * P, 1);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncwarp();
+        double* p0 = pass ? ws + r * P : ws + r;
+        const int stp = pass ? 1 : P;
+        if (VBS && split) { idct1d<S>(p0, stp); idct1d<S>(p0 + (pass ? S : S * P), stp); } else idct1d<BS>(p0, stp);
+    }
     unsigned long long se = 0;
     {
         uint32_t pk[4] = {0, 0, 0, 0};

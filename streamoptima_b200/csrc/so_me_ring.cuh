@@ -42,7 +42,7 @@ struct MeRingArgs {
     int z_per_unit;              // planes per unit in the ring tensor = nslots * 16
     int z_unit0;                 // plane offset of unit 0 of this launch
     unsigned int slot_packed;    // list index -> ring slot, 4 bits each
-    unsigned int* work;          // device-wide chunk counter, zero at launch
+    unsigned int* work;          // [0] device-wide chunk counter, [1] finished CTAs; both zero at launch, reset by the last CTA
 };
 
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
         *final_cnt = 0x7FFFFFFF;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();          // everything below reads what earlier kernels of the stream wrote (ring planes, keys, the work counter)
 
     const long long total = (long long)a.units * a.items_per_unit;
     const int nchunks = (int)((total + MR_CHUNK - 1) / MR_CHUNK);
@@ -142,9 +144,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
             q = __shfl_sync(0xFFFFFFFFu, qn, 0);
         }
         if (lane == 0) *final_cnt = n;          // no item with local index >= n will ever exist
-        return;
-    }
-
+    } else {
     // ================================= search warps =================================
     unsigned b = 0;
     if (lane == 0) b = atomicAdd(counter, 1u);
@@ -485,5 +485,12 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
             if (two) mbar_arrive_cnt(&empty[slot1], 32u - c0);
         }
         b = __shfl_sync(0xFFFFFFFFu, nb, 0);
+    }
+    }   // search warps
+    // the last CTA to get here resets the device-wide counters for the next launch (every producer has stopped fetching)
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(a.work + 1, 1u);
+        if (prev == gridDim.x - 1) { a.work[0] = 0u; a.work[1] = 0u; }
     }
 }

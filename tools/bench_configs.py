@@ -29,7 +29,7 @@ def run(name, U, F, H, W, args, kw, reps=2):
         dev_ms += c.last_timing["device_ms"]
     wall = (time.perf_counter() - t0) / reps
     out = dict(config=name, units=U, frames=F, size=f"{W}x{H}", fps_kernel=U * F / (dev_ms / reps / 1e3), fps_e2e=U * F / wall,
-               me_ms_per_frame=c.last_timing["me_ms"] / (U * F), launches=c.last_timing["launches"])
+               me_ms_per_frame=c.last_timing["me_ms"] / max(1, c.last_timing["timed_frames"]) / U, launches=c.last_timing["launches"])
     print(json.dumps(out), flush=True)
     c._ctx.close()
 

@@ -14,5 +14,5 @@ for (F, H, W, U, kw) in ((20, 1088, 1920, 1, dict(fast_me=True, FMEEnable=True, 
     for _ in range(2):
         c.encode_arrays(frames)
     t = c.last_timing
-    print(H, W, U, kw, {k: round(v / F, 4) for k, v in t.items() if k.endswith("_ms")}, "ms/frame ->", round(U * F / t["device_ms"] * 1e3, 1), "fps")
+    print(H, W, U, kw, {k: round(v / (F if k == "device_ms" else max(1, t["timed_frames"])), 4) for k, v in t.items() if k.endswith("_ms")}, "ms/frame ->", round(U * F / t["device_ms"] * 1e3, 1), "fps")
     c._ctx.close()

@@ -10,4 +10,4 @@ c = Y_Video_codec(H, W, F, 16, 16, 4, 1, 0, y_only_frame_arr=frames)
 for _ in range(3):
     c.encode_arrays(frames)
 t = c.last_timing
-print({k: (round(v / F, 4) if k.endswith("_ms") else v) for k, v in t.items()}, "per frame (ms)")
+print({k: (round(v / (F if k == "device_ms" else max(1, t["timed_frames"])), 4) if k.endswith("_ms") else v) for k, v in t.items()}, "per frame (ms)")
