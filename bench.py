@@ -251,8 +251,9 @@ def main():
     for k in range(args.warmup):
         step_resident(k)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank)          # rank 0 samples its own GPU; the other ranks do not spawn nvidia-smi
+    if rank == 0:
+        sampler.start()
     t0 = time.perf_counter()
     dev_ms = me_ms = tq_ms = xs_ms = 0.0
     launches = me_launches = xs_launches = timed_frames = 0
@@ -264,7 +265,8 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
-    sampler.join()
+    if rank == 0:
+        sampler.join()
 
     # ---- end to end through the public API: host frames in, host results out, copies inside the timed region
     for k in range(min(args.warmup, 2)):

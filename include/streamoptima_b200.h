@@ -200,6 +200,13 @@ int64_t so_format_mv_frame(int frame_type, const uint8_t* split, const int16_t* 
 int64_t so_format_residual_frame(const uint8_t* split, const int16_t* levels, int width, int height, int block_size,
                                  char* dst, int64_t cap);
 
+/* transmit_bitstream (Encoder.py:1544-1573) for a whole sequence: both text files, frames formatted in parallel on host
+ * threads (n_threads <= 0: hardware concurrency) and written in order; byte-identical to joining the per-frame formatters
+ * with '\n'.  qp_rows_per_frame i32 [n_frames][height / block_size] or NULL.  Host only: no device needed. */
+int so_write_bitstream_files(const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
+                             const int32_t* qp_rows_per_frame, int n_frames, int width, int height, int block_size,
+                             const char* mv_path, const char* residual_path, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -427,11 +427,21 @@ class Y_Video_codec:
         if not self.encoded_package_f:
             print("[ERROR] No encoded package available, please run encode() first")
             return
-        mv_lines, res_lines = self.bitstream_lines()
-        with open(mv_file, "w") as f:
-            f.write("".join(l + "\n" for l in mv_lines))
-        with open(residual_file, "w") as f:
-            f.write("".join(l + "\n" for l in res_lines))
+        # both files are written by the library: frames are formatted in parallel on host threads (so_write_bitstream_files);
+        # byte-identical to joining bitstream_lines() with newlines
+        pkg = self.encoded_package if self.encoded_package is not None else self._last_package
+        p = pkg.packed
+        F, H, W = p["levels"].shape
+        qp = pkg["Qp_per_row_per_frame"]
+        qp_arr = np.ascontiguousarray(qp, np.int32) if len(qp) and len(qp[0]) else None
+        lib = _native.load()
+        ft, sp = np.ascontiguousarray(p["frame_types"], np.uint8), np.ascontiguousarray(p["split"], np.uint8)   # kept alive
+        mvs, lev = np.ascontiguousarray(p["mv"], np.int16), np.ascontiguousarray(p["levels"], np.int16)         # across the call
+        rc = lib.so_write_bitstream_files(ft.ctypes.data, sp.ctypes.data, mvs.ctypes.data, lev.ctypes.data,
+                                          qp_arr.ctypes.data if qp_arr is not None else None, F, W, H, pkg["block size"],
+                                          os.fsencode(mv_file), os.fsencode(residual_file), 0)
+        if rc != 0:
+            raise OSError(f"cannot write the bitstream files {mv_file!r} / {residual_file!r}")
         if os.path.isdir("files"):       # debug dump of the reference (Encoder.py:1559,1568); only when ./files exists
             with open("files/mvs_per_frame_raw.txt", "w") as f:
                 pkg = self.encoded_package if self.encoded_package is not None else self._last_package

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "so_kernels.cuh"
@@ -1348,6 +1349,56 @@ extern "C" int64_t so_format_residual_frame(const uint8_t* split, const int16_t*
         }
     }
     return o.finish();
+}
+
+// Whole-sequence text bitstream (transmit_bitstream, Encoder.py:1544-1573 with the parseable residual format): every frame
+// is formatted by the per-frame formatters above on a pool of host threads, the two files are written in frame order.
+// qp_rows_per_frame i32 [n_frames][height / block_size] or NULL (RCFlag off).  n_threads <= 0: hardware concurrency.
+extern "C" int so_write_bitstream_files(const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
+                                        const int32_t* qp_rows_per_frame, int n_frames, int width, int height, int block_size,
+                                        const char* mv_path, const char* residual_path, int n_threads) {
+    if (!frame_types || !split || !mv || !levels || !mv_path || !residual_path || n_frames < 1 || block_size < 2 ||
+        width % block_size || height % block_size) return SO_E_INVALID;
+    const int nbx = width / block_size, nby = height / block_size, nblk = nbx * nby;
+    const size_t px = (size_t)width * height;
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::min(n_frames, 64)));
+    FILE* fm = fopen(mv_path, "wb");
+    FILE* fr = fopen(residual_path, "wb");
+    if (!fm || !fr) { if (fm) fclose(fm); if (fr) fclose(fr); return SO_E_INVALID; }
+    auto fmt = [](auto&& call, size_t guess, std::string& out) {
+        out.resize(guess);
+        int64_t n = call(&out[0], (int64_t)out.size());
+        if (n < 0) { out.resize((size_t)(-n) + 16); n = call(&out[0], (int64_t)out.size()); }
+        out.resize((size_t)std::max<int64_t>(n, 0));
+    };
+    bool ok = true;
+    // batches of nt frames: format in parallel, then write in order (bounds the memory held as text)
+    std::vector<std::string> mvt(nt), rst(nt);
+    for (int f0 = 0; f0 < n_frames && ok; f0 += nt) {
+        const int nb = std::min(nt, n_frames - f0);
+        std::vector<std::thread> th;
+        for (int i = 0; i < nb; ++i) {
+            th.emplace_back([&, i]() {
+                const int f = f0 + i;
+                const uint8_t* sp = split + (size_t)f * nblk;
+                const int16_t* m = mv + (size_t)f * nblk * 12;
+                const int16_t* lv = levels + (size_t)f * px;
+                const int32_t* qp = qp_rows_per_frame ? qp_rows_per_frame + (size_t)f * nby : nullptr;
+                fmt([&](char* d, int64_t c) { return so_format_mv_frame(frame_types[f], sp, m, nblk, nbx, qp, d, c); }, 64 + (size_t)nblk * 48, mvt[i]);
+                fmt([&](char* d, int64_t c) { return so_format_residual_frame(sp, lv, width, height, block_size, d, c); }, 1024 + px / 2, rst[i]);
+            });
+        }
+        for (auto& t : th) t.join();
+        for (int i = 0; i < nb; ++i) {
+            mvt[i].push_back('\n'); rst[i].push_back('\n');
+            ok = ok && fwrite(mvt[i].data(), 1, mvt[i].size(), fm) == mvt[i].size();
+            ok = ok && fwrite(rst[i].data(), 1, rst[i].size(), fr) == rst[i].size();
+        }
+    }
+    ok = (fclose(fm) == 0) && ok;
+    ok = (fclose(fr) == 0) && ok;
+    return ok ? SO_OK : SO_E_INVALID;
 }
 
 #ifdef SO_ME_DEBUG

@@ -72,3 +72,26 @@ def test_lazy_package_matches_reference_structure():
     np.testing.assert_array_equal(split, g["split"])
     np.testing.assert_array_equal(mv, g["mv"])
     np.testing.assert_array_equal(levels, g["levels"])
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_sequence_bitstream_writer_matches_reference_files(name, tmp_path):
+    """so_write_bitstream_files (multi-threaded whole-sequence writer behind transmit_bitstream) against the reference's
+    own text streams for every golden case."""
+    lib = _lib()
+    frames, enc, g = load_case(name)
+    F, H, W = frames.shape
+    bs = enc["block_size"]
+    ft = np.ascontiguousarray(g["frame_types"], np.uint8)
+    split = np.ascontiguousarray(g["split"], np.uint8)
+    mv = np.ascontiguousarray(g["mv"], np.int16)
+    lev = np.ascontiguousarray(g["levels"], np.int16)
+    rc_on = (g["qp_rows"] >= 0).any()
+    qp = np.ascontiguousarray(g["qp_rows"], np.int32) if rc_on else None
+    mvf, rsf = tmp_path / "mv.txt", tmp_path / "res.txt"
+    for threads in (1, 3):
+        rc = lib.so_write_bitstream_files(ft.ctypes.data, split.ctypes.data, mv.ctypes.data, lev.ctypes.data,
+                                          qp.ctypes.data if qp is not None else None, F, W, H, bs, os.fsencode(mvf), os.fsencode(rsf), threads)
+        assert rc == 0
+        assert open(mvf).read() == g["mv_text"]
+        assert open(rsf).read() == g["res_text"]
