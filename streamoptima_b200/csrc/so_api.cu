@@ -189,7 +189,6 @@ extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
     if (p->qp < 0 || p->qp > 15) return bad("qp out of range");
     if (p->parallel_mode < 0 || p->parallel_mode > 2) return bad("parallel_mode must be 0, 1 or 2 (3 is broken in the reference)");
     if (p->rc_flag < 0 || p->rc_flag > 2) return bad("rc_flag must be 0, 1 or 2");
-    if ((p->flags & SO_FLAG_VBS) && p->block_size == 4) return bad("VBS with block_size 4 (2x2 sub-blocks) is not supported");
     if ((p->flags & SO_FLAG_VBS) && (p->flags & SO_FLAG_FAST_ME) && p->parallel_mode != 0)
         return bad("VBS + fast_me in ParallelMode 1/2 raises UnboundLocalError in the reference (Encoder.py:616)");
     if (p->intra_dur < 1) return bad("intra_dur must be >= 1");
@@ -500,6 +499,24 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
 // geometry allowed it (16x16 blocks, DIRECT staging) -- otherwise the caller runs a second search on the sub-block grid
 static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
                       size_t out_stride, cudaStream_t st, MeResult* out_sub = nullptr, size_t out_sub_stride = 0, bool* used_quad = nullptr) {
+    static const bool force_simple = std::getenv("SO_ME_SIMPLE") != nullptr;      // tests: cross-check of the packed kernels
+    if (bs < 4 || force_simple) {
+        // 2x2 sub-blocks of VBS with block_size 4 (or the test switch): plain one-warp-per-block search
+        if (used_quad) *used_quad = false;
+        FlowArgs f{};
+        f.g = ctx->g; f.g.nref = (int)ctx->list.size();
+        f.unit0 = unit0;
+        f.cur = cur; f.cur_unit_stride = cur_stride;
+        f.ring = make_ring(ctx);
+        const int nb = (ctx->g.W / bs) * (ctx->g.H / bs);
+        ev_pair(ctx, ctx->ev_me, st, true);
+        if (ctx->timing_on) ctx->ev_xs.push_back(ctx->ev_me.size() - 1);
+        me_simple_kernel<<<dim3((nb + 3) / 4, units), 128, 0, st>>>(f, bs, out, out_stride);
+        ev_pair(ctx, ctx->ev_me, st, false);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        return SO_OK;
+    }
     MeTmaArgs a{};
     a.g = ctx->g;
     a.g.bs = bs; a.g.nbx = ctx->g.W / bs; a.g.nby = ctx->g.H / bs;

@@ -185,6 +185,54 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Plain exhaustive search, one warp per block, any block size >= 2 (find_best_match, Encoder.py:678-717).  Lanes stride
+// over the candidates (ref, dx, dy); the packed 64-bit key (SAD, |dx|+|dy|, ref, dx, dy) carries the reference's replace
+// rule (appendix A4), so the visiting order is free.  It serves the 2x2 sub-blocks of VBS with block_size 4, which are
+// too narrow for the word-packed kernels, and (SO_ME_SIMPLE=1) as an independent cross-check of those kernels in tests.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) me_simple_kernel(const FlowArgs a, int bs, MeResult* out, size_t out_unit_stride) {
+    const FrameGeom& g = a.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nbx = g.W / bs, nby = g.H / bs;
+    const int blk = blockIdx.x * 4 + warp, unit = a.unit0 + blockIdx.y;
+    if (blk >= nbx * nby) return;
+    const int bx = blk % nbx, by = blk / nbx;
+    const int x = bx * bs, y = by * bs;
+    const int mult = g.fme ? 2 : 1;
+    int xlo, xhi, ylo, yhi;
+    valid_range(x, g.W, bs, g.fme, g.fme, xlo, xhi);
+    valid_range(y, g.H, bs, g.fme, g.fme, ylo, yhi);
+    xlo = max(xlo, -g.R); xhi = min(xhi, g.R);
+    ylo = max(ylo, -g.R); yhi = min(yhi, g.R);
+    const uint8_t* cur = a.cur + unit * a.cur_unit_stride + (size_t)y * g.W + x;
+    unsigned long long best = ~0ull;
+    const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
+    if (nx > 0 && ny > 0) {
+        const int per_ref = nx * ny, total = per_ref * g.nref;
+        for (int c = lane; c < total; c += 32) {
+            const int ref = c / per_ref, rem = c - ref * per_ref;
+            const int dx = xlo + rem / ny, dy = ylo + rem % ny;
+            const int Xh = x * mult + dx, Yh = y * mult + dy;
+            const int ph = g.fme ? (((Yh & 1) << 1) | (Xh & 1)) : 0;
+            const int X0 = g.fme ? (Xh >> 1) : Xh, Y0 = g.fme ? (Yh >> 1) : Yh;
+            const uint8_t* pl = a.ring.plane(unit, ref, ph) + (size_t)Y0 * g.pitch + X0;
+            unsigned sad = 0;
+            for (int j = 0; j < bs; ++j)
+                for (int i = 0; i < bs; ++i) sad += (unsigned)abs((int)cur[(size_t)j * g.W + i] - (int)pl[(size_t)j * g.pitch + i]);
+            const unsigned long long key = ((unsigned long long)sad << 40) | ((unsigned long long)(abs(dx) + abs(dy)) << 24) |
+                                           ((unsigned long long)ref << 16) | ((unsigned long long)(dx + g.R) << 8) | (unsigned long long)(dy + g.R);
+            best = key < best ? key : best;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        best = other < best ? other : best;
+    }
+    if (lane == 0) *reinterpret_cast<unsigned long long*>(out + unit * out_unit_stride + blk) = best;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // inter finish: residual -> DCT -> [VBS RD decision] -> quant -> RLE size -> dequant -> IDCT -> reconstruct
 // (inter_prediction tail Encoder.py:564-581, complete_inter_flow :1680-1697, reconstruct_frame :831-932)
 // one CTA per block, one thread per pixel (blockDim = max(BS*BS, 32); extra threads are inactive pixels)

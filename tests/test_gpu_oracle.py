@@ -217,3 +217,37 @@ def test_fast_me16_kernel_equals_generic():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1]
+
+
+_SIMPLE_SCRIPT = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+from streamoptima_b200 import synth
+from streamoptima_b200.Encoder import Y_Video_codec
+Y_Video_codec.write_recon_yuv = False
+h = hashlib.sha256()
+for (F, H, W, bs, r, kw) in ((4, 96, 128, 16, 16, dict(FMEEnable=True, nRefFrames=3, VBSEnable=True, lam=0.02)),
+                             (3, 96, 128, 16, 16, dict(nRefFrames=2)),
+                             (3, 64, 96, 8, 5, dict(FMEEnable=True, VBSEnable=True, lam=0.03)),
+                             (3, 64, 96, 16, 24, dict(FMEEnable=True))):
+    frames = synth.flat_ties(F, H, W, seed=14)
+    c = Y_Video_codec(H, W, F, bs, r, 2, 8, 0, y_only_frame_arr=frames, **kw)
+    c.encode()
+    p = c.encoded_package.packed
+    for k in ("split", "mv", "levels", "recon"):
+        h.update(np.ascontiguousarray(p[k]).tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_packed_search_kernels_equal_plain_search():
+    """The word-packed TMA search kernels (item ring, stage-based, fused VBS, search chunks) against the plain
+    one-warp-per-block search (me_simple_kernel, SO_ME_SIMPLE=1) on tie-heavy input: identical vectors, levels, frames."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {"SO_ME_SIMPLE": "1"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", _SIMPLE_SCRIPT % root], capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
