@@ -466,10 +466,17 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
     for (int i = 0; i < BS; ++i) ws[r * P + i] = (double)(c[i] - predp[i]);
     // column r, then row r: one copy of the straight-line transform in the instruction stream (the kernel is latency-bound
     // and its code does not fit the instruction cache when every pass is inlined separately)
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
+    if constexpr (VBS) {                       // the VBS variant is register-bound: run-time strides cost it 29 registers
         __syncwarp();
-        dct1d<BS>(pass ? ws + r * P : ws + r, pass ? 1 : P);
+        dct1d<BS>(ws + r, P);
+        __syncwarp();
+        dct1d<BS>(ws + r * P, 1);
+    } else {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            __syncwarp();
+            dct1d<BS>(pass ? ws + r * P : ws + r, pass ? 1 : P);
+        }
     }
     int tcp[BS];
 #pragma unroll
@@ -590,12 +597,17 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
         lp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         lp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
+    if constexpr (VBS) {
         __syncwarp();
-        double* p0 = pass ? ws + r * P : ws + r;
-        const int stp = pass ? 1 : P;
-        if (VBS && split) { idct1d<S>(p0, stp); idct1d<S>(p0 + (pass ? S : S * P), stp); } else idct1d<BS>(p0, stp);
+        if (split) { idct1d<S>(ws + r, P); idct1d<S>(ws + S * P + r, P); } else idct1d<BS>(ws + r, P);
+        __syncwarp();
+        if (split) { idct1d<S>(ws + r * P, 1); idct1d<S>(ws + r * P + S, 1); } else idct1d<BS>(ws + r * P, 1);
+    } else {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            __syncwarp();
+            idct1d<BS>(pass ? ws + r * P : ws + r, pass ? 1 : P);
+        }
     }
     unsigned long long se = 0;
     {
