@@ -238,108 +238,99 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
             }
             uint32_t bq[5] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // parent, TL, TR, BL, BR
             const bool fast_valid = __all_sync(0xFFFFFFFFu, (mt.w >> 16) & 1);
-            if (fast_valid) {
-                // interior block: parent and sub-blocks share the two special cases (ox = 16 on odd horizontal phases, oy = 16
-                // on odd vertical ones); keys are folded rows-first like in the plain search (3 IMAD + min3 + add per column)
-                const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;
-                const uint32_t ybl = (grp == MR_NG - 1 && py) ? 0xFFFFFFFFu : 0u;
-                uint32_t ly8[3], lx8[9];
+            // distance parts of the keys
+            uint32_t ly8[3], lx8[9];
 #pragma unroll
-                for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
+            for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative
-                    lx8[k] = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
-                }
-                auto fold = [&](uint32_t s0, uint32_t s1, uint32_t s2, int k) {
-                    const uint32_t t0 = s0 * 65536u + ly8[0], t1 = s1 * 65536u + ly8[1], t2 = (s2 * 65536u + ly8[2]) | ybl;
-                    uint32_t v = min(min(t0, t1), t2) + lx8[k];
-                    if (k == 8) v |= xbl;
-                    return v;
-                };
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t aL[3][8], aR[3][8];
-#pragma unroll
-                    for (int gg = 0; gg < 3; ++gg)
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) { aL[gg][k] = 0; aR[gg][k] = 0; }
-                    sad_pass_g3<WPR, 8, 8, BS / 2, MR_WP, true>(win + half * (BS / 2) * MR_WP, cb + half * (BS / 2) * WPR, aL, aR);
-                    uint32_t bl = fold(exq[1 + 2 * half][0], exq[1 + 2 * half][1], exq[1 + 2 * half][2], 8);
-                    uint32_t br = fold(exq[2 + 2 * half][0], exq[2 + 2 * half][1], exq[2 + 2 * half][2], 8);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        bl = min(bl, fold(aL[0][k], aL[1][k], aL[2][k], k));
-                        br = min(br, fold(aR[0][k], aR[1][k], aR[2][k], k));
-#pragma unroll
-                        for (int gg = 0; gg < 3; ++gg) par[gg][k] += aL[gg][k] + aR[gg][k];
-                    }
-                    bq[1 + half * 2] = bl; bq[2 + half * 2] = br;
-                }
-                uint32_t bp = fold(exq[0][0], exq[0][1], exq[0][2], 8);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) bp = min(bp, fold(par[0][k], par[1][k], par[2][k], k));
-                bq[0] = bp;
-            } else {
-            // validity masks: parent and sub-blocks have different rectangles (Encoder.py:695-698 with their own size / position)
-            uint32_t lyk[3], lxk[9];
-            uint32_t ybadP[3], ybadT[3], ybadB[3], xbadP[9], xbadL[9], xbadR[9];
-            {
-                int l0, h0, l1, h1, l2, h2;
-                valid_range(by * BS, g.H, BS, g.fme, g.fme, l0, h0);
-                valid_range(by * BS, g.H, BS / 2, g.fme, g.fme, l1, h1);
-                valid_range(by * BS + BS / 2, g.H, BS / 2, g.fme, g.fme, l2, h2);
-#pragma unroll
-                for (int gg = 0; gg < 3; ++gg) {
-                    const int dy = mul * (oy0 + gg) + py;
-                    const bool in = dy >= -g.R && dy <= g.R;
-                    lyk[gg] = (uint32_t)(abs(dy) << 8) + gg;
-                    ybadP[gg] = (in && dy >= l0 && dy <= h0) ? 0u : 0xFFFFFFFFu;
-                    ybadT[gg] = (in && dy >= l1 && dy <= h1) ? 0u : 0xFFFFFFFFu;
-                    ybadB[gg] = (in && dy >= l2 && dy <= h2) ? 0u : 0xFFFFFFFFu;
-                }
-                valid_range(bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
-                valid_range(bx * BS, g.W, BS / 2, g.fme, g.fme, l1, h1);
-                valid_range(bx * BS + BS / 2, g.W, BS / 2, g.fme, g.fme, l2, h2);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const int dx = mul * (-16 + c + 4 * k) + px;
-                    const bool in = (k < 8 || c == 0) && dx >= -g.R && dx <= g.R;
-                    lxk[k] = (uint32_t)(abs(dx) << 8) + k * 3;
-                    xbadP[k] = (in && dx >= l0 && dx <= h0) ? 0u : 0xFFFFFFFFu;
-                    xbadL[k] = (in && dx >= l1 && dx <= h1) ? 0u : 0xFFFFFFFFu;
-                    xbadR[k] = (in && dx >= l2 && dx <= h2) ? 0u : 0xFFFFFFFFu;
-                }
+            for (int k = 0; k < 9; ++k) {
+                const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative
+                lx8[k] = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
             }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            // interior block: parent and sub-blocks share the two special cases (ox = 16 on odd horizontal phases, oy = 16
+            // on odd vertical ones); keys are folded rows-first like in the plain search (3 IMAD + min3 + add per column)
+            const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;
+            const uint32_t ybl = (grp == MR_NG - 1 && py) ? 0xFFFFFFFFu : 0u;
+            auto fold = [&](uint32_t s0, uint32_t s1, uint32_t s2, int k) {
+                const uint32_t t0 = s0 * 65536u + ly8[0], t1 = s1 * 65536u + ly8[1], t2 = (s2 * 65536u + ly8[2]) | ybl;
+                uint32_t v = min(min(t0, t1), t2) + lx8[k];
+                if (k == 8) v |= xbl;
+                return v;
+            };
+            // edge block: parent and sub-blocks have their own rectangles (Encoder.py:695-698 with their own size / position)
+            auto xbad = [&](int k, int pos, int n) {
+                int l, h;
+                valid_range(pos, g.W, n, g.fme, g.fme, l, h);
+                const int dx = mul * (-16 + c + 4 * k) + px;
+                return ((k < 8 || c == 0) && dx >= -g.R && dx <= g.R && dx >= l && dx <= h) ? 0u : 0xFFFFFFFFu;
+            };
+            auto ybad = [&](int gg, int pos, int n) {
+                int l, h;
+                valid_range(pos, g.H, n, g.fme, g.fme, l, h);
+                const int dy = mul * (oy0 + gg) + py;
+                return (dy >= -g.R && dy <= g.R && dy >= l && dy <= h) ? 0u : 0xFFFFFFFFu;
+            };
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {            // rolled: one copy of the SAD pass in the instruction stream
                 uint32_t aL[3][8], aR[3][8];
 #pragma unroll
                 for (int gg = 0; gg < 3; ++gg)
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { aL[gg][k] = 0; aR[gg][k] = 0; }
                 sad_pass_g3<WPR, 8, 8, BS / 2, MR_WP, true>(win + half * (BS / 2) * MR_WP, cb + half * (BS / 2) * WPR, aL, aR);
+                uint32_t eL[3], eR[3];
 #pragma unroll
-                for (int k = 0; k < 9; ++k)
+                for (int gg = 0; gg < 3; ++gg) { eL[gg] = half ? exq[3][gg] : exq[1][gg]; eR[gg] = half ? exq[4][gg] : exq[2][gg]; }
+                uint32_t bl = 0xFFFFFFFFu, br = 0xFFFFFFFFu;
+                if (fast_valid) {
+                    bl = fold(eL[0], eL[1], eL[2], 8);
+                    br = fold(eR[0], eR[1], eR[2], 8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        bl = min(bl, fold(aL[0][k], aL[1][k], aL[2][k], k));
+                        br = min(br, fold(aR[0][k], aR[1][k], aR[2][k], k));
+                    }
+                } else {
+                    uint32_t yb[3];
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg) yb[gg] = ybad(gg, by * BS + half * (BS / 2), BS / 2);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const uint32_t xl = xbad(k, bx * BS, BS / 2), xr = xbad(k, bx * BS + BS / 2, BS / 2);
+#pragma unroll
+                        for (int gg = 0; gg < 3; ++gg) {
+                            const uint32_t l1v = lx8[k] + ly8[gg];
+                            const uint32_t sl = k < 8 ? aL[gg][k < 8 ? k : 0] : eL[gg], sr = k < 8 ? aR[gg][k < 8 ? k : 0] : eR[gg];
+                            bl = min(bl, (sl * 65536u + l1v) | xl | yb[gg]);
+                            br = min(br, (sr * 65536u + l1v) | xr | yb[gg]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg) par[gg][k] += aL[gg][k] + aR[gg][k];
+                if (half == 0) { bq[1] = bl; bq[2] = br; } else { bq[3] = bl; bq[4] = br; }
+            }
+            if (fast_valid) {
+                uint32_t bp = fold(exq[0][0], exq[0][1], exq[0][2], 8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bp = min(bp, fold(par[0][k], par[1][k], par[2][k], k));
+                bq[0] = bp;
+            } else {
+                uint32_t yb[3];
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) yb[gg] = ybad(gg, by * BS, BS);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const uint32_t xp = xbad(k, bx * BS, BS);
 #pragma unroll
                     for (int gg = 0; gg < 3; ++gg) {
-                        const uint32_t l1v = lxk[k] + lyk[gg];
-                        const uint32_t yb = half ? ybadB[gg] : ybadT[gg];
-                        const uint32_t sl = k < 8 ? aL[gg][k < 8 ? k : 0] : exq[1 + 2 * half][gg];
-                        const uint32_t sr = k < 8 ? aR[gg][k < 8 ? k : 0] : exq[2 + 2 * half][gg];
-                        bq[1 + half * 2] = min(bq[1 + half * 2], (sl * 65536u + l1v) | xbadL[k] | yb);
-                        bq[2 + half * 2] = min(bq[2 + half * 2], (sr * 65536u + l1v) | xbadR[k] | yb);
-                        if (k < 8) par[gg][k < 8 ? k : 0] += sl + sr;
+                        const uint32_t sp = k < 8 ? par[gg][k < 8 ? k : 0] : exq[0][gg];
+                        bq[0] = min(bq[0], (sp * 65536u + (lx8[k] + ly8[gg])) | xp | yb[gg]);
                     }
-            }
-#pragma unroll
-            for (int k = 0; k < 9; ++k)
-#pragma unroll
-                for (int gg = 0; gg < 3; ++gg) {
-                    const uint32_t sp = k < 8 ? par[gg][k < 8 ? k : 0] : exq[0][gg];
-                    bq[0] = min(bq[0], (sp * 65536u + (lxk[k] + lyk[gg])) | xbadP[k] | ybadP[gg]);
                 }
-            }   // generic validity
+            }
             // ---- merge: five keys per segment
 #pragma unroll
             for (int e = 0; e < 5; ++e) {
