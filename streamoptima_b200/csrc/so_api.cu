@@ -64,6 +64,8 @@ struct so_ctx {
     int* qp_rows_dev = nullptr;
     std::vector<int> qp_rows;
     unsigned int* me_work = nullptr;        // chunk counter of the item-ring search kernel
+    uint16_t* fm_table = nullptr;           // fast ME: whole-block SAD tables around the previous frame's predictors
+    short4* fm_state = nullptr;             // fast ME: predictor (x, y, ref) every block used in the last P frame, [batch][nblk]
     int* qp_blocks_dev = nullptr;           // ROI extension: [frames][nblk] per-block QPs of the next sequence, or nullptr
     int qp_blocks_frames = 0;
     // sequence buffers
@@ -165,7 +167,7 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     free_seq(c);
     cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->in_parent); cudaFree(c->in_sub);
     cudaFree(c->res_frame); cudaFree(c->band);
-    cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev); cudaFree(c->me_work);
+    cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev); cudaFree(c->me_work); cudaFree(c->fm_table); cudaFree(c->fm_state);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto b : c->pipe.stage) if (b) cudaFreeHost(b);
     for (auto e : c->pipe.up) cudaEventDestroy(e);
@@ -769,7 +771,30 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
         ev_pair(ctx, ctx->ev_me, st, true);
         dim3 grid(a.chain ? 1 : ctx->nblk, units);
         static const bool fast_generic = std::getenv("SO_FAST_GENERIC") != nullptr;      // tests: force the generic kernel
-        if (g.bs == 16 && g.W % 16 == 0 && !fast_generic) fast_me16_kernel<<<grid, 576, 0, st>>>(a);
+        static const bool fast_no_table = std::getenv("SO_FAST_NO_TABLE") != nullptr;    // A/B: chained fast_me16_kernel
+        if (g.bs == 16 && g.W % 16 == 0 && !fast_generic && a.chain && !fast_no_table) {
+            // table-driven chain: SAD tables around last frame's predictors -> one-warp walk -> parallel results
+            const int tper = (ctx->p.n_ref_frames * FT_N * FT_N + 7) & ~7;          // entries per block, 16-byte granules
+            if (!ctx->fm_table) {
+                CU(cudaMalloc(&ctx->fm_table, (size_t)ctx->batch * ctx->nblk * tper * sizeof(uint16_t)));
+                CU(cudaMalloc(&ctx->fm_state, (size_t)ctx->batch * ctx->nblk * sizeof(short4)));
+                CU(cudaMemsetAsync(ctx->fm_state, 0, (size_t)ctx->batch * ctx->nblk * sizeof(short4), st));
+            }
+            fast_table16_kernel<<<dim3(ctx->nblk, units), 128, 0, st>>>(a, ctx->fm_table, (size_t)ctx->nblk * tper, ctx->fm_state, ctx->nblk, tper);
+            {
+                const int npass = (std::min(a.nref_fast, a.g.nref) * 9 + 31) / 32;
+                const size_t sm = (size_t)17 * (tper * 2 + 16);
+                const size_t tus = (size_t)ctx->nblk * tper;
+                if (npass <= 1) fast_chain16_kernel<1><<<dim3(1, units), 32, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
+                else if (npass == 2) fast_chain16_kernel<2><<<dim3(1, units), 32, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
+                else fast_chain16_kernel<3><<<dim3(1, units), 32, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
+            }
+            FlowArgs b = a;
+            b.chain = 0; b.mvp_in = ctx->fm_state; b.mvp_in_stride = ctx->nblk;
+            fast_me16_kernel<<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
+            ctx->launches += 2;
+        }
+        else if (g.bs == 16 && g.W % 16 == 0 && !fast_generic) fast_me16_kernel<<<grid, 576, 0, st>>>(a);
         else if (g.bs == 16) fast_me_kernel<16><<<grid, nt, 0, st>>>(a);
         else if (g.bs == 8) fast_me_kernel<8><<<grid, nt, 0, st>>>(a);
         else fast_me_kernel<4><<<grid, nt, 0, st>>>(a);

@@ -135,6 +135,8 @@ struct FlowArgs {
     uint8_t* split; int16_t* mv; int16_t* levels; uint8_t* recon; uint32_t* row_sizes; so_frame_stats* stats;
     size_t split_stride, mv_stride, frame_stride, rows_stride, stats_stride;   // per-unit strides in elements
     size_t scratch_stride;       // per-unit stride of res_frame / band (one frame)
+    const short4* mvp_in;        // fast ME, table-driven chain: predictor (x, y, ref) of every block, [unit][nblk]; else nullptr
+    size_t mvp_in_stride;
 };
 
 // ME results are either plain MeResult records (fast ME, intra search) or the packed 64-bit keys the exhaustive search
@@ -763,7 +765,8 @@ __global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
     for (int blk = b0; blk < b1; ++blk) {
         const int bx = blk % g.nbx, by = blk / g.nbx;
         const int x = bx * BS, y = by * BS;
-        const int mvx = s_mvp[0], mvy = s_mvp[1], mvr = s_mvp[2];
+        int mvx = s_mvp[0], mvy = s_mvp[1], mvr = s_mvp[2];
+        if (a.mvp_in) { const short4 m = a.mvp_in[unit * a.mvp_in_stride + blk]; mvx = m.x; mvy = m.y; mvr = m.z; }
         uint32_t cnext = 0;
         if (t < 64 && blk + 1 < b1) {
             const int nb = blk + 1;
@@ -846,6 +849,176 @@ __global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
             }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Table-driven fast-ME chain for 16x16 blocks.  The chain mvp(b+1) = argmin around mvp(b) is serial over all blocks of a
+// frame (Encoder.py:581), but only the WHOLE-block decision feeds it, each step moves the predictor by at most one unit
+// per axis, and motion repeats from frame to frame.  So:
+//   1. fast_table16_kernel (parallel): whole-block SADs of every reference at the (2K+3)^2 offsets around the predictor
+//      the same block used in the previous P frame of the stream (`state`, zero at start);
+//   2. fast_chain16_kernel (one warp walks the chain): a step is 9*nRef 16-bit table lookups + one REDUX while the
+//      predictor stays within K of the table centre (the warp stages the tables 16 blocks ahead into shared memory with
+//      cp.async); outside, it computes the step's SADs directly.  It records the predictor of every block in `state`;
+//   3. fast_me16_kernel with mvp_in = state (parallel over blocks): whole-block and sub-block results exactly as the
+//      chained kernel would produce them.
+// Results do not depend on the table centres; only the speed does.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FT_K = 4;
+constexpr int FT_N = 2 * FT_K + 3;          // table offsets per axis: centre +- (K + 1)
+
+// whole-block SAD of the 16x16 block at (x, y) against reference `ref` displaced by (dx, dy) search units; rows of the
+// predictor are 16 contiguous bytes of one phase plane, read as aligned words from the copy shifted by (column & 3)
+__device__ __forceinline__ uint32_t fast_sad16(const FlowArgs& a, int unit, int ref, int x, int y, int dx, int dy, const uint8_t* cur) {
+    const FrameGeom& g = a.g;
+    const int mult = g.fme ? 2 : 1;
+    const int Xh = x * mult + dx, Yh = y * mult + dy;
+    const int ph = g.fme ? (((Yh & 1) << 1) | (Xh & 1)) : 0;
+    const int col0 = g.fme ? (Xh >> 1) : Xh, Y0 = g.fme ? (Yh >> 1) : Yh;
+    const int cs = col0 & 3, colA = col0 - cs;
+    const uint8_t* pl = a.ring.plane(unit, ref, ph);
+    const uint8_t* plc = pl + (size_t)cs * (a.ring.plane_stride >> 2);
+    uint32_t sad = 0;
+#pragma unroll 4
+    for (int row = 0; row < 16; ++row) {
+        const int Y = Y0 + row;
+        const uint4 cw = *reinterpret_cast<const uint4*>(cur + (size_t)(y + row) * g.W + x);
+        const uint32_t cwv[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t pw = 0u;
+            if (Y >= 0 && Y < g.H) {
+                const int cA = colA + 4 * w;
+                if (cA >= 0 && col0 + 4 * w + 3 < g.W) pw = __ldg(reinterpret_cast<const uint32_t*>(plc + (size_t)Y * g.pitch + cA));
+                else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int col = col0 + 4 * w + b;
+                        if (col >= 0 && col < g.W) pw |= (uint32_t)pl[(size_t)Y * g.pitch + col] << (8 * b);
+                    }
+                }
+            }
+            sad = sad4_acc(cwv[w], pw, sad);
+        }
+    }
+    return sad;
+}
+
+__global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uint16_t* table, size_t table_unit_stride, const short4* state,
+                                                           size_t state_unit_stride, int tper) {
+    constexpr int BS = 16;
+    const FrameGeom& g = a.g;
+    const int blk = blockIdx.x, unit = a.unit0 + blockIdx.y;
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int nref = min(a.nref_fast, g.nref);
+    const short4 c = state[unit * state_unit_stride + blk];
+    const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
+    const int mult = g.fme ? 2 : 1;
+    const int Wr = g.fme ? 2 * g.W - 1 : g.W, Hr = g.fme ? 2 * g.H - 1 : g.H;
+    uint16_t* tb = table + unit * table_unit_stride + (size_t)blk * tper;
+    for (int e = threadIdx.x; e < nref * FT_N * FT_N; e += blockDim.x) {
+        const int ref = e / (FT_N * FT_N), rem = e - ref * (FT_N * FT_N);
+        const int ix = rem / FT_N, iy = rem - ix * FT_N;
+        // invalid offsets (Encoder.py:728-730: 0 <= p and p + 2*bs < size - bs on both axes) are stored as 0xFFFF (> any SAD),
+        // so the chain walker needs no bounds tests of its own
+        const int dx = c.x - (FT_K + 1) + ix, dy = c.y - (FT_K + 1) + iy;
+        const int px = bx * BS * mult + dx, py = by * BS * mult + dy;
+        const bool ok = px >= 0 && px <= Wr - 3 * BS - 1 && py >= 0 && py <= Hr - 3 * BS - 1;
+        tb[e] = ok ? (uint16_t)fast_sad16(a, unit, ref, bx * BS, by * BS, dx, dy, cur) : (uint16_t)0xFFFFu;
+    }
+}
+
+// slow path of the chain walker (predictor outside the table window): key of one candidate computed from the frames
+__device__ __noinline__ uint32_t fast_chain_miss_key(const FlowArgs& a, int unit, int blk, int cand, int mvx, int mvy, const uint8_t* cur) {
+    constexpr int BS = 16;
+    const FrameGeom& g = a.g;
+    const int mult = g.fme ? 2 : 1;
+    const int Wr = g.fme ? 2 * g.W - 1 : g.W, Hr = g.fme ? 2 * g.H - 1 : g.H;
+    const int bx = blk % g.nbx, by = blk / g.nbx;
+    const int ref = cand / 9, r9 = cand - ref * 9, dx = mvx - 1 + r9 / 3, dy = mvy - 1 + r9 % 3;
+    const int px = bx * BS * mult + dx, py = by * BS * mult + dy;
+    if (!(px >= 0 && px <= Wr - 3 * BS - 1 && py >= 0 && py <= Hr - 3 * BS - 1)) return 0xFFFFFFFFu;
+    return (fast_sad16(a, unit, ref, bx * BS, by * BS, dx, dy, cur) << 7) | (uint32_t)cand;
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(32) fast_chain16_kernel(const FlowArgs a, const uint16_t* table, size_t table_unit_stride, short4* state,
+                                                          size_t state_unit_stride, int tper) {
+    // tper: table entries per block, padded to a multiple of 8 (16 bytes).  The warp stages the table and the centre of
+    // block b + D into a shared-memory ring with cp.async while it decides block b, so a step never waits on L2.  One warp
+    // alone issues a dependent instruction only every few cycles, so the step is kept to a few dozen instructions: table
+    // entries of invalid offsets are 0xFFFF (no bounds tests here), the winner is decoded with one shuffle, the slow path
+    // is out of line.
+    constexpr int D = 16, SLOTS = D + 1;
+    extern __shared__ __align__(16) unsigned char fc_smem[];
+    const FrameGeom& g = a.g;
+    const int unit = a.unit0 + blockIdx.y;
+    const int lane = threadIdx.x;
+    const int nblk = g.nbx * g.nby;
+    const int nref = min(a.nref_fast, g.nref), ncand = nref * 9;
+    const int tbytes = tper * 2, slot_bytes = tbytes + 16;          // table + the block's state record
+    const char* src = reinterpret_cast<const char*>(table + unit * table_unit_stride);
+    short4* st = state + unit * state_unit_stride;
+    const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fc_smem);
+    int st_blk = 0, st_slot = 0;                                     // next block to stage / its slot
+    auto stage = [&]() {
+        if (st_blk < nblk) {
+            const uint32_t dst = smem0 + st_slot * slot_bytes;
+            const char* sp = src + (size_t)st_blk * tbytes;
+            for (int o = lane * 16; o < tbytes; o += 32 * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(sp + o) : "memory");
+            if (lane == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + tbytes), "l"(st + st_blk) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        ++st_blk;
+        if (++st_slot == SLOTS) st_slot = 0;
+    };
+    for (int p = 0; p < D; ++p) stage();
+    // lane = candidate (ref, dx, dy) in scan order, NPASS passes of 32; per-candidate constants are computed once
+    int c_off[NPASS], c_pk = 0;
+#pragma unroll
+    for (int p = 0; p < NPASS; ++p) {
+        const int cand = lane + 32 * p;
+        const int ref = cand / 9, r9 = cand - ref * 9, ox = r9 / 3, oy = r9 - ox * 3;
+        c_off[p] = cand < ncand ? (ref * (FT_N * FT_N) + ox * FT_N + oy) * 2 : -1;
+        c_pk |= (ref | (ox << 4) | (oy << 6)) << (8 * p);
+    }
+    int mvx = 0, mvy = 0, mvr = 0, slot_i = 0;
+    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");           // block 0 is staged
+    __syncwarp();
+    int craw = *reinterpret_cast<const int*>(fc_smem + tbytes);               // centre of block 0: x | y << 16
+    for (int blk = 0; blk < nblk; ++blk) {
+        const unsigned char* slot = fc_smem + slot_i * slot_bytes;
+        const int sx = mvx - (int)(short)(craw & 0xFFFF) + FT_K, sy = mvy - (craw >> 16) + FT_K;
+        const bool hit = (unsigned)sx <= 2u * FT_K && (unsigned)sy <= 2u * FT_K;
+        uint32_t best = 0xFFFFFFFFu;
+        if (hit) {
+            const unsigned char* tb = slot + (sx * FT_N + sy) * 2;
+#pragma unroll
+            for (int p = 0; p < NPASS; ++p)
+                if (c_off[p] >= 0) best = min(best, ((uint32_t)*reinterpret_cast<const uint16_t*>(tb + c_off[p]) << 7) | (uint32_t)(lane + 32 * p));
+        } else {
+#pragma unroll 1
+            for (int p = 0; p < NPASS; ++p)
+                if (c_off[p] >= 0) best = min(best, fast_chain_miss_key(a, unit, blk, lane + 32 * p, mvx, mvy, cur));
+        }
+        // off the critical path (nothing here depends on the predictor): stage block blk + D, make sure block blk + 1 has
+        // landed and fetch its centre; the table reads of this step were issued above
+        if (lane == 0) st[blk] = make_short4((short)mvx, (short)mvy, (short)mvr, 0);      // the predictor this block used
+        __syncwarp();                               // every lane has read this step's slot entries ... (*)
+        stage();                                    // ... before the slot of block blk - 1 is refilled
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+        __syncwarp();
+        if (++slot_i == SLOTS) slot_i = 0;
+        const int craw_next = *reinterpret_cast<const int*>(fc_smem + slot_i * slot_bytes + tbytes);
+        best = __reduce_min_sync(0xFFFFFFFFu, best);
+        if (best < (0xFFFFu << 7)) {               // some candidate is valid: the winner's (ref, ox, oy) from the lane that owns it
+            const int w = __shfl_sync(0xFFFFFFFFu, c_pk, (int)(best & 31u)) >> (8 * (int)((best >> 5) & 3u));
+            mvr = w & 15; mvx += ((w >> 4) & 3) - 1; mvy += ((w >> 6) & 3) - 1;
+        }
+        craw = craw_next;
     }
 }
 
