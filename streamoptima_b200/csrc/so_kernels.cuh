@@ -962,18 +962,24 @@ __global__ void __launch_bounds__(32) fast_chain16_kernel(const FlowArgs a, cons
     short4* st = state + unit * state_unit_stride;
     const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fc_smem);
-    int st_blk = 0, st_slot = 0;                                     // next block to stage / its slot
+    // staging of one block per call, kept branch-light: running pointers, at most four 16-byte chunks per lane (2 KB of table)
+    int st_left = nblk;                                              // blocks still to stage
+    uint32_t st_dst = smem0 + lane * 16;                             // this lane's first chunk in the next slot
+    const char* st_src = src + lane * 16;
+    const short4* st_state = st;
+    int st_slot = 0;
     auto stage = [&]() {
-        if (st_blk < nblk) {
-            const uint32_t dst = smem0 + st_slot * slot_bytes;
-            const char* sp = src + (size_t)st_blk * tbytes;
-            for (int o = lane * 16; o < tbytes; o += 32 * 16)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(sp + o) : "memory");
-            if (lane == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + tbytes), "l"(st + st_blk) : "memory");
+        if (st_left > 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (lane * 16 + q * 512 < tbytes)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_dst + q * 512), "l"(st_src + q * 512) : "memory");
+            if (lane == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st_dst + tbytes), "l"(st_state) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        ++st_blk;
-        if (++st_slot == SLOTS) st_slot = 0;
+        --st_left; st_src += tbytes; ++st_state;
+        st_dst += slot_bytes;
+        if (++st_slot == SLOTS) { st_slot = 0; st_dst = smem0 + lane * 16; }
     };
     for (int p = 0; p < D; ++p) stage();
     // lane = candidate (ref, dx, dy) in scan order, NPASS passes of 32; per-candidate constants are computed once
