@@ -112,19 +112,22 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
                 if (!first_round) {
                     while (!mbar_try(&empty[slot], par)) __nanosleep(40);
                 }
+                // phase planes are visited in the order 0, 2, 1, 3: two even-px items, then two odd-px ones, so that many bundles
+                // hold odd horizontal phases only and skip the 33rd-offset pass (it is invalid there: dx = 33 > R)
+                const int phz = a.nph == 4 ? (((ph & 1) << 1) | (ph >> 1)) : ph;
                 if (lane == 0) {
                     int l0, h0, l1, h1;
                     valid_range(bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
                     valid_range(by * BS, g.H, BS, g.fme, g.fme, l1, h1);
                     const int interior = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;   // every offset of the range is valid
-                    meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (ph << 8) | (interior << 16) | (unit << 17));
+                    meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (phz << 8) | (interior << 16) | (unit << 17));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive_expect_tx(&ready[slot], (uint32_t)(4 * MR_BOXROWS * MR_WP + BS * BS));
                 __syncwarp();
                 if (lane == 0) {
-                    const int z = a.z_unit0 + unit * a.z_per_unit + (int)((a.slot_packed >> (4 * ref)) & 15u) * 16 + ph * 4;
+                    const int z = a.z_unit0 + unit * a.z_per_unit + (int)((a.slot_packed >> (4 * ref)) & 15u) * 16 + phz * 4;
                     tma_load_3d(wins + slot * MR_SLOT, &ring_map, &ready[slot], bx * BS - 16, by * BS - 16 - (slot & 1), z);
                 } else if (lane == 1) {
                     tma_load_3d(curs + slot * MR_CUR, &cur_map, &ready[slot], bx * BS, by * BS, unit);
@@ -207,7 +210,11 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
                 for (int k = 0; k < 8; ++k) par[gg][k] = 0;
             // 33rd horizontal offset first: lane c takes block rows 4c..4c+3 (c = 0, 1: top half; 2, 3: bottom half)
             uint32_t exq[5][3];                      // parent, TL, TR, BL, BR sums of candidate k = 8, complete on every lane
-            {
+#pragma unroll
+            for (int e = 0; e < 5; ++e)
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) exq[e][gg] = 0u;
+            if (__any_sync(0xFFFFFFFFu, px == 0)) {  // odd horizontal phases have no 33rd offset (dx = 33 > R): masked below
                 uint32_t eL[3] = {0u, 0u, 0u}, eR[3] = {0u, 0u, 0u};
                 const unsigned char* w0 = wslot + (p + G * grp + 4 * c) * MR_WP + 32;
                 uint4 cr[4];
