@@ -89,3 +89,34 @@ def test_reference_decoder_accepts_the_golden_text(name):
                                    VBSEnable=enc.get("VBSEnable", False), RCFlag=enc.get("RCFlag"), targetBR=enc.get("targetBR"),
                                    qp_rate_tables=enc.get("qp_rate_tables"), ParallelMode=enc.get("ParallelMode", 0))
     np.testing.assert_array_equal(out, g["recon"])
+
+
+@pytest.mark.gpu
+def test_baseline_config2_full_length_round_trip_and_determinism():
+    """BASELINE config 2 at full size and length (1920x1088, 300 frames, i=16, r=16 half-pel, 4 references, I_Period 30):
+    size-independent properties the oracle cannot check in reasonable time -- decode(encode) reproduces the encoder's
+    reconstruction bit for bit, two encodes are identical (the search merges with atomics: the result must not depend on
+    their order), frame types follow I_Period, and the symbol streams account for exactly quantized_sized symbols."""
+    import torch
+    from bench import synth_frames_torch
+    from streamoptima_b200 import decoder as dec
+    from streamoptima_b200.Encoder import Y_Video_codec
+    Y_Video_codec.write_recon_yuv = False
+    F, H, W = 300, 1088, 1920
+    frames = synth_frames_torch(F, H, W, seed=7, device=torch.device("cuda", 0)).cpu().numpy()
+    c = Y_Video_codec(H, W, F, 16, 16, 4, 30, 0, nRefFrames=4, FMEEnable=True)
+    o1 = {k: np.array(v) for k, v in c.encode_arrays(frames).items() if k in ("split", "mv", "levels", "recon", "frame_types", "row_sizes")}
+    qsize = np.array(c.encode_arrays(frames)["stats"]["qsize"][0])          # second encode; its outputs are compared below
+    o2 = c._pin
+    np.testing.assert_array_equal(o1["mv"][0], o2["mv"][1][0])
+    np.testing.assert_array_equal(o1["levels"][0], o2["lev"][1][0])
+    np.testing.assert_array_equal(o1["recon"][0], o2["rec"][1][0])
+    assert [int(t) for t in o1["frame_types"][0]] == [0 if f % 30 == 0 else 1 for f in range(F)]
+    assert (o1["row_sizes"][0].sum(axis=1) == qsize).all()
+    offsets, symbols, base = c.symbol_streams()
+    assert (np.diff(base.astype(np.int64)) == qsize).all() and symbols.size == int(qsize.sum())
+    d = dec.decoder(0, 30, 16, F, H, W, 4, 4, True, None, False)
+    out = d.decode_arrays(o1["frame_types"][0], o1["split"][0], o1["mv"][0], o1["levels"][0], None, reset_at_intra=False)
+    np.testing.assert_array_equal(out, o1["recon"][0])
+    mse = ((out.astype(np.float64) - frames) ** 2).mean(axis=(1, 2))
+    assert (10 * np.log10(255.0 ** 2 / mse) > 30).all()                      # QP 4: a sane reconstruction on every frame
