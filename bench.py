@@ -302,12 +302,14 @@ def main():
         # the work of the timed launches: the reported fraction errs on the low side)
         avg_launch_ms = xs_ms / max(1, xs_launches)
         achieved = (w_me / 4 / me_l) / (avg_launch_ms / 1e3) / 1e12
-        traffic = None                                                  # DRAM bytes per ME launch from the committed ncu capture
+        traffic, traffic_detail = None, None                            # DRAM bytes per ME launch from the committed ncu capture
         tpath = os.path.join(ROOT, "profiles", "r01_me_traffic.json")
         if os.path.exists(tpath) and F >= 30:
             tj = json.load(open(tpath))
-            traffic = {"dram_bytes_per_launch": tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"], "unit": "B",
-                       "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"), "source": tj["source"], "note": tj.get("note")}
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]      # bytes per launch, one ncu --set full capture
+            traffic_detail = {"unit": "B per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                              "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"), "source": tj["source"],
+                              "note": tj.get("note")}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
@@ -318,7 +320,7 @@ def main():
                              "algorithmic_sad_pixel_ops_per_step": w_me, "launches_per_step": me_l,
                              "avg_launch_ms": avg_launch_ms, "launches_timed": xs_launches,
                              "me_share_of_step": avg_launch_ms * me_l * args.steps / dev_ms,
-                             "traffic": traffic},
+                             "traffic": traffic, "traffic_detail": traffic_detail},
                 "roofline_transform": {"bound": "hbm", "achieved": 5.0 * H * W * timed_frames / (tq_ms / 1e3) / 1e9,
                                        "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                                        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
