@@ -785,9 +785,9 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
                 const int npass = (std::min(a.nref_fast, a.g.nref) * 9 + 31) / 32;
                 const size_t sm = (size_t)17 * (tper * 2 + 16);
                 const size_t tus = (size_t)ctx->nblk * tper;
-                if (npass <= 1) fast_chain16_kernel<1><<<dim3(1, units), 32, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
-                else if (npass == 2) fast_chain16_kernel<2><<<dim3(1, units), 32, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
-                else fast_chain16_kernel<3><<<dim3(1, units), 32, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
+                if (npass <= 1) fast_chain16_kernel<1><<<dim3(1, units), 576, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
+                else if (npass == 2) fast_chain16_kernel<2><<<dim3(1, units), 576, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
+                else fast_chain16_kernel<3><<<dim3(1, units), 576, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
             }
             FlowArgs b = a;
             b.chain = 0; b.mvp_in = ctx->fm_state; b.mvp_in_stride = ctx->nblk;

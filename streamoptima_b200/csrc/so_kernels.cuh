@@ -742,31 +742,33 @@ __global__ void fast_me_kernel(const FlowArgs a) {
 // one warp per entity (whole block + four sub-blocks) picks the winner with a REDUX on (SAD, scan index): strict '<' in
 // scan order (ref, dx, dy) (Encoder.py:726-740) == lexicographic minimum.  The current block of the next step is
 // fetched during this one.
-__global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
+// blocks [b0, b1) of one unit by the 576 threads of a CTA; chain: the predictor is carried from block to block starting at
+// mv0 (otherwise it is a.mvp_in[blk] or zero); state_out (optional) receives the predictor every block used, mv_out
+// (optional, shared memory) the whole-block vector of the last block
+__device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b0, int b1, bool chain, int mvx0, int mvy0, int mvr0,
+                                              short4* state_out, int* mv_out) {
     constexpr int BS = 16, S = 8, CPP = 36;           // candidates per pass
     __shared__ unsigned int sadq[SO_MAX_REF * 9][4];
     __shared__ __align__(16) uint32_t s_cur[BS][4];
     __shared__ int s_mvp[3];
     const FrameGeom& g = a.g;
-    const int unit = a.unit0 + blockIdx.y;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int cl = t >> 4, row = t & 15;
     const int mult = g.fme ? 2 : 1;
     const int nref = min(a.nref_fast, g.nref);
     const int ncand = nref * 9;
-    const int nblk = g.nbx * g.nby;
-    const int b0 = a.chain ? 0 : blockIdx.x, b1 = a.chain ? nblk : blockIdx.x + 1;
     const int Wr = g.fme ? 2 * g.W - 1 : g.W, Hr = g.fme ? 2 * g.H - 1 : g.H;
     const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
     const size_t shift_stride = a.ring.plane_stride >> 2;
-    if (t < 3) s_mvp[t] = 0;
+    if (t == 0) { s_mvp[0] = mvx0; s_mvp[1] = mvy0; s_mvp[2] = mvr0; }
     if (t < 64) s_cur[t >> 2][t & 3] = *reinterpret_cast<const uint32_t*>(cur + (size_t)((b0 / g.nbx) * BS + (t >> 2)) * g.W + (b0 % g.nbx) * BS + (t & 3) * 4);
     __syncthreads();
     for (int blk = b0; blk < b1; ++blk) {
         const int bx = blk % g.nbx, by = blk / g.nbx;
         const int x = bx * BS, y = by * BS;
         int mvx = s_mvp[0], mvy = s_mvp[1], mvr = s_mvp[2];
-        if (a.mvp_in) { const short4 m = a.mvp_in[unit * a.mvp_in_stride + blk]; mvx = m.x; mvy = m.y; mvr = m.z; }
+        if (!chain && a.mvp_in) { const short4 m = a.mvp_in[unit * a.mvp_in_stride + blk]; mvx = m.x; mvy = m.y; mvr = m.z; }
+        if (state_out && t == 0) state_out[blk] = make_short4((short)mvx, (short)mvy, (short)mvr, 0);
         uint32_t cnext = 0;
         if (t < 64 && blk + 1 < b1) {
             const int nb = blk + 1;
@@ -845,11 +847,17 @@ __global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
                     const int kk = e - 1;
                     a.me_sub[unit * a.me_sub_stride + (by * 2 + (kk >> 1)) * (g.nbx * 2) + bx * 2 + (kk & 1)] = r;
                 }
-                if (e == 0 && a.chain) { s_mvp[0] = bdx; s_mvp[1] = bdy; s_mvp[2] = bref; }
+                if (e == 0 && chain) { s_mvp[0] = bdx; s_mvp[1] = bdy; s_mvp[2] = bref; }
+                if (e == 0 && mv_out) { mv_out[0] = bdx; mv_out[1] = bdy; mv_out[2] = bref; }
             }
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
+    const int nblk = a.g.nbx * a.g.nby;
+    fast_me16_run(a, a.unit0 + blockIdx.y, a.chain ? 0 : (int)blockIdx.x, a.chain ? nblk : (int)blockIdx.x + 1, a.chain != 0, 0, 0, 0, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -860,7 +868,8 @@ __global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
 //      the same block used in the previous P frame of the stream (`state`, zero at start);
 //   2. fast_chain16_kernel (one warp walks the chain): a step is 9*nRef 16-bit table lookups + one REDUX while the
 //      predictor stays within K of the table centre (the warp stages the tables 16 blocks ahead into shared memory with
-//      cp.async); outside, it computes the step's SADs directly.  It records the predictor of every block in `state`;
+//      cp.async); outside (cold start, scene change) the block is decided by the whole CTA with the cooperative step of
+//      fast_me16_run.  It records the predictor of every block in `state`;
 //   3. fast_me16_kernel with mvp_in = state (parallel over blocks): whole-block and sub-block results exactly as the
 //      chained kernel would produce them.
 // Results do not depend on the table centres; only the speed does.
@@ -929,38 +938,31 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
     }
 }
 
-// slow path of the chain walker (predictor outside the table window): key of one candidate computed from the frames
-__device__ __noinline__ uint32_t fast_chain_miss_key(const FlowArgs& a, int unit, int blk, int cand, int mvx, int mvy, const uint8_t* cur) {
-    constexpr int BS = 16;
-    const FrameGeom& g = a.g;
-    const int mult = g.fme ? 2 : 1;
-    const int Wr = g.fme ? 2 * g.W - 1 : g.W, Hr = g.fme ? 2 * g.H - 1 : g.H;
-    const int bx = blk % g.nbx, by = blk / g.nbx;
-    const int ref = cand / 9, r9 = cand - ref * 9, dx = mvx - 1 + r9 / 3, dy = mvy - 1 + r9 % 3;
-    const int px = bx * BS * mult + dx, py = by * BS * mult + dy;
-    if (!(px >= 0 && px <= Wr - 3 * BS - 1 && py >= 0 && py <= Hr - 3 * BS - 1)) return 0xFFFFFFFFu;
-    return (fast_sad16(a, unit, ref, bx * BS, by * BS, dx, dy, cur) << 7) | (uint32_t)cand;
-}
+__device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b0, int b1, bool chain, int mvx0, int mvy0, int mvr0,
+                                              short4* state_out, int* mv_out);
 
 template <int NPASS>
-__global__ void __launch_bounds__(32) fast_chain16_kernel(const FlowArgs a, const uint16_t* table, size_t table_unit_stride, short4* state,
-                                                          size_t state_unit_stride, int tper) {
-    // tper: table entries per block, padded to a multiple of 8 (16 bytes).  The warp stages the table and the centre of
-    // block b + D into a shared-memory ring with cp.async while it decides block b, so a step never waits on L2.  One warp
-    // alone issues a dependent instruction only every few cycles, so the step is kept to a few dozen instructions: table
-    // entries of invalid offsets are 0xFFFF (no bounds tests here), the winner is decoded with one shuffle, the slow path
-    // is out of line.
+__global__ void __launch_bounds__(576) fast_chain16_kernel(const FlowArgs a, const uint16_t* table, size_t table_unit_stride, short4* state,
+                                                           size_t state_unit_stride, int tper) {
+    // tper: table entries per block, padded to a multiple of 8 (16 bytes).  Warp 0 walks the chain: it stages the table and
+    // the centre of block b + D into a shared-memory ring with cp.async while it decides block b, so a step never waits on
+    // L2.  One warp alone issues a dependent instruction only every few cycles, so the step is kept to a few dozen
+    // instructions: table entries of invalid offsets are 0xFFFF (no bounds tests here), the winner is decoded with one
+    // shuffle.  When the predictor leaves the table window (cold start, scene change) the block is decided by the whole
+    // CTA with the cooperative step of fast_me16_run (the other 17 warps sleep at the barrier until then).
     constexpr int D = 16, SLOTS = D + 1;
     extern __shared__ __align__(16) unsigned char fc_smem[];
+    __shared__ int s_req[4];                    // {block to decide cooperatively (nblk: done), predictor x, y, ref}
+    __shared__ int s_mvout[3];                  // its result
     const FrameGeom& g = a.g;
     const int unit = a.unit0 + blockIdx.y;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool walker = threadIdx.x < 32;
     const int nblk = g.nbx * g.nby;
     const int nref = min(a.nref_fast, g.nref), ncand = nref * 9;
     const int tbytes = tper * 2, slot_bytes = tbytes + 16;          // table + the block's state record
     const char* src = reinterpret_cast<const char*>(table + unit * table_unit_stride);
     short4* st = state + unit * state_unit_stride;
-    const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fc_smem);
     // staging of one block per call, kept branch-light: running pointers, at most four 16-byte chunks per lane (2 KB of table)
     int st_left = nblk;                                              // blocks still to stage
@@ -981,7 +983,6 @@ __global__ void __launch_bounds__(32) fast_chain16_kernel(const FlowArgs a, cons
         st_dst += slot_bytes;
         if (++st_slot == SLOTS) { st_slot = 0; st_dst = smem0 + lane * 16; }
     };
-    for (int p = 0; p < D; ++p) stage();
     // lane = candidate (ref, dx, dy) in scan order, NPASS passes of 32; per-candidate constants are computed once
     int c_off[NPASS], c_pk = 0;
 #pragma unroll
@@ -991,41 +992,53 @@ __global__ void __launch_bounds__(32) fast_chain16_kernel(const FlowArgs a, cons
         c_off[p] = cand < ncand ? (ref * (FT_N * FT_N) + ox * FT_N + oy) * 2 : -1;
         c_pk |= (ref | (ox << 4) | (oy << 6)) << (8 * p);
     }
-    int mvx = 0, mvy = 0, mvr = 0, slot_i = 0;
-    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");           // block 0 is staged
-    __syncwarp();
-    int craw = *reinterpret_cast<const int*>(fc_smem + tbytes);               // centre of block 0: x | y << 16
-    for (int blk = 0; blk < nblk; ++blk) {
-        const unsigned char* slot = fc_smem + slot_i * slot_bytes;
-        const int sx = mvx - (int)(short)(craw & 0xFFFF) + FT_K, sy = mvy - (craw >> 16) + FT_K;
-        const bool hit = (unsigned)sx <= 2u * FT_K && (unsigned)sy <= 2u * FT_K;
-        uint32_t best = 0xFFFFFFFFu;
-        if (hit) {
-            const unsigned char* tb = slot + (sx * FT_N + sy) * 2;
-#pragma unroll
-            for (int p = 0; p < NPASS; ++p)
-                if (c_off[p] >= 0) best = min(best, ((uint32_t)*reinterpret_cast<const uint16_t*>(tb + c_off[p]) << 7) | (uint32_t)(lane + 32 * p));
-        } else {
-#pragma unroll 1
-            for (int p = 0; p < NPASS; ++p)
-                if (c_off[p] >= 0) best = min(best, fast_chain_miss_key(a, unit, blk, lane + 32 * p, mvx, mvy, cur));
-        }
-        // off the critical path (nothing here depends on the predictor): stage block blk + D, make sure block blk + 1 has
-        // landed and fetch its centre; the table reads of this step were issued above
-        if (lane == 0) st[blk] = make_short4((short)mvx, (short)mvy, (short)mvr, 0);      // the predictor this block used
-        __syncwarp();                               // every lane has read this step's slot entries ... (*)
+    int mvx = 0, mvy = 0, mvr = 0, slot_i = 0, blk = 0, craw = 0;
+    bool pending = false;                        // block `blk` was handed to the cooperative step
+    // bookkeeping of one finished block: stage block blk + D, make sure block blk + 1 has landed, fetch its centre
+    auto advance = [&]() {
+        __syncwarp();                               // every lane has read this step's slot entries ...
         stage();                                    // ... before the slot of block blk - 1 is refilled
         asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
         __syncwarp();
         if (++slot_i == SLOTS) slot_i = 0;
-        const int craw_next = *reinterpret_cast<const int*>(fc_smem + slot_i * slot_bytes + tbytes);
-        best = __reduce_min_sync(0xFFFFFFFFu, best);
-        if (best < (0xFFFFu << 7)) {               // some candidate is valid: the winner's (ref, ox, oy) from the lane that owns it
-            const int w = __shfl_sync(0xFFFFFFFFu, c_pk, (int)(best & 31u)) >> (8 * (int)((best >> 5) & 3u));
-            mvr = w & 15; mvx += ((w >> 4) & 3) - 1; mvy += ((w >> 6) & 3) - 1;
-        }
-        craw = craw_next;
+        craw = *reinterpret_cast<const int*>(fc_smem + slot_i * slot_bytes + tbytes);
+        ++blk;
+    };
+    if (walker) {
+        for (int p = 0; p < D; ++p) stage();
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");       // block 0 is staged
+        __syncwarp();
+        craw = *reinterpret_cast<const int*>(fc_smem + tbytes);                // centre of block 0: x | y << 16
     }
+    while (true) {
+        if (walker) {
+            if (pending) { mvx = s_mvout[0]; mvy = s_mvout[1]; mvr = s_mvout[2]; advance(); pending = false; }
+            while (blk < nblk) {
+                const unsigned char* slot = fc_smem + slot_i * slot_bytes;
+                const int sx = mvx - (int)(short)(craw & 0xFFFF) + FT_K, sy = mvy - (craw >> 16) + FT_K;
+                if (!((unsigned)sx <= 2u * FT_K && (unsigned)sy <= 2u * FT_K)) { pending = true; break; }
+                const unsigned char* tb = slot + (sx * FT_N + sy) * 2;
+                uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                for (int p = 0; p < NPASS; ++p)
+                    if (c_off[p] >= 0) best = min(best, ((uint32_t)*reinterpret_cast<const uint16_t*>(tb + c_off[p]) << 7) | (uint32_t)(lane + 32 * p));
+                // off the critical path (nothing here depends on the predictor); the table reads of this step were issued above
+                if (lane == 0) st[blk] = make_short4((short)mvx, (short)mvy, (short)mvr, 0);      // the predictor this block used
+                advance();
+                best = __reduce_min_sync(0xFFFFFFFFu, best);
+                if (best < (0xFFFFu << 7)) {           // some candidate is valid: the winner's (ref, ox, oy) from the lane that owns it
+                    const int w = __shfl_sync(0xFFFFFFFFu, c_pk, (int)(best & 31u)) >> (8 * (int)((best >> 5) & 3u));
+                    mvr = w & 15; mvx += ((w >> 4) & 3) - 1; mvy += ((w >> 6) & 3) - 1;
+                }
+            }
+            if (lane == 0) { s_req[0] = pending ? blk : nblk; s_req[1] = mvx; s_req[2] = mvy; s_req[3] = mvr; }
+        }
+        __syncthreads();
+        const int rb = s_req[0];
+        if (rb >= nblk) break;
+        fast_me16_run(a, unit, rb, rb + 1, true, s_req[1], s_req[2], s_req[3], st, s_mvout);     // records st[rb], ends with a barrier
+    }
+    if (walker) asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------------------
