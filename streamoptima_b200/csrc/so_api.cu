@@ -780,7 +780,11 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
                 CU(cudaMalloc(&ctx->fm_state, (size_t)ctx->batch * ctx->nblk * sizeof(short4)));
                 CU(cudaMemsetAsync(ctx->fm_state, 0, (size_t)ctx->batch * ctx->nblk * sizeof(short4), st));
             }
-            fast_table16_kernel<<<dim3(ctx->nblk, units), 128, 0, st>>>(a, ctx->fm_table, (size_t)ctx->nblk * tper, ctx->fm_state, ctx->nblk, tper);
+            {
+                const int nr = std::min(a.nref_fast, a.g.nref), nph = a.g.fme ? 4 : 1;
+                const size_t tsm = (size_t)nr * nph * FTR_H * FTR_W + 256;
+                fast_table16_kernel<<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, (size_t)ctx->nblk * tper, ctx->fm_state, ctx->nblk, tper);
+            }
             {
                 const int npass = (std::min(a.nref_fast, a.g.nref) * 9 + 31) / 32;
                 const size_t sm = (size_t)17 * (tper * 2 + 16);

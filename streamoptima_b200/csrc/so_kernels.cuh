@@ -914,27 +914,73 @@ __device__ __forceinline__ uint32_t fast_sad16(const FlowArgs& a, int unit, int 
     return sad;
 }
 
+// One CTA per block.  The pixels any of the 11 x 11 offsets can touch form, per (reference, phase plane), a region of
+// 26 rows x 32 bytes: it is copied to shared memory once (aligned words, zero outside the frame), then each thread takes
+// candidates and reads its 16 rows as five words + funnel shifts -- no scattered global loads.
+constexpr int FTR_H = 16 + FT_N - 1, FTR_W = 32;              // region rows (integer search: 16 + 10; half-pel needs 16 + 5) / bytes per row
+
 __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uint16_t* table, size_t table_unit_stride, const short4* state,
                                                            size_t state_unit_stride, int tper) {
     constexpr int BS = 16;
+    extern __shared__ __align__(16) unsigned char ft_smem[];   // [nref * nph][FTR_H][FTR_W] regions, then the current block
     const FrameGeom& g = a.g;
     const int blk = blockIdx.x, unit = a.unit0 + blockIdx.y;
     const int bx = blk % g.nbx, by = blk / g.nbx;
-    const int nref = min(a.nref_fast, g.nref);
+    const int x = bx * BS, y = by * BS;
+    const int nref = min(a.nref_fast, g.nref), nph = g.fme ? 4 : 1;
     const short4 c = state[unit * state_unit_stride + blk];
-    const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
     const int mult = g.fme ? 2 : 1;
     const int Wr = g.fme ? 2 * g.W - 1 : g.W, Hr = g.fme ? 2 * g.H - 1 : g.H;
+    // first offset of the window in search units and the region origin in plane pixels (floor), columns aligned to 4
+    const int dx0 = c.x - (FT_K + 1), dy0 = c.y - (FT_K + 1);
+    const int X0 = g.fme ? ((x * 2 + dx0) >> 1) : x + dx0, Y0 = g.fme ? ((y * 2 + dy0) >> 1) : y + dy0;
+    const int XA = X0 & ~3;
+    uint32_t* s_cur = reinterpret_cast<uint32_t*>(ft_smem + (size_t)nref * nph * FTR_H * FTR_W);
+    for (int e = threadIdx.x; e < nref * nph * FTR_H * (FTR_W / 4); e += blockDim.x) {
+        const int w = e % (FTR_W / 4), row = (e / (FTR_W / 4)) % FTR_H, rp = e / ((FTR_W / 4) * FTR_H);
+        const int ref = rp / nph, ph = rp % nph;
+        const int X = XA + 4 * w, Y = Y0 + row;
+        uint32_t v = 0u;
+        if (Y >= 0 && Y < g.H) {
+            const uint8_t* pl = a.ring.plane(unit, ref, ph) + (size_t)Y * g.pitch;
+            if (X >= 0 && X + 3 < g.W) v = __ldg(reinterpret_cast<const uint32_t*>(pl + X));
+            else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < g.W) v |= (uint32_t)pl[X + b] << (8 * b);
+            }
+        }
+        reinterpret_cast<uint32_t*>(ft_smem)[e] = v;
+    }
+    if (threadIdx.x < 64)
+        s_cur[threadIdx.x] = *reinterpret_cast<const uint32_t*>(a.cur + unit * a.cur_unit_stride + (size_t)(y + (threadIdx.x >> 2)) * g.W + x + (threadIdx.x & 3) * 4);
+    __syncthreads();
     uint16_t* tb = table + unit * table_unit_stride + (size_t)blk * tper;
     for (int e = threadIdx.x; e < nref * FT_N * FT_N; e += blockDim.x) {
         const int ref = e / (FT_N * FT_N), rem = e - ref * (FT_N * FT_N);
         const int ix = rem / FT_N, iy = rem - ix * FT_N;
         // invalid offsets (Encoder.py:728-730: 0 <= p and p + 2*bs < size - bs on both axes) are stored as 0xFFFF (> any SAD),
         // so the chain walker needs no bounds tests of its own
-        const int dx = c.x - (FT_K + 1) + ix, dy = c.y - (FT_K + 1) + iy;
-        const int px = bx * BS * mult + dx, py = by * BS * mult + dy;
-        const bool ok = px >= 0 && px <= Wr - 3 * BS - 1 && py >= 0 && py <= Hr - 3 * BS - 1;
-        tb[e] = ok ? (uint16_t)fast_sad16(a, unit, ref, bx * BS, by * BS, dx, dy, cur) : (uint16_t)0xFFFFu;
+        const int dx = dx0 + ix, dy = dy0 + iy;
+        const int px = x * mult + dx, py = y * mult + dy;
+        uint32_t sad = 0xFFFFu;
+        if (px >= 0 && px <= Wr - 3 * BS - 1 && py >= 0 && py <= Hr - 3 * BS - 1) {
+            const int ph = g.fme ? (((py & 1) << 1) | (px & 1)) : 0;
+            const int co = (g.fme ? (px >> 1) : px) - XA, ro = (g.fme ? (py >> 1) : py) - Y0;     // half-pel: co <= 8, ro <= 5; integer: co <= 13, ro <= 10
+            const unsigned char* rg = ft_smem + ((size_t)(ref * nph + ph) * FTR_H + ro) * FTR_W + (co & ~3);
+            const int sh = (co & 3) * 8;
+            sad = 0;
+#pragma unroll 4
+            for (int row = 0; row < BS; ++row) {
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(rg + row * FTR_W);
+                const uint4 cw = *reinterpret_cast<const uint4*>(s_cur + row * 4);
+                const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3], q4 = rw[4];
+                sad = sad4_acc(cw.x, __funnelshift_r(q0, q1, sh), sad);
+                sad = sad4_acc(cw.y, __funnelshift_r(q1, q2, sh), sad);
+                sad = sad4_acc(cw.z, __funnelshift_r(q2, q3, sh), sad);
+                sad = sad4_acc(cw.w, __funnelshift_r(q3, q4, sh), sad);
+            }
+        }
+        tb[e] = (uint16_t)sad;
     }
 }
 
