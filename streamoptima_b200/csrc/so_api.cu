@@ -64,7 +64,7 @@ struct so_ctx {
     int* qp_rows_dev = nullptr;
     std::vector<int> qp_rows;
     unsigned int* me_work = nullptr;        // chunk counter of the item-ring search kernel
-    uint16_t* fm_table = nullptr;           // fast ME: whole-block SAD tables around the previous frame's predictors
+    uint8_t* fm_table = nullptr;            // fast ME: per-block transition tables around the previous frame's predictors
     short4* fm_state = nullptr;             // fast ME: predictor (x, y, ref) every block used in the last P frame, [batch][nblk]
     int* qp_blocks_dev = nullptr;           // ROI extension: [frames][nblk] per-block QPs of the next sequence, or nullptr
     int qp_blocks_frames = 0;
@@ -774,27 +774,21 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
         static const bool fast_no_table = std::getenv("SO_FAST_NO_TABLE") != nullptr;    // A/B: chained fast_me16_kernel
         if (g.bs == 16 && g.W % 16 == 0 && !fast_generic && a.chain && !fast_no_table) {
             // table-driven chain: SAD tables around last frame's predictors -> one-warp walk -> parallel results
-            const int tper = (ctx->p.n_ref_frames * FT_N * FT_N + 7) & ~7;          // entries per block, 16-byte granules
+            const size_t nblk_pad = ((size_t)ctx->nblk + 3) & ~(size_t)3;           // the chain stages groups of four blocks
             if (!ctx->fm_table) {
-                CU(cudaMalloc(&ctx->fm_table, (size_t)ctx->batch * ctx->nblk * tper * sizeof(uint16_t)));
-                CU(cudaMalloc(&ctx->fm_state, (size_t)ctx->batch * ctx->nblk * sizeof(short4)));
-                CU(cudaMemsetAsync(ctx->fm_state, 0, (size_t)ctx->batch * ctx->nblk * sizeof(short4), st));
+                CU(cudaMalloc(&ctx->fm_table, (size_t)ctx->batch * nblk_pad * FT_TRANS));
+                CU(cudaMalloc(&ctx->fm_state, (size_t)ctx->batch * nblk_pad * sizeof(short4)));
+                CU(cudaMemsetAsync(ctx->fm_table, 0xFF, (size_t)ctx->batch * nblk_pad * FT_TRANS, st));
+                CU(cudaMemsetAsync(ctx->fm_state, 0, (size_t)ctx->batch * nblk_pad * sizeof(short4), st));
             }
             {
                 const int nr = std::min(a.nref_fast, a.g.nref), nph = a.g.fme ? 4 : 1;
-                const size_t tsm = (size_t)nr * nph * FTR_H * FTR_W + 256;
-                fast_table16_kernel<<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, (size_t)ctx->nblk * tper, ctx->fm_state, ctx->nblk, tper);
-            }
-            {
-                const int npass = (std::min(a.nref_fast, a.g.nref) * 9 + 31) / 32;
-                const size_t sm = (size_t)17 * (tper * 2 + 16);
-                const size_t tus = (size_t)ctx->nblk * tper;
-                if (npass <= 1) fast_chain16_kernel<1><<<dim3(1, units), 576, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
-                else if (npass == 2) fast_chain16_kernel<2><<<dim3(1, units), 576, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
-                else fast_chain16_kernel<3><<<dim3(1, units), 576, sm, st>>>(a, ctx->fm_table, tus, ctx->fm_state, ctx->nblk, tper);
+                const size_t tsm = (size_t)nr * nph * FTR_H * FTR_W + 256 + (size_t)nr * FT_N * FT_N * 2;
+                fast_table16_kernel<<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
+                fast_chain16_kernel<<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
             }
             FlowArgs b = a;
-            b.chain = 0; b.mvp_in = ctx->fm_state; b.mvp_in_stride = ctx->nblk;
+            b.chain = 0; b.mvp_in = ctx->fm_state; b.mvp_in_stride = nblk_pad;
             fast_me16_kernel<<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
             ctx->launches += 2;
         }

@@ -864,12 +864,14 @@ __global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
 // Table-driven fast-ME chain for 16x16 blocks.  The chain mvp(b+1) = argmin around mvp(b) is serial over all blocks of a
 // frame (Encoder.py:581), but only the WHOLE-block decision feeds it, each step moves the predictor by at most one unit
 // per axis, and motion repeats from frame to frame.  So:
-//   1. fast_table16_kernel (parallel): whole-block SADs of every reference at the (2K+3)^2 offsets around the predictor
-//      the same block used in the previous P frame of the stream (`state`, zero at start);
-//   2. fast_chain16_kernel (one warp walks the chain): a step is 9*nRef 16-bit table lookups + one REDUX while the
-//      predictor stays within K of the table centre (the warp stages the tables 16 blocks ahead into shared memory with
-//      cp.async); outside (cold start, scene change) the block is decided by the whole CTA with the cooperative step of
-//      fast_me16_run.  It records the predictor of every block in `state`;
+//   1. fast_table16_kernel (parallel over blocks): whole-block SADs of every reference at the (2K+3)^2 offsets around the
+//      predictor the same block used in the previous P frame of the stream (`state`, zero at start), kept in shared
+//      memory, and from them the block's TRANSITION TABLE: for each of the (2K+1)^2 predictors within K of that centre,
+//      which candidate fast_motion_estimation picks (one byte);
+//   2. fast_chain16_kernel (one warp walks the chain): next predictor = T_b[predictor - centre_b] -- one dependent
+//      shared-memory byte load and a few integer instructions per block (tables staged ahead with cp.async).  A block
+//      whose predictor lies outside its window (cold start, scene change) is decided by the whole CTA with the cooperative
+//      step of fast_me16_run.  The predictor of every block is recorded in `state`;
 //   3. fast_me16_kernel with mvp_in = state (parallel over blocks): whole-block and sub-block results exactly as the
 //      chained kernel would produce them.
 // Results do not depend on the table centres; only the speed does.
@@ -919,8 +921,11 @@ __device__ __forceinline__ uint32_t fast_sad16(const FlowArgs& a, int unit, int 
 // candidates and reads its 16 rows as five words + funnel shifts -- no scattered global loads.
 constexpr int FTR_H = 16 + FT_N - 1, FTR_W = 32;              // region rows (integer search: 16 + 10; half-pel needs 16 + 5) / bytes per row
 
-__global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uint16_t* table, size_t table_unit_stride, const short4* state,
-                                                           size_t state_unit_stride, int tper) {
+constexpr int FT_S = 2 * FT_K + 1;          // predictor states per axis served by a table
+constexpr int FT_TRANS = 96;                // bytes of transition table per block (81 used, 16-byte granules)
+
+__global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uint8_t* trans, size_t trans_unit_stride, const short4* state,
+                                                           size_t state_unit_stride) {
     constexpr int BS = 16;
     extern __shared__ __align__(16) unsigned char ft_smem[];   // [nref * nph][FTR_H][FTR_W] regions, then the current block
     const FrameGeom& g = a.g;
@@ -954,12 +959,11 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
     if (threadIdx.x < 64)
         s_cur[threadIdx.x] = *reinterpret_cast<const uint32_t*>(a.cur + unit * a.cur_unit_stride + (size_t)(y + (threadIdx.x >> 2)) * g.W + x + (threadIdx.x & 3) * 4);
     __syncthreads();
-    uint16_t* tb = table + unit * table_unit_stride + (size_t)blk * tper;
+    uint16_t* s_sad = reinterpret_cast<uint16_t*>(s_cur + 64);               // [nref][FT_N][FT_N]
     for (int e = threadIdx.x; e < nref * FT_N * FT_N; e += blockDim.x) {
         const int ref = e / (FT_N * FT_N), rem = e - ref * (FT_N * FT_N);
         const int ix = rem / FT_N, iy = rem - ix * FT_N;
-        // invalid offsets (Encoder.py:728-730: 0 <= p and p + 2*bs < size - bs on both axes) are stored as 0xFFFF (> any SAD),
-        // so the chain walker needs no bounds tests of its own
+        // invalid offsets (Encoder.py:728-730: 0 <= p and p + 2*bs < size - bs on both axes) get 0xFFFF (> any SAD)
         const int dx = dx0 + ix, dy = dy0 + iy;
         const int px = x * mult + dx, py = y * mult + dy;
         uint32_t sad = 0xFFFFu;
@@ -980,101 +984,96 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
                 sad = sad4_acc(cw.w, __funnelshift_r(q3, q4, sh), sad);
             }
         }
-        tb[e] = (uint16_t)sad;
+        s_sad[e] = (uint16_t)sad;
+    }
+    __syncthreads();
+    // transition table: for every predictor within K of the centre, the winner of fast_motion_estimation's scan (ref, dx,
+    // dy ascending, strict '<': the minimum of (SAD, scan index)) packed as ref << 4 | (dx - mvp.x + 1) << 2 | (dy - mvp.y + 1);
+    // 0xFF = no valid candidate (the predictor is kept, Encoder.py:722)
+    uint8_t* tr = trans + unit * trans_unit_stride + (size_t)blk * FT_TRANS;
+    for (int sI = threadIdx.x; sI < FT_S * FT_S; sI += blockDim.x) {
+        const int sx = sI / FT_S, sy = sI - sx * FT_S;                      // predictor = centre - K + (sx, sy)
+        uint32_t best = 0xFFFFFFFFu;
+        for (int ref = 0; ref < nref; ++ref)
+#pragma unroll
+            for (int o = 0; o < 9; ++o) {
+                const uint32_t sad = s_sad[ref * (FT_N * FT_N) + (sx + o / 3) * FT_N + sy + o % 3];
+                best = min(best, (sad << 7) | (uint32_t)((ref << 4) | ((o / 3) << 2) | (o % 3)));
+            }
+        tr[sI] = best < (0xFFFFu << 7) ? (uint8_t)(best & 127u) : (uint8_t)0xFF;
     }
 }
 
 __device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b0, int b1, bool chain, int mvx0, int mvy0, int mvr0,
                                               short4* state_out, int* mv_out);
 
-template <int NPASS>
-__global__ void __launch_bounds__(576) fast_chain16_kernel(const FlowArgs a, const uint16_t* table, size_t table_unit_stride, short4* state,
-                                                           size_t state_unit_stride, int tper) {
-    // tper: table entries per block, padded to a multiple of 8 (16 bytes).  Warp 0 walks the chain: it stages the table and
-    // the centre of block b + D into a shared-memory ring with cp.async while it decides block b, so a step never waits on
-    // L2.  One warp alone issues a dependent instruction only every few cycles, so the step is kept to a few dozen
-    // instructions: table entries of invalid offsets are 0xFFFF (no bounds tests here), the winner is decoded with one
-    // shuffle.  When the predictor leaves the table window (cold start, scene change) the block is decided by the whole
-    // CTA with the cooperative step of fast_me16_run (the other 17 warps sleep at the barrier until then).
-    constexpr int D = 16, SLOTS = D + 1;
-    extern __shared__ __align__(16) unsigned char fc_smem[];
+__global__ void __launch_bounds__(576) fast_chain16_kernel(const FlowArgs a, const uint8_t* trans, size_t trans_unit_stride, short4* state,
+                                                           size_t state_unit_stride) {
+    // Warp 0 walks the chain.  With the transition tables a step is one dependent shared-memory byte load plus a few integer
+    // instructions: next predictor = T_b[predictor - centre_b].  Tables and centres are staged in groups of four blocks,
+    // FT_DG groups ahead, with cp.async.  When the predictor leaves the window of a block (cold start, scene change) the
+    // block is decided by the whole CTA with the cooperative step of fast_me16_run (the other 17 warps sleep at the barrier
+    // until then).
+    constexpr int GB = 4, DG = 6, GSLOTS = DG + 1;                   // blocks per group, groups in flight
+    constexpr int GBYTES = GB * FT_TRANS + GB * 8;                   // tables + state records of a group (416 B)
+    __shared__ __align__(16) unsigned char ring[GSLOTS * GBYTES];
     __shared__ int s_req[4];                    // {block to decide cooperatively (nblk: done), predictor x, y, ref}
     __shared__ int s_mvout[3];                  // its result
     const FrameGeom& g = a.g;
     const int unit = a.unit0 + blockIdx.y;
     const int lane = threadIdx.x & 31;
     const bool walker = threadIdx.x < 32;
-    const int nblk = g.nbx * g.nby;
-    const int nref = min(a.nref_fast, g.nref), ncand = nref * 9;
-    const int tbytes = tper * 2, slot_bytes = tbytes + 16;          // table + the block's state record
-    const char* src = reinterpret_cast<const char*>(table + unit * table_unit_stride);
+    const int nblk = g.nbx * g.nby, ngroups = (nblk + GB - 1) / GB;
+    const char* tsrc = reinterpret_cast<const char*>(trans + unit * trans_unit_stride);      // buffers are padded to whole groups
     short4* st = state + unit * state_unit_stride;
-    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fc_smem);
-    // staging of one block per call, kept branch-light: running pointers, at most four 16-byte chunks per lane (2 KB of table)
-    int st_left = nblk;                                              // blocks still to stage
-    uint32_t st_dst = smem0 + lane * 16;                             // this lane's first chunk in the next slot
-    const char* st_src = src + lane * 16;
-    const short4* st_state = st;
-    int st_slot = 0;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(ring);
+    int sg = 0, sg_slot = 0;                     // next group to stage / its slot
     auto stage = [&]() {
-        if (st_left > 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (lane * 16 + q * 512 < tbytes)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_dst + q * 512), "l"(st_src + q * 512) : "memory");
-            if (lane == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st_dst + tbytes), "l"(st_state) : "memory");
+        if (sg < ngroups) {
+            const uint32_t dst = smem0 + sg_slot * GBYTES;
+            if (lane < GB * FT_TRANS / 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + lane * 16), "l"(tsrc + (size_t)sg * (GB * FT_TRANS) + lane * 16) : "memory");
+            else if (lane < GB * FT_TRANS / 16 + GB / 2)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + lane * 16),
+                             "l"(reinterpret_cast<const char*>(st + (size_t)sg * GB) + (lane - GB * FT_TRANS / 16) * 16) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        --st_left; st_src += tbytes; ++st_state;
-        st_dst += slot_bytes;
-        if (++st_slot == SLOTS) { st_slot = 0; st_dst = smem0 + lane * 16; }
+        ++sg;
+        if (++sg_slot == GSLOTS) sg_slot = 0;
     };
-    // lane = candidate (ref, dx, dy) in scan order, NPASS passes of 32; per-candidate constants are computed once
-    int c_off[NPASS], c_pk = 0;
-#pragma unroll
-    for (int p = 0; p < NPASS; ++p) {
-        const int cand = lane + 32 * p;
-        const int ref = cand / 9, r9 = cand - ref * 9, ox = r9 / 3, oy = r9 - ox * 3;
-        c_off[p] = cand < ncand ? (ref * (FT_N * FT_N) + ox * FT_N + oy) * 2 : -1;
-        c_pk |= (ref | (ox << 4) | (oy << 6)) << (8 * p);
-    }
-    int mvx = 0, mvy = 0, mvr = 0, slot_i = 0, blk = 0, craw = 0;
+    int mvx = 0, mvy = 0, mvr = 0, blk = 0, gslot = 0;
     bool pending = false;                        // block `blk` was handed to the cooperative step
-    // bookkeeping of one finished block: stage block blk + D, make sure block blk + 1 has landed, fetch its centre
-    auto advance = [&]() {
-        __syncwarp();                               // every lane has read this step's slot entries ...
-        stage();                                    // ... before the slot of block blk - 1 is refilled
-        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
-        __syncwarp();
-        if (++slot_i == SLOTS) slot_i = 0;
-        craw = *reinterpret_cast<const int*>(fc_smem + slot_i * slot_bytes + tbytes);
-        ++blk;
-    };
     if (walker) {
-        for (int p = 0; p < D; ++p) stage();
-        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");       // block 0 is staged
+        for (int p = 0; p < DG; ++p) stage();
+        stage();
+        asm volatile("cp.async.wait_group %0;" ::"n"(DG) : "memory");         // group 0 has landed
         __syncwarp();
-        craw = *reinterpret_cast<const int*>(fc_smem + tbytes);                // centre of block 0: x | y << 16
     }
     while (true) {
         if (walker) {
-            if (pending) { mvx = s_mvout[0]; mvy = s_mvout[1]; mvr = s_mvout[2]; advance(); pending = false; }
+            if (pending) {
+                mvx = s_mvout[0]; mvy = s_mvout[1]; mvr = s_mvout[2]; pending = false;
+                if ((++blk & (GB - 1)) == 0) {                                  // next group
+                    __syncwarp(); stage();
+                    asm volatile("cp.async.wait_group %0;" ::"n"(DG) : "memory");
+                    __syncwarp();
+                    if (++gslot == GSLOTS) gslot = 0;
+                }
+            }
             while (blk < nblk) {
-                const unsigned char* slot = fc_smem + slot_i * slot_bytes;
+                const unsigned char* grp = ring + gslot * GBYTES;
+                const int bi = blk & (GB - 1);
+                const int craw = *reinterpret_cast<const int*>(grp + GB * FT_TRANS + bi * 8);     // centre: x | y << 16
                 const int sx = mvx - (int)(short)(craw & 0xFFFF) + FT_K, sy = mvy - (craw >> 16) + FT_K;
-                if (!((unsigned)sx <= 2u * FT_K && (unsigned)sy <= 2u * FT_K)) { pending = true; break; }
-                const unsigned char* tb = slot + (sx * FT_N + sy) * 2;
-                uint32_t best = 0xFFFFFFFFu;
-#pragma unroll
-                for (int p = 0; p < NPASS; ++p)
-                    if (c_off[p] >= 0) best = min(best, ((uint32_t)*reinterpret_cast<const uint16_t*>(tb + c_off[p]) << 7) | (uint32_t)(lane + 32 * p));
-                // off the critical path (nothing here depends on the predictor); the table reads of this step were issued above
+                if (!((unsigned)sx < (unsigned)FT_S && (unsigned)sy < (unsigned)FT_S)) { pending = true; break; }
+                const int t = grp[bi * FT_TRANS + sx * FT_S + sy];
                 if (lane == 0) st[blk] = make_short4((short)mvx, (short)mvy, (short)mvr, 0);      // the predictor this block used
-                advance();
-                best = __reduce_min_sync(0xFFFFFFFFu, best);
-                if (best < (0xFFFFu << 7)) {           // some candidate is valid: the winner's (ref, ox, oy) from the lane that owns it
-                    const int w = __shfl_sync(0xFFFFFFFFu, c_pk, (int)(best & 31u)) >> (8 * (int)((best >> 5) & 3u));
-                    mvr = w & 15; mvx += ((w >> 4) & 3) - 1; mvy += ((w >> 6) & 3) - 1;
+                if (t != 0xFF) { mvr = t >> 4; mvx += ((t >> 2) & 3) - 1; mvy += (t & 3) - 1; }
+                if ((++blk & (GB - 1)) == 0) {                                  // next group: stage one more, wait for the next one
+                    __syncwarp(); stage();
+                    asm volatile("cp.async.wait_group %0;" ::"n"(DG) : "memory");
+                    __syncwarp();
+                    if (++gslot == GSLOTS) gslot = 0;
                 }
             }
             if (lane == 0) { s_req[0] = pending ? blk : nblk; s_req[1] = mvx; s_req[2] = mvy; s_req[3] = mvr; }
