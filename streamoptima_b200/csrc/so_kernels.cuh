@@ -1041,40 +1041,44 @@ __global__ void __launch_bounds__(576) fast_chain16_kernel(const FlowArgs a, con
         ++sg;
         if (++sg_slot == GSLOTS) sg_slot = 0;
     };
-    int mvx = 0, mvy = 0, mvr = 0, blk = 0, gslot = 0;
+    int mvx = 0, mvy = 0, mvr = 0, blk = 0, gslot = 0, craw = 0;
     bool pending = false;                        // block `blk` was handed to the cooperative step
+    // centre (x | y << 16) of block b, whose group sits in slot gs
+    auto centre = [&](int b, int gs) { return *reinterpret_cast<const int*>(ring + gs * GBYTES + GB * FT_TRANS + (b & (GB - 1)) * 8); };
+    // block blk is done: move on; at a group boundary stage one more group and make sure the group after the next has landed
+    auto next_block = [&]() {
+        if ((++blk & (GB - 1)) == 0) {
+            __syncwarp(); stage();
+            asm volatile("cp.async.wait_group %0;" ::"n"(DG - 1) : "memory");
+            __syncwarp();
+            if (++gslot == GSLOTS) gslot = 0;
+        }
+    };
     if (walker) {
         for (int p = 0; p < DG; ++p) stage();
         stage();
-        asm volatile("cp.async.wait_group %0;" ::"n"(DG) : "memory");         // group 0 has landed
+        asm volatile("cp.async.wait_group %0;" ::"n"(DG - 1) : "memory");     // groups 0 and 1 have landed
         __syncwarp();
+        craw = centre(0, 0);
     }
     while (true) {
         if (walker) {
             if (pending) {
                 mvx = s_mvout[0]; mvy = s_mvout[1]; mvr = s_mvout[2]; pending = false;
-                if ((++blk & (GB - 1)) == 0) {                                  // next group
-                    __syncwarp(); stage();
-                    asm volatile("cp.async.wait_group %0;" ::"n"(DG) : "memory");
-                    __syncwarp();
-                    if (++gslot == GSLOTS) gslot = 0;
-                }
+                next_block();
+                craw = centre(blk, gslot);
             }
             while (blk < nblk) {
-                const unsigned char* grp = ring + gslot * GBYTES;
-                const int bi = blk & (GB - 1);
-                const int craw = *reinterpret_cast<const int*>(grp + GB * FT_TRANS + bi * 8);     // centre: x | y << 16
                 const int sx = mvx - (int)(short)(craw & 0xFFFF) + FT_K, sy = mvy - (craw >> 16) + FT_K;
                 if (!((unsigned)sx < (unsigned)FT_S && (unsigned)sy < (unsigned)FT_S)) { pending = true; break; }
-                const int t = grp[bi * FT_TRANS + sx * FT_S + sy];
+                const int t = ring[gslot * GBYTES + (blk & (GB - 1)) * FT_TRANS + sx * FT_S + sy];
+                // while the table byte is on its way: the next block's centre (its group has landed already) and the record
+                const int gnext = ((blk & (GB - 1)) == GB - 1) ? (gslot + 1 == GSLOTS ? 0 : gslot + 1) : gslot;
+                const int craw_next = centre(blk + 1, gnext);
                 if (lane == 0) st[blk] = make_short4((short)mvx, (short)mvy, (short)mvr, 0);      // the predictor this block used
                 if (t != 0xFF) { mvr = t >> 4; mvx += ((t >> 2) & 3) - 1; mvy += (t & 3) - 1; }
-                if ((++blk & (GB - 1)) == 0) {                                  // next group: stage one more, wait for the next one
-                    __syncwarp(); stage();
-                    asm volatile("cp.async.wait_group %0;" ::"n"(DG) : "memory");
-                    __syncwarp();
-                    if (++gslot == GSLOTS) gslot = 0;
-                }
+                next_block();
+                craw = craw_next;
             }
             if (lane == 0) { s_req[0] = pending ? blk : nblk; s_req[1] = mvx; s_req[2] = mvy; s_req[3] = mvr; }
         }
