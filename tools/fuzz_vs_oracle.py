@@ -1,0 +1,52 @@
+"""Randomised differential test: small random configurations, CUDA path vs the CPU oracle, everything bit for bit.
+    python tools/fuzz_vs_oracle.py [n_cases] [seed]        (GPU box; about 2 s per case)"""
+import os, sys, time, traceback
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import codec_oracle as co
+from oracle.packing import package_to_arrays
+from streamoptima_b200 import synth
+from streamoptima_b200.Encoder import Y_Video_codec
+Y_Video_codec.write_recon_yuv = False
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+TAB = [[9000, 7000, 5200, 3900, 2800, 1900, 1300, 900, 600, 400, 250, 100], [6000, 4600, 3400, 2500, 1800, 1200, 800, 560, 380, 250, 160, 60]]
+bad = 0
+t0 = time.time()
+for n in range(n_cases):
+    bs = int(rng.choice([4, 8, 16, 16]))
+    H = bs * int(rng.integers(2, max(3, 80 // bs))); W = bs * int(rng.integers(3, max(4, 112 // bs)))
+    F = int(rng.integers(2, 5))
+    r = int(rng.choice([0, 1, 2, 3, 4, 5, 7, 8, 16])) if bs == 16 else int(rng.choice([0, 1, 2, 3, 4, 6]))
+    kw = dict(block_size=bs, search_range=r, Qp=int(rng.integers(0, 8)), intra_dur=int(rng.integers(1, 6)))
+    if rng.random() < 0.5: kw["FMEEnable"] = True
+    if rng.random() < 0.5: kw["nRefFrames"] = int(rng.integers(2, 5))
+    if rng.random() < 0.4: kw.update(VBSEnable=True, lam=float(rng.choice([0.005, 0.02, 0.3])))
+    mode = rng.random()
+    if mode < 0.3: kw["fast_me"] = True
+    pm = rng.random()
+    if pm < 0.15 and not (kw.get("VBSEnable") and kw.get("fast_me")): kw["ParallelMode"] = 2
+    elif pm < 0.25 and not (kw.get("VBSEnable") and kw.get("fast_me")): kw["ParallelMode"] = 1
+    if rng.random() < 0.2: kw.update(RCFlag=1, targetBR=f"{int(rng.integers(300, 1500))} kbps", qp_rate_tables=TAB)
+    kind = str(rng.choice(["translating", "zooming", "flat_ties"]))
+    frames = synth.make(kind, F=F, H=H, W=W, seed=int(rng.integers(0, 1000)))
+    try:
+        try:
+            o = co.OracleCodec(H, W, F, y_only_frame_arr=frames, **kw).encode()
+        except TypeError:
+            continue            # rate table has no QP under the row budget: the reference crashes the same way
+        e = dict(kw)
+        c = Y_Video_codec(H, W, F, e.pop("block_size"), e.pop("search_range"), e.pop("Qp"), e.pop("intra_dur"), 0, y_only_frame_arr=frames, **e)
+        c.encode()
+        p = c.encoded_package.packed
+        split, mv, lev = package_to_arrays(o["frame_types"], o["mvs"], o["levels"], H, W, bs)
+        ok = (np.array_equal(p["split"], split) and np.array_equal(p["mv"], mv) and np.array_equal(p["levels"], lev)
+              and np.array_equal(p["recon"], o["recon"]) and c.encoded_package["frame_type_seq"] == o["frame_types"])
+    except Exception:
+        traceback.print_exc()
+        ok = False
+    if not ok:
+        bad += 1
+        print("MISMATCH", n, kind, (F, H, W), kw, flush=True)
+print(f"{n_cases} cases, {bad} mismatches, {time.time() - t0:.0f} s")
+sys.exit(1 if bad else 0)
