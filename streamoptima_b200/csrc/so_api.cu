@@ -772,8 +772,9 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
         dim3 grid(a.chain ? 1 : ctx->nblk, units);
         static const bool fast_generic = std::getenv("SO_FAST_GENERIC") != nullptr;      // tests: force the generic kernel
         static const bool fast_no_table = std::getenv("SO_FAST_NO_TABLE") != nullptr;    // A/B: chained fast_me16_kernel
-        if (g.bs == 16 && g.W % 16 == 0 && !fast_generic && a.chain && !fast_no_table) {
-            // table-driven chain: SAD tables around last frame's predictors -> one-warp walk -> parallel results
+        const bool packed = (g.bs == 16 || g.bs == 8) && g.W % g.bs == 0 && !fast_generic;      // word-packed kernels: 16x16 and 8x8
+        if (packed && a.chain && !fast_no_table) {
+            // table-driven chain: transition tables around last frame's predictors -> one-warp walk -> parallel results
             const size_t nblk_pad = ((size_t)ctx->nblk + 3) & ~(size_t)3;           // the chain stages groups of four blocks
             if (!ctx->fm_table) {
                 CU(cudaMalloc(&ctx->fm_table, (size_t)ctx->batch * nblk_pad * FT_TRANS));
@@ -781,18 +782,23 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
                 CU(cudaMemsetAsync(ctx->fm_table, 0xFF, (size_t)ctx->batch * nblk_pad * FT_TRANS, st));
                 CU(cudaMemsetAsync(ctx->fm_state, 0, (size_t)ctx->batch * nblk_pad * sizeof(short4), st));
             }
-            {
-                const int nr = std::min(a.nref_fast, a.g.nref), nph = a.g.fme ? 4 : 1;
-                const size_t tsm = (size_t)nr * nph * FTR_H * FTR_W + 256 + (size_t)nr * FT_N * FT_N * 2;
-                fast_table16_kernel<<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
-                fast_chain16_kernel<<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
-            }
+            const int nr = std::min(a.nref_fast, a.g.nref), nph = a.g.fme ? 4 : 1;
+            const size_t tsm = (size_t)nr * nph * FTR_H * FTR_W + 256 + (size_t)nr * FT_N * FT_N * 2;
             FlowArgs b = a;
             b.chain = 0; b.mvp_in = ctx->fm_state; b.mvp_in_stride = nblk_pad;
-            fast_me16_kernel<<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
+            if (g.bs == 16) {
+                fast_table16_kernel<16><<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
+                fast_chain16_kernel<16><<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
+                fast_me16_kernel<16><<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
+            } else {
+                fast_table16_kernel<8><<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
+                fast_chain16_kernel<8><<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
+                fast_me16_kernel<8><<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
+            }
             ctx->launches += 2;
         }
-        else if (g.bs == 16 && g.W % 16 == 0 && !fast_generic) fast_me16_kernel<<<grid, 576, 0, st>>>(a);
+        else if (packed && g.bs == 16) fast_me16_kernel<16><<<grid, 576, 0, st>>>(a);
+        else if (packed) fast_me16_kernel<8><<<grid, 576, 0, st>>>(a);
         else if (g.bs == 16) fast_me_kernel<16><<<grid, nt, 0, st>>>(a);
         else if (g.bs == 8) fast_me_kernel<8><<<grid, nt, 0, st>>>(a);
         else fast_me_kernel<4><<<grid, nt, 0, st>>>(a);

@@ -745,15 +745,17 @@ __global__ void fast_me_kernel(const FlowArgs a) {
 // blocks [b0, b1) of one unit by the 576 threads of a CTA; chain: the predictor is carried from block to block starting at
 // mv0 (otherwise it is a.mvp_in[blk] or zero); state_out (optional) receives the predictor every block used, mv_out
 // (optional, shared memory) the whole-block vector of the last block
+template <int BS>
 __device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b0, int b1, bool chain, int mvx0, int mvy0, int mvr0,
                                               short4* state_out, int* mv_out) {
-    constexpr int BS = 16, S = 8, CPP = 36;           // candidates per pass
+    static_assert(BS == 16 || BS == 8, "word-packed rows: 16x16 or 8x8 blocks");
+    constexpr int S = BS / 2, WPR = BS / 4, CPP = 576 / BS;           // words per row, candidates per pass
     __shared__ unsigned int sadq[SO_MAX_REF * 9][4];
-    __shared__ __align__(16) uint32_t s_cur[BS][4];
+    __shared__ __align__(16) uint32_t s_cur[BS][WPR];
     __shared__ int s_mvp[3];
     const FrameGeom& g = a.g;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int cl = t >> 4, row = t & 15;
+    const int cl = t / BS, row = t % BS;
     const int mult = g.fme ? 2 : 1;
     const int nref = min(a.nref_fast, g.nref);
     const int ncand = nref * 9;
@@ -761,7 +763,7 @@ __device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b
     const uint8_t* cur = a.cur + unit * a.cur_unit_stride;
     const size_t shift_stride = a.ring.plane_stride >> 2;
     if (t == 0) { s_mvp[0] = mvx0; s_mvp[1] = mvy0; s_mvp[2] = mvr0; }
-    if (t < 64) s_cur[t >> 2][t & 3] = *reinterpret_cast<const uint32_t*>(cur + (size_t)((b0 / g.nbx) * BS + (t >> 2)) * g.W + (b0 % g.nbx) * BS + (t & 3) * 4);
+    if (t < BS * WPR) s_cur[t / WPR][t % WPR] = *reinterpret_cast<const uint32_t*>(cur + (size_t)((b0 / g.nbx) * BS + t / WPR) * g.W + (b0 % g.nbx) * BS + (t % WPR) * 4);
     __syncthreads();
     for (int blk = b0; blk < b1; ++blk) {
         const int bx = blk % g.nbx, by = blk / g.nbx;
@@ -770,11 +772,13 @@ __device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b
         if (!chain && a.mvp_in) { const short4 m = a.mvp_in[unit * a.mvp_in_stride + blk]; mvx = m.x; mvy = m.y; mvr = m.z; }
         if (state_out && t == 0) state_out[blk] = make_short4((short)mvx, (short)mvy, (short)mvr, 0);
         uint32_t cnext = 0;
-        if (t < 64 && blk + 1 < b1) {
+        if (t < BS * WPR && blk + 1 < b1) {
             const int nb = blk + 1;
-            cnext = *reinterpret_cast<const uint32_t*>(cur + (size_t)((nb / g.nbx) * BS + (t >> 2)) * g.W + (nb % g.nbx) * BS + (t & 3) * 4);
+            cnext = *reinterpret_cast<const uint32_t*>(cur + (size_t)((nb / g.nbx) * BS + t / WPR) * g.W + (nb % g.nbx) * BS + (t % WPR) * 4);
         }
-        const uint4 cw = *reinterpret_cast<const uint4*>(&s_cur[row][0]);
+        uint32_t cwv[WPR];
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) cwv[w] = s_cur[row][w];
         for (int c0 = 0; c0 < ncand; c0 += CPP) {
             const int cand = c0 + cl;
             uint32_t sl = 0, sr = 0;
@@ -783,13 +787,15 @@ __device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b
                 const int Xh = x * mult + dx, Yh = y * mult + dy;
                 const int ph = g.fme ? (((Yh & 1) << 1) | (Xh & 1)) : 0;
                 const int col0 = g.fme ? (Xh >> 1) : Xh, Y = (g.fme ? (Yh >> 1) : Yh) + row;
-                uint32_t pw[4] = {0u, 0u, 0u, 0u};
+                uint32_t pw[WPR];
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) pw[w] = 0u;
                 if (Y >= 0 && Y < g.H) {
                     const uint8_t* pl = a.ring.plane(unit, ref, ph);
                     const int cs = col0 & 3, colA = col0 - cs;
                     const uint8_t* rowp = pl + (size_t)Y * g.pitch;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
+                    for (int w = 0; w < WPR; ++w) {
                         const int cA = colA + 4 * w;
                         if (cA >= 0 && col0 + 4 * w + 3 < g.W) {
                             pw[w] = __ldg(reinterpret_cast<const uint32_t*>(rowp + (size_t)cs * shift_stride + cA));
@@ -802,21 +808,23 @@ __device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b
                         }
                     }
                 }
-                sl = sad4_acc(cw.x, pw[0], 0u); sl = sad4_acc(cw.y, pw[1], sl);
-                sr = sad4_acc(cw.z, pw[2], 0u); sr = sad4_acc(cw.w, pw[3], sr);
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) {
+                    if (w < WPR / 2) sl = sad4_acc(cwv[w], pw[w], sl); else sr = sad4_acc(cwv[w], pw[w], sr);
+                }
             }
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
+            for (int o = 1; o < S; o <<= 1) {
                 sl += __shfl_xor_sync(0xFFFFFFFFu, sl, o);
                 sr += __shfl_xor_sync(0xFFFFFFFFu, sr, o);
             }
-            if (cand < ncand && (row & 7) == 0) {
-                sadq[cand][(row >> 3) * 2] = sl;
-                sadq[cand][(row >> 3) * 2 + 1] = sr;
+            if (cand < ncand && (row % S) == 0) {
+                sadq[cand][(row / S) * 2] = sl;
+                sadq[cand][(row / S) * 2 + 1] = sr;
             }
         }
         __syncthreads();
-        if (t < 64 && blk + 1 < b1) s_cur[t >> 2][t & 3] = cnext;
+        if (t < BS * WPR && blk + 1 < b1) s_cur[t / WPR][t % WPR] = cnext;
         const bool eligible = a.vbs && bx != 0 && by != 0;
         if (warp < 5 && (warp == 0 || eligible)) {
             const int e = warp;
@@ -855,9 +863,10 @@ __device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b
     }
 }
 
+template <int BS>
 __global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
     const int nblk = a.g.nbx * a.g.nby;
-    fast_me16_run(a, a.unit0 + blockIdx.y, a.chain ? 0 : (int)blockIdx.x, a.chain ? nblk : (int)blockIdx.x + 1, a.chain != 0, 0, 0, 0, nullptr, nullptr);
+    fast_me16_run<BS>(a, a.unit0 + blockIdx.y, a.chain ? 0 : (int)blockIdx.x, a.chain ? nblk : (int)blockIdx.x + 1, a.chain != 0, 0, 0, 0, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -879,43 +888,6 @@ __global__ void __launch_bounds__(576) fast_me16_kernel(const FlowArgs a) {
 constexpr int FT_K = 4;
 constexpr int FT_N = 2 * FT_K + 3;          // table offsets per axis: centre +- (K + 1)
 
-// whole-block SAD of the 16x16 block at (x, y) against reference `ref` displaced by (dx, dy) search units; rows of the
-// predictor are 16 contiguous bytes of one phase plane, read as aligned words from the copy shifted by (column & 3)
-__device__ __forceinline__ uint32_t fast_sad16(const FlowArgs& a, int unit, int ref, int x, int y, int dx, int dy, const uint8_t* cur) {
-    const FrameGeom& g = a.g;
-    const int mult = g.fme ? 2 : 1;
-    const int Xh = x * mult + dx, Yh = y * mult + dy;
-    const int ph = g.fme ? (((Yh & 1) << 1) | (Xh & 1)) : 0;
-    const int col0 = g.fme ? (Xh >> 1) : Xh, Y0 = g.fme ? (Yh >> 1) : Yh;
-    const int cs = col0 & 3, colA = col0 - cs;
-    const uint8_t* pl = a.ring.plane(unit, ref, ph);
-    const uint8_t* plc = pl + (size_t)cs * (a.ring.plane_stride >> 2);
-    uint32_t sad = 0;
-#pragma unroll 4
-    for (int row = 0; row < 16; ++row) {
-        const int Y = Y0 + row;
-        const uint4 cw = *reinterpret_cast<const uint4*>(cur + (size_t)(y + row) * g.W + x);
-        const uint32_t cwv[4] = {cw.x, cw.y, cw.z, cw.w};
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            uint32_t pw = 0u;
-            if (Y >= 0 && Y < g.H) {
-                const int cA = colA + 4 * w;
-                if (cA >= 0 && col0 + 4 * w + 3 < g.W) pw = __ldg(reinterpret_cast<const uint32_t*>(plc + (size_t)Y * g.pitch + cA));
-                else {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int col = col0 + 4 * w + b;
-                        if (col >= 0 && col < g.W) pw |= (uint32_t)pl[(size_t)Y * g.pitch + col] << (8 * b);
-                    }
-                }
-            }
-            sad = sad4_acc(cwv[w], pw, sad);
-        }
-    }
-    return sad;
-}
-
 // One CTA per block.  The pixels any of the 11 x 11 offsets can touch form, per (reference, phase plane), a region of
 // 26 rows x 32 bytes: it is copied to shared memory once (aligned words, zero outside the frame), then each thread takes
 // candidates and reads its 16 rows as five words + funnel shifts -- no scattered global loads.
@@ -924,9 +896,10 @@ constexpr int FTR_H = 16 + FT_N - 1, FTR_W = 32;              // region rows (in
 constexpr int FT_S = 2 * FT_K + 1;          // predictor states per axis served by a table
 constexpr int FT_TRANS = 96;                // bytes of transition table per block (81 used, 16-byte granules)
 
+template <int BS>
 __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uint8_t* trans, size_t trans_unit_stride, const short4* state,
                                                            size_t state_unit_stride) {
-    constexpr int BS = 16;
+    constexpr int WPR = BS / 4;
     extern __shared__ __align__(16) unsigned char ft_smem[];   // [nref * nph][FTR_H][FTR_W] regions, then the current block
     const FrameGeom& g = a.g;
     const int blk = blockIdx.x, unit = a.unit0 + blockIdx.y;
@@ -956,10 +929,10 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
         }
         reinterpret_cast<uint32_t*>(ft_smem)[e] = v;
     }
-    if (threadIdx.x < 64)
-        s_cur[threadIdx.x] = *reinterpret_cast<const uint32_t*>(a.cur + unit * a.cur_unit_stride + (size_t)(y + (threadIdx.x >> 2)) * g.W + x + (threadIdx.x & 3) * 4);
+    if (threadIdx.x < BS * WPR)
+        s_cur[threadIdx.x] = *reinterpret_cast<const uint32_t*>(a.cur + unit * a.cur_unit_stride + (size_t)(y + threadIdx.x / WPR) * g.W + x + (threadIdx.x % WPR) * 4);
     __syncthreads();
-    uint16_t* s_sad = reinterpret_cast<uint16_t*>(s_cur + 64);               // [nref][FT_N][FT_N]
+    uint16_t* s_sad = reinterpret_cast<uint16_t*>(s_cur + BS * WPR);         // [nref][FT_N][FT_N]
     for (int e = threadIdx.x; e < nref * FT_N * FT_N; e += blockDim.x) {
         const int ref = e / (FT_N * FT_N), rem = e - ref * (FT_N * FT_N);
         const int ix = rem / FT_N, iy = rem - ix * FT_N;
@@ -976,12 +949,11 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
 #pragma unroll 4
             for (int row = 0; row < BS; ++row) {
                 const uint32_t* rw = reinterpret_cast<const uint32_t*>(rg + row * FTR_W);
-                const uint4 cw = *reinterpret_cast<const uint4*>(s_cur + row * 4);
-                const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3], q4 = rw[4];
-                sad = sad4_acc(cw.x, __funnelshift_r(q0, q1, sh), sad);
-                sad = sad4_acc(cw.y, __funnelshift_r(q1, q2, sh), sad);
-                sad = sad4_acc(cw.z, __funnelshift_r(q2, q3, sh), sad);
-                sad = sad4_acc(cw.w, __funnelshift_r(q3, q4, sh), sad);
+                uint32_t q[WPR + 1];
+#pragma unroll
+                for (int w = 0; w <= WPR; ++w) q[w] = rw[w];
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) sad = sad4_acc(s_cur[row * WPR + w], __funnelshift_r(q[w], q[w + 1], sh), sad);
             }
         }
         s_sad[e] = (uint16_t)sad;
@@ -1004,9 +976,11 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
     }
 }
 
+template <int BS>
 __device__ __forceinline__ void fast_me16_run(const FlowArgs& a, int unit, int b0, int b1, bool chain, int mvx0, int mvy0, int mvr0,
                                               short4* state_out, int* mv_out);
 
+template <int BS>
 __global__ void __launch_bounds__(576) fast_chain16_kernel(const FlowArgs a, const uint8_t* trans, size_t trans_unit_stride, short4* state,
                                                            size_t state_unit_stride) {
     // Warp 0 walks the chain.  With the transition tables a step is one dependent shared-memory byte load plus a few integer
@@ -1085,7 +1059,7 @@ __global__ void __launch_bounds__(576) fast_chain16_kernel(const FlowArgs a, con
         __syncthreads();
         const int rb = s_req[0];
         if (rb >= nblk) break;
-        fast_me16_run(a, unit, rb, rb + 1, true, s_req[1], s_req[2], s_req[3], st, s_mvout);     // records st[rb], ends with a barrier
+        fast_me16_run<BS>(a, unit, rb, rb + 1, true, s_req[1], s_req[2], s_req[3], st, s_mvout);     // records st[rb], ends with a barrier
     }
     if (walker) asm volatile("cp.async.wait_group 0;" ::: "memory");
 }

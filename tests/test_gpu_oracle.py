@@ -192,12 +192,15 @@ from streamoptima_b200 import synth
 from streamoptima_b200.Encoder import Y_Video_codec
 Y_Video_codec.write_recon_yuv = False
 h = hashlib.sha256()
-for (F, H, W, kw) in ((4, 272, 480, dict(fast_me=True, FMEEnable=True, nRefFrames=4, VBSEnable=True, lam=0.015)),
-                      (3, 144, 176, dict(fast_me=True, nRefFrames=2)),
-                      (3, 272, 480, dict(fast_me=True, FMEEnable=True, ParallelMode=2)),
-                      (3, 1088, 1920, dict(fast_me=True, FMEEnable=True, nRefFrames=2))):
+for (F, H, W, bs, kw) in ((4, 272, 480, 16, dict(fast_me=True, FMEEnable=True, nRefFrames=4, VBSEnable=True, lam=0.015)),
+                          (3, 144, 176, 16, dict(fast_me=True, nRefFrames=2)),
+                          (3, 272, 480, 16, dict(fast_me=True, FMEEnable=True, ParallelMode=2)),
+                          (3, 1088, 1920, 16, dict(fast_me=True, FMEEnable=True, nRefFrames=2)),
+                          (5, 288, 352, 8, dict(fast_me=True, FMEEnable=True, nRefFrames=3, VBSEnable=True, lam=0.02)),
+                          (4, 144, 176, 8, dict(fast_me=True, nRefFrames=8)),
+                          (3, 288, 352, 8, dict(fast_me=True, FMEEnable=True, ParallelMode=2))):
     frames = synth.zooming(F, H, W, seed=12)
-    c = Y_Video_codec(H, W, F, 16, 16, 4, 8, 0, y_only_frame_arr=frames, **kw)
+    c = Y_Video_codec(H, W, F, bs, 16, 4, 8, 0, y_only_frame_arr=frames, **kw)
     c.encode()
     p = c.encoded_package.packed
     for k in ("split", "mv", "levels", "recon"):
@@ -207,8 +210,9 @@ print(h.hexdigest())
 
 
 def test_fast_me16_kernel_equals_generic():
-    """Latency-oriented fast-ME kernel for 16x16 blocks (thread = candidate x row, REDUX decision) against the generic
-    chain kernel that the goldens pin: half-pel + 4 refs + VBS, integer, ParallelMode 2 and a 1080p chain."""
+    """Fast-ME pipeline for 16x16 and 8x8 blocks (transition tables, one-warp chain walker, cooperative step, parallel
+    results) against the generic chain kernel that the goldens pin: half-pel + up to 8 refs + VBS, integer, ParallelMode 2
+    and a 1080p chain."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
     for extra in ({}, {"SO_FAST_GENERIC": "1"}):
