@@ -142,12 +142,17 @@ def test_batched_units_equal_single_sequences_r16():
     Y_Video_codec.write_recon_yuv = False
     U, F, H, W = 3, 4, 96, 128
     seqs = np.stack([synth.make(k, F=F, H=H, W=W, seed=70 + i) for i, k in enumerate(("translating", "zooming", "flat_ties"))])
-    for kw in (dict(FMEEnable=True, nRefFrames=3), dict(nRefFrames=2)):
-        cb = Y_Video_codec(H, W, F, 16, 16, 2, 8, 0, **kw)
+    for bs, kw in ((16, dict(FMEEnable=True, nRefFrames=3)), (16, dict(nRefFrames=2)),
+                   (16, dict(fast_me=True, FMEEnable=True, VBSEnable=True, lam=0.02, nRefFrames=2)),      # table-driven fast-ME chain,
+                   (8, dict(fast_me=True, FMEEnable=True, nRefFrames=3))):                                # one walker per unit
+        cb = Y_Video_codec(H, W, F, bs, 16, 2, 8, 0, **kw)
         ob = cb.encode_arrays(seqs)
         got = {k: np.array(ob[k]) for k in ("split", "mv", "levels", "recon", "row_sizes")}
+        ob2 = cb.encode_arrays(seqs)                    # again: the fast-ME tables are now centred on the previous run's predictors
+        for k in got:
+            np.testing.assert_array_equal(got[k], ob2[k], err_msg=f"second run {k} {kw}")
         for u in range(U):
-            cs = Y_Video_codec(H, W, F, 16, 16, 2, 8, 0, **kw)
+            cs = Y_Video_codec(H, W, F, bs, 16, 2, 8, 0, **kw)
             o1 = cs.encode_arrays(seqs[u])
             for k in got:
                 np.testing.assert_array_equal(got[k][u], o1[k][0], err_msg=f"{k} unit {u} {kw}")
