@@ -27,7 +27,10 @@ for n in range(n_cases):
     pm = rng.random()
     if pm < 0.15 and not (kw.get("VBSEnable") and kw.get("fast_me")): kw["ParallelMode"] = 2
     elif pm < 0.25 and not (kw.get("VBSEnable") and kw.get("fast_me")): kw["ParallelMode"] = 1
-    if rng.random() < 0.2: kw.update(RCFlag=1, targetBR=f"{int(rng.integers(300, 1500))} kbps", qp_rate_tables=TAB)
+    rc = rng.random()
+    if rc < 0.2: kw.update(RCFlag=1, targetBR=f"{int(rng.integers(300, 1500))} kbps", qp_rate_tables=TAB)
+    elif rc < 0.3: kw.update(RCFlag=2, targetBR=f"{int(rng.integers(300, 1500))} kbps", qp_rate_tables=TAB,
+                             intra_thresh=int(rng.integers(200, 6000)))      # scene-cut re-encode (Encoder.py:1851-1856)
     kind = str(rng.choice(["translating", "zooming", "flat_ties"]))
     frames = synth.make(kind, F=F, H=H, W=W, seed=int(rng.integers(0, 1000)))
     try:
