@@ -1216,7 +1216,10 @@ extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const
         o.row_sizes = ctx->sq_rows;
         o.stats = ctx->sq_stats;
         if (qp_rows_per_frame) CU(cudaMemcpyAsync(ctx->qp_rows_dev, qp_rows_per_frame + (size_t)f * g.nby, sizeof(int) * g.nby, cudaMemcpyHostToDevice, st));
-        const bool intra = frame_types[f] == 0 && ctx->p.parallel_mode != 1;
+        // decoder.py:504-509 decodes EVERY frame of a ParallelMode-1 stream as inter, so it cannot read the I frames a scene
+        // cut (RCFlag 2, Encoder.py:1851-1856) puts into such a stream; with the encoder's list semantics
+        // (reset_at_intra == 0, the round-trip mode) the frame type is honoured instead
+        const bool intra = frame_types[f] == 0 && (ctx->p.parallel_mode != 1 || !reset_at_intra);
         if (!intra && ctx->p.parallel_mode == 1) { rc = ref_reset_impl(ctx, st, false); if (rc) return rc; }     // decoder.py:504-509
         if (!intra) {
             if (ctx->list.empty()) { set_err(ctx, "inter frame with an empty reference list"); return SO_E_STATE; }

@@ -1,11 +1,12 @@
-"""Randomised differential test: small random configurations, CUDA path vs the CPU oracle, everything bit for bit.
+"""Randomised differential test: small random configurations, CUDA path vs the CPU oracle, everything bit for bit (packed
+outputs, both text streams, device-generated symbols, decode round trip).
     python tools/fuzz_vs_oracle.py [n_cases] [seed]        (GPU box; about 2 s per case)"""
 import os, sys, time, traceback
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import codec_oracle as co
 from oracle.packing import package_to_arrays
-from streamoptima_b200 import synth
+from streamoptima_b200 import synth, decoder as dec
 from streamoptima_b200.Encoder import Y_Video_codec
 Y_Video_codec.write_recon_yuv = False
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
@@ -46,6 +47,17 @@ for n in range(n_cases):
         split, mv, lev = package_to_arrays(o["frame_types"], o["mvs"], o["levels"], H, W, bs)
         ok = (np.array_equal(p["split"], split) and np.array_equal(p["mv"], mv) and np.array_equal(p["levels"], lev)
               and np.array_equal(p["recon"], o["recon"]) and c.encoded_package["frame_type_seq"] == o["frame_types"])
+        if ok:      # text bitstreams (host formatters and device-generated symbols) and a decode round trip on the GPU
+            rcf = kw.get("RCFlag")
+            want_mv = [co.mv_text_frame(t, m, q, W // bs, rcf) for t, m, q in zip(o["frame_types"], o["mvs"], o["qp_rows"])]
+            want_res = [co.res_text_frame(l) for l in o["levels"]]
+            mv_lines, res_lines = c.bitstream_lines()
+            ok = mv_lines == want_mv and res_lines == want_res and c.residual_lines_from_symbols() == want_res
+            d = dec.decoder(0, kw["intra_dur"], bs, F, H, W, kw["Qp"], kw.get("nRefFrames", 1), kw.get("FMEEnable", False), kw.get("lam"),
+                            kw.get("VBSEnable", False), RCFlag=rcf, ParallelMode=kw.get("ParallelMode", 0))
+            qp = c.encoded_package["Qp_per_row_per_frame"] if (rcf or 0) > 0 else None
+            out = d.decode_arrays(p["frame_types"], p["split"], p["mv"], p["levels"], qp, reset_at_intra=False)
+            ok = ok and np.array_equal(out, p["recon"])
     except Exception:
         traceback.print_exc()
         ok = False
