@@ -175,7 +175,9 @@ int64_t so_format_residual_frame_symbols(const uint8_t* split, const uint32_t* o
  * buffers in and out, one sequence (unit).  frame_types u8 [n_frames]; split / mv / levels as so_encode_sequence writes
  * them; qp_rows_per_frame i32 [n_frames][height/block_size] or NULL (RCFlag off).  reset_at_intra != 0 clears the
  * reference list at I frames like decoder.py:520 does; 0 keeps the ENCODER's list semantics (Encoder.py:1864-1867),
- * which is what round-trips streams encoded with nRefFrames > 1 (quirk Q7).  out_frames u8 [n_frames][height][width]. */
+ * which is what round-trips streams encoded with nRefFrames > 1 (quirk Q7); in that mode the I frames a scene cut puts into
+ * a ParallelMode-1 stream are decoded as intra (decoder.py:504-509 decodes every frame of such a stream as inter).
+ * out_frames u8 [n_frames][height][width]. */
 int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
                        const int32_t* qp_rows_per_frame, int n_frames, int reset_at_intra, uint8_t* out_frames);
 
