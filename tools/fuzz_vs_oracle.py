@@ -19,9 +19,11 @@ for n in range(n_cases):
     H = bs * int(rng.integers(2, max(3, 80 // bs))); W = bs * int(rng.integers(3, max(4, 112 // bs)))
     F = int(rng.integers(2, 5))
     r = int(rng.choice([0, 1, 2, 3, 4, 5, 7, 8, 16])) if bs == 16 else int(rng.choice([0, 1, 2, 3, 4, 6]))
-    kw = dict(block_size=bs, search_range=r, Qp=int(rng.integers(0, 8)), intra_dur=int(rng.integers(1, 6)))
+    if rng.random() < 0.04: r = int(rng.choice([17, 20, 33]))                      # search chunks (ranges above 16)
+    kw = dict(block_size=bs, search_range=r, Qp=int(rng.integers(0, {4: 10, 8: 11, 16: 12}[bs])), intra_dur=int(rng.integers(1, 6)))
     if rng.random() < 0.5: kw["FMEEnable"] = True
-    if rng.random() < 0.5: kw["nRefFrames"] = int(rng.integers(2, 5))
+    if rng.random() < 0.5: kw["nRefFrames"] = int(rng.integers(2, 5)) if rng.random() < 0.85 else int(rng.integers(5, 9))
+    if r > 16: F = min(F, 3)
     if rng.random() < 0.4: kw.update(VBSEnable=True, lam=float(rng.choice([0.005, 0.02, 0.3])))
     mode = rng.random()
     if mode < 0.3: kw["fast_me"] = True
