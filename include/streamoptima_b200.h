@@ -209,6 +209,14 @@ int so_write_bitstream_files(const uint8_t* frame_types, const uint8_t* split, c
                              const int32_t* qp_rows_per_frame, int n_frames, int width, int height, int block_size,
                              const char* mv_path, const char* residual_path, int n_threads);
 
+/* decode_differential_entropy (decoder.py:590-690): the two text streams -> packed arrays (as so_encode_sequence writes
+ * them), lines parsed in parallel on host threads.  frame_types u8 [n_frames], split u8 [n_frames][n_blocks], mv i16
+ * [n_frames][n_blocks][4][3], levels i16 [n_frames][height][width], qp_rows i32 [n_frames][height / block_size] (filled when
+ * rc_on != 0).  SO_E_INVALID on unreadable, short or malformed input.  Host only: no device needed. */
+int so_parse_bitstream_files(const char* mv_path, const char* residual_path, int n_frames, int width, int height, int block_size,
+                             int rc_on, uint8_t* frame_types, uint8_t* split, int16_t* mv, int16_t* levels, int32_t* qp_rows,
+                             int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

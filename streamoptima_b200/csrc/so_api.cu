@@ -1450,6 +1450,178 @@ extern "C" int so_write_bitstream_files(const uint8_t* frame_types, const uint8_
     return ok ? SO_OK : SO_E_INVALID;
 }
 
+// Parser of the two text streams (decode_differential_entropy, decoder.py:590-690): the inverse of
+// so_write_bitstream_files.  Frames are independent (the differential vectors restart at every frame), so the lines are
+// parsed in parallel on host threads.  Outputs as so_encode_sequence packs them; qp_rows i32 [n_frames][height /
+// block_size] is filled when rc_on != 0 (may be NULL otherwise).  Returns SO_E_INVALID on malformed or short input.
+namespace {
+struct Cursor {
+    const char* p; const char* e;
+    bool more() const { return p < e; }
+    bool number(long& v) {                       // next integer at or after p (skips anything that is not a digit or '-')
+        while (p < e && !((*p >= '0' && *p <= '9') || (*p == '-' && p + 1 < e && p[1] >= '0' && p[1] <= '9'))) ++p;
+        if (p >= e) return false;
+        bool neg = false;
+        if (*p == '-') { neg = true; ++p; }
+        long x = 0;
+        while (p < e && *p >= '0' && *p <= '9') { x = x * 10 + (*p - '0'); ++p; }
+        v = neg ? -x : x;
+        return true;
+    }
+};
+
+static void scan_order_tab(int n, std::vector<int>& idx) {      // Encoder.py:1095-1123 / decoder.py:573-586
+    idx.clear();
+    for (int k = 0; k < 2 * n - 1; ++k) {
+        int i = k < n ? 0 : k - n + 1, j = k < n ? k : n - 1;
+        while (i < n && j >= 0) { idx.push_back(i * n + j); ++i; --j; }
+    }
+}
+
+static bool parse_mv_line_c(const char* b, const char* e, int nblk, int bpr, bool rc_on, uint8_t* ftype, uint8_t* split, int16_t* mv,
+                            int32_t* qp_rows) {
+    Cursor c{b, e};
+    long t;
+    if (!c.number(t) || c.p >= e || *c.p != '|') return false;
+    ++c.p;
+    *ftype = (uint8_t)t;
+    long ref[3] = {0, 0, 0}, ref_qp = 0;
+    memset(split, 0, (size_t)nblk);
+    memset(mv, 0, (size_t)nblk * 12 * sizeof(int16_t));
+    for (int j = 0; j < nblk; ++j) {
+        const char* ie = (const char*)memchr(c.p, ';', (size_t)(e - c.p));
+        if (!ie) ie = e;
+        Cursor it{c.p, ie};
+        if (rc_on && j % bpr == 0) {
+            const char* at = (const char*)memchr(it.p, '@', (size_t)(ie - it.p));
+            long q;
+            Cursor qc{it.p, at ? at : ie};
+            if (!at || !qc.number(q)) return false;
+            ref_qp += q;
+            if (qp_rows) qp_rows[j / bpr] = (int32_t)ref_qp;
+            it.p = at + 1;
+        }
+        if (it.p >= ie || (*it.p != '0' && *it.p != '1') || it.p + 1 >= ie || it.p[1] != '\'') return false;
+        const bool sp = *it.p == '1';
+        it.p += 2;
+        split[j] = sp ? 1 : 0;
+        const int nvec = sp ? 4 : 1;
+        for (int k = 0; k < nvec; ++k) {
+            long v[3] = {0, 0, 0};
+            const int nc = t == 0 ? 1 : 3;
+            for (int q = 0; q < nc; ++q) if (!it.number(v[q])) return false;
+            if (t == 0) { ref[0] += v[0]; mv[(size_t)j * 12 + k * 3] = (int16_t)ref[0]; }
+            else {
+                for (int q = 0; q < 3; ++q) { ref[q] += v[q]; mv[(size_t)j * 12 + k * 3 + q] = (int16_t)ref[q]; }
+            }
+        }
+        c.p = ie < e ? ie + 1 : e;
+        if (j < nblk - 1 && ie >= e) return false;
+    }
+    return true;
+}
+
+static bool parse_res_line_c(const char* b, const char* e, int W, int H, int bs, const uint8_t* split, int16_t* lev,
+                             const std::vector<int>& o_full, const std::vector<int>& o_sub) {
+    const int nbx = W / bs, nblk = nbx * (H / bs), sub = bs / 2;
+    memset(lev, 0, (size_t)W * H * sizeof(int16_t));
+    const char* p = b;
+    for (int blk = 0; blk < nblk; ++blk) {
+        const char* ie = (const char*)memchr(p, ';', (size_t)(e - p));
+        if (!ie) ie = e;
+        if (p + 1 >= ie || p[1] != '\'' || (p[0] - '0') != split[blk]) return false;
+        const int y = (blk / nbx) * bs, x = (blk % nbx) * bs;
+        const int nl = split[blk] ? 4 : 1, n = split[blk] ? sub : bs;
+        const std::vector<int>& ord = split[blk] ? o_sub : o_full;
+        const char* q = p + 2;
+        for (int k = 0; k < nl; ++k) {
+            const char* lb = (const char*)memchr(q, '[', (size_t)(ie - q));
+            if (!lb) return false;
+            const char* le = (const char*)memchr(lb, ']', (size_t)(ie - lb));
+            if (!le) return false;
+            int16_t* dst = lev + (size_t)(y + (split[blk] ? (k >> 1) * sub : 0)) * W + x + (split[blk] ? (k & 1) * sub : 0);
+            Cursor c{lb + 1, le};
+            int pos = 0;
+            long s;
+            while (c.number(s)) {                  // entropy_decoder_block, decoder.py:548-586
+                if (s < 0) {
+                    for (long i = 0; i < -s; ++i) {
+                        long v;
+                        if (!c.number(v) || pos >= n * n) return false;
+                        const int o = ord[pos++];
+                        dst[(size_t)(o / n) * W + o % n] = (int16_t)v;
+                    }
+                } else if (s == 0) break;
+                else pos += (int)s;
+            }
+            q = le + 1;
+        }
+        p = ie < e ? ie + 1 : e;
+        if (blk < nblk - 1 && ie >= e) return false;
+    }
+    return true;
+}
+
+static bool read_file(const char* path, std::string& out) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize((size_t)std::max(0L, n));
+    const bool ok = n <= 0 || fread(&out[0], 1, (size_t)n, f) == (size_t)n;
+    fclose(f);
+    return ok;
+}
+
+static void line_spans(const std::string& s, std::vector<std::pair<const char*, const char*>>& out) {
+    const char* p = s.data();
+    const char* e = p + s.size();
+    while (p < e) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+        const char* le = nl ? nl : e;
+        bool blank = true;
+        for (const char* q = p; q < le; ++q) if (*q != ' ' && *q != '\r' && *q != '\t') { blank = false; break; }
+        if (!blank) out.emplace_back(p, le);
+        p = nl ? nl + 1 : e;
+    }
+}
+}  // namespace
+
+extern "C" int so_parse_bitstream_files(const char* mv_path, const char* residual_path, int n_frames, int width, int height, int block_size,
+                                        int rc_on, uint8_t* frame_types, uint8_t* split, int16_t* mv, int16_t* levels, int32_t* qp_rows,
+                                        int n_threads) {
+    if (!mv_path || !residual_path || !frame_types || !split || !mv || !levels || n_frames < 1 || block_size < 2 ||
+        width % block_size || height % block_size || (rc_on && !qp_rows)) return SO_E_INVALID;
+    std::string mvs, rss;
+    if (!read_file(mv_path, mvs) || !read_file(residual_path, rss)) return SO_E_INVALID;
+    std::vector<std::pair<const char*, const char*>> ml, rl;
+    line_spans(mvs, ml); line_spans(rss, rl);
+    if ((int)ml.size() < n_frames || (int)rl.size() < n_frames) return SO_E_INVALID;
+    const int nbx = width / block_size, nby = height / block_size, nblk = nbx * nby;
+    const size_t px = (size_t)width * height;
+    std::vector<int> o_full, o_sub;
+    scan_order_tab(block_size, o_full); scan_order_tab(block_size / 2, o_sub);
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::min(n_frames, 64)));
+    std::vector<int> okv(nt, 1);
+    std::vector<std::thread> th;
+    for (int w = 0; w < nt; ++w) {
+        th.emplace_back([&, w]() {
+            for (int f = w; f < n_frames; f += nt) {
+                uint8_t* sp = split + (size_t)f * nblk;
+                bool ok = parse_mv_line_c(ml[f].first, ml[f].second, nblk, nbx, rc_on != 0, frame_types + f, sp, mv + (size_t)f * nblk * 12,
+                                          rc_on ? qp_rows + (size_t)f * nby : nullptr);
+                ok = ok && parse_res_line_c(rl[f].first, rl[f].second, width, height, block_size, sp, levels + (size_t)f * px, o_full, o_sub);
+                if (!ok) okv[w] = 0;
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int v : okv) if (!v) return SO_E_INVALID;
+    return SO_OK;
+}
+
 #ifdef SO_ME_DEBUG
 extern "C" int so_debug_read(long long* dst) { return (int)cudaMemcpyFromSymbol(dst, g_me_dbg, sizeof(long long) * 4096); }
 #endif

@@ -153,8 +153,30 @@ class decoder:
         _native.check(ctx.handle, rc)
         return out
 
-    def parse_bitstream(self, mv_file, residual_file, block_size=None):
-        """decode_differential_entropy (decoder.py:673-690)."""
+    def parse_bitstream(self, mv_file, residual_file, block_size=None, frames=None):
+        """decode_differential_entropy (decoder.py:673-690): the two text files -> packed arrays.  The lines are parsed by
+        the library on host threads (``so_parse_bitstream_files``); ``parse_bitstream_py`` is the line-by-line Python
+        restatement the tests compare it with."""
+        import os
+        bs = block_size or self.block_size
+        H, W = self.h_pixels, self.w_pixels
+        F = frames or self.frames
+        nblk, rows = (H // bs) * (W // bs), H // bs
+        rc_on = self.RCFlag is not None and self.RCFlag > 0
+        lib = _native.load()
+        ft = np.zeros(F, np.uint8)
+        split = np.zeros((F, nblk), np.uint8)
+        mv = np.zeros((F, nblk, 4, 3), np.int16)
+        lev = np.zeros((F, H, W), np.int16)
+        qp = np.zeros((F, rows), np.int32)
+        rc = lib.so_parse_bitstream_files(os.fsencode(mv_file), os.fsencode(residual_file), F, W, H, bs, 1 if rc_on else 0,
+                                          ft.ctypes.data, split.ctypes.data, mv.ctypes.data, lev.ctypes.data, qp.ctypes.data, 0)
+        if rc != 0:
+            raise ValueError(f"cannot parse {mv_file!r} / {residual_file!r} as {F} frames of {W}x{H}, block size {bs}")
+        return ft, split, mv, lev, ([list(map(int, q)) for q in qp] if rc_on else [[] for _ in range(F)])
+
+    def parse_bitstream_py(self, mv_file, residual_file, block_size=None):
+        """Line-by-line Python restatement of decode_differential_entropy (decoder.py:673-690)."""
         bs = block_size or self.block_size
         H, W = self.h_pixels, self.w_pixels
         nblk = (H // bs) * (W // bs)

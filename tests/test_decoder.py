@@ -30,7 +30,13 @@ def test_parser_recovers_packed_arrays_from_reference_text(name):
     d = _decoder(frames, enc)
     with tempfile.TemporaryDirectory() as tmp:
         mvf, rsf = _write(tmp, g)
-        ft, split, mv, lev, qps = d.parse_bitstream(mvf, rsf)
+        ft, split, mv, lev, qps = d.parse_bitstream(mvf, rsf)                 # C++ parser (host threads)
+        ft2, split2, mv2, lev2, qps2 = d.parse_bitstream_py(mvf, rsf)           # Python restatement
+        with pytest.raises(ValueError):
+            d.parse_bitstream(mvf, rsf, frames=len(g["frame_types"]) + 1)       # fewer lines than frames
+    for a, b in ((ft, ft2), (split, split2), (mv, mv2), (lev, lev2)):
+        np.testing.assert_array_equal(a, b)
+    assert [list(q) for q in qps] == [list(q) for q in qps2]
     np.testing.assert_array_equal(ft, g["frame_types"])
     np.testing.assert_array_equal(split, g["split"])
     np.testing.assert_array_equal(mv, g["mv"])
