@@ -64,3 +64,17 @@ def test_yuv_file_errors(tmp_path):
     _write_yuv420(short, synth.translating(2, 96, 128, seed=83))
     with pytest.raises(NativeError):
         c.encode_yuv_file(str(short), n_frames=4)
+
+
+def test_reference_main_flow_end_to_end(tmp_path):
+    """examples/main.py: the reference's main.py settings (CIF, i = 16, r = 16, half-pel + fast ME + VBS) from a YUV 4:2:0
+    file through encode, the two text files, the host parser and the GPU decoder; decoded frames == encoder reconstruction."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("so_example_main", os.path.join(root, "examples", "main.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    psnr, same = mod.main(qp=5, frames=21, workdir=str(tmp_path)).main(debug_prints=False)
+    assert same and len(psnr) == 21 and min(psnr) > 25
+    assert os.path.getsize(tmp_path / "mvs_per_frame_0.txt") > 0 and os.path.getsize(tmp_path / "res_per_frame_0.txt") > 0
