@@ -1,6 +1,6 @@
 """Randomised differential test: small random configurations, CUDA path vs the CPU oracle, everything bit for bit (packed
 outputs, both text streams, device-generated symbols, decode round trip).
-    python tools/fuzz_vs_oracle.py [n_cases] [seed]        (GPU box; about 2 s per case)"""
+    python tools/fuzz_vs_oracle.py [n_cases] [seed] [big]        (GPU box; about 0.1 s per case, 1 s with `big`)"""
 import os, sys, time, traceback
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,12 +11,13 @@ from streamoptima_b200.Encoder import Y_Video_codec
 Y_Video_codec.write_recon_yuv = False
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+BIG = len(sys.argv) > 3 and sys.argv[3] == "big"       # frames up to 160 x 224: several CTAs / chunks per launch (slower oracle)
 TAB = [[9000, 7000, 5200, 3900, 2800, 1900, 1300, 900, 600, 400, 250, 100], [6000, 4600, 3400, 2500, 1800, 1200, 800, 560, 380, 250, 160, 60]]
 bad = skipped = 0
 t0 = time.time()
 for n in range(n_cases):
     bs = int(rng.choice([4, 8, 16, 16]))
-    H = bs * int(rng.integers(2, max(3, 80 // bs))); W = bs * int(rng.integers(3, max(4, 112 // bs)))
+    H = bs * int(rng.integers(2, max(3, (160 if BIG else 80) // bs))); W = bs * int(rng.integers(3, max(4, (224 if BIG else 112) // bs)))
     F = int(rng.integers(2, 5))
     r = int(rng.choice([0, 1, 2, 3, 4, 5, 7, 8, 16])) if bs == 16 else int(rng.choice([0, 1, 2, 3, 4, 6]))
     if rng.random() < 0.04: r = int(rng.choice([17, 20, 33]))                      # search chunks (ranges above 16)
