@@ -63,24 +63,24 @@ class EncodedPackage(dict):
     def _materialise(self):
         F, H, W = self._lev.shape
         bs, sub = self._bs, self._bs // 2
-        nbx = W // bs
+        nbx, nby = W // bs, H // bs
         mvs_all, lev_all = [], []
         for f in range(F):
-            fm, fl = [], []
             intra = self._ft[f] == 0
-            mvf, spf, lf = self._mv[f], self._split[f], self._lev[f]
-            for b in range(spf.shape[0]):
-                y, x = (b // nbx) * bs, (b % nbx) * bs
-                if spf[b] == 0:
-                    fm.append((0, int(mvf[b, 0, 0]) if intra else (int(mvf[b, 0, 0]), int(mvf[b, 0, 1]), int(mvf[b, 0, 2]))))
-                    fl.append((0, lf[y:y + bs, x:x + bs].astype(int)))
+            spf = self._split[f].tolist()
+            mvl = self._mv[f].tolist()                                   # [nblk][4][3] python ints
+            # all blocks of the frame as views of one int array: [nby, nbx, bs, bs] (and the four quadrants of each)
+            blocks = self._lev[f].astype(int).reshape(nby, bs, nbx, bs).swapaxes(1, 2)
+            fm, fl = [], []
+            for b, sp in enumerate(spf):
+                m = mvl[b]
+                blk = blocks[b // nbx, b % nbx]
+                if sp == 0:
+                    fm.append((0, m[0][0] if intra else tuple(m[0])))
+                    fl.append((0, blk))
                 else:
-                    if intra:
-                        fm.append((1, [int(mvf[b, k, 0]) for k in range(4)]))
-                    else:
-                        fm.append((1, [(int(mvf[b, k, 0]), int(mvf[b, k, 1]), int(mvf[b, k, 2])) for k in range(4)]))
-                    fl.append((1, [lf[y + (k // 2) * sub:y + (k // 2) * sub + sub,
-                                      x + (k % 2) * sub:x + (k % 2) * sub + sub].astype(int) for k in range(4)]))
+                    fm.append((1, [m[k][0] for k in range(4)] if intra else [tuple(m[k]) for k in range(4)]))
+                    fl.append((1, [blk[(k // 2) * sub:(k // 2) * sub + sub, (k % 2) * sub:(k % 2) * sub + sub] for k in range(4)]))
             mvs_all.append(fm)
             lev_all.append(fl)
         dict.__setitem__(self, "MVS per Frame", mvs_all)
