@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SO_ABI_VERSION 1
+#define SO_ABI_VERSION 2
 
 /* error codes */
 #define SO_OK          0
@@ -44,6 +44,7 @@ extern "C" {
 #define SO_FLAG_VBS     4u   /* VBSEnable : 4-way split with RD decision (Encoder.py:512-573) */
 
 #define SO_MAX_REF 8
+#define SO_ALL_UNITS (-1)    /* `unit` argument of the per-frame calls: every unit of the context in lock step */
 
 /* Encoder parameters; mirrors the Y_Video_codec constructor (Encoder.py:24). */
 typedef struct so_params {
@@ -111,13 +112,18 @@ int so_set_row_qps(so_ctx* ctx, const int32_t* qp_rows, int n);
  * starts, so a per-block map is side information the unchanged decoder.py cannot read. */
 int so_set_block_qps(so_ctx* ctx, const int32_t* qp_blocks, int n_frames);
 
-/* Reference ring (Encoder.py:1798, :1864-1867).  unit selects one of max_batch independent chains. */
-int so_ref_reset(so_ctx* ctx, int unit, void* stream);                 /* ring := [constant-128 float frame] */
-int so_ref_push(so_ctx* ctx, int unit, const uint8_t* recon_dev, void* stream);   /* FIFO append of a uint8 frame [height][width] */
+/* Reference list (Encoder.py:1798, :1864-1867).  A context holds max_batch independent chains ("units": streams or closed
+ * GOPs).  unit = 0 .. max_batch-1 addresses ONE chain: the frame buffers of the call are single frames.  unit =
+ * SO_ALL_UNITS addresses every chain in lock step: frame buffers are dense [max_batch][...] arrays.  Mixing is allowed
+ * in one direction -- after lock-step calls every unit continues from the shared state; going back to SO_ALL_UNITS
+ * needs identical chains or so_ref_reset(ctx, SO_ALL_UNITS, ..), else SO_E_STATE. */
+int so_ref_reset(so_ctx* ctx, int unit, void* stream);                 /* list := [constant-128 float frame] */
+int so_ref_push(so_ctx* ctx, int unit, const uint8_t* recon_dev, void* stream);   /* FIFO append of uint8 frame(s) [height][width] */
 
-/* One frame of one unit; cur_dev is u8 [height][width] on the device.  Asynchronous on `stream`.
- * so_encode_inter does NOT push the reconstruction into the ring (the caller decides, which is what makes
- * teacher-forced parity tests possible). */
+/* One frame: cur_dev is u8 [height][width] on the device (unit >= 0) or [max_batch][height][width] (SO_ALL_UNITS); the
+ * planes of `out` follow the same rule.  Asynchronous on `stream`.  The type of the frame is the caller's decision
+ * (Encoder.py:1839).  so_encode_inter does NOT push the reconstruction into the list (Encoder.py:1864-1867 is the
+ * caller's so_ref_push), which is what makes teacher-forced parity tests possible (tests/test_gpu_seam.py). */
 int so_encode_intra(so_ctx* ctx, int unit, const uint8_t* cur_dev, const so_frame_out* out, void* stream);
 int so_encode_inter(so_ctx* ctx, int unit, const uint8_t* cur_dev, const so_frame_out* out, void* stream);
 
@@ -182,7 +188,7 @@ int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const uint8_t* s
                        const int32_t* qp_rows_per_frame, int n_frames, int reset_at_intra, uint8_t* out_frames);
 
 /* Timing of the last so_seq_run, CUDA events on the context stream (ms): [0] whole device region, [1] motion-search
- * kernels only (exhaustive search: the me_full_kernel launches; fast ME: the chain kernel; intra frames: intra search),
+ * kernels only (exhaustive search: the me_ring_kernel / me_tma_kernel launches; fast ME: the chain kernel; intra frames: intra search),
  * [2] transform/quant/recon kernels, [3] number of kernel launches.  Waits for the run to finish.  [1] and [2] cover the
  * frames that carry per-kernel events (see so_last_search_timing). */
 int so_last_timing(so_ctx* ctx, double out[4]);

@@ -75,6 +75,8 @@ def main(argv):
     names = argv or [n for n in CASES if not os.path.exists(os.path.join(GOLDEN_DIR, n + ".npz"))]
     for n in names:
         info = generate(n)
+        if os.path.exists(man_path):          # another generator process may have added cases meanwhile
+            manifest["cases"].update(json.load(open(man_path)).get("cases", {}))
         manifest["cases"][n] = info
         print(n, info, flush=True)
         with open(man_path, "w") as f:

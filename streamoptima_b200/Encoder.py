@@ -202,7 +202,18 @@ class Y_Video_codec:
         return qps
 
     def _context(self, block_size, search_range, intra_dur, max_batch=1):
-        key = (block_size, search_range, intra_dur, max_batch, self.device)
+        """Native context for the CURRENT attribute values: the reference reads ``self.*`` every frame, so everything a
+        context is created from is part of the cache key (only ``const_init_Qp`` is re-pushed on reuse)."""
+        rc_on = self.RCFlag is not None and self.RCFlag > 0
+        # the reference fails with TypeError in these two cases (``lam * bits`` Encoder.py:1158, ``size > None`` :1852)
+        if self.VBSEnable and self.lam is None:
+            raise TypeError("VBSEnable needs lam (the RD cost multiplies it, Encoder.py:1158)")
+        if rc_on and self.RCFlag > 1 and self.intra_thresh is None:
+            raise TypeError("RCFlag=2 needs intra_thresh (scene-cut test, Encoder.py:1852)")
+        row_qps = tuple(self._rc_row_qps(self.h_pixels // block_size)) if rc_on else ()
+        key = (block_size, search_range, intra_dur, max_batch, self.device, self.h_pixels, self.w_pixels, self.nRefFrames,
+               bool(self.FMEEnable), bool(self.fast_me), bool(self.VBSEnable), self.RCFlag or 0, self.ParallelMode,
+               float(self.lam or 0.0), int(self.intra_thresh or 0), row_qps)
         if self._ctx is not None and self._ctx_key == key:
             self._ctx.set_qp(self.const_init_Qp)
             return self._ctx
@@ -214,8 +225,8 @@ class Y_Video_codec:
                                     parallel_mode=self.ParallelMode, lam=self.lam or 0.0, intra_thresh=self.intra_thresh or 0,
                                     max_batch=max_batch, device=self.device)
         self._ctx_key = key
-        if self.RCFlag is not None and self.RCFlag > 0:
-            self._ctx.set_row_qps(self._rc_row_qps(self.h_pixels // block_size))
+        if rc_on:
+            self._ctx.set_row_qps(list(row_qps))
         return self._ctx
 
     def encode_arrays(self, frames_u8, block_size=None, search_range=None, intra_dur=None, want_levels=True, want_recon=True,

@@ -53,9 +53,20 @@ struct so_ctx {
     uint8_t* ring = nullptr;
     size_t plane_bytes = 0, slot_stride = 0, unit_stride = 0;
     int nslots = 0;
-    std::vector<int> list;                  // ring slots in list order (oldest first)
-    std::vector<char> slot_u8;              // slot holds a uint8 reconstruction (false: the float 128 frame)
-    std::vector<int> slot_wrap;             // wrap mode the half-pel planes of the slot were built with (-1 none)
+    // Reference-list state.  Whole-sequence calls advance all units in lock step (one state, rstates[0], cur_unit = -1); the
+    // per-frame calls with unit >= 0 give every unit its own chain (rstates[unit]).
+    struct RingState {
+        std::vector<int> list;              // ring slots in list order (oldest first)
+        std::vector<char> slot_u8;          // slot holds a uint8 reconstruction (false: the float 128 frame)
+        std::vector<int> slot_wrap;         // wrap mode the half-pel planes of the slot were built with (-1 none)
+        bool operator==(const RingState& o) const { return list == o.list && slot_u8 == o.slot_u8 && slot_wrap == o.slot_wrap; }
+    };
+    std::vector<RingState> rstates;
+    bool lockstep = true;
+    int cur_unit = -1;                      // unit the ring helpers act on (-1: all units, lock step)
+    RingState& rs() { return rstates[cur_unit < 0 ? 0 : cur_unit]; }
+    int u0() const { return cur_unit < 0 ? 0 : cur_unit; }              // first unit / number of units of a ring operation
+    int un() const { return cur_unit < 0 ? batch : 1; }
     // scratch
     MeResult *me_parent = nullptr, *me_sub = nullptr;       // exhaustive search: packed keys (all ones between frames); fast ME: records
     MeResult *in_parent = nullptr, *in_sub = nullptr;       // intra search results (separate: they must not disturb the keys)
@@ -237,8 +248,8 @@ extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
     CUC(cudaMalloc(&ctx->res_frame, sizeof(int16_t) * ctx->frame_px * ctx->batch));
     CUC(cudaMalloc(&ctx->band, sizeof(int32_t) * ctx->frame_px * ctx->batch));
     CUC(cudaMalloc(&ctx->qp_rows_dev, sizeof(int) * g.nby));
-    ctx->slot_u8.assign(ctx->nslots, 0);
-    ctx->slot_wrap.assign(ctx->nslots, -1);
+    ctx->rstates.resize(ctx->batch);
+    for (auto& r : ctx->rstates) { r.slot_u8.assign(ctx->nslots, 0); r.slot_wrap.assign(ctx->nslots, -1); }
     if (upload_tables(ctx) != SO_OK) return fail(SO_E_CUDA);
     *out = ctx;
     return SO_OK;
@@ -288,29 +299,53 @@ static uint8_t* slot_ptr(so_ctx* c, int slot) { return c->ring + (size_t)slot * 
 static int take_free_slot(so_ctx* c) {
     for (int s = 0; s < c->nslots; ++s) {
         bool used = false;
-        for (int l : c->list) used = used || (l == s);
+        for (int l : c->rs().list) used = used || (l == s);
         if (!used) return s;
     }
     return -1;
 }
 
+// Choose the chain the following ring operations act on: SO_ALL_UNITS (-1) = every unit in lock step, otherwise one unit.
+// Going from lock step to single units forks the shared state; going back needs identical chains (or a reset).
+static int select_unit(so_ctx* ctx, int unit, bool resetting = false) {
+    if (unit < -1 || unit >= ctx->batch) { set_err(ctx, "unit out of range (0 .. max_batch-1, or SO_ALL_UNITS)"); return SO_E_INVALID; }
+    if (unit >= 0) {
+        if (ctx->lockstep) { for (int u = 1; u < ctx->batch; ++u) ctx->rstates[u] = ctx->rstates[0]; ctx->lockstep = false; }
+    } else if (!ctx->lockstep) {
+        if (!resetting) {
+            for (int u = 1; u < ctx->batch; ++u)
+                if (!(ctx->rstates[u] == ctx->rstates[0])) {
+                    set_err(ctx, "SO_ALL_UNITS after per-unit calls left the chains in different states: so_ref_reset(ctx, SO_ALL_UNITS) first");
+                    return SO_E_STATE;
+                }
+        }
+        ctx->lockstep = true;
+    }
+    ctx->cur_unit = unit;
+    return SO_OK;
+}
+
 // exhaustive-search key arrays := all ones (the identity of the atomicMin merge)
 static int keys_reset(so_ctx* ctx, cudaStream_t st) {
-    CU(cudaMemsetAsync(ctx->me_parent, 0xFF, sizeof(MeResult) * ctx->nblk * ctx->batch, st));
-    CU(cudaMemsetAsync(ctx->me_sub, 0xFF, sizeof(MeResult) * ctx->nblk * 4 * ctx->batch, st));
+    const size_t u0 = ctx->u0(), un = ctx->un();
+    CU(cudaMemsetAsync(ctx->me_parent + u0 * ctx->nblk, 0xFF, sizeof(MeResult) * ctx->nblk * un, st));
+    CU(cudaMemsetAsync(ctx->me_sub + u0 * ctx->nblk * 4, 0xFF, sizeof(MeResult) * ctx->nblk * 4 * un, st));
     return SO_OK;
 }
 
 static int ref_reset_impl(so_ctx* ctx, cudaStream_t st, bool reset_keys);
 
-extern "C" int so_ref_reset(so_ctx* ctx, int /*unit*/, void* stream) {
+extern "C" int so_ref_reset(so_ctx* ctx, int unit, void* stream) {
     if (!ctx) return SO_E_INVALID;
     CU(cudaSetDevice(ctx->device));
+    int rc = select_unit(ctx, unit, true);
+    if (rc) return rc;
     return ref_reset_impl(ctx, (cudaStream_t)stream, true);
 }
 
 static int ref_reset_impl(so_ctx* ctx, cudaStream_t st, bool reset_keys) {
-    ctx->list.clear();
+    so_ctx::RingState& R = ctx->rs();
+    R.list.clear();
     if (reset_keys) {
         const int rc = keys_reset(ctx, st);
         if (rc) return rc;
@@ -318,47 +353,53 @@ static int ref_reset_impl(so_ctx* ctx, cudaStream_t st, bool reset_keys) {
     const int s = 0;
     // ref_frames = [np.ones((h, w)) * 128]  (Encoder.py:1798): a float frame -> never triggers the uint8 wrap
     const size_t n16 = ctx->slot_stride / 16;
-    ring_fill_kernel<<<dim3((unsigned)((n16 + 255) / 256), ctx->batch), 256, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, n16, 0x80808080u);
+    ring_fill_kernel<<<dim3((unsigned)((n16 + 255) / 256), ctx->un()), 256, 0, st>>>(slot_ptr(ctx, s) + (size_t)ctx->u0() * ctx->unit_stride,
+                                                                                     ctx->unit_stride, n16, 0x80808080u);
     ctx->launches++;
     CU(cudaGetLastError());
-    ctx->list.push_back(s);
-    ctx->slot_u8[s] = 0;
-    ctx->slot_wrap[s] = 0;          // planes of a constant frame are the constant in both modes
+    R.list.push_back(s);
+    R.slot_u8[s] = 0;
+    R.slot_wrap[s] = 0;          // planes of a constant frame are the constant in both modes
     return SO_OK;
 }
 
-// FIFO append (Encoder.py:1864-1867); recon_dev is [batch][H][W] dense with unit stride src_unit_stride
+// FIFO append (Encoder.py:1864-1867) to the selected chain(s); recon_dev is [units][H][W] dense with unit stride src_unit_stride
 static int ring_push(so_ctx* ctx, const uint8_t* recon_dev, size_t src_unit_stride, int units, cudaStream_t st) {
-    if ((int)ctx->list.size() >= ctx->p.n_ref_frames) ctx->list.erase(ctx->list.begin());
+    so_ctx::RingState& R = ctx->rs();
+    if ((int)R.list.size() >= ctx->p.n_ref_frames) R.list.erase(R.list.begin());
     const int s = take_free_slot(ctx);
     if (s < 0) { set_err(ctx, "reference ring has no free slot"); return SO_E_STATE; }
     const FrameGeom& g = ctx->g;
-    ctx->list.push_back(s);
-    ctx->slot_u8[s] = 1;
+    R.list.push_back(s);
+    R.slot_u8[s] = 1;
     // One kernel stores the frame and derives its half-pel phases and byte-shifted copies.  The uint8-wrap mode (quirk
     // Q1) of the next inter frame is already known: the list does not change before it (ensure_planes re-derives the
     // planes from the stored frame in the one case it does: ParallelMode 1 resets the list every frame).
     bool all_u8 = true;
-    for (int l : ctx->list) all_u8 = all_u8 && ctx->slot_u8[l];
+    for (int l : R.list) all_u8 = all_u8 && R.slot_u8[l];
     const int wrap = (g.fme && all_u8) ? 1 : 0;
-    CU(launch_pdl(ring_planes_kernel, dim3((g.W / 4 + 127) / 128, g.H, units), dim3(128), 0, st, slot_ptr(ctx, s), ctx->unit_stride,
+    CU(launch_pdl(ring_planes_kernel, dim3((g.W / 4 + 127) / 128, g.H, units), dim3(128), 0, st,
+                  slot_ptr(ctx, s) + (size_t)ctx->u0() * ctx->unit_stride, ctx->unit_stride,
                   ctx->plane_bytes, recon_dev, src_unit_stride, g.W, g.W, g.H, g.pitch, g.fme, wrap, 1));
     ctx->launches++;
     CU(cudaGetLastError());
-    ctx->slot_wrap[s] = wrap;
+    R.slot_wrap[s] = wrap;
     return SO_OK;
 }
 
-extern "C" int so_ref_push(so_ctx* ctx, int /*unit*/, const uint8_t* recon_dev, void* stream) {
+extern "C" int so_ref_push(so_ctx* ctx, int unit, const uint8_t* recon_dev, void* stream) {
     if (!ctx || !recon_dev) return SO_E_INVALID;
     CU(cudaSetDevice(ctx->device));
-    return ring_push(ctx, recon_dev, ctx->frame_px, ctx->batch, (cudaStream_t)stream);
+    int rc = select_unit(ctx, unit);
+    if (rc) return rc;
+    return ring_push(ctx, recon_dev, ctx->frame_px, ctx->un(), (cudaStream_t)stream);
 }
 
 static RefRing make_ring(so_ctx* c) {
     RefRing r;
     r.base = c->ring; r.unit_stride = c->unit_stride; r.slot_stride = c->slot_stride; r.plane_stride = c->plane_bytes * 4;
-    for (int i = 0; i < SO_MAX_REF; ++i) r.slot[i] = i < (int)c->list.size() ? c->list[i] : 0;
+    const std::vector<int>& list = c->rs().list;
+    for (int i = 0; i < SO_MAX_REF; ++i) r.slot[i] = i < (int)list.size() ? list[i] : 0;
     return r;
 }
 
@@ -366,7 +407,11 @@ static void ev_pair(so_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>
     if (!ctx->timing_on) return;
     if (start) {
         if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
-            for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+            for (int i = 0; i < 64; ++i) {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); ctx->timing_on = false; return; }   // no events: this frame goes untimed
+                ctx->ev_pool.push_back(e);
+            }
         }
         cudaEvent_t a = ctx->ev_pool[ctx->ev_used++], b = ctx->ev_pool[ctx->ev_used++];
         v.emplace_back(a, b);
@@ -421,12 +466,12 @@ static int make_ring_map(so_ctx* ctx, int box_w, int box_h, CUtensorMap* map, in
 
 template <int BS, int NDX, int G, bool QUAD = false>
 static cudaError_t launch_me_tma(const CUtensorMap& map, const CUtensorMap& cmap, const MeTmaArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
-    static bool attr_done[16] = {};
+    static bool attr_done[64] = {};      // per device ordinal; beyond 64 devices the attribute is simply set again
     int dev = 0; cudaGetDevice(&dev);
-    if (!attr_done[dev & 15]) {
+    if (dev >= 64 || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(me_tma_kernel<BS, NDX, G, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done[dev & 15] = true;
+        if (dev < 64) attr_done[dev] = true;
     }
     me_tma_kernel<BS, NDX, G, QUAD><<<grid, threads, smem, st>>>(map, cmap, a);
     return cudaGetLastError();
@@ -452,7 +497,7 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
     MeRingArgs a{};
     a.g = ctx->g;
     a.g.bs = 16; a.g.nbx = ctx->g.W / 16; a.g.nby = ctx->g.H / 16;
-    a.g.nref = (int)ctx->list.size();
+    a.g.nref = (int)ctx->rs().list.size();
     a.out = reinterpret_cast<unsigned long long*>(out + (size_t)unit0 * out_stride);
     a.out_unit_stride = out_stride;
     a.out_sub = out_sub ? reinterpret_cast<unsigned long long*>(out_sub + (size_t)unit0 * out_sub_stride) : nullptr;   // fused VBS search
@@ -463,22 +508,22 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
     a.z_per_unit = ctx->nslots * 16;
     a.z_unit0 = unit0 * a.z_per_unit;
     a.slot_packed = 0;
-    for (int i = 0; i < SO_MAX_REF && i < (int)ctx->list.size(); ++i) a.slot_packed |= (unsigned)(ctx->list[i] & 15) << (4 * i);
+    for (int i = 0; i < SO_MAX_REF && i < (int)ctx->rs().list.size(); ++i) a.slot_packed |= (unsigned)(ctx->rs().list[i] & 15) << (4 * i);
     CUtensorMap map, cmap;
     int rc = make_ring_map(ctx, MR_WP, MR_BOXROWS, &map, 4);      // one box = the four shift planes of a phase
     if (rc) return rc;
-    rc = make_map3d(ctx, cur + (size_t)unit0 * cur_stride, ctx->g.W, ctx->g.H, units, ctx->g.W, cur_stride, 16, 16, &cmap);
+    rc = make_map3d(ctx, cur + (size_t)unit0 * cur_stride, ctx->g.W, ctx->g.H, units, ctx->g.W, cur_stride ? cur_stride : ctx->frame_px, 16, 16, &cmap);
     if (rc) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const long long total = (long long)units * a.items_per_unit;
     const long long nchunks = (total + MR_CHUNK - 1) / MR_CHUNK;
     const int grid = nchunks < sms ? (int)nchunks : sms;
-    static bool attr_done[16] = {};
-    if (!attr_done[ctx->device & 15]) {
+    static bool attr_done[64] = {};
+    if (ctx->device >= 64 || !attr_done[ctx->device]) {
         CU(cudaFuncSetAttribute(me_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
         CU(cudaFuncSetAttribute(me_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
-        attr_done[ctx->device & 15] = true;
+        if (ctx->device < 64) attr_done[ctx->device] = true;
     }
     if (!ctx->me_work) {      // {chunk counter, finished CTAs}: zero at every launch -- the last CTA of a launch resets both
         CU(cudaMalloc(&ctx->me_work, 256));
@@ -506,7 +551,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
         // 2x2 sub-blocks of VBS with block_size 4 (or the test switch): plain one-warp-per-block search
         if (used_quad) *used_quad = false;
         FlowArgs f{};
-        f.g = ctx->g; f.g.nref = (int)ctx->list.size();
+        f.g = ctx->g; f.g.nref = (int)ctx->rs().list.size();
         f.unit0 = unit0;
         f.cur = cur; f.cur_unit_stride = cur_stride;
         f.ring = make_ring(ctx);
@@ -522,7 +567,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     MeTmaArgs a{};
     a.g = ctx->g;
     a.g.bs = bs; a.g.nbx = ctx->g.W / bs; a.g.nby = ctx->g.H / bs;
-    a.g.nref = (int)ctx->list.size();
+    a.g.nref = (int)ctx->rs().list.size();
     a.cur = cur + (size_t)unit0 * cur_stride;
     a.cur_unit_stride = cur_stride;
     a.out = reinterpret_cast<unsigned long long*>(out + (size_t)unit0 * out_stride);
@@ -605,7 +650,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     a.NB = (SI * tasks_per_item + 31) / 32;
     a.stages_per_unit = (a.items_per_unit + SI - 1) / SI;
     a.z_per_unit = ctx->nslots * 16;
-    for (int i = 0; i < SO_MAX_REF; ++i) a.slot[i] = i < (int)ctx->list.size() ? ctx->list[i] : 0;
+    for (int i = 0; i < SO_MAX_REF; ++i) a.slot[i] = i < (int)ctx->rs().list.size() ? ctx->rs().list[i] : 0;
     // 1 producer warp + up to 11 search warps.  No more search warps than bundles per stage: a warp may then be at most one
     // stage ahead of the slowest one, which is what the 1-bit mbarrier phase parity can distinguish.
     const int threads = 32 * (1 + (a.NB < 11 ? a.NB : 11));
@@ -613,7 +658,7 @@ static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int un
     int rc = make_ring_map(ctx, a.raw_w, a.rows + (a.row_pad ? 7 : 0), &map);
     if (rc) return rc;
     if (a.direct) {     // current blocks: {W, H, units} view of the frames of this launch
-        rc = make_map3d(ctx, cur + (size_t)unit0 * cur_stride, ctx->g.W, ctx->g.H, units, ctx->g.W, cur_stride, bs, bs, &cmap);
+        rc = make_map3d(ctx, cur + (size_t)unit0 * cur_stride, ctx->g.W, ctx->g.H, units, ctx->g.W, cur_stride ? cur_stride : ctx->frame_px, bs, bs, &cmap);
         if (rc) return rc;
     } else {
         cmap = map;     // unused
@@ -652,7 +697,7 @@ static FlowArgs make_flow(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, co
     // out_frames_stride: number of frames between consecutive units in the output arrays
     FlowArgs a{};
     a.g = ctx->g;
-    a.g.nref = (int)ctx->list.size();
+    a.g.nref = (int)ctx->rs().list.size();
     a.ring = make_ring(ctx);
     a.cur = cur; a.cur_unit_stride = cur_stride;
     a.unit0 = unit0;
@@ -729,19 +774,22 @@ static int encode_intra_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     return SO_OK;
 }
 
+// units: how many units of the selected chain(s) to touch (lock step: units 0 .. units-1; single unit: 1)
 static int ensure_planes(so_ctx* ctx, int units, cudaStream_t st) {
+    so_ctx::RingState& R = ctx->rs();
     bool all_u8 = true;
-    for (int s : ctx->list) all_u8 = all_u8 && ctx->slot_u8[s];
+    for (int s : R.list) all_u8 = all_u8 && R.slot_u8[s];
     const FrameGeom& g = ctx->g;
     const int wrap = (g.fme && all_u8) ? 1 : 0;      // np.copy(list) is uint8 only if every frame is (quirk Q1)
-    for (int s : ctx->list) {
-        if (!ctx->slot_u8[s]) continue;              // the constant frame: every plane was filled at reset
-        if (ctx->slot_wrap[s] == wrap) continue;
-        ring_planes_kernel<<<dim3((g.W / 4 + 127) / 128, g.H, units), 128, 0, st>>>(slot_ptr(ctx, s), ctx->unit_stride, ctx->plane_bytes,
-                                                                                  slot_ptr(ctx, s), ctx->unit_stride, g.pitch,
+    for (int s : R.list) {
+        if (!R.slot_u8[s]) continue;                 // the constant frame: every plane was filled at reset
+        if (R.slot_wrap[s] == wrap) continue;
+        uint8_t* base = slot_ptr(ctx, s) + (size_t)ctx->u0() * ctx->unit_stride;
+        ring_planes_kernel<<<dim3((g.W / 4 + 127) / 128, g.H, units), 128, 0, st>>>(base, ctx->unit_stride, ctx->plane_bytes,
+                                                                                  base, ctx->unit_stride, g.pitch,
                                                                                   g.W, g.H, g.pitch, g.fme, wrap, 0);
         ctx->launches++;
-        ctx->slot_wrap[s] = wrap;
+        R.slot_wrap[s] = wrap;
     }
     CU(cudaGetLastError());
     return SO_OK;
@@ -750,8 +798,8 @@ static int ensure_planes(so_ctx* ctx, int units, cudaStream_t st) {
 static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, const so_frame_out* o, size_t ofs,
                              int unit0, int units, cudaStream_t st) {
     const FrameGeom& g = ctx->g;
-    if (ctx->list.empty()) { set_err(ctx, "inter frame with an empty reference list (call so_ref_reset)"); return SO_E_STATE; }
-    int rc = ensure_planes(ctx, ctx->batch, st);
+    if (ctx->rs().list.empty()) { set_err(ctx, "inter frame with an empty reference list (call so_ref_reset)"); return SO_E_STATE; }
+    int rc = ensure_planes(ctx, ctx->un(), st);
     if (rc) return rc;
     FlowArgs a = make_flow(ctx, cur, cur_stride, o, ofs, unit0, ctx->p.qp);
     const bool parallel = ctx->p.parallel_mode != 0;
@@ -830,20 +878,30 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     return SO_OK;
 }
 
-extern "C" int so_encode_intra(so_ctx* ctx, int /*unit*/, const uint8_t* cur_dev, const so_frame_out* out, void* stream) {
+// Per-frame seam (complete_intra_flow Encoder.py:1582 / complete_inter_flow :1644).  unit >= 0: ONE frame of that unit's
+// chain (cur / out are single-frame buffers); SO_ALL_UNITS: one frame of every unit in lock step (cur and every output
+// plane are dense [max_batch][...] arrays).
+static int frame_call(so_ctx* ctx, int unit, const uint8_t* cur_dev, const so_frame_out* out, cudaStream_t st, bool intra) {
     if (!ctx || !cur_dev) return SO_E_INVALID;
     int rc = check_out(ctx, out);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
-    return encode_intra_impl(ctx, cur_dev, ctx->frame_px, out, 1, 0, ctx->batch, ctx->p.qp, (cudaStream_t)stream);
+    rc = select_unit(ctx, unit);
+    if (rc) return rc;
+    ctx->timing_on = false;
+    const bool one = unit >= 0;
+    // single unit: every per-unit stride is zero, so the kernels' `unit * stride` terms vanish and the buffers are the frame
+    const size_t cur_stride = one ? 0 : ctx->frame_px, ofs = one ? 0 : 1;
+    if (intra) return encode_intra_impl(ctx, cur_dev, cur_stride, out, ofs, ctx->u0(), ctx->un(), ctx->p.qp, st);
+    return encode_inter_impl(ctx, cur_dev, cur_stride, out, ofs, ctx->u0(), ctx->un(), st);
 }
 
-extern "C" int so_encode_inter(so_ctx* ctx, int /*unit*/, const uint8_t* cur_dev, const so_frame_out* out, void* stream) {
-    if (!ctx || !cur_dev) return SO_E_INVALID;
-    int rc = check_out(ctx, out);
-    if (rc) return rc;
-    CU(cudaSetDevice(ctx->device));
-    return encode_inter_impl(ctx, cur_dev, ctx->frame_px, out, 1, 0, ctx->batch, (cudaStream_t)stream);
+extern "C" int so_encode_intra(so_ctx* ctx, int unit, const uint8_t* cur_dev, const so_frame_out* out, void* stream) {
+    return frame_call(ctx, unit, cur_dev, out, (cudaStream_t)stream, true);
+}
+
+extern "C" int so_encode_inter(so_ctx* ctx, int unit, const uint8_t* cur_dev, const so_frame_out* out, void* stream) {
+    return frame_call(ctx, unit, cur_dev, out, (cudaStream_t)stream, false);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -958,10 +1016,10 @@ extern "C" int so_seq_run(so_ctx* ctx) {
     ctx->launches = 0;
     ctx->ev_used = 0; ctx->ev_me.clear(); ctx->ev_tq.clear(); ctx->ev_xs.clear();
     ctx->timing_on = true;
-    if (ctx->ev_pool.size() < 2) { for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); } }
+    while (ctx->ev_pool.size() < 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev_pool.push_back(e); }
     ctx->ev0 = ctx->ev_pool[ctx->ev_used++]; ctx->ev1 = ctx->ev_pool[ctx->ev_used++];
     CU(cudaEventRecord(ctx->ev0, st));
-    int rc = so_ref_reset(ctx, 0, st);
+    int rc = so_ref_reset(ctx, SO_ALL_UNITS, st);
     if (rc) return rc;
     CU(cudaMemsetAsync(ctx->sq_stats, 0, (size_t)n_units * n_frames * sizeof(so_frame_stats), st));
     CU(cudaMemsetAsync(ctx->sq_rows, 0, (size_t)n_units * n_frames * nby * sizeof(uint32_t), st));
@@ -1195,6 +1253,21 @@ extern "C" int so_seq_download_symbols(so_ctx* ctx, uint32_t* offsets, int16_t* 
 extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
                                   const int32_t* qp_rows_per_frame, int n_frames, int reset_at_intra, uint8_t* out_frames) {
     if (!ctx || !frame_types || !split || !mv || !levels || !out_frames || n_frames < 1) return SO_E_INVALID;
+    // the arrays are indexed with the CONTEXT's geometry (n_frames x n_blocks of ctx): reject contents that cannot come from
+    // a stream of this geometry before anything is enqueued (reference indices select ring slots on the device)
+    for (int f = 0; f < n_frames; ++f) {
+        if (frame_types[f] > 1) { set_err(ctx, "frame type must be 0 or 1"); return SO_E_INVALID; }
+        const uint8_t* sp = split + (size_t)f * ctx->nblk;
+        const int16_t* m = mv + (size_t)f * ctx->nblk * 12;
+        for (int b = 0; b < ctx->nblk; ++b) {
+            if (sp[b] > 1) { set_err(ctx, "split flag must be 0 or 1"); return SO_E_INVALID; }
+            if (frame_types[f] == 1)
+                for (int k = 0; k < 4; ++k)
+                    if (m[(size_t)b * 12 + k * 3 + 2] < 0 || m[(size_t)b * 12 + k * 3 + 2] >= ctx->p.n_ref_frames) {
+                        set_err(ctx, "reference index outside nRefFrames of the context"); return SO_E_INVALID;
+                    }
+        }
+    }
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_seq(ctx, (size_t)n_frames);
     if (rc) return rc;
@@ -1204,7 +1277,7 @@ extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const
     CU(cudaMemcpyAsync(ctx->sq_split, split, (size_t)n_frames * ctx->nblk, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->sq_mv, mv, (size_t)n_frames * ctx->nblk * 12 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->sq_levels, levels, (size_t)n_frames * px * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-    rc = so_ref_reset(ctx, 0, st);
+    rc = so_ref_reset(ctx, SO_ALL_UNITS, st);
     if (rc) return rc;
     const int nt = nthreads_px(g.bs);
     for (int f = 0; f < n_frames; ++f) {
@@ -1222,7 +1295,7 @@ extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const
         const bool intra = frame_types[f] == 0 && (ctx->p.parallel_mode != 1 || !reset_at_intra);
         if (!intra && ctx->p.parallel_mode == 1) { rc = ref_reset_impl(ctx, st, false); if (rc) return rc; }     // decoder.py:504-509
         if (!intra) {
-            if (ctx->list.empty()) { set_err(ctx, "inter frame with an empty reference list"); return SO_E_STATE; }
+            if (ctx->rs().list.empty()) { set_err(ctx, "inter frame with an empty reference list"); return SO_E_STATE; }
             rc = ensure_planes(ctx, 1, st);
             if (rc) return rc;
         }
@@ -1239,7 +1312,7 @@ extern "C" int so_decode_sequence(so_ctx* ctx, const uint8_t* frame_types, const
             else if (g.bs == 16) intra_recon_kernel<16><<<grid2, nt, 0, st>>>(a);
             else if (g.bs == 8) intra_recon_kernel<8><<<grid2, nt, 0, st>>>(a);
             else intra_recon_kernel<4><<<grid2, nt, 0, st>>>(a);
-            if (reset_at_intra) ctx->list.clear();                                     // decoder.py:520 `ref_frames = []`
+            if (reset_at_intra) ctx->rs().list.clear();                                     // decoder.py:520 `ref_frames = []`
         }
         CU(cudaGetLastError());
         if (f < n_frames - 1 && ctx->p.parallel_mode != 1) {
@@ -1457,14 +1530,18 @@ extern "C" int so_write_bitstream_files(const uint8_t* frame_types, const uint8_
 namespace {
 struct Cursor {
     const char* p; const char* e;
-    bool more() const { return p < e; }
+    bool bad = false;                            // a number with too many digits was met: the line is malformed
     bool number(long& v) {                       // next integer at or after p (skips anything that is not a digit or '-')
         while (p < e && !((*p >= '0' && *p <= '9') || (*p == '-' && p + 1 < e && p[1] >= '0' && p[1] <= '9'))) ++p;
         if (p >= e) return false;
         bool neg = false;
         if (*p == '-') { neg = true; ++p; }
         long x = 0;
-        while (p < e && *p >= '0' && *p <= '9') { x = x * 10 + (*p - '0'); ++p; }
+        int digits = 0;
+        while (p < e && *p >= '0' && *p <= '9') {
+            if (++digits > 9) { bad = true; return false; }      // nothing in the format exceeds 9 digits: no overflow
+            x = x * 10 + (*p - '0'); ++p;
+        }
         v = neg ? -x : x;
         return true;
     }
@@ -1482,7 +1559,7 @@ static bool parse_mv_line_c(const char* b, const char* e, int nblk, int bpr, boo
                             int32_t* qp_rows) {
     Cursor c{b, e};
     long t;
-    if (!c.number(t) || c.p >= e || *c.p != '|') return false;
+    if (!c.number(t) || c.p >= e || *c.p != '|' || (t != 0 && t != 1)) return false;      // frame type: 0 intra, 1 inter
     ++c.p;
     *ftype = (uint8_t)t;
     long ref[3] = {0, 0, 0}, ref_qp = 0;
@@ -1498,6 +1575,7 @@ static bool parse_mv_line_c(const char* b, const char* e, int nblk, int bpr, boo
             Cursor qc{it.p, at ? at : ie};
             if (!at || !qc.number(q)) return false;
             ref_qp += q;
+            if (ref_qp < 0 || ref_qp > 15) return false;
             if (qp_rows) qp_rows[j / bpr] = (int32_t)ref_qp;
             it.p = at + 1;
         }
@@ -1510,9 +1588,18 @@ static bool parse_mv_line_c(const char* b, const char* e, int nblk, int bpr, boo
             long v[3] = {0, 0, 0};
             const int nc = t == 0 ? 1 : 3;
             for (int q = 0; q < nc; ++q) if (!it.number(v[q])) return false;
-            if (t == 0) { ref[0] += v[0]; mv[(size_t)j * 12 + k * 3] = (int16_t)ref[0]; }
-            else {
-                for (int q = 0; q < 3; ++q) { ref[q] += v[q]; mv[(size_t)j * 12 + k * 3 + q] = (int16_t)ref[q]; }
+            // accumulated vectors must fit the packed int16 fields (and a reference index its range)
+            if (t == 0) {
+                ref[0] += v[0];
+                if (ref[0] < -32768 || ref[0] > 32767) return false;
+                mv[(size_t)j * 12 + k * 3] = (int16_t)ref[0];
+            } else {
+                for (int q = 0; q < 3; ++q) {
+                    ref[q] += v[q];
+                    if (ref[q] < -32768 || ref[q] > 32767) return false;
+                    mv[(size_t)j * 12 + k * 3 + q] = (int16_t)ref[q];
+                }
+                if (ref[2] < 0 || ref[2] >= SO_MAX_REF) return false;
             }
         }
         c.p = ie < e ? ie + 1 : e;
@@ -1545,15 +1632,20 @@ static bool parse_res_line_c(const char* b, const char* e, int W, int H, int bs,
             long s;
             while (c.number(s)) {                  // entropy_decoder_block, decoder.py:548-586
                 if (s < 0) {
+                    if (-s > (long)(n * n - pos)) return false;         // a run cannot be longer than what is left of the block
                     for (long i = 0; i < -s; ++i) {
                         long v;
-                        if (!c.number(v) || pos >= n * n) return false;
+                        if (!c.number(v) || v < -32768 || v > 32767) return false;
                         const int o = ord[pos++];
                         dst[(size_t)(o / n) * W + o % n] = (int16_t)v;
                     }
                 } else if (s == 0) break;
-                else pos += (int)s;
+                else {
+                    if (s > (long)(n * n - pos)) return false;
+                    pos += (int)s;
+                }
             }
+            if (c.bad) return false;
             q = le + 1;
         }
         p = ie < e ? ie + 1 : e;
@@ -1621,10 +1713,6 @@ extern "C" int so_parse_bitstream_files(const char* mv_path, const char* residua
     for (int v : okv) if (!v) return SO_E_INVALID;
     return SO_OK;
 }
-
-#ifdef SO_ME_DEBUG
-extern "C" int so_debug_read(long long* dst) { return (int)cudaMemcpyFromSymbol(dst, g_me_dbg, sizeof(long long) * 4096); }
-#endif
 
 extern "C" int64_t so_format_residual_frame_symbols(const uint8_t* split, const uint32_t* offsets, const int16_t* symbols, int n_blocks,
                                                     char* dst, int64_t cap) {

@@ -123,21 +123,3 @@ __device__ __forceinline__ int quant_rhe(int tc, int s) {
     const int half = 1 << (s - 1);
     return q + (rem > half ? 1 : (rem == half ? (q & 1) : 0));
 }
-
-// out[] holds packed 64-bit keys (SAD<<40 | L1<<24 | ref<<16 | dx+R<<8 | dy+R) after the search kernel; convert in place.
-__global__ void me_unpack_kernel(MeResult* out, int n, int R) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long key = *reinterpret_cast<unsigned long long*>(out + i);
-    MeResult r;
-    if (key == ~0ull) {
-        r.dx = 0; r.dy = 0; r.ref = 0; r.none = 1; r.sad = 0;      // best_mv = (0,0,0), MAE = inf (Encoder.py:684-685)
-    } else {
-        r.sad = (uint32_t)(key >> 40);
-        r.ref = (int16_t)((key >> 16) & 0xFF);
-        r.dx = (int16_t)((int)((key >> 8) & 0xFF) - R);
-        r.dy = (int16_t)((int)(key & 0xFF) - R);
-        r.none = 0;
-    }
-    out[i] = r;
-}

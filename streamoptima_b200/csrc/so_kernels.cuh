@@ -94,15 +94,6 @@ __global__ void ring_planes_kernel(uint8_t* slot0, size_t unit_stride, size_t pl
     }
 }
 
-// dense [H][W] frame -> pitched phase-0 / shift-0 plane of a ring slot, all units
-__global__ void ring_store_kernel(uint8_t* dst, size_t dst_unit_stride, int pitch, const uint8_t* src, size_t src_unit_stride, int W, int H) {
-    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x4 * 4 >= W) return;
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(src + blockIdx.z * src_unit_stride + (size_t)y * W + x4 * 4);
-    *reinterpret_cast<uint32_t*>(dst + blockIdx.z * dst_unit_stride + (size_t)y * pitch + x4 * 4) = v;
-}
-
 __global__ void ring_fill_kernel(uint8_t* dst, size_t dst_unit_stride, size_t bytes16, uint32_t v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < bytes16) reinterpret_cast<uint4*>(dst + blockIdx.y * dst_unit_stride)[i] = make_uint4(v, v, v, v);
@@ -140,7 +131,7 @@ struct FlowArgs {
 };
 
 // ME results are either plain MeResult records (fast ME, intra search) or the packed 64-bit keys the exhaustive search
-// merges with atomicMin (decoded like me_unpack_kernel does).
+// merges with atomicMin.
 __device__ __forceinline__ MeResult me_get(const MeResult* p, int packed, int R) {
     if (!packed) return *p;
     const unsigned long long key = *reinterpret_cast<const unsigned long long*>(p);

@@ -165,19 +165,19 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring_kernel(const __gr
         bool two = r0 + 31u >= (unsigned)MR_TPI;
         {
             bool exists = true;
-            unsigned long long spins = 0;
+            SpinWait sw;
             while (true) {
                 const int iss = *issued, fin = *final_cnt;
                 if (iss > (int)first) break;
                 if (fin <= (int)first) { exists = false; break; }
-                if (++spins > (1ull << 26)) __trap();
+                sw.pause();
             }
             if (!exists) break;
             while (two) {
                 const int iss = *issued, fin = *final_cnt;
                 if (iss > (int)first + 1) break;
                 if (fin <= (int)first + 1) two = false;
-                if (++spins > (1ull << 26)) __trap();
+                else sw.pause();
             }
         }
         const bool has = second == 0u || two;

@@ -68,14 +68,38 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Spin-wait back-off.  The first polls are free (the common wait is a few hundred cycles); after that the warp sleeps
+// between polls.  A waiter that has made no progress for SO_WATCHDOG_NS of *wall* time (%globaltimer, so time-slicing,
+// MPS, compute-sanitizer or a debugger do not shorten it) reports through the trap: a protocol bug must surface as a
+// launch failure, never hang the device.  Compile with -DSO_NO_WATCHDOG to wait forever instead.
+#ifndef SO_WATCHDOG_NS
+#define SO_WATCHDOG_NS 20000000000ull        // 20 s; a 1080p search launch lasts < 1 ms
+#endif
+struct SpinWait {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ void pause() {
+        if (++spins < 64u) return;
+        __nanosleep(spins < 4096u ? 32u : 256u);
+#ifndef SO_NO_WATCHDOG
+        if ((spins & 0x3FFFu) == 0u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > SO_WATCHDOG_NS) __trap();
+        }
+#endif
+    }
+};
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
-    unsigned long long spins = 0;
+    SpinWait sw;
     while (true) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (ok) break;
-        if (++spins > (1ull << 24)) __trap();        // a lost arrival must fault, never hang the GPU
+        sw.pause();
     }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
@@ -163,12 +187,6 @@ __device__ __forceinline__ void sad_pass_g3(const unsigned char* win, const uint
 }
 
 constexpr int ME_MAX_STAGES = 3;
-#ifdef SO_ME_DEBUG
-__device__ long long g_me_dbg[4096];
-#define ME_DBG(slot, j) do { if (blockIdx.x == 0 && lane == 0 && (j) < 100) g_me_dbg[(j) * 32 + (slot)] = clock64(); } while (0)
-#else
-#define ME_DBG(slot, j) do {} while (0)
-#endif
 constexpr int ME_CUR_REGS = 16;          // per-lane staging of current-block words in the producer (SI*bs*bs/4 <= 32*16)
 
 template <int BS, int NDX, int G, bool QUAD>
@@ -321,11 +339,8 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
                     creg[q] = i < ncw ? cur_word(i) : 0u;
                 }
             }
-            ME_DBG(0, j);
             mbar_wait(&rawfull[sb], par);
-            ME_DBG(1, j);
             mbar_wait(&empty[sb], par ^ 1);
-            ME_DBG(2, j);
             uint32_t* cdst = curs + sb * a.SI * BS * WPR;
             if (cur_in_regs) {
 #pragma unroll
@@ -403,9 +418,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[sb]);
-            ME_DBG(3, j);
             if (j + 2 < nloc) issue_raw(j + 2);          // raw[sb] has been consumed
-            ME_DBG(4, j);
         }
     } else {
         // ================================= search warps =================================
@@ -419,11 +432,7 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
             const int unit = sg / a.stages_per_unit, sidx = sg % a.stages_per_unit;
             const int item0 = sidx * a.SI;
             const int nitems = min(a.SI, a.items_per_unit - item0);
-            if (kb == 0) ME_DBG(5, j);
-            if (kb == 10) ME_DBG(8, j);
             mbar_wait(&ready[sb], (uint32_t)((j / S) & 1));
-            if (kb == 0) ME_DBG(6, j);
-            if (kb == 10) ME_DBG(9, j);
             // task order inside a stage: shift-major, then item, then vertical group (keeps warps nearly uniform in c)
             const int task = kb * 32 + lane;
             int c, li, grp;
@@ -705,8 +714,6 @@ __global__ void __launch_bounds__(384, 1) me_tma_kernel(const __grid_constant__ 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[sb]);
-            if (kb == 0) ME_DBG(7, j);
-            if (kb == 10) ME_DBG(10, j);
         }
     }
 }

@@ -124,42 +124,64 @@ class decoder:
         self.decoded_vid = None
         self.decoded_vid_f = False
         self._ctx = None
+        self._ctx_key = None
 
-    def _context(self):
-        if self._ctx is None:
-            self._ctx = _native.Context(width=self.w_pixels, height=self.h_pixels, block_size=self.block_size, search_range=0,
+    def _context(self, block_size=None, width=None, height=None):
+        """Native context for the EFFECTIVE geometry (the reference's decode_bitstream overrides, decoder.py:692-698, win
+        over the constructor values); rebuilt whenever anything it was created from changes."""
+        bs = block_size or self.block_size
+        W, H = width or self.w_pixels, height or self.h_pixels
+        key = (bs, W, H, self.Qp, self.intra_dur, self.nRefFrames, bool(self.FMEEnable), bool(self.VBSEnable), self.ParallelMode,
+               self.device)
+        if self._ctx is None or self._ctx_key != key:
+            if self._ctx is not None:
+                self._ctx.close()
+            self._ctx = _native.Context(width=W, height=H, block_size=bs, search_range=0,
                                         qp=self.Qp, intra_dur=self.intra_dur, n_ref_frames=self.nRefFrames, fme=self.FMEEnable,
                                         vbs=self.VBSEnable, rc_flag=0, parallel_mode=self.ParallelMode, lam=0.0, device=self.device)
+            self._ctx_key = key
         return self._ctx
 
-    def decode_arrays(self, frame_types, split, mv, levels, qp_rows=None, reset_at_intra=True, qp_map=None):
+    def decode_arrays(self, frame_types, split, mv, levels, qp_rows=None, reset_at_intra=True, qp_map=None, block_size=None):
         """Packed arrays (as ``Y_Video_codec.encoded_package.packed``) -> uint8 [F, H, W].
 
+        The frame size is taken from ``levels`` and the block size from ``block_size`` (default: the constructor's); every
+        array must have the extents that geometry implies -- the native side indexes them with it.
         ``qp_map`` (extension): the per-block QPs an ROI encode used -- side information the text streams cannot carry."""
-        ctx = self._context()
-        ctx.set_block_qps(qp_map)
         F = len(frame_types)
         ft = np.ascontiguousarray(frame_types, np.uint8)
         split = np.ascontiguousarray(split, np.uint8)
         mv = np.ascontiguousarray(mv, np.int16)
         levels = np.ascontiguousarray(levels, np.int16)
+        bs = block_size or self.block_size
+        if levels.ndim != 3 or levels.shape[0] != F:
+            raise ValueError("levels must be [frames, height, width]")
+        H, W = levels.shape[1:]
+        if H % bs or W % bs:
+            raise ValueError("frame dimensions must be multiples of the block size")
+        nblk = (H // bs) * (W // bs)
+        if split.shape != (F, nblk) or mv.shape != (F, nblk, 4, 3):
+            raise ValueError(f"split / mv do not have the extents of {F} frames of {W}x{H} with block size {bs}")
+        ctx = self._context(bs, W, H)
+        ctx.set_block_qps(qp_map)
         qp = None
         if qp_rows is not None and len(qp_rows) and len(qp_rows[0]):
             qp = np.ascontiguousarray(qp_rows, np.int32).reshape(F, -1)
-            assert qp.shape[1] == self.h_pixels // self.block_size
-        out = np.empty((F, self.h_pixels, self.w_pixels), np.uint8)
+            if qp.shape[1] != H // bs:
+                raise ValueError("qp_rows must have height / block_size entries per frame")
+        out = np.empty((F, H, W), np.uint8)
         rc = ctx.lib.so_decode_sequence(ctx.handle, ft.ctypes.data, split.ctypes.data, mv.ctypes.data, levels.ctypes.data,
                                         qp.ctypes.data if qp is not None else None, F, 1 if reset_at_intra else 0, out.ctypes.data)
         _native.check(ctx.handle, rc)
         return out
 
-    def parse_bitstream(self, mv_file, residual_file, block_size=None, frames=None):
+    def parse_bitstream(self, mv_file, residual_file, block_size=None, frames=None, width=None, height=None):
         """decode_differential_entropy (decoder.py:673-690): the two text files -> packed arrays.  The lines are parsed by
         the library on host threads (``so_parse_bitstream_files``); ``parse_bitstream_py`` is the line-by-line Python
         restatement the tests compare it with."""
         import os
         bs = block_size or self.block_size
-        H, W = self.h_pixels, self.w_pixels
+        H, W = height or self.h_pixels, width or self.w_pixels
         F = frames or self.frames
         nblk, rows = (H // bs) * (W // bs), H // bs
         rc_on = self.RCFlag is not None and self.RCFlag > 0
@@ -196,8 +218,12 @@ class decoder:
     def decode_bitstream(self, mv_file, residual_file, intra_mode=None, intra_dur=None, block_size=None, frames=None, width=None,
                          height=None, save_decoded_frames=True):
         """decoder.py:692: returns the list of decoded frames."""
-        ft, split, mv, lev, qps = self.parse_bitstream(mv_file, residual_file, block_size)
-        out = self.decode_arrays(ft, split, mv, lev, qps if (self.RCFlag or 0) > 0 else None)
+        if intra_mode not in (None, 0):
+            raise NotImplementedError("intra_mode=1 is broken in the reference")
+        if intra_dur is not None:
+            self.intra_dur = intra_dur            # only frame typing used it in the reference; types come from the stream
+        ft, split, mv, lev, qps = self.parse_bitstream(mv_file, residual_file, block_size, frames, width, height)
+        out = self.decode_arrays(ft, split, mv, lev, qps if (self.RCFlag or 0) > 0 else None, block_size=block_size)
         frames_list = [out[i] for i in range(out.shape[0])]
         if save_decoded_frames:
             self.decoded_vid_f = True

@@ -126,3 +126,72 @@ def test_baseline_config2_full_length_round_trip_and_determinism():
     np.testing.assert_array_equal(out, o1["recon"][0])
     mse = ((out.astype(np.float64) - frames) ** 2).mean(axis=(1, 2))
     assert (10 * np.log10(255.0 ** 2 / mse) > 30).all()                      # QP 4: a sane reconstruction on every frame
+
+
+def test_parser_rejects_malformed_and_hostile_streams(tmp_path):
+    """so_parse_bitstream_files must fail cleanly (ValueError), never index outside its arrays: run lengths larger than
+    the block, absurd digit strings, bad frame types, vectors that do not fit int16, truncated lines -- plus a seeded
+    mutation fuzz of a valid stream (any outcome but a crash / out-of-bounds write is fine)."""
+    name = "s_vbs_fme_nref2"
+    frames, enc, g = load_case(name)
+    d = _decoder(frames, enc)
+    mv_lines = g["mv_text"].splitlines()
+    res_lines = g["res_text"].splitlines()
+
+    def parse(mv, res):
+        mvf, rsf = tmp_path / "mv.txt", tmp_path / "res.txt"
+        mvf.write_text("\n".join(mv) + "\n")
+        rsf.write_text("\n".join(res) + "\n")
+        return d.parse_bitstream(str(mvf), str(rsf))
+
+    parse(mv_lines, res_lines)                                        # sanity: the unmodified stream parses
+
+    def res_with(first_block):                                        # replace the first block of frame 0
+        rest = res_lines[0].split(";", 1)[1]
+        return [first_block + ";" + rest] + res_lines[1:]
+
+    bad_res = [
+        res_with("0'([4294967295, -1, 5])"),                          # zero run that truncates to a negative int
+        res_with("0'([2147483647, 2147483647, -1, 5])"),               # repeated runs driving the position negative
+        res_with("0'([300, -1, 7])"),                                 # run past the end of a 16x16 block
+        res_with("0'([-300, 1, 2, 3])"),                              # non-zero run longer than the block
+        res_with("0'([99999999999999999999999999, 0])"),              # overflows long
+        res_with("0'([-1, 70000, 0])"),                               # level outside int16
+        res_with("0'([-1, 5, 0)"),                                    # missing ']'
+        res_with("2'([0])"),                                          # split flag that is neither 0 nor 1
+        [res_lines[0][: len(res_lines[0]) // 2]] + res_lines[1:],     # truncated line
+    ]
+    for res in bad_res:
+        with pytest.raises(ValueError):
+            parse(mv_lines, res)
+    t, body = mv_lines[1].split("|", 1)
+    first, rest = body.split(";", 1)
+    bad_mv = [
+        ["7|" + mv_lines[0].split("|", 1)[1]] + mv_lines[1:],                        # frame type
+        [mv_lines[0], t + "|0'(40000, 0, 0);" + rest] + mv_lines[2:],                # vector outside int16
+        [mv_lines[0], t + "|0'(0, 0, 99);" + rest] + mv_lines[2:],                   # reference index
+        [mv_lines[0], t + "|0'(99999999999999999999, 0, 0);" + rest] + mv_lines[2:],
+        [mv_lines[0], t + "|" + first] + mv_lines[2:],                               # too few blocks
+        [mv_lines[0].replace("|", "", 1)] + mv_lines[1:],
+    ]
+    for mv in bad_mv:
+        with pytest.raises(ValueError):
+            parse(mv, res_lines)
+    # mutation fuzz: random single-character edits of both streams; must return or raise ValueError, nothing else
+    rng = np.random.default_rng(7)
+    alphabet = "0123456789-,;'()[]|@ "
+    for _ in range(300):
+        mv, res = list(mv_lines), list(res_lines)
+        for lines in (mv, res):
+            f = int(rng.integers(len(lines)))
+            s = lines[f]
+            for _ in range(int(rng.integers(1, 4))):
+                p = int(rng.integers(len(s)))
+                kind = int(rng.integers(3))
+                ch = alphabet[int(rng.integers(len(alphabet)))]
+                s = s[:p] + (ch + s[p + 1:] if kind == 0 else (ch + s[p:] if kind == 1 else s[p + 1:]))
+            lines[f] = s
+        try:
+            parse(mv, res)
+        except ValueError:
+            pass

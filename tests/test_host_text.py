@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.so_abi_version() == 1
+    assert lib.so_abi_version() == 2
     assert ctypes.sizeof(_native.so_frame_stats) == 32 and ctypes.sizeof(_native.so_params) == 64
 
 

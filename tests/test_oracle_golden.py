@@ -6,7 +6,7 @@ from oracle import codec_oracle as co
 from oracle.packing import package_to_arrays
 from tests.golden_util import case_names, load_case
 
-SLOW = {"cif_fme_nref4_vbs"}
+SLOW = {"cif_fme_nref4_vbs", "w1920_fme_nref4", "w1920_fme_nref4_vbs"}      # minutes in the NumPy port: SO_SLOW=1 replays them
 
 
 @pytest.mark.parametrize("name", case_names())
