@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""Benchmark of the StreamOptima B200 encode hot path (contract: see the task statement / DESIGN.md §Measurement).
+"""Benchmark of the StreamOptima B200 encode hot path (contract: see the task statement / DESIGN.md section 6).
 
     python bench.py --gpus N --steps K --warmup W            our arm (CUDA kernels through the C ABI)
-    python bench.py --impl reference --gpus N --steps K ...  CPU arm: the oracle port of the reference's algorithm
+    python bench.py --impl reference --gpus N --steps K ...  CPU arm: the reference's own encoder on the host cores
 
-Workload (BASELINE.json configs[1]): synthetic 1080p (coded 1920x1088) Y sequence, 300 frames, i=16, r=16 exhaustive
-half-pel search over nRefFrames=4, I_Period 30; step k encodes the whole sequence at QP = k mod 12 (the QP sweep).
-One step = one pass of the hot path over that 300-frame batch.  With N GPUs every rank encodes its own stream of the
-same shape (weak scaling, no data-path collective) and the per-frame statistics that two-pass rate control consumes
-are all-gathered over NCCL inside the timed region.
+Workload (BASELINE.json configs[1], "C2"): synthetic 1080p (coded 1920x1088) Y sequence, 300 frames, i=16, r=16 exhaustive
+half-pel search over nRefFrames=4, I_Period 30; step k encodes the whole sequence at QP = k mod 12 (the QP sweep).  One
+step = one pass of the hot path over that 300-frame batch.  With N GPUs every rank encodes its own stream of the same shape
+(weak scaling, no data-path collective; the per-frame statistics two-pass rate control consumes are all-gathered over NCCL
+inside the timed region).  On top of the contract line the same JSON carries:
+  * ``c5_sharded``  -- BASELINE configs[4]: a FIXED batch of 32 4K streams x 32 frames, I_Period 16, closed GOPs dealt to the
+                       ranks (strong scaling; this is the multi-GPU number that can fail);
+  * ``e2e_full_flow`` -- ``encode()`` + ``transmit_bitstream()`` of the C2 sequence: what the reference's main.py does;
+  * ``c1``          -- BASELINE configs[0] (CIF) through ``encode()`` on the GPU next to the unmodified reference on the host.
 """
 from __future__ import annotations
 
@@ -17,6 +21,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -26,10 +31,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(W=1920, H=1088, F=300, bs=16, r=16, nref=4, fme=True, intra_dur=30)
+C1 = dict(W=352, H=288, F=10, bs=8, r=2, qp=6, intra_dur=8)
+C5 = dict(W=3840, H=2160, F=32, S=32, bs=16, r=16, qp=4, intra_dur=16)
 METRIC = "1080p_encode_frames_per_s"
 # measured by tools/int_peak.cu on this pool's B200 (profiles/int_peak_r01.json): VABSDIFF4.U8.ACC issues at
 # 64 lanes/clk/SM -> 18.33e12 lane-instructions/s at 1.965 GHz; plain IADD reaches 36.3e12 (both integer pipes)
 INT_PEAK_FILE = os.path.join(ROOT, "profiles", "int_peak_r01.json")
+# CPU sample of the C2 geometry: frames 0-4 (I + four P frames searching 2, 3, 4, 4 references: the last two are the steady
+# state) of a small window, same i / r / half-pel / nRefFrames
+CPU_SAMPLE = dict(H=64, W=96, F=5)
 
 
 def synth_frames_torch(F, H, W, seed, device):
@@ -52,12 +62,11 @@ def synth_frames_numpy(F, H, W, seed):
     return synth.translating(F, H, W, seed=seed)
 
 
-def me_work_per_sequence(cfg):
-    """Algorithmic SAD pixel-ops W_me = sum over P frames, blocks, refs of N_valid * bs^2 (SURVEY.md §8d), using the
-    validity tests of Encoder.py:695-698, and the number of exhaustive-search launches."""
-    W, H, bs, r = cfg["W"], cfg["H"], cfg["bs"], cfg["r"]
-    fme = cfg["fme"]
+def me_work(W, H, bs, r, fme, F, intra_dur, nref):
+    """Algorithmic SAD pixel-ops W_me = sum over P frames, blocks, refs of N_valid * bs^2 (SURVEY.md 8d), using the
+    validity tests of Encoder.py:695-698.  -> (total, exhaustive-search launches, work of one steady-state P frame)."""
     R = 2 * r if fme else r
+
     def count(pos, size_px):
         size = 2 * size_px - 1 if fme else size_px
         p0 = 2 * pos if fme else pos
@@ -71,14 +80,19 @@ def me_work_per_sequence(cfg):
     ny = sum(count(y, H) for y in range(0, H, bs))
     per_ref = nx * ny * bs * bs
     total, launches = 0, 0
-    nlist = 1
-    for f in range(cfg["F"]):
-        if f % cfg["intra_dur"] != 0:
+    nlist = 1                                   # ref_frames = [128 frame] (Encoder.py:1798); FIFO of nRefFrames (:1864-1867)
+    for f in range(F):
+        if f % intra_dur != 0:
             total += per_ref * nlist
             launches += 1
-        if f < cfg["F"] - 1:
-            nlist = min(nlist + 1, cfg["nref"]) if nlist < cfg["nref"] else cfg["nref"]
-    return total, launches
+        if f < F - 1:
+            nlist = min(nlist + 1, nref)
+    return total, launches, per_ref * nref
+
+
+def me_work_per_sequence(cfg):
+    t, l, _ = me_work(cfg["W"], cfg["H"], cfg["bs"], cfg["r"], cfg["fme"], cfg["F"], cfg["intra_dur"], cfg["nref"])
+    return t, l
 
 
 class ClockSampler(threading.Thread):
@@ -110,32 +124,65 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def _cpu_worker(job):
-    """One oracle encode of a crop (runs in a worker process)."""
-    crop, cfg = job
-    from oracle import codec_oracle as co
-    cf, ch, cw = crop.shape
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own Python encoder (byte code in oracle/_ref, made by oracle/build_ref.py in the build container)
+# when it is there, else the oracle port.  The only place besides tests/ and smoke() that may execute oracle/.
+# ---------------------------------------------------------------------------------------------------------------------
+def _reference_kind():
+    from oracle import build_ref
+    return "reference" if build_ref.load_compiled_reference() is not None else "port"
+
+
+def _encode_cpu(frames, bs, r, qp, intra_dur, **kw):
+    """One whole encode() of ``frames`` with the unmodified reference (or the port).  -> seconds."""
+    import contextlib
+    import io
+    from oracle import build_ref
+    F, H, W = frames.shape
+    ref = build_ref.load_compiled_reference()
     t0 = time.perf_counter()
-    co.OracleCodec(ch, cw, cf, cfg["bs"], cfg["r"], 4, cfg["intra_dur"], 0, nRefFrames=cfg["nref"], FMEEnable=cfg["fme"],
-                   y_only_frame_arr=crop).encode()
+    if ref is not None:
+        enc_mod, _ = ref
+        old = os.getcwd()
+        with tempfile.TemporaryDirectory() as d:            # the reference writes ./yuv/y_only_reconstructed.yuv (Encoder.py:1894)
+            os.makedirs(os.path.join(d, "yuv"))
+            os.chdir(d)
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    c = enc_mod.Y_Video_codec(H, W, F, bs, r, qp, intra_dur, 0, y_only_frame_arr=frames, **kw)
+                    if kw.get("nRefFrames", 1) > 1:
+                        c.decoder.decode = lambda *a, **k: None     # the throw-away internal decode raises for nRef > 1 (quirk Q7)
+                    c.encode()
+            finally:
+                os.chdir(old)
+    else:
+        from oracle import codec_oracle as co
+        co.OracleCodec(H, W, F, bs, r, qp, intra_dur, 0, y_only_frame_arr=frames, **kw).encode()
     return time.perf_counter() - t0
 
 
+def _cpu_worker(job):
+    crop, cfg = job
+    return _encode_cpu(crop, cfg["bs"], cfg["r"], 4, cfg["intra_dur"], nRefFrames=cfg["nref"], FMEEnable=cfg["fme"])
+
+
 def cpu_sample(frames_np, cfg, procs=None):
-    """Oracle port of the reference's algorithm on a bounded sample of the same workload: 3 frames (I, P, P) of 640x256
-    windows, same i / r / nRef / half-pel.  The reference is single-threaded (ParallelMode 0); to use the host's cores the
-    sample runs one independent window per worker process.  Returns (frames/s extrapolated to the full frame, description,
-    seconds, workers)."""
+    """The reference encoder on a bounded sample of the C2 workload: frames 0-4 of a CPU_SAMPLE window per worker process
+    (the reference is single-threaded in ParallelMode 0; one independent window per host core uses the machine).  The
+    sample's time is almost all candidate evaluations, so it is scaled to the full frame by SAD work:
+    frames/s = (sample SAD work x workers / wall) / (SAD work of one steady-state 1080p P frame with 4 references).
+    Returns (frames/s, description, seconds, workers)."""
     import multiprocessing as mp
-    ch, cw, cf = 256, 640, 3
+    ch, cw, cf = CPU_SAMPLE["H"], CPU_SAMPLE["W"], CPU_SAMPLE["F"]
     H, W = cfg["H"], cfg["W"]
     ncpu = os.cpu_count() or 1
     procs = procs or max(1, min(ncpu, 64))
-    spots = [(y, x) for y in range(0, H - ch + 1, ch) for x in range(0, W - cw + 1, cw)]        # 4 x 3 distinct windows at 1080p
+    spots = [(y, x) for y in range(0, H - ch + 1, ch) for x in range(0, W - cw + 1, cw)]
     jobs = []
     for i in range(procs):
-        y, x = spots[i % len(spots)]
+        y, x = spots[(i * 7) % len(spots)]
         jobs.append((np.ascontiguousarray(frames_np[:cf, y:y + ch, x:x + cw]), cfg))
+    kind = _reference_kind()
     t0 = time.perf_counter()
     if procs == 1:
         _cpu_worker(jobs[0])
@@ -143,13 +190,139 @@ def cpu_sample(frames_np, cfg, procs=None):
         with mp.get_context("spawn").Pool(procs) as pool:      # spawn: the parent may hold a CUDA context
             pool.map(_cpu_worker, jobs, chunksize=1)
     dt = time.perf_counter() - t0
-    frac = (ch * cw) / (H * W)
-    fps = procs * cf * frac / dt
-    desc = (f"oracle/codec_oracle.py (NumPy/SciPy port of the reference; single-threaded like the reference's ParallelMode 0) run as "
-            f"{procs} independent worker processes ({ncpu} host CPUs), each on frames 0-2 (I,P,P) of a {cw}x{ch} window, i={cfg['bs']} "
-            f"r={cfg['r']} half-pel nRef={cfg['nref']} QP=4: {dt:.1f} s wall; frames/s = workers x 3 frames x window area / frame area "
-            f"({frac:.4f}) / wall -- labelled extrapolation")
-    return fps, desc, dt, procs
+    w_sample, _, _ = me_work(cw, ch, cfg["bs"], cfg["r"], cfg["fme"], cf, cfg["intra_dur"], cfg["nref"])
+    _, _, w_frame = me_work(W, H, cfg["bs"], cfg["r"], cfg["fme"], cfg["F"], cfg["intra_dur"], cfg["nref"])
+    fps = procs * w_sample / dt / w_frame
+    what = ("the UNMODIFIED reference encoder (oracle/_ref byte code of /root/reference, Y_Video_codec.encode())" if kind == "reference"
+            else "oracle/codec_oracle.py (NumPy port of the reference; oracle/_ref absent)")
+    desc = (f"{what}, single-threaded like ParallelMode 0, run as {procs} independent worker processes ({ncpu} host CPUs), each on "
+            f"frames 0-{cf - 1} (I + P frames searching 2,3,4,4 references) of a {cw}x{ch} window of the C2 sequence, i={cfg['bs']} "
+            f"r={cfg['r']} half-pel nRef={cfg['nref']} QP=4: {dt:.1f} s wall; scaled to the full frame by SAD work "
+            f"({w_sample:.3e} pixel-SADs per window vs {w_frame:.3e} per steady-state 1080p P frame) -- labelled extrapolation")
+    return fps, desc, dt, procs, kind
+
+
+def cpu_c1_full():
+    """BASELINE configs[0] run IN FULL by the reference on one host core (it is its own CPU-runnable case)."""
+    frames = synth_frames_numpy(C1["F"], C1["H"], C1["W"], seed=0)
+    dt = _encode_cpu(frames, C1["bs"], C1["r"], C1["qp"], C1["intra_dur"])
+    return {"frames_per_s": C1["F"] / dt, "seconds": dt, "cores": 1, "kind": _reference_kind(),
+            "what": "C1: CIF 352x288, 10 frames, i=8, r=2, QP=6, I_Period=8, whole encode() incl. its internal decode"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm pieces
+# ---------------------------------------------------------------------------------------------------------------------
+def gpu_c1(device):
+    """C1 through the drop-in class on the GPU: wall time of encode() (host arrays in, package out)."""
+    from streamoptima_b200.Encoder import Y_Video_codec
+    frames = synth_frames_numpy(C1["F"], C1["H"], C1["W"], seed=0)
+    c = Y_Video_codec(C1["H"], C1["W"], C1["F"], C1["bs"], C1["r"], C1["qp"], C1["intra_dur"], 0, y_only_frame_arr=frames)
+    c.device = device
+    c.encode()
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        psnr = c.encode()
+    dt = (time.perf_counter() - t0) / reps
+    return {"frames_per_s": C1["F"] / dt, "seconds": dt, "psnr_first": psnr[0],
+            "what": "C1 through Y_Video_codec.encode() on the GPU (wall, H2D + D2H inside), mean of 20 calls"}
+
+
+def full_flow(codec, frames, qp):
+    """encode() + transmit_bitstream() of the C2 sequence (what the reference's main.py:9-73 does with the class)."""
+    codec.const_init_Qp = qp
+    codec.y_only_f_arr = frames
+    with tempfile.TemporaryDirectory() as d:
+        mvf, rsf = os.path.join(d, "mv.txt"), os.path.join(d, "res.txt")
+        t0 = time.perf_counter()
+        codec.encode()
+        t1 = time.perf_counter()
+        codec.transmit_bitstream(mv_file=mvf, residual_file=rsf)
+        t2 = time.perf_counter()
+        nbytes = os.path.getsize(mvf) + os.path.getsize(rsf)
+    F = frames.shape[0]
+    return {"frames_per_s": F / (t2 - t0), "encode_s": t1 - t0, "transmit_bitstream_s": t2 - t1, "text_bytes": nbytes, "qp": qp,
+            "what": "Y_Video_codec.encode() + transmit_bitstream() on the 300-frame C2 sequence, host arrays in, both text files "
+                    "written (tmpfs/disk of the box), residual text formatted from the packed symbols on host threads"}
+
+
+def c5_sharded(rank, world, local_rank, dist, reps=2):
+    """BASELINE configs[4]: FIXED batch (strong scaling) of C5.S 4K streams x C5.F frames, I_Period 16, nRefFrames 1 (closed GOPs,
+    quirk Q7), r=16 integer search; the S*F/16 GOPs are dealt round-robin to the ranks (streamoptima_b200/sharding.py), every
+    rank encodes its GOPs as one batched call, statistics are all-gathered over NCCL.  -> dict (rank 0) or None."""
+    import torch
+    from streamoptima_b200 import sharding
+    from streamoptima_b200.Encoder import Y_Video_codec
+    dev = torch.device("cuda", local_rank)
+    H, W, F, S, IP = C5["H"], C5["W"], C5["F"], C5["S"], C5["intra_dur"]
+    units = sharding.plan_units(S, F, IP, 1)
+    mine = sharding.assign(units, world)[rank]
+    pinned = torch.empty((len(mine), IP, H, W), dtype=torch.uint8, pin_memory=True)
+    cache = {}
+    for k, ui in enumerate(mine):           # every rank synthesises only the GOPs it owns (same generator, seed = stream)
+        u = units[ui]
+        if u.stream not in cache:
+            cache = {u.stream: synth_frames_torch(F, H, W, seed=u.stream, device=dev)}
+        pinned[k].copy_(cache[u.stream][u.start:u.start + u.length])
+    del cache
+    torch.cuda.empty_cache()
+    c = Y_Video_codec(H, W, IP, C5["bs"], C5["r"], C5["qp"], IP, 0)
+    c.device = local_rank
+    frames = pinned.numpy()
+    kw = dict(want_levels=False, want_recon=False, want_symbols=True)
+    c.encode_arrays(frames, **kw)
+    c.encode_arrays(frames, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = tq_ms = 0.0
+    timed_frames = 0
+    d2h = 0
+    for _ in range(reps):
+        out = c.encode_arrays(frames, **kw)
+        t = c.last_timing
+        dev_ms += t["device_ms"]; tq_ms += t["tq_ms"]; timed_frames += t["timed_frames"]
+        d2h += out["sym_needed"] * 2 + out["split"].nbytes + out["mv"].nbytes + out["row_sizes"].nbytes + out["stats"].nbytes
+        if world > 1:       # the statistics two-pass rate control consumes, all-gathered (SURVEY.md 8e)
+            st = out["stats"]
+            mine_t = torch.zeros((len(units) // world + 1, IP, 2), dtype=torch.int64, device=dev)
+            mine_t[:len(mine)] = torch.from_numpy(np.stack([st["qsize"].astype(np.int64), st["sse"].astype(np.int64)], axis=-1)).to(dev)
+            parts = [torch.empty_like(mine_t) for _ in range(world)]
+            dist.all_gather(parts, mine_t)
+    barrier()
+    wall = time.perf_counter() - t0
+    tm = torch.tensor([dev_ms, wall * 1e3, float(d2h), tq_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tm.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tm.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    else:
+        mx = sm = tm
+    c._ctx.close()
+    if rank != 0:
+        return None
+    total = S * F * reps
+    e2e_s = float(mx[1]) / 1e3
+    hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    # the finish kernels of rank 0 on the frames that carry per-kernel events: 5*H*W algorithmic bytes per frame and unit
+    fin_gbs = 5.0 * H * W * len(mine) * timed_frames / (tq_ms / 1e3) / 1e9 if tq_ms > 0 else None
+    return {"workload": f"C5: {S} x 4K (3840x2160) streams x {F} frames, I_Period {IP}, i=16 r=16 integer search, nRef=1, QP {C5['qp']}: "
+                        f"{len(units)} closed GOPs dealt round-robin to {world} rank(s), one batched call per rank",
+            "scaling": "strong", "n_gpus": world, "units": len(units), "reps": reps,
+            "device_frames_per_s": total / (float(mx[0]) / 1e3), "e2e_frames_per_s": total / e2e_s,
+            "h2d_GBps_aggregate": total * H * W / e2e_s / 1e9, "d2h_GBps_aggregate": float(sm[2]) / e2e_s / 1e9,
+            "d2h_bytes_per_frame": float(sm[2]) / total, "h2d_bytes_per_frame": H * W,
+            "limiter": "e2e is bounded by the host->device copy of the raw frames (8.3 MB per 4K frame over this rank's PCIe link; "
+                       "h2d_GBps_aggregate / n_gpus is the per-link rate reached) -- the device-side number is what the kernels sustain",
+            "roofline_transform_batched": {"bound": "hbm", "kernel": "inter_finish16_kernel<false> / intra_finish_kernel<16>, %d units per launch" % len(mine),
+                                           "achieved": fin_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fin_gbs / hbm_peak if fin_gbs else None,
+                                           "algorithmic_bytes_per_frame": 5 * H * W}}
 
 
 def main():
@@ -168,6 +341,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=CFG["F"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip c5_sharded / e2e_full_flow / c1 (the contract line only)")
     args = ap.parse_args()
     cfg = dict(CFG)
     cfg["F"] = args.frames
@@ -184,7 +358,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        frames = synth_frames_numpy(3, cfg["H"], cfg["W"], seed=0)
+        frames = synth_frames_numpy(CPU_SAMPLE["F"], cfg["H"], cfg["W"], seed=0)
         for _ in range(min(args.warmup, 1)):
             cpu_sample(frames, cfg)
         t0 = time.perf_counter()
@@ -192,11 +366,12 @@ def main():
         dt = time.perf_counter() - t0
         fps = float(np.mean([v[0] for v in vals]))
         emit({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": config,
-                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": vals[0][3], "kind": "port", "sample": vals[0][1]},
-                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+              "config": config,
+              "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": vals[0][3], "kind": vals[0][4], "sample": vals[0][1]},
+              "c1_reference_full": cpu_c1_full(),
+              "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -224,6 +399,7 @@ def main():
     codec.device = local_rank
     ctx = codec._context(cfg["bs"], cfg["r"], cfg["intra_dur"], max_batch=1)
     lib = ctx.lib
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -264,37 +440,45 @@ def main():
         timed_frames += t["timed_frames"]
     barrier()
     wall = time.perf_counter() - t0
-    sampler.stop_flag = True
-    if rank == 0:
-        sampler.join()
 
-    # ---- end to end through the public API: host frames in, host results out, copies inside the timed region
-    for k in range(min(args.warmup, 2)):
+    # ---- end to end through the public API: host frames in, host results out, copies inside the timed region.  The
+    # residual comes back as packed run-level symbols generated on the device (the text bitstream is formatted from them);
+    # the reconstruction stays in HBM as the reference frame -- encode() fetches it once, for the .yuv the reference writes
+    e2e_kw = dict(want_levels=False, want_recon=False, want_symbols=True)
+    for k in range(min(args.warmup, 3)):
         codec.const_init_Qp = k % 12
-        codec.encode_arrays(frames)
+        codec.encode_arrays(frames, **e2e_kw)
     barrier()
     t1 = time.perf_counter()
     e2e_dev_ms = 0.0
+    d2h = 0
+    e2e_launches = 0
     for k in range(args.steps):
         codec.const_init_Qp = k % 12
-        out = codec.encode_arrays(frames)
+        out = codec.encode_arrays(frames, **e2e_kw)
         _ = int(out["stats"]["sse"][0, -1])
         e2e_dev_ms += codec.last_timing["device_ms"]
+        e2e_launches += codec.last_timing["launches"]
+        d2h += out["sym_needed"] * 2 + out["split"].nbytes + out["mv"].nbytes + out["row_sizes"].nbytes + out["stats"].nbytes
     barrier()
     e2e_wall = time.perf_counter() - t1
-    nblk = (H // cfg["bs"]) * (W // cfg["bs"])
-    d2h = F * (H * W * 3 + nblk * (1 + 24) + (H // cfg["bs"]) * 4 + 32)
+    sampler.stop_flag = True
+    if rank == 0:
+        sampler.join()
+    del out
 
     tm = torch.tensor([dev_ms, wall * 1e3, e2e_wall * 1e3, me_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max, e2e_ms_max, me_ms_max = [float(v) for v in tm.tolist()]
+    line = None
     if rank == 0:
         total_frames = args.steps * F * world
         value = total_frames / (dev_ms_max / 1e3)
         w_me, me_l = me_work_per_sequence(cfg)
         peaks = json.load(open(INT_PEAK_FILE)) if os.path.exists(INT_PEAK_FILE) else {}
         peak = peaks.get("vabsdiff4_lane_Tops", 18.33)
+        peak_iadd = peaks.get("iadd_lane_Tops", 36.3)
         # rank 0's own exhaustive-search launches, CUDA events around the launch on the context stream.  The library records
         # per-kernel events on every 8th frame only (they cost ~10 us of stream serialisation per frame), so the per-launch
         # duration is the mean over those xs_launches launches of the timed region.  Work per launch = W_me / launches of the
@@ -303,20 +487,28 @@ def main():
         avg_launch_ms = xs_ms / max(1, xs_launches)
         achieved = (w_me / 4 / me_l) / (avg_launch_ms / 1e3) / 1e12
         traffic, traffic_detail = None, None                            # DRAM bytes per ME launch from the committed ncu capture
-        tpath = os.path.join(ROOT, "profiles", "r01_me_traffic.json")
-        if os.path.exists(tpath) and F >= 30:
+        tpath = next((p for p in (os.path.join(ROOT, "profiles", n) for n in ("r02_me_traffic.json", "r01_me_traffic.json")) if os.path.exists(p)), None)
+        if tpath and F >= 30:
             tj = json.load(open(tpath))
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]      # bytes per launch, one ncu --set full capture
+            algo = (cfg["nref"] + 1) * H * W         # the current frame and nRefFrames reference frames, once
             traffic_detail = {"unit": "B per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                              "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"), "source": tj["source"],
-                              "note": tj.get("note")}
+                              "algorithmic_bytes_per_launch": algo, "traffic_over_algorithmic": traffic / algo,
+                              "design_footprint_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"),
+                              "source": tj["source"],
+                              "note": "the search reads 16 planes per reference (4 half-pel phases x 4 byte-shifted copies, the price of "
+                                      "16-byte aligned TMA boxes): %.1fx the algorithmic bytes, each plane once per launch; at < 3 %% of "
+                                      "DRAM peak it costs no time in this ALU-bound kernel" % (traffic / algo)}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "wall_ms_per_step": wall_ms_max / args.steps,
                 "roofline": {"bound": "int32-alu (VABSDIFF4 pipe)", "kernel": "me_ring_kernel<false>", "achieved": achieved,
                              "peak": peak, "unit": "T lane-instr/s (1 instr = 4 pixel SADs)", "frac": achieved / peak,
-                             "peak_source": "measured: tools/int_peak.cu vabsdiff4.add, profiles/int_peak_r01.json (MEASURED_PEAKS.json has no integer figure)",
+                             "peak_int32": peak_iadd, "frac_int32": achieved / peak_iadd,
+                             "peak_source": "measured: tools/int_peak.cu, profiles/int_peak_r01.json (MEASURED_PEAKS.json has no integer figure); "
+                                            "frac = against the VABSDIFF4.U8.ACC issue rate (64 lanes/clk/SM, the instruction that does the work), "
+                                            "frac_int32 = against plain IADD on both integer pipes (128 lanes/clk/SM)",
                              "algorithmic_sad_pixel_ops_per_step": w_me, "launches_per_step": me_l,
                              "avg_launch_ms": avg_launch_ms, "launches_timed": xs_launches,
                              "me_share_of_step": avg_launch_ms * me_l * args.steps / dev_ms,
@@ -324,15 +516,33 @@ def main():
                 "roofline_transform": {"bound": "hbm", "achieved": 5.0 * H * W * timed_frames / (tq_ms / 1e3) / 1e9,
                                        "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                                        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
-                                       "unit": "GB/s", "note": "5*H*W algorithmic bytes per frame (SURVEY §8d) over the transform/quant/recon kernels of the frames that carry per-kernel events; latency-bound at one 1080p frame per launch"},
+                                       "unit": "GB/s", "note": "5*H*W algorithmic bytes per frame (SURVEY 8d) over the transform/quant/recon kernels of the frames that carry per-kernel events; ONE 1080p frame per launch is latency-bound -- c5_sharded.roofline_transform_batched is the same kernel on a batched launch"},
                 "e2e": {"value": total_frames / (e2e_ms_max / 1e3), "unit": "frames/s", "h2d_bytes_per_step": F * H * W,
-                        "d2h_bytes_per_step": d2h, "wall_ms_per_step": e2e_ms_max / args.steps,
-                        "device_ms_per_step_rank0": e2e_dev_ms / args.steps},
-                "gpu_launches": launches, "clocks": sampler.summary()}
+                        "d2h_bytes_per_step": d2h / args.steps, "wall_ms_per_step": e2e_ms_max / args.steps,
+                        "device_ms_per_step_rank0": e2e_dev_ms / args.steps,
+                        "api": "Y_Video_codec.encode_arrays(frames, want_levels=False, want_recon=False, want_symbols=True): pinned host frames in; "
+                               "split / MVs / packed run-level symbols / row sizes / statistics out"},
+                "gpu_launches": launches + e2e_launches, "clocks": sampler.summary()}
         line["roofline_transform"]["frac"] = line["roofline_transform"]["achieved"] / line["roofline_transform"]["peak"]
         if world == 1 and not args.no_cpu_baseline:
-            fps, desc, dt, procs = cpu_sample(frames, cfg)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": procs, "kind": "port", "sample": desc}
+            fps, desc, dt, procs, kind = cpu_sample(frames, cfg)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": procs, "kind": kind, "sample": desc}
+    if not args.no_extras:
+        if rank == 0 and world == 1:
+            line["e2e_full_flow"] = full_flow(codec, frames, 4)
+            line["c1"] = {"gpu": gpu_c1(local_rank)}
+            if not args.no_cpu_baseline:
+                line["c1"]["cpu"] = cpu_c1_full()
+        # free the C2 buffers, then the fixed 4K batch sharded over all ranks
+        codec._ctx.close()
+        codec._ctx = None
+        del frames, frames_pinned
+        Y_Video_codec._pool.free.clear()
+        torch.cuda.empty_cache()
+        c5 = c5_sharded(rank, world, local_rank, dist)
+        if rank == 0:
+            line["c5_sharded"] = c5
+    if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -90,6 +90,20 @@ typedef struct so_frame_out {
     so_frame_stats* stats;
 } so_frame_out;
 
+/* Packed run-level symbols of a sequence as a HOST output of the sequence encodes (so_set_symbol_output): the symbol lists
+ * entropy_encoder_block (Encoder.py:1086-1131) produces, int16, frame after frame.  A frame is the concatenation of its
+ * blocks' lists in raster order (the four lists of a split block in Z order); lists are self-delimiting -- a list ends
+ * with the symbol 0 or when its runs have covered the block (decoder.py:548-586).  They replace the 2 B/px raw levels on
+ * the device-to-host path: the residual text is formatted from them (so_write_bitstream_files_symbols) and the levels
+ * can be rebuilt on the host when wanted (so_symbols_to_levels). */
+typedef struct so_symbol_out {
+    int16_t*  symbols;      /* host buffer (pinned for asynchronous copies), `capacity` symbols                      */
+    uint64_t  capacity;
+    uint64_t* pos;          /* out [n_units][n_frames]: index of the frame's first symbol in `symbols`                */
+    uint32_t* count;        /* out [n_units][n_frames]: symbols of the frame                                         */
+    uint64_t  needed;       /* out: symbols of the whole sequence (> capacity: SO_E_NOMEM, see so_fetch_symbols)      */
+} so_symbol_out;
+
 typedef struct so_ctx so_ctx;
 
 int         so_abi_version(void);
@@ -142,6 +156,16 @@ int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_fr
                        uint8_t* split, int16_t* mv, int16_t* levels, uint8_t* recon,
                        uint32_t* row_sizes, so_frame_stats* stats);
 
+/* Arm (sym != NULL) or disarm (NULL) symbol output for the following so_encode_sequence / so_encode_yuv420_file calls of
+ * this context.  While armed, every chunk of frames is run through count -> device prefix scan -> emit on the device as
+ * soon as it is encoded and its symbols are copied into sym->symbols with their exact sizes, overlapped with the encode
+ * of the next chunk (frames are stored in the order they finish: use pos / count).  `levels` may then be NULL in those
+ * calls.  The struct must stay alive while armed.  If the buffer is too small the call still completes every other
+ * output, sets sym->needed and returns SO_E_NOMEM; the symbols stay resident on the device:
+ * so_fetch_symbols(ctx, sym) with a larger buffer copies them (in unit, frame order) without encoding again. */
+int so_set_symbol_output(so_ctx* ctx, so_symbol_out* sym);
+int so_fetch_symbols(so_ctx* ctx, so_symbol_out* sym);
+
 /* Frame ingest fused with the encode of ONE sequence (read_yuv Encoder.py:110-126, pad_hw :140-155): frames
  * first_frame .. first_frame + n_frames - 1 of a planar YUV 4:2:0 file whose luma is src_width x src_height (<= the coded
  * size of the context; the missing rows / columns are padded with 128 like pad_hw does).  Only the luma planes are read,
@@ -176,6 +200,20 @@ int so_seq_symbols(so_ctx* ctx);
 int so_seq_download_symbols(so_ctx* ctx, uint32_t* offsets, int16_t* symbols, uint64_t sym_capacity, uint64_t* sym_base, uint64_t* needed);
 int64_t so_format_residual_frame_symbols(const uint8_t* split, const uint32_t* offsets, const int16_t* symbols, int n_blocks,
                                          char* dst, int64_t cap);
+
+/* Host side of the packed symbol streams (the so_symbol_out layout); no device needed:
+ *   so_format_residual_frame_packed   residual text of one frame (same bytes as so_format_residual_frame); INT64_MIN when
+ *                                     the stream is not a valid sequence of lists for these split flags
+ *   so_symbols_to_levels              inverse RLE of whole frames -> levels i16 [n_frames][height][width], frames in
+ *                                     parallel on host threads; SO_E_INVALID on a corrupt stream
+ *   so_write_bitstream_files_symbols  so_write_bitstream_files with the residual text formatted from the symbols */
+int64_t so_format_residual_frame_packed(const uint8_t* split, const int16_t* symbols, int64_t n_symbols, int n_blocks, int block_size,
+                                        char* dst, int64_t cap);
+int so_symbols_to_levels(const uint8_t* split, const int16_t* symbols, const uint64_t* sym_pos, const uint32_t* sym_count, int n_frames,
+                         int width, int height, int block_size, int16_t* levels, int n_threads);
+int so_write_bitstream_files_symbols(const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* symbols,
+                                     const uint64_t* sym_pos, const uint32_t* sym_count, const int32_t* qp_rows_per_frame, int n_frames,
+                                     int width, int height, int block_size, const char* mv_path, const char* residual_path, int n_threads);
 
 /* Decoder (decoder.py:487-545 `decode` with decode_frame_inter :97 / decode_frame_intra :330) on packed arrays, host
  * buffers in and out, one sequence (unit).  frame_types u8 [n_frames]; split / mv / levels as so_encode_sequence writes

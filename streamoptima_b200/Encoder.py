@@ -19,6 +19,8 @@ from __future__ import annotations
 
 import math
 import os
+import sys
+import weakref
 
 import numpy as np
 
@@ -32,15 +34,92 @@ def generate_Q_matrix(i, QP):
     return np.where(s < i - 1, 2 ** QP, np.where(s == i - 1, 2 ** (QP + 1), 2 ** (QP + 2))).astype(int)
 
 
-def _pinned_empty(shape, dtype):
-    """Host buffer for DMA: pinned through torch when CUDA is up (PyTorch is used for buffers only)."""
-    import torch
-    tdt = {np.uint8: torch.uint8, np.int16: torch.int16, np.uint32: torch.int32}[dtype]
-    t = torch.empty(tuple(shape), dtype=tdt, pin_memory=torch.cuda.is_available())
-    arr = t.numpy()
-    if dtype is np.uint32:
-        arr = arr.view(np.uint32)
-    return t, arr
+class _PinnedPool:
+    """Pinned host buffers recycled across encodes (``cudaHostAlloc`` of GBs costs more than the encode itself).  PyTorch
+    supplies the pinned memory; nothing else of it is used here."""
+
+    def __init__(self, max_free=12):
+        self.free, self.max_free = [], max_free        # entries: (nbytes, tensor, uint8 ndarray over it)
+
+    def take(self, nbytes):
+        nbytes = max(int(nbytes), 1)
+        best = None
+        for i, (n, _, _) in enumerate(self.free):
+            if nbytes <= n <= max(2 * nbytes, nbytes + (1 << 20)) and (best is None or n < self.free[best][0]):
+                best = i
+        if best is not None:
+            return self.free.pop(best)
+        import torch
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        return (nbytes, t, t.numpy())
+
+    def give(self, item):
+        if len(self.free) < self.max_free:
+            self.free.append(item)
+
+
+class _Lease:
+    """The buffers one result owns.  When the result dies they go back to the pool -- unless somebody still holds a view
+    of one (its ndarray is then referenced from outside), in which case that buffer is simply left to its holders: a
+    result is never overwritten behind its owner's back."""
+
+    def __init__(self, pool):
+        self.items = []
+        self.pool = pool
+        weakref.finalize(self, _Lease._release, pool, self.items)
+
+    def array(self, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        item = self.pool.take(n)
+        self.items.append(item)
+        return item[2][:n].view(dtype).reshape(shape)
+
+    @staticmethod
+    def _release(pool, items):
+        while items:
+            it = items.pop()
+            if sys.getrefcount(it[2]) <= 2:        # the tuple and getrefcount's argument: no view is alive
+                pool.give(it)
+
+
+class EncodeResult(dict):
+    """Outputs of one encode call: host arrays that belong to this object (``levels`` is rebuilt from the symbol
+    streams on first access when the call did not download it)."""
+
+    lease = None
+    _levels_from_symbols = None
+
+    def __missing__(self, key):
+        if key == "levels" and self._levels_from_symbols is not None:
+            lev = self._levels_from_symbols()
+            dict.__setitem__(self, "levels", lev)
+            return lev
+        raise KeyError(key)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
+class _Packed(dict):
+    """``encoded_package.packed``: the arrays of one encoded sequence.  It owns the ``EncodeResult`` they live in (so a later
+    encode on the same codec cannot touch them); ``levels`` is rebuilt from the symbol streams on first access."""
+
+    def __init__(self, result, **arrays):
+        super().__init__(arrays)
+        self.result = result
+
+    def __missing__(self, key):
+        if key == "levels":
+            lev = self.result["levels"][0]
+            dict.__setitem__(self, "levels", lev)
+            return lev
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return key == "levels" or dict.__contains__(self, key)
 
 
 class EncodedPackage(dict):
@@ -49,10 +128,16 @@ class EncodedPackage(dict):
 
     _LAZY = ("MVS per Frame", "approx residual")
 
-    def __init__(self, eager, frame_types, split, mv, levels, bs):
+    def __init__(self, eager, frame_types, split, mv, levels, bs, packed=None):
         super().__init__(eager)
-        self._ft, self._split, self._mv, self._lev, self._bs = frame_types, split, mv, levels, bs
-        self.packed = dict(frame_types=frame_types, split=split, mv=mv, levels=levels)
+        self._ft, self._split, self._mv, self._bs = frame_types, split, mv, bs
+        # ``packed``: the arrays behind the package (split, mv, levels, recon, symbol streams ...).  ``levels`` may be lazy
+        # (rebuilt from the symbol streams on first access), hence the indirection.
+        self.packed = packed if packed is not None else dict(frame_types=frame_types, split=split, mv=mv, levels=levels)
+
+    @property
+    def _lev(self):
+        return self.packed["levels"]
 
     def __missing__(self, key):
         if key not in self._LAZY:
@@ -230,11 +315,14 @@ class Y_Video_codec:
         return self._ctx
 
     def encode_arrays(self, frames_u8, block_size=None, search_range=None, intra_dur=None, want_levels=True, want_recon=True,
-                      qp_map=None):
+                      qp_map=None, want_symbols=False):
         """Encode ``frames_u8`` ([F,H,W] or [U,F,H,W] for U independent sequences) and return the packed outputs.
 
         This is the call the reference-facing ``encode()`` is built on; inputs and outputs are HOST arrays and the
-        host<->device copies happen inside ``so_encode_sequence``.
+        host<->device copies happen inside ``so_encode_sequence``.  ``want_symbols``: the run-level symbol streams
+        (Encoder.py:1086-1131) are generated on the device and downloaded packed (``symbols`` / ``sym_pos`` / ``sym_count``);
+        with ``want_levels=False`` they replace the 2 B/px raw levels on the device-to-host path and ``levels`` is rebuilt
+        from them on first access.  The returned arrays belong to the returned ``EncodeResult``.
         """
         block_size = block_size or self.block_size
         search_range = self.search_range if search_range is None else search_range
@@ -255,11 +343,11 @@ class Y_Video_codec:
         # the input is handed to the library as is (pinned or pageable): its upload is chunked and overlapped with the
         # encode of earlier chunks, so an extra staging copy would only add host time
         a_in = np.ascontiguousarray(arr)
-        return self._run(ctx, U, F, want_levels, want_recon,
+        return self._run(ctx, U, F, want_levels, want_recon, want_symbols,
                          lambda o: ctx.lib.so_encode_sequence(ctx.handle, a_in.ctypes.data, U, F, *o))
 
     def encode_yuv_file(self, path, src_height=None, src_width=None, first_frame=0, n_frames=None, block_size=None,
-                        search_range=None, intra_dur=None, want_levels=True, want_recon=True, qp_map=None):
+                        search_range=None, intra_dur=None, want_levels=True, want_recon=True, qp_map=None, want_symbols=False):
         """Encode frames of a planar YUV 4:2:0 file without materialising them on the Python side (read_yuv + pad_hw,
         Encoder.py:110-126 / :140-155, fused with the encode: ``so_encode_yuv420_file``).  ``src_height`` / ``src_width``: luma
         size in the file (default: the codec's size); smaller sources are padded with 128 to the codec's size."""
@@ -274,37 +362,70 @@ class Y_Video_codec:
         ctx = self._context(block_size, search_range, intra_dur, max_batch=1)
         ctx.set_block_qps(self.roi_qp_map if qp_map is None else qp_map)
         bpath = os.fsencode(path)
-        return self._run(ctx, 1, F, want_levels, want_recon,
+        return self._run(ctx, 1, F, want_levels, want_recon, want_symbols,
                          lambda o: ctx.lib.so_encode_yuv420_file(ctx.handle, bpath, sw, sh, first_frame, F, *o))
 
-    def _run(self, ctx, U, F, want_levels, want_recon, call):
-        """Pinned output buffers (cached per shape) + one library call ``call(output pointers)`` + result dict."""
+    _pool = _PinnedPool()
+    _sym_guess = 0.35          # symbols per pixel the first symbol buffer is sized for (grows to what encodes needed)
+
+    def _run(self, ctx, U, F, want_levels, want_recon, want_symbols, call):
+        """Pinned output buffers (leased from the pool, owned by the result) + one library call ``call(output pointers)``."""
         H, W = self.h_pixels, self.w_pixels
         nblk, rows = ctx.nblk, ctx.rows
-        # pinned staging buffers are cached per shape: cudaHostAlloc of GBs costs more than the encode itself.
-        # NOTE the returned arrays are views of these buffers and are overwritten by the next call.
-        key = (U, F, H, W, nblk, rows)
-        if getattr(self, "_pin_key", None) != key:
-            self._pin = dict(split=_pinned_empty((U, F, nblk), np.uint8),
-                             mv=_pinned_empty((U, F, nblk, 4, 3), np.int16), rows=_pinned_empty((U, F, rows), np.uint32),
-                             stats=_pinned_empty((U, F, 32), np.uint8))
-            self._pin_key = key
-        if want_levels and "lev" not in self._pin:
-            self._pin["lev"] = _pinned_empty((U, F, H, W), np.int16)
-        if want_recon and "rec" not in self._pin:
-            self._pin["rec"] = _pinned_empty((U, F, H, W), np.uint8)
-        split, mv, row_sizes = self._pin["split"][1], self._pin["mv"][1], self._pin["rows"][1]
-        levels = self._pin["lev"][1] if want_levels else None
-        recon = self._pin["rec"][1] if want_recon else None
-        # pinned too: a pageable target makes the per-chunk D2H synchronous and stalls the host behind the GPU
-        stats = self._pin["stats"][1].view(_native.STATS_DTYPE).reshape(U, F)
-        rc = call((split.ctypes.data, mv.ctypes.data, levels.ctypes.data if want_levels else None,
-                   recon.ctypes.data if want_recon else None, row_sizes.ctypes.data, stats.ctypes.data))
+        C = _native.C
+        lease = _Lease(self._pool)
+        # pinned targets: a pageable target makes the per-chunk D2H synchronous and stalls the host behind the GPU
+        split = lease.array((U, F, nblk), np.uint8)
+        mv = lease.array((U, F, nblk, 4, 3), np.int16)
+        row_sizes = lease.array((U, F, rows), np.uint32)
+        stats = lease.array((U, F, 32), np.uint8).view(_native.STATS_DTYPE).reshape(U, F)
+        levels = lease.array((U, F, H, W), np.int16) if want_levels else None
+        recon = lease.array((U, F, H, W), np.uint8) if want_recon else None
+        sym = None
+        if want_symbols:
+            cap = int(self._sym_guess * U * F * H * W) + 4 * nblk * U * F + 1024
+            symbols = lease.array((cap,), np.int16)
+            pos, cnt = np.zeros((U, F), np.uint64), np.zeros((U, F), np.uint32)
+            sym = _native.so_symbol_out(symbols.ctypes.data, cap, pos.ctypes.data, cnt.ctypes.data, 0)
+            _native.check(ctx.handle, ctx.lib.so_set_symbol_output(ctx.handle, C.byref(sym)))
+        try:
+            rc = call((split.ctypes.data, mv.ctypes.data, levels.ctypes.data if want_levels else None,
+                       recon.ctypes.data if want_recon else None, row_sizes.ctypes.data, stats.ctypes.data))
+        finally:
+            if want_symbols:
+                ctx.lib.so_set_symbol_output(ctx.handle, None)
+        if want_symbols and rc == -3 and sym.needed > sym.capacity:
+            # the guess was too small: everything else is complete and the symbols are still on the device -- fetch them into
+            # a buffer of the right size (no second encode) and remember the density for the next call
+            cap = int(sym.needed) + 1024
+            symbols = lease.array((cap,), np.int16)
+            sym.symbols, sym.capacity = symbols.ctypes.data, cap
+            rc = ctx.lib.so_fetch_symbols(ctx.handle, C.byref(sym))
         _native.check(ctx.handle, rc)
         self.last_timing = ctx.last_timing()
         self._last_shape = (U, F)
-        return dict(split=split, mv=mv, levels=levels, recon=recon, row_sizes=row_sizes, stats=stats,
-                    frame_types=stats["frame_type"].astype(np.uint8))
+        out = EncodeResult(split=split, mv=mv, recon=recon, row_sizes=row_sizes, stats=stats,
+                           frame_types=stats["frame_type"].astype(np.uint8))
+        out.lease = lease
+        if want_levels:
+            out["levels"] = levels
+        if want_symbols:
+            type(self)._sym_guess = max(self._sym_guess, 1.15 * sym.needed / float(U * F * H * W))
+            out.update(symbols=symbols[:max(int(sym.needed), 1)], sym_pos=pos, sym_count=cnt, sym_needed=int(sym.needed))
+            if not want_levels:
+                bs = ctx.bs
+
+                def rebuild(split=split, symbols=symbols, pos=pos, cnt=cnt):
+                    lev = np.empty((U, F, H, W), np.int16)
+                    rc2 = _native.load().so_symbols_to_levels(split.ctypes.data, symbols.ctypes.data, pos.ctypes.data, cnt.ctypes.data,
+                                                       U * F, W, H, bs, lev.ctypes.data, 0)
+                    if rc2 != 0:
+                        raise RuntimeError("corrupt symbol stream")
+                    return lev
+                out._levels_from_symbols = rebuild
+        elif not want_levels:
+            out["levels"] = None
+        return out
 
     @staticmethod
     def psnr_from_sse(sse, npx):
@@ -324,10 +445,13 @@ class Y_Video_codec:
         if self.ParallelMode == 3:
             raise NotImplementedError("ParallelMode=3 is racy / crashes in the reference (Encoder.py:1712-1787)")
         if self._yuv_file is not None and self._y_arr is None:
-            out = self.encode_yuv_file(self._yuv_file, block_size=block_size, search_range=search_range, intra_dur=intra_dur)
+            out = self.encode_yuv_file(self._yuv_file, block_size=block_size, search_range=search_range, intra_dur=intra_dur,
+                                       want_levels=False, want_symbols=True)
         else:
             frames = np.ascontiguousarray(self.y_only_f_arr[:self.frames])
-            out = self.encode_arrays(frames, block_size, search_range, intra_dur)
+            # the residual travels as packed run-level symbols (generated on the device), not as 2 B/px raw levels: the text
+            # bitstream is formatted from them and ``packed["levels"]`` / ``"approx residual"`` are rebuilt on demand
+            out = self.encode_arrays(frames, block_size, search_range, intra_dur, want_levels=False, want_symbols=True)
         st = out["stats"][0]
         H, W = self.h_pixels, self.w_pixels
         nblk = (H // block_size) * (W // block_size)
@@ -341,8 +465,10 @@ class Y_Video_codec:
                  "search range": search_range, "PSNR per frame": psnr_per_frame,
                  "SSIM per frame": [float("nan")] * self.frames, "MAE per Frame": mae_per_frame,
                  "Qp_per_row_per_frame": [list(qp_rows) for _ in range(self.frames)], "frame_type_seq": frame_types}
-        pkg = EncodedPackage(eager, np.asarray(frame_types, np.uint8), out["split"][0], out["mv"][0], out["levels"][0], block_size)
-        pkg.packed.update(recon=out["recon"][0], row_sizes=out["row_sizes"][0], qsize=st["qsize"].copy())
+        packed = _Packed(out, frame_types=np.asarray(frame_types, np.uint8), split=out["split"][0], mv=out["mv"][0],
+                         recon=out["recon"][0], row_sizes=out["row_sizes"][0], qsize=st["qsize"].copy(),
+                         symbols=out["symbols"], sym_pos=out["sym_pos"][0], sym_count=out["sym_count"][0])
+        pkg = EncodedPackage(eager, packed["frame_types"], packed["split"], packed["mv"], None, block_size, packed=packed)
         self.encoded_package_f = True
         if save_enc_pkg:
             self.encoded_package = pkg
@@ -431,8 +557,25 @@ class Y_Video_codec:
         for f in range(len(p["frame_types"])):
             t = int(p["frame_types"][f])
             mv_lines.append(str(t) + "|" + self.differential_encoder_frame(t, p["split"][f], p["mv"][f], pkg["Qp_per_row_per_frame"][f]))
-            res_lines.append(self.entropy_encoder_frame(p["split"][f], p["levels"][f], pkg["block size"]))
+            if dict.__contains__(p, "symbols"):
+                res_lines.append(self._residual_line_packed(p, f, pkg["block size"]))
+            else:
+                res_lines.append(self.entropy_encoder_frame(p["split"][f], p["levels"][f], pkg["block size"]))
         return mv_lines, res_lines
+
+    def _residual_line_packed(self, p, f, block_size):
+        """Residual text of frame ``f`` straight from its packed symbol stream (``so_format_residual_frame_packed``)."""
+        lib = _native.load()
+        sp = np.ascontiguousarray(p["split"][f], np.uint8)
+        n = int(p["sym_count"][f])
+        sy = np.ascontiguousarray(p["symbols"][int(p["sym_pos"][f]):int(p["sym_pos"][f]) + n]) if n else np.zeros(1, np.int16)
+
+        def call(cbuf, cap):
+            r = lib.so_format_residual_frame_packed(sp.ctypes.data, sy.ctypes.data, n, sp.shape[0], block_size, cbuf, cap)
+            if r == -2 ** 63:
+                raise RuntimeError("corrupt symbol stream")
+            return r
+        return self._fmt(call, 1024 + n * 8 + sp.shape[0] * 24)
 
     def transmit_bitstream(self, intra_dur=None, block_size=None, mv_file=None, residual_file=None):
         if not self.encoded_package_f:
@@ -442,15 +585,24 @@ class Y_Video_codec:
         # byte-identical to joining bitstream_lines() with newlines
         pkg = self.encoded_package if self.encoded_package is not None else self._last_package
         p = pkg.packed
-        F, H, W = p["levels"].shape
+        F = len(p["frame_types"])
+        H, W = pkg["height in pixels"], pkg["width in pixels"]
         qp = pkg["Qp_per_row_per_frame"]
         qp_arr = np.ascontiguousarray(qp, np.int32) if len(qp) and len(qp[0]) else None
         lib = _native.load()
         ft, sp = np.ascontiguousarray(p["frame_types"], np.uint8), np.ascontiguousarray(p["split"], np.uint8)   # kept alive
-        mvs, lev = np.ascontiguousarray(p["mv"], np.int16), np.ascontiguousarray(p["levels"], np.int16)         # across the call
-        rc = lib.so_write_bitstream_files(ft.ctypes.data, sp.ctypes.data, mvs.ctypes.data, lev.ctypes.data,
-                                          qp_arr.ctypes.data if qp_arr is not None else None, F, W, H, pkg["block size"],
-                                          os.fsencode(mv_file), os.fsencode(residual_file), 0)
+        mvs = np.ascontiguousarray(p["mv"], np.int16)                                                           # across the call
+        qpp = qp_arr.ctypes.data if qp_arr is not None else None
+        if dict.__contains__(p, "symbols"):      # residual text from the packed symbol streams: no levels on the host
+            sy = np.ascontiguousarray(p["symbols"], np.int16)
+            pos, cnt = np.ascontiguousarray(p["sym_pos"], np.uint64), np.ascontiguousarray(p["sym_count"], np.uint32)
+            rc = lib.so_write_bitstream_files_symbols(ft.ctypes.data, sp.ctypes.data, mvs.ctypes.data, sy.ctypes.data, pos.ctypes.data,
+                                                      cnt.ctypes.data, qpp, F, W, H, pkg["block size"], os.fsencode(mv_file),
+                                                      os.fsencode(residual_file), 0)
+        else:
+            lev = np.ascontiguousarray(p["levels"], np.int16)
+            rc = lib.so_write_bitstream_files(ft.ctypes.data, sp.ctypes.data, mvs.ctypes.data, lev.ctypes.data, qpp, F, W, H,
+                                              pkg["block size"], os.fsencode(mv_file), os.fsencode(residual_file), 0)
         if rc != 0:
             raise OSError(f"cannot write the bitstream files {mv_file!r} / {residual_file!r}")
         if os.path.isdir("files"):       # debug dump of the reference (Encoder.py:1559,1568); only when ./files exists

@@ -38,6 +38,11 @@ class so_frame_out(C.Structure):
                 ("row_sizes", C.c_void_p), ("stats", C.c_void_p)]
 
 
+class so_symbol_out(C.Structure):
+    _fields_ = [("symbols", C.c_void_p), ("capacity", C.c_uint64), ("pos", C.c_void_p), ("count", C.c_void_p),
+                ("needed", C.c_uint64)]
+
+
 STATS_DTYPE = [("sse", "<u8"), ("mae_num", "<u8"), ("mae_den", "<u4"), ("mae_inf", "<u4"), ("qsize", "<u4"),
                ("frame_type", "<u4")]
 
@@ -45,6 +50,8 @@ STATS_DTYPE = [("sse", "<u8"), ("mae_num", "<u8"), ("mae_den", "<u4"), ("mae_inf
 EXPORTS = ["so_abi_version", "so_last_error", "so_device_count", "so_ctx_create", "so_ctx_destroy", "so_set_qp", "so_set_row_qps", "so_set_block_qps",
            "so_ref_reset", "so_ref_push", "so_encode_intra", "so_encode_inter", "so_encode_sequence", "so_encode_yuv420_file", "so_seq_upload", "so_seq_run", "so_seq_download", "so_seq_sync", "so_decode_sequence", "so_seq_symbols", "so_seq_download_symbols",
            "so_format_residual_frame_symbols", "so_write_bitstream_files", "so_parse_bitstream_files",
+           "so_set_symbol_output", "so_fetch_symbols", "so_format_residual_frame_packed", "so_symbols_to_levels",
+           "so_write_bitstream_files_symbols",
            "so_last_timing", "so_last_me_launches", "so_last_search_timing",
            "so_format_mv_frame", "so_format_residual_frame"]
 
@@ -91,6 +98,12 @@ def load():
     lib.so_decode_sequence.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.so_encode_yuv420_file.argtypes = [vp, C.c_char_p, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.so_write_bitstream_files.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_char_p, C.c_char_p, i32]
+    lib.so_set_symbol_output.argtypes = [vp, C.POINTER(so_symbol_out)]
+    lib.so_fetch_symbols.argtypes = [vp, C.POINTER(so_symbol_out)]
+    lib.so_format_residual_frame_packed.restype = i64
+    lib.so_format_residual_frame_packed.argtypes = [vp, vp, i64, i32, i32, C.c_char_p, i64]
+    lib.so_symbols_to_levels.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, i32]
+    lib.so_write_bitstream_files_symbols.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_char_p, C.c_char_p, i32]
     lib.so_parse_bitstream_files.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32]
     lib.so_last_search_timing.argtypes = [vp, C.POINTER(C.c_double)]
     lib.so_last_timing.argtypes = [vp, C.POINTER(C.c_double)]

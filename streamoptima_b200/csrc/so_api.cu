@@ -14,6 +14,7 @@
 #include <fcntl.h>
 #include <unistd.h>
 #include <algorithm>
+#include <climits>
 
 #define CU(expr)                                                                                  \
     do {                                                                                          \
@@ -86,9 +87,14 @@ struct so_ctx {
     so_frame_stats* sq_stats = nullptr;
     size_t sq_cap_frames = 0;               // capacity in (unit*frame) frames
     // run-level symbol streams of the resident sequence (so_seq_symbols)
-    uint32_t *sym_lens = nullptr, *sym_offs = nullptr;
+    uint32_t *sym_lens = nullptr, *sym_offs = nullptr, *sym_tot = nullptr;
     int16_t* sym_data = nullptr;
     size_t sym_cap_frames = 0, sym_frame_stride = 0;
+    uint32_t* h_tot = nullptr;              // pinned: symbols per frame, [unit][frame]
+    bool sym_resident = false;              // sym_data holds the symbols of the whole resident sequence
+    so_symbol_out* sym_out = nullptr;       // armed by so_set_symbol_output: sequence encodes deliver packed symbols
+    uint64_t sym_used = 0;                  // symbols handed out so far in the running sequence encode
+    bool sym_overflow = false;
     double timing[7] = {0, 0, 0, 0, 0, 0, 0};
     bool timing_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -103,7 +109,7 @@ struct so_ctx {
         int16_t *h_mv = nullptr, *h_levels = nullptr;
         uint32_t* h_rows = nullptr;
         so_frame_stats* h_stats = nullptr;
-        std::vector<cudaEvent_t> up, done;
+        std::vector<cudaEvent_t> up, done, tot;
         // file ingest (so_encode_yuv420_file): luma planes are pread() chunk by chunk into three rotating pinned buffers
         int fd = -1;
         int src_w = 0, src_h = 0, first_frame = 0;
@@ -168,8 +174,10 @@ static void free_seq(so_ctx* c) {
     cudaFree(c->sq_levels); cudaFree(c->sq_rows); cudaFree(c->sq_stats);
     c->sq_frames = c->sq_split = c->sq_recon = nullptr; c->sq_mv = c->sq_levels = nullptr;
     c->sq_rows = nullptr; c->sq_stats = nullptr; c->sq_cap_frames = 0;
-    cudaFree(c->sym_lens); cudaFree(c->sym_offs); cudaFree(c->sym_data);
-    c->sym_lens = c->sym_offs = nullptr; c->sym_data = nullptr; c->sym_cap_frames = 0;
+    cudaFree(c->sym_lens); cudaFree(c->sym_offs); cudaFree(c->sym_data); cudaFree(c->sym_tot);
+    if (c->h_tot) cudaFreeHost(c->h_tot);
+    c->sym_lens = c->sym_offs = c->sym_tot = nullptr; c->sym_data = nullptr; c->h_tot = nullptr; c->sym_cap_frames = 0;
+    c->sym_resident = false;
 }
 
 extern "C" void so_ctx_destroy(so_ctx* c) {
@@ -183,6 +191,7 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     for (auto b : c->pipe.stage) if (b) cudaFreeHost(b);
     for (auto e : c->pipe.up) cudaEventDestroy(e);
     for (auto e : c->pipe.done) cudaEventDestroy(e);
+    for (auto e : c->pipe.tot) cudaEventDestroy(e);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -923,6 +932,10 @@ static int ensure_seq(so_ctx* ctx, size_t nframes_total) {
 }
 
 // ---- chunk pipeline helpers ------------------------------------------------------------------------------------
+static int ensure_sym(so_ctx* ctx, size_t total);
+static int sym_run_range(so_ctx* ctx, int f0, int nf);
+static int pipe_symbols_chunk(so_ctx* ctx, int c);
+
 static int pipe_upload_chunk(so_ctx* ctx, int c) {
     auto& P = ctx->pipe;
     const int U = ctx->sq_units, F = ctx->sq_nframes;
@@ -985,7 +998,9 @@ static int pipe_download_chunk(so_ctx* ctx, int c) {
         if (P.h_recon) CU(cudaMemcpyAsync(P.h_recon + o * px, ctx->sq_recon + o * px, n * px, cudaMemcpyDeviceToHost, s));
         if (P.h_rows) CU(cudaMemcpyAsync(P.h_rows + o * nby, ctx->sq_rows + o * nby, n * nby * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(P.h_stats + o, ctx->sq_stats + o, n * sizeof(so_frame_stats), cudaMemcpyDeviceToHost, s));
+        if (ctx->sym_out) CU(cudaMemcpyAsync(ctx->h_tot + o, ctx->sym_tot + o, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     }
+    if (ctx->sym_out) CU(cudaEventRecord(P.tot[c], s));
     return SO_OK;
 }
 
@@ -1078,9 +1093,17 @@ extern "C" int so_seq_run(so_ctx* ctx) {
         }
         if (ctx->pipe.active && ((f + 1) % ctx->pipe.chunk == 0 || f == n_frames - 1)) {
             const int c = f / ctx->pipe.chunk;
+            if (ctx->sym_out) {     // run-level symbols of the chunk: count -> scan -> emit, then they travel instead of the levels
+                rc = sym_run_range(ctx, c * ctx->pipe.chunk, f + 1 - c * ctx->pipe.chunk);
+                if (rc) return rc;
+            }
             CU(cudaEventRecord(ctx->pipe.done[c], st));
             rc = pipe_download_chunk(ctx, c);
             if (rc) return rc;
+            // the symbol copies of the PREVIOUS chunk need its per-frame counts on the host: by now the GPU has a whole chunk
+            // of work queued behind them, so this wait throttles the host without starving the device
+            if (ctx->sym_out && c > 0) { rc = pipe_symbols_chunk(ctx, c - 1); if (rc) return rc; }
+            if (ctx->sym_out && f == n_frames - 1) { rc = pipe_symbols_chunk(ctx, c); if (rc) return rc; }
         }
     }
     CU(cudaEventRecord(ctx->ev1, st));
@@ -1114,6 +1137,45 @@ extern "C" int so_seq_sync(so_ctx* ctx) {
     return SO_OK;
 }
 
+// The chunked pipeline shared by so_encode_sequence and so_encode_yuv420_file (pipe.* and sq_units / sq_nframes are set):
+// uploads two chunks ahead, the frame loop, downloads one chunk behind; with so_set_symbol_output the packed run-level
+// symbols are produced per chunk on the device and copied out with their exact sizes.
+static int pipe_run(so_ctx* ctx) {
+    auto& P = ctx->pipe;
+    while ((int)P.up.size() < P.nchunks) {
+        cudaEvent_t a, b, c;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+        P.up.push_back(a); P.done.push_back(b); P.tot.push_back(c);
+    }
+    int rc = SO_OK;
+    ctx->sym_resident = false;
+    if (ctx->sym_out) {
+        rc = ensure_sym(ctx, (size_t)ctx->sq_units * ctx->sq_nframes);
+        if (rc) return rc;
+        ctx->sym_used = 0; ctx->sym_overflow = false;
+        ctx->sym_out->needed = 0;
+    }
+    P.active = true;
+    rc = pipe_upload_chunk(ctx, 0);
+    if (!rc && P.nchunks > 1) rc = pipe_upload_chunk(ctx, 1);
+    if (!rc) rc = so_seq_run(ctx);
+    P.active = false;
+    if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st_d2h); return rc; }
+    CU(cudaStreamSynchronize(ctx->st_d2h));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->sym_out) {
+        ctx->sym_resident = true;
+        ctx->sym_out->needed = ctx->sym_used;
+        if (ctx->sym_overflow) {
+            set_err(ctx, "symbol buffer too small: every other output is complete; enlarge it to `needed` and call so_fetch_symbols");
+            return SO_E_NOMEM;
+        }
+    }
+    return SO_OK;
+}
+
 extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_units, int n_frames, uint8_t* split, int16_t* mv,
                                   int16_t* levels, uint8_t* recon, uint32_t* row_sizes, so_frame_stats* stats) {
     if (!ctx || !frames || !split || !mv || !stats || n_units < 1 || n_frames < 1) return SO_E_INVALID;
@@ -1125,22 +1187,8 @@ extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_unit
     auto& P = ctx->pipe;
     P.chunk = 8;
     P.nchunks = (n_frames + P.chunk - 1) / P.chunk;
-    while ((int)P.up.size() < P.nchunks) {
-        cudaEvent_t a, b;
-        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        P.up.push_back(a); P.done.push_back(b);
-    }
     P.h_frames = frames; P.h_split = split; P.h_mv = mv; P.h_levels = levels; P.h_recon = recon; P.h_rows = row_sizes; P.h_stats = stats;
-    P.active = true;
-    rc = pipe_upload_chunk(ctx, 0);
-    if (!rc && P.nchunks > 1) rc = pipe_upload_chunk(ctx, 1);
-    if (!rc) rc = so_seq_run(ctx);
-    P.active = false;
-    if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st_d2h); return rc; }
-    CU(cudaStreamSynchronize(ctx->st_d2h));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return SO_OK;
+    return pipe_run(ctx);
 }
 
 // Frame ingest from a planar YUV 4:2:0 file (Encoder.py:110-126 read_yuv + :140-155 pad_hw) fused with the encode of one
@@ -1171,53 +1219,110 @@ extern "C" int so_encode_yuv420_file(so_ctx* ctx, const char* path, int src_widt
         for (auto& b : P.stage) CU(cudaHostAlloc(&b, need, cudaHostAllocDefault));
         P.stage_bytes = need;
     }
-    while ((int)P.up.size() < P.nchunks) {
-        cudaEvent_t a, b;
-        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        P.up.push_back(a); P.done.push_back(b);
-    }
     P.h_frames = nullptr; P.h_split = split; P.h_mv = mv; P.h_levels = levels; P.h_recon = recon; P.h_rows = row_sizes; P.h_stats = stats;
-    P.active = true;
-    rc = pipe_upload_chunk(ctx, 0);
-    if (!rc && P.nchunks > 1) rc = pipe_upload_chunk(ctx, 1);
-    if (!rc) rc = so_seq_run(ctx);
-    P.active = false;
-    if (rc) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->st_h2d); cudaStreamSynchronize(ctx->st_d2h); return rc; }
-    CU(cudaStreamSynchronize(ctx->st_d2h));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return SO_OK;
+    return pipe_run(ctx);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // run-level symbols of the resident sequence: count -> device prefix scan -> emit (packed per frame)
 // ---------------------------------------------------------------------------------------------------------
+static int ensure_sym(so_ctx* ctx, size_t total) {
+    if (total <= ctx->sym_cap_frames) return SO_OK;
+    const int nblk = ctx->nblk;
+    cudaFree(ctx->sym_lens); cudaFree(ctx->sym_offs); cudaFree(ctx->sym_data); cudaFree(ctx->sym_tot);
+    if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
+    ctx->sym_lens = ctx->sym_offs = ctx->sym_tot = nullptr; ctx->sym_data = nullptr; ctx->h_tot = nullptr; ctx->sym_cap_frames = 0;
+    ctx->sym_frame_stride = ctx->frame_px + ctx->frame_px / 2 + (size_t)4 * nblk;      // worst case: 1.5 symbols per coefficient + 1 per (sub-)block
+    CU(cudaMalloc(&ctx->sym_lens, total * nblk * 4 * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->sym_offs, total * (nblk * 4 + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->sym_tot, total * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->sym_data, total * ctx->sym_frame_stride * sizeof(int16_t)));
+    CU(cudaHostAlloc(&ctx->h_tot, total * sizeof(uint32_t), cudaHostAllocDefault));
+    ctx->sym_cap_frames = total;
+    return SO_OK;
+}
+
+// count -> scan -> emit for frames [f0, f0 + nf) of every unit of the resident sequence, on the context stream
+static int sym_run_range(so_ctx* ctx, int f0, int nf) {
+    const FrameGeom& g = ctx->g;
+    const int nblk = ctx->nblk, F = ctx->sq_nframes, U = ctx->sq_units;
+    cudaStream_t st = ctx->stream;
+    dim3 grid(nblk, (unsigned)(U * nf));
+    const int nt = nthreads_px(g.bs);
+    for (int emit = 0; emit < 2; ++emit) {
+        if (g.bs == 16) rle_symbols_kernel<16><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, f0, nf, F);
+        else if (g.bs == 8) rle_symbols_kernel<8><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, f0, nf, F);
+        else rle_symbols_kernel<4><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, f0, nf, F);
+        if (!emit) scan_lens_kernel<<<(unsigned)(U * nf), 1024, 0, st>>>(ctx->sym_lens, ctx->sym_offs, nblk * 4, ctx->sym_tot, f0, nf, F);
+    }
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return SO_OK;
+}
+
 extern "C" int so_seq_symbols(so_ctx* ctx) {
     if (!ctx) return SO_E_INVALID;
     if (ctx->sq_units < 1) { set_err(ctx, "so_seq_symbols before a sequence was encoded"); return SO_E_STATE; }
     CU(cudaSetDevice(ctx->device));
-    const size_t total = (size_t)ctx->sq_units * ctx->sq_nframes;
-    const FrameGeom& g = ctx->g;
-    const int nblk = ctx->nblk;
-    if (total > ctx->sym_cap_frames) {
-        cudaFree(ctx->sym_lens); cudaFree(ctx->sym_offs); cudaFree(ctx->sym_data);
-        ctx->sym_frame_stride = ctx->frame_px + ctx->frame_px / 2 + (size_t)4 * nblk;      // worst case: 1.5 symbols per coefficient + 1 per (sub-)block
-        CU(cudaMalloc(&ctx->sym_lens, total * nblk * 4 * sizeof(uint32_t)));
-        CU(cudaMalloc(&ctx->sym_offs, total * (nblk * 4 + 1) * sizeof(uint32_t)));
-        CU(cudaMalloc(&ctx->sym_data, total * ctx->sym_frame_stride * sizeof(int16_t)));
-        ctx->sym_cap_frames = total;
-    }
+    int rc = ensure_sym(ctx, (size_t)ctx->sq_units * ctx->sq_nframes);
+    if (rc) return rc;
+    rc = sym_run_range(ctx, 0, ctx->sq_nframes);
+    if (rc) return rc;
+    ctx->sym_resident = true;
+    return SO_OK;
+}
+
+// ---- packed symbols as an output of the sequence encodes (so_set_symbol_output) --------------------------------------
+extern "C" int so_set_symbol_output(so_ctx* ctx, so_symbol_out* sym) {
+    if (!ctx) return SO_E_INVALID;
+    if (sym && (!sym->pos || !sym->count || (!sym->symbols && sym->capacity))) { set_err(ctx, "so_symbol_out needs pos, count and a buffer for its capacity"); return SO_E_INVALID; }
+    ctx->sym_out = sym;
+    return SO_OK;
+}
+
+// the totals of chunk c have been copied to h_tot (event pipe.tot[c]): hand every frame of the chunk its place in the
+// caller's buffer and enqueue the copies of exactly that many symbols
+static int pipe_symbols_chunk(so_ctx* ctx, int c) {
+    auto& P = ctx->pipe;
+    so_symbol_out* so = ctx->sym_out;
+    const int U = ctx->sq_units, F = ctx->sq_nframes;
+    const int f0 = c * P.chunk, n = std::min(P.chunk, F - f0);
+    CU(cudaEventSynchronize(P.tot[c]));
+    for (int u = 0; u < U; ++u)
+        for (int i = 0; i < n; ++i) {
+            const size_t fr = (size_t)u * F + f0 + i;
+            const uint64_t cnt = ctx->h_tot[fr];
+            so->count[fr] = (uint32_t)cnt;
+            so->pos[fr] = ctx->sym_used;
+            if (ctx->sym_used + cnt <= so->capacity) {
+                if (cnt) CU(cudaMemcpyAsync(so->symbols + ctx->sym_used, ctx->sym_data + fr * ctx->sym_frame_stride, cnt * sizeof(int16_t),
+                                            cudaMemcpyDeviceToHost, ctx->st_d2h));
+            } else {
+                ctx->sym_overflow = true;         // keep counting: `needed` tells the caller how large the buffer has to be
+            }
+            ctx->sym_used += cnt;
+        }
+    return SO_OK;
+}
+
+// After a sequence encode that reported SO_E_NOMEM for the symbols (or simply again): copy the symbols of the resident
+// sequence into sym->symbols in (unit, frame) order; fills pos / count / needed.
+extern "C" int so_fetch_symbols(so_ctx* ctx, so_symbol_out* sym) {
+    if (!ctx || !sym || !sym->pos || !sym->count) return SO_E_INVALID;
+    if (!ctx->sym_resident) { set_err(ctx, "no symbol streams resident (encode with so_set_symbol_output, or call so_seq_symbols)"); return SO_E_STATE; }
+    CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    dim3 grid(nblk, (unsigned)total);
-    const int nt = nthreads_px(g.bs);
-    for (int emit = 0; emit < 2; ++emit) {
-        if (g.bs == 16) rle_symbols_kernel<16><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit);
-        else if (g.bs == 8) rle_symbols_kernel<8><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit);
-        else rle_symbols_kernel<4><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit);
-        if (!emit) scan_lens_kernel<<<(unsigned)total, 1024, 0, st>>>(ctx->sym_lens, ctx->sym_offs, nblk * 4);
-    }
-    ctx->launches += 3;
-    CU(cudaGetLastError());
+    const size_t total = (size_t)ctx->sq_units * ctx->sq_nframes;
+    CU(cudaMemcpyAsync(ctx->h_tot, ctx->sym_tot, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint64_t acc = 0;
+    for (size_t f = 0; f < total; ++f) { sym->pos[f] = acc; sym->count[f] = ctx->h_tot[f]; acc += ctx->h_tot[f]; }
+    sym->needed = acc;
+    if (acc > sym->capacity || (!sym->symbols && acc)) { set_err(ctx, "symbol buffer too small"); return SO_E_NOMEM; }
+    for (size_t f = 0; f < total; ++f)
+        if (sym->count[f]) CU(cudaMemcpyAsync(sym->symbols + sym->pos[f], ctx->sym_data + f * ctx->sym_frame_stride,
+                                              (size_t)sym->count[f] * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SO_OK;
 }
 
@@ -1476,10 +1581,11 @@ extern "C" int64_t so_format_residual_frame(const uint8_t* split, const int16_t*
 // Whole-sequence text bitstream (transmit_bitstream, Encoder.py:1544-1573 with the parseable residual format): every frame
 // is formatted by the per-frame formatters above on a pool of host threads, the two files are written in frame order.
 // qp_rows_per_frame i32 [n_frames][height / block_size] or NULL (RCFlag off).  n_threads <= 0: hardware concurrency.
-extern "C" int so_write_bitstream_files(const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
-                                        const int32_t* qp_rows_per_frame, int n_frames, int width, int height, int block_size,
-                                        const char* mv_path, const char* residual_path, int n_threads) {
-    if (!frame_types || !split || !mv || !levels || !mv_path || !residual_path || n_frames < 1 || block_size < 2 ||
+static int write_bitstream_impl(const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
+                                const int16_t* symbols, const uint64_t* sym_pos, const uint32_t* sym_count,
+                                const int32_t* qp_rows_per_frame, int n_frames, int width, int height, int block_size,
+                                const char* mv_path, const char* residual_path, int n_threads) {
+    if (!frame_types || !split || !mv || !mv_path || !residual_path || n_frames < 1 || block_size < 2 ||
         width % block_size || height % block_size) return SO_E_INVALID;
     const int nbx = width / block_size, nby = height / block_size, nblk = nbx * nby;
     const size_t px = (size_t)width * height;
@@ -1491,12 +1597,15 @@ extern "C" int so_write_bitstream_files(const uint8_t* frame_types, const uint8_
     auto fmt = [](auto&& call, size_t guess, std::string& out) {
         out.resize(guess);
         int64_t n = call(&out[0], (int64_t)out.size());
+        if (n == INT64_MIN) return false;
         if (n < 0) { out.resize((size_t)(-n) + 16); n = call(&out[0], (int64_t)out.size()); }
         out.resize((size_t)std::max<int64_t>(n, 0));
+        return true;
     };
     bool ok = true;
     // batches of nt frames: format in parallel, then write in order (bounds the memory held as text)
     std::vector<std::string> mvt(nt), rst(nt);
+    std::vector<char> good(nt, 1);
     for (int f0 = 0; f0 < n_frames && ok; f0 += nt) {
         const int nb = std::min(nt, n_frames - f0);
         std::vector<std::thread> th;
@@ -1505,14 +1614,23 @@ extern "C" int so_write_bitstream_files(const uint8_t* frame_types, const uint8_
                 const int f = f0 + i;
                 const uint8_t* sp = split + (size_t)f * nblk;
                 const int16_t* m = mv + (size_t)f * nblk * 12;
-                const int16_t* lv = levels + (size_t)f * px;
                 const int32_t* qp = qp_rows_per_frame ? qp_rows_per_frame + (size_t)f * nby : nullptr;
-                fmt([&](char* d, int64_t c) { return so_format_mv_frame(frame_types[f], sp, m, nblk, nbx, qp, d, c); }, 64 + (size_t)nblk * 48, mvt[i]);
-                fmt([&](char* d, int64_t c) { return so_format_residual_frame(sp, lv, width, height, block_size, d, c); }, 1024 + px / 2, rst[i]);
+                bool g = fmt([&](char* d, int64_t c) { return so_format_mv_frame(frame_types[f], sp, m, nblk, nbx, qp, d, c); }, 64 + (size_t)nblk * 48, mvt[i]);
+                if (levels) {
+                    const int16_t* lv = levels + (size_t)f * px;
+                    g = fmt([&](char* d, int64_t c) { return so_format_residual_frame(sp, lv, width, height, block_size, d, c); }, 1024 + px / 2, rst[i]) && g;
+                } else {
+                    const int16_t* sy = symbols + sym_pos[f];
+                    const int64_t ns = sym_count[f];
+                    g = fmt([&](char* d, int64_t c) { return so_format_residual_frame_packed(sp, sy, ns, nblk, block_size, d, c); },
+                            1024 + (size_t)ns * 6 + (size_t)nblk * 16, rst[i]) && g;
+                }
+                good[i] = g ? 1 : 0;
             });
         }
         for (auto& t : th) t.join();
         for (int i = 0; i < nb; ++i) {
+            ok = ok && good[i];
             mvt[i].push_back('\n'); rst[i].push_back('\n');
             ok = ok && fwrite(mvt[i].data(), 1, mvt[i].size(), fm) == mvt[i].size();
             ok = ok && fwrite(rst[i].data(), 1, rst[i].size(), fr) == rst[i].size();
@@ -1521,6 +1639,24 @@ extern "C" int so_write_bitstream_files(const uint8_t* frame_types, const uint8_
     ok = (fclose(fm) == 0) && ok;
     ok = (fclose(fr) == 0) && ok;
     return ok ? SO_OK : SO_E_INVALID;
+}
+
+extern "C" int so_write_bitstream_files(const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* levels,
+                                        const int32_t* qp_rows_per_frame, int n_frames, int width, int height, int block_size,
+                                        const char* mv_path, const char* residual_path, int n_threads) {
+    if (!levels) return SO_E_INVALID;
+    return write_bitstream_impl(frame_types, split, mv, levels, nullptr, nullptr, nullptr, qp_rows_per_frame, n_frames, width, height,
+                                block_size, mv_path, residual_path, n_threads);
+}
+
+// the same two files from packed symbol streams (so_set_symbol_output): no levels needed on the host
+extern "C" int so_write_bitstream_files_symbols(const uint8_t* frame_types, const uint8_t* split, const int16_t* mv, const int16_t* symbols,
+                                                const uint64_t* sym_pos, const uint32_t* sym_count, const int32_t* qp_rows_per_frame,
+                                                int n_frames, int width, int height, int block_size, const char* mv_path,
+                                                const char* residual_path, int n_threads) {
+    if (!sym_pos || !sym_count) return SO_E_INVALID;
+    return write_bitstream_impl(frame_types, split, mv, nullptr, symbols, sym_pos, sym_count, qp_rows_per_frame, n_frames, width, height,
+                                block_size, mv_path, residual_path, n_threads);
 }
 
 // Parser of the two text streams (decode_differential_entropy, decoder.py:590-690): the inverse of
@@ -1731,4 +1867,102 @@ extern "C" int64_t so_format_residual_frame_symbols(const uint8_t* split, const 
         o.ch(')');
     }
     return o.finish();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// packed symbol streams on the host (what sequence encodes deliver with so_set_symbol_output): a frame is the
+// concatenation of its blocks' run-level lists in raster order, the four lists of a split block in Z order.  The lists
+// are self-delimiting (entropy_decoder_block, decoder.py:548-586): a list ends with the symbol 0 (trailing zeros) or
+// when its runs have covered all n*n coefficients.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+// walk one list: calls val(position in scan order, value) for every non-zero coefficient; returns the number of symbols
+// consumed, or -1 when the stream is inconsistent with an n x n block
+template <typename V>
+static int64_t walk_list(const int16_t* sy, int64_t avail, int n, V&& val) {
+    const int nn = n * n;
+    int pos = 0;
+    int64_t i = 0;
+    while (pos < nn) {
+        if (i >= avail) return -1;
+        const int s = sy[i++];
+        if (s == 0) return i;                           // trailing zeros
+        if (s > 0) { if (s >= nn - pos) return -1; pos += s; continue; }      // a zero run never reaches the end (that is the 0 symbol)
+        const int cnt = -s;
+        if (cnt > nn - pos || i + cnt > avail) return -1;
+        for (int k = 0; k < cnt; ++k) { if (sy[i + k] == 0) return -1; val(pos + k, sy[i + k]); }
+        i += cnt; pos += cnt;
+    }
+    return i;
+}
+}  // namespace
+
+// residual text of one frame (entropy_encoder_frame, Encoder.py:1522-1542) from its packed symbols; same bytes as
+// so_format_residual_frame.  Returns bytes written, -(needed + 1) when cap is too small, or INT64_MIN on a corrupt stream.
+extern "C" int64_t so_format_residual_frame_packed(const uint8_t* split, const int16_t* symbols, int64_t n_symbols, int n_blocks,
+                                                   int block_size, char* dst, int64_t cap) {
+    Out o{dst, cap};
+    int64_t at = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        if (b) o.ch(';');
+        const int nseg = split[b] ? 4 : 1, n = split[b] ? block_size / 2 : block_size;
+        o.str(split[b] ? "1'(" : "0'(");
+        for (int k = 0; k < nseg; ++k) {
+            if (k) o.ch(',');
+            const int64_t used = walk_list(symbols + at, n_symbols - at, n, [](int, int) {});
+            if (used < 0) return INT64_MIN;
+            o.ch('[');
+            for (int64_t i = 0; i < used; ++i) { if (i) o.str(", "); o.num(symbols[at + i]); }
+            o.ch(']');
+            at += used;
+        }
+        o.ch(')');
+    }
+    if (at != n_symbols) return INT64_MIN;
+    return o.finish();
+}
+
+// packed symbols -> quantised levels (the inverse of entropy_encoder_block over whole frames), frames in parallel on host
+// threads.  levels i16 [n_frames][height][width] is fully overwritten.
+extern "C" int so_symbols_to_levels(const uint8_t* split, const int16_t* symbols, const uint64_t* sym_pos, const uint32_t* sym_count,
+                                    int n_frames, int width, int height, int block_size, int16_t* levels, int n_threads) {
+    if (!split || !sym_pos || !sym_count || !levels || n_frames < 1 || block_size < 2 || width % block_size || height % block_size)
+        return SO_E_INVALID;
+    const int nbx = width / block_size, nblk = nbx * (height / block_size), sub = block_size / 2;
+    const size_t px = (size_t)width * height;
+    std::vector<int> o_full, o_sub;
+    scan_order_tab(block_size, o_full); scan_order_tab(sub, o_sub);
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::min(n_frames, 64)));
+    std::vector<int> okv(nt, 1);
+    auto work = [&](int w) {
+        for (int f = w; f < n_frames; f += nt) {
+            int16_t* lev = levels + (size_t)f * px;
+            memset(lev, 0, px * sizeof(int16_t));
+            const uint8_t* sp = split + (size_t)f * nblk;
+            const int16_t* sy = symbols + sym_pos[f];
+            const int64_t ns = sym_count[f];
+            int64_t at = 0;
+            bool ok = symbols != nullptr || ns == 0;
+            for (int b = 0; b < nblk && ok; ++b) {
+                const int y = (b / nbx) * block_size, x = (b % nbx) * block_size;
+                const int nseg = sp[b] ? 4 : 1, n = sp[b] ? sub : block_size;
+                const std::vector<int>& ord = sp[b] ? o_sub : o_full;
+                for (int k = 0; k < nseg && ok; ++k) {
+                    int16_t* dst = lev + (size_t)(y + (sp[b] ? (k >> 1) * sub : 0)) * width + x + (sp[b] ? (k & 1) * sub : 0);
+                    const int64_t used = walk_list(sy + at, ns - at, n, [&](int p, int v) { const int o = ord[p]; dst[(size_t)(o / n) * width + o % n] = (int16_t)v; });
+                    if (used < 0) ok = false; else at += used;
+                }
+            }
+            if (!ok || at != ns) okv[w] = 0;
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int w = 0; w < nt; ++w) th.emplace_back(work, w);
+        for (auto& t : th) t.join();
+    }
+    for (int v : okv) if (!v) return SO_E_INVALID;
+    return SO_OK;
 }

@@ -1464,15 +1464,18 @@ __global__ void decode_block_kernel(const FlowArgs a, int intra) {
 //   slot(header of run starting at p) = #nonzeros before p + #run starts before p
 //   slot(value at p)                  = #nonzeros before p + #run starts up to and including p's run
 // ------------------------------------------------------------------------------------------------------------
+// The launch covers frames [f0, f0 + nf) of every unit of a [unit][F] sequence: blockIdx.y = unit * nf + i -> frame
+// unit * F + f0 + i (whole sequence: f0 = 0, nf = F).
+__device__ __forceinline__ int seq_frame(int y, int f0, int nf, int F) { return (y / nf) * F + f0 + (y % nf); }
+
 template <int BS>
 __global__ void rle_symbols_kernel(const int16_t* levels, const uint8_t* split, uint32_t* lens, const uint32_t* offs, int16_t* syms,
-                                   size_t sym_frame_stride, int W, int nbx, int nblk, int emit) {
+                                   size_t sym_frame_stride, int W, int nbx, int nblk, int emit, int f0, int nf, int F) {
     constexpr int S = BS / 2;
-    constexpr int NT = BS * BS < 32 ? 32 : BS * BS;
     __shared__ int16_t sv[BS * BS];         // coefficient at (segment, scan position)
     __shared__ int snz[BS * BS + 1], sst[BS * BS + 1];     // inclusive prefix sums of non-zero / run-start flags
     __shared__ int wsum[2][32];
-    const int blk = blockIdx.x, frame = blockIdx.y;
+    const int blk = blockIdx.x, frame = seq_frame(blockIdx.y, f0, nf, F);
     const int t = threadIdx.x;
     const bool active = t < BS * BS;
     const int bx = blk % nbx, by = blk / nbx;
@@ -1534,11 +1537,11 @@ __global__ void rle_symbols_kernel(const int16_t* levels, const uint8_t* split, 
     if (nz) out[nzb + (sst[t + 1] - sst[lo])] = (int16_t)val;
 }
 
-// exclusive prefix sum of n entries per frame (one CTA per frame): offs[frame][0..n], offs[frame][n] = total
-__global__ void scan_lens_kernel(const uint32_t* lens, uint32_t* offs, int n) {
+// exclusive prefix sum of n entries per frame (one CTA per frame): offs[frame][0..n], offs[frame][n] = totals[frame] = total
+__global__ void scan_lens_kernel(const uint32_t* lens, uint32_t* offs, int n, uint32_t* totals, int f0, int nf, int F) {
     __shared__ uint32_t wtot[32];
     __shared__ uint32_t carry;
-    const int frame = blockIdx.x, t = threadIdx.x;
+    const int frame = seq_frame(blockIdx.x, f0, nf, F), t = threadIdx.x;
     const uint32_t* in = lens + (size_t)frame * n;
     uint32_t* out = offs + (size_t)frame * (n + 1);
     if (t == 0) carry = 0;
@@ -1562,5 +1565,5 @@ __global__ void scan_lens_kernel(const uint32_t* lens, uint32_t* offs, int n) {
         if (t == blockDim.x - 1) carry = c0 + wb + s;
         __syncthreads();
     }
-    if (t == 0) out[n] = carry;
+    if (t == 0) { out[n] = carry; totals[frame] = carry; }
 }
