@@ -537,7 +537,7 @@ def main():
         codec._ctx.close()
         codec._ctx = None
         del frames, frames_pinned
-        Y_Video_codec._pool.free.clear()
+        Y_Video_codec._pool.clear()
         torch.cuda.empty_cache()
         c5 = c5_sharded(rank, world, local_rank, dist)
         if rank == 0:

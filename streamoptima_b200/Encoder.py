@@ -36,13 +36,28 @@ def generate_Q_matrix(i, QP):
 
 class _PinnedPool:
     """Pinned host buffers recycled across encodes (``cudaHostAlloc`` of GBs costs more than the encode itself).  PyTorch
-    supplies the pinned memory; nothing else of it is used here."""
+    supplies the pinned memory; nothing else of it is used here.
+
+    A buffer handed back by a dead result waits in ``pending`` until nothing references its ndarray any more (views the
+    caller kept out of a result stay valid for as long as they are held: a result is never overwritten behind its
+    owner's back); only then is it offered to the next encode."""
 
     def __init__(self, max_free=12):
-        self.free, self.max_free = [], max_free        # entries: (nbytes, tensor, uint8 ndarray over it)
+        self.free, self.pending, self.max_free = [], [], max_free        # entries: (nbytes, tensor, uint8 ndarray over it)
+
+    def _sweep(self):
+        keep = []
+        for it in self.pending:
+            if sys.getrefcount(it[2]) <= 2:            # the tuple and getrefcount's argument: no view is alive
+                if len(self.free) < self.max_free:
+                    self.free.append(it)
+            else:
+                keep.append(it)
+        self.pending = keep
 
     def take(self, nbytes):
         nbytes = max(int(nbytes), 1)
+        self._sweep()
         best = None
         for i, (n, _, _) in enumerate(self.free):
             if nbytes <= n <= max(2 * nbytes, nbytes + (1 << 20)) and (best is None or n < self.free[best][0]):
@@ -54,14 +69,14 @@ class _PinnedPool:
         return (nbytes, t, t.numpy())
 
     def give(self, item):
-        if len(self.free) < self.max_free:
-            self.free.append(item)
+        self.pending.append(item)
+
+    def clear(self):
+        self.free, self.pending = [], []
 
 
 class _Lease:
-    """The buffers one result owns.  When the result dies they go back to the pool -- unless somebody still holds a view
-    of one (its ndarray is then referenced from outside), in which case that buffer is simply left to its holders: a
-    result is never overwritten behind its owner's back."""
+    """The buffers one result owns; they go back to the pool when the result dies."""
 
     def __init__(self, pool):
         self.items = []
@@ -77,9 +92,7 @@ class _Lease:
     @staticmethod
     def _release(pool, items):
         while items:
-            it = items.pop()
-            if sys.getrefcount(it[2]) <= 2:        # the tuple and getrefcount's argument: no view is alive
-                pool.give(it)
+            pool.give(items.pop())
 
 
 class EncodeResult(dict):

@@ -78,16 +78,20 @@ struct so_ctx {
     unsigned int* me_work = nullptr;        // chunk counter of the item-ring search kernel
     uint8_t* fm_table = nullptr;            // fast ME: per-block transition tables around the previous frame's predictors
     short4* fm_state = nullptr;             // fast ME: predictor (x, y, ref) every block used in the last P frame, [batch][nblk]
+    int2 *fs_F = nullptr, *fs_entry = nullptr;   // fast ME scan: per-chunk composed transition functions / chunk entry predictors
+    int fs_L = 0, fs_nchunks = 0;
     int* qp_blocks_dev = nullptr;           // ROI extension: [frames][nblk] per-block QPs of the next sequence, or nullptr
     int qp_blocks_frames = 0;
     // sequence buffers
     uint8_t *sq_frames = nullptr, *sq_split = nullptr, *sq_recon = nullptr;
     int16_t *sq_mv = nullptr, *sq_levels = nullptr;
-    uint32_t* sq_rows = nullptr;
+    uint32_t *sq_rows = nullptr, *sq_blklen = nullptr;      // sq_blklen: RLE symbols per block, [unit][frame][nblk] (count pass of the symbol packer)
     so_frame_stats* sq_stats = nullptr;
     size_t sq_cap_frames = 0;               // capacity in (unit*frame) frames
     // run-level symbol streams of the resident sequence (so_seq_symbols)
-    uint32_t *sym_lens = nullptr, *sym_offs = nullptr, *sym_tot = nullptr;
+    uint32_t *sym_lens = nullptr, *sym_offs = nullptr, *sym_tot = nullptr, *sym_boffs = nullptr;
+    size_t sym_sub_cap_frames = 0;          // capacity of sym_lens / sym_offs (per-sub-block API, so_seq_symbols)
+    uint32_t* cur_blk_len = nullptr;        // block symbol counts of the frame being encoded (sequence path), or nullptr
     int16_t* sym_data = nullptr;
     size_t sym_cap_frames = 0, sym_frame_stride = 0;
     uint32_t* h_tot = nullptr;              // pinned: symbols per frame, [unit][frame]
@@ -171,12 +175,13 @@ static int upload_tables(so_ctx* ctx) {
 // ---------------------------------------------------------------------------------------------------------
 static void free_seq(so_ctx* c) {
     cudaFree(c->sq_frames); cudaFree(c->sq_split); cudaFree(c->sq_recon); cudaFree(c->sq_mv);
-    cudaFree(c->sq_levels); cudaFree(c->sq_rows); cudaFree(c->sq_stats);
+    cudaFree(c->sq_levels); cudaFree(c->sq_rows); cudaFree(c->sq_stats); cudaFree(c->sq_blklen);
     c->sq_frames = c->sq_split = c->sq_recon = nullptr; c->sq_mv = c->sq_levels = nullptr;
-    c->sq_rows = nullptr; c->sq_stats = nullptr; c->sq_cap_frames = 0;
-    cudaFree(c->sym_lens); cudaFree(c->sym_offs); cudaFree(c->sym_data); cudaFree(c->sym_tot);
+    c->sq_rows = c->sq_blklen = nullptr; c->sq_stats = nullptr; c->sq_cap_frames = 0;
+    cudaFree(c->sym_lens); cudaFree(c->sym_offs); cudaFree(c->sym_data); cudaFree(c->sym_tot); cudaFree(c->sym_boffs);
     if (c->h_tot) cudaFreeHost(c->h_tot);
-    c->sym_lens = c->sym_offs = c->sym_tot = nullptr; c->sym_data = nullptr; c->h_tot = nullptr; c->sym_cap_frames = 0;
+    c->sym_lens = c->sym_offs = c->sym_tot = c->sym_boffs = nullptr; c->sym_data = nullptr; c->h_tot = nullptr;
+    c->sym_cap_frames = c->sym_sub_cap_frames = 0;
     c->sym_resident = false;
 }
 
@@ -187,6 +192,7 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->in_parent); cudaFree(c->in_sub);
     cudaFree(c->res_frame); cudaFree(c->band);
     cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev); cudaFree(c->me_work); cudaFree(c->fm_table); cudaFree(c->fm_state);
+    cudaFree(c->fs_F); cudaFree(c->fs_entry);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto b : c->pipe.stage) if (b) cudaFreeHost(b);
     for (auto e : c->pipe.up) cudaEventDestroy(e);
@@ -727,6 +733,8 @@ static FlowArgs make_flow(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, co
     a.rows_stride = out_frames_stride * ctx->g.nby;
     a.stats_stride = out_frames_stride;
     a.scratch_stride = ctx->frame_px;
+    a.blk_len = ctx->cur_blk_len;
+    a.blk_len_stride = out_frames_stride * ctx->nblk;
     return a;
 }
 
@@ -843,13 +851,35 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
             const size_t tsm = (size_t)nr * nph * FTR_H * FTR_W + 256 + (size_t)nr * FT_N * FT_N * 2;
             FlowArgs b = a;
             b.chain = 0; b.mvp_in = ctx->fm_state; b.mvp_in_stride = nblk_pad;
+            // the chain itself: a scan over composed transition tables (chunks of fs_L blocks, <= 256 chunks), or -- A/B switch and
+            // cross-check in the tests -- the one-warp walk over all blocks
+            static const bool chain_walk = std::getenv("SO_FAST_CHAIN_WALK") != nullptr;
+            if (!ctx->fs_F) {
+                ctx->fs_L = std::max(32, (ctx->nblk + 255) / 256);
+                ctx->fs_nchunks = (ctx->nblk + ctx->fs_L - 1) / ctx->fs_L;
+                CU(cudaMalloc(&ctx->fs_F, (size_t)ctx->batch * ctx->fs_nchunks * FS_ROW * sizeof(int2)));
+                CU(cudaMalloc(&ctx->fs_entry, (size_t)ctx->batch * ctx->fs_nchunks * sizeof(int2)));
+                CU(cudaFuncSetAttribute(fast_scan_walk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                CU(cudaFuncSetAttribute(fast_scan_walk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            }
+            const int L = ctx->fs_L, nch = ctx->fs_nchunks;
+            const size_t tstride = nblk_pad * FT_TRANS, fstride = (size_t)nch * FS_ROW;
+            const size_t csm = (size_t)L * FT_TRANS + (size_t)L * 4, wsm = (size_t)nch * FS_ROW * sizeof(int2) + (size_t)L * 4;
+            auto scan = [&](auto walk_kernel) {
+                fast_scan_chunk_kernel<<<dim3(nch, units), 96, csm, st>>>(ctx->fm_table, tstride, ctx->fm_state, nblk_pad, a.unit0, ctx->nblk, L, ctx->fs_F, fstride);
+                walk_kernel<<<dim3(1, units), 576, wsm, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad, L, nch, ctx->fs_F, fstride, ctx->fs_entry, (size_t)nch);
+                fast_scan_fill_kernel<<<dim3(nch, units), 32, csm, st>>>(ctx->fm_table, tstride, ctx->fm_state, nblk_pad, a.unit0, ctx->nblk, L, ctx->fs_entry, (size_t)nch);
+                ctx->launches += 2;
+            };
             if (g.bs == 16) {
-                fast_table16_kernel<16><<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
-                fast_chain16_kernel<16><<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
+                fast_table16_kernel<16><<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad);
+                if (chain_walk) fast_chain16_kernel<16><<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad);
+                else scan(fast_scan_walk_kernel<16>);
                 fast_me16_kernel<16><<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
             } else {
-                fast_table16_kernel<8><<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
-                fast_chain16_kernel<8><<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, nblk_pad * FT_TRANS, ctx->fm_state, nblk_pad);
+                fast_table16_kernel<8><<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad);
+                if (chain_walk) fast_chain16_kernel<8><<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad);
+                else scan(fast_scan_walk_kernel<8>);
                 fast_me16_kernel<8><<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
             }
             ctx->launches += 2;
@@ -926,6 +956,7 @@ static int ensure_seq(so_ctx* ctx, size_t nframes_total) {
     CU(cudaMalloc(&ctx->sq_split, n * ctx->nblk));
     CU(cudaMalloc(&ctx->sq_mv, n * ctx->nblk * 12 * sizeof(int16_t)));
     CU(cudaMalloc(&ctx->sq_rows, n * ctx->g.nby * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->sq_blklen, n * ctx->nblk * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->sq_stats, n * sizeof(so_frame_stats)));
     ctx->sq_cap_frames = n;
     return SO_OK;
@@ -1064,7 +1095,8 @@ extern "C" int so_seq_run(so_ctx* ctx) {
         const size_t cur_stride = (size_t)n_frames * px;
         const bool intra = (f % ctx->p.intra_dur == 0) && ctx->p.parallel_mode != 1;       // Encoder.py:1839
         ctx->cur_qp_blocks = (ctx->qp_blocks_dev && f < ctx->qp_blocks_frames) ? ctx->qp_blocks_dev + (size_t)f * ctx->nblk : nullptr;
-        struct ClearQ { so_ctx* c; ~ClearQ() { c->cur_qp_blocks = nullptr; } } clearq{ctx};
+        ctx->cur_blk_len = ctx->sq_blklen + (size_t)f * ctx->nblk;
+        struct ClearQ { so_ctx* c; ~ClearQ() { c->cur_qp_blocks = nullptr; c->cur_blk_len = nullptr; } } clearq{ctx};
         if (intra) {
             rc = encode_intra_impl(ctx, cur, cur_stride, &o, n_frames, 0, n_units, ctx->p.qp, st);
             if (rc) return rc;
@@ -1229,12 +1261,11 @@ extern "C" int so_encode_yuv420_file(so_ctx* ctx, const char* path, int src_widt
 static int ensure_sym(so_ctx* ctx, size_t total) {
     if (total <= ctx->sym_cap_frames) return SO_OK;
     const int nblk = ctx->nblk;
-    cudaFree(ctx->sym_lens); cudaFree(ctx->sym_offs); cudaFree(ctx->sym_data); cudaFree(ctx->sym_tot);
+    cudaFree(ctx->sym_boffs); cudaFree(ctx->sym_data); cudaFree(ctx->sym_tot);
     if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
-    ctx->sym_lens = ctx->sym_offs = ctx->sym_tot = nullptr; ctx->sym_data = nullptr; ctx->h_tot = nullptr; ctx->sym_cap_frames = 0;
+    ctx->sym_boffs = ctx->sym_tot = nullptr; ctx->sym_data = nullptr; ctx->h_tot = nullptr; ctx->sym_cap_frames = 0;
     ctx->sym_frame_stride = ctx->frame_px + ctx->frame_px / 2 + (size_t)4 * nblk;      // worst case: 1.5 symbols per coefficient + 1 per (sub-)block
-    CU(cudaMalloc(&ctx->sym_lens, total * nblk * 4 * sizeof(uint32_t)));
-    CU(cudaMalloc(&ctx->sym_offs, total * (nblk * 4 + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->sym_boffs, total * (nblk + 1) * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->sym_tot, total * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->sym_data, total * ctx->sym_frame_stride * sizeof(int16_t)));
     CU(cudaHostAlloc(&ctx->h_tot, total * sizeof(uint32_t), cudaHostAllocDefault));
@@ -1242,32 +1273,53 @@ static int ensure_sym(so_ctx* ctx, size_t total) {
     return SO_OK;
 }
 
-// count -> scan -> emit for frames [f0, f0 + nf) of every unit of the resident sequence, on the context stream
+// Symbol packer of the end-to-end path for frames [f0, f0 + nf) of every unit of the resident sequence, on the context
+// stream: the per-block counts were written by the finish kernels (sq_blklen); exclusive scan per frame, then one warp per
+// block writes its symbols at their final place of the frame's packed stream.
 static int sym_run_range(so_ctx* ctx, int f0, int nf) {
     const FrameGeom& g = ctx->g;
     const int nblk = ctx->nblk, F = ctx->sq_nframes, U = ctx->sq_units;
     cudaStream_t st = ctx->stream;
-    dim3 grid(nblk, (unsigned)(U * nf));
-    const int nt = nthreads_px(g.bs);
-    for (int emit = 0; emit < 2; ++emit) {
-        if (g.bs == 16) rle_symbols_kernel<16><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, f0, nf, F);
-        else if (g.bs == 8) rle_symbols_kernel<8><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, f0, nf, F);
-        else rle_symbols_kernel<4><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, f0, nf, F);
-        if (!emit) scan_lens_kernel<<<(unsigned)(U * nf), 1024, 0, st>>>(ctx->sym_lens, ctx->sym_offs, nblk * 4, ctx->sym_tot, f0, nf, F);
-    }
-    ctx->launches += 3;
+    scan_lens_kernel<<<(unsigned)(U * nf), 1024, 0, st>>>(ctx->sq_blklen, ctx->sym_boffs, nblk, ctx->sym_tot, f0, nf, F);
+    dim3 grid((nblk + 7) / 8, (unsigned)(U * nf));
+    if (g.bs == 16) rle_emit_warp_kernel<16><<<grid, 256, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_boffs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.H, g.nbx, nblk, f0, nf, F);
+    else if (g.bs == 8) rle_emit_warp_kernel<8><<<grid, 256, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_boffs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.H, g.nbx, nblk, f0, nf, F);
+    else rle_emit_warp_kernel<4><<<grid, 256, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_boffs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.H, g.nbx, nblk, f0, nf, F);
+    ctx->launches += 2;
     CU(cudaGetLastError());
     return SO_OK;
 }
 
+// The symbol API with per-sub-block offsets (so_seq_symbols / so_seq_download_symbols): its own count pass (one CTA per
+// block), scan and emit over the whole resident sequence.  It shares sym_data / sym_tot with the packer above -- both
+// produce the same stream.
 extern "C" int so_seq_symbols(so_ctx* ctx) {
     if (!ctx) return SO_E_INVALID;
     if (ctx->sq_units < 1) { set_err(ctx, "so_seq_symbols before a sequence was encoded"); return SO_E_STATE; }
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_sym(ctx, (size_t)ctx->sq_units * ctx->sq_nframes);
+    const size_t total = (size_t)ctx->sq_units * ctx->sq_nframes;
+    int rc = ensure_sym(ctx, total);
     if (rc) return rc;
-    rc = sym_run_range(ctx, 0, ctx->sq_nframes);
-    if (rc) return rc;
+    const FrameGeom& g = ctx->g;
+    const int nblk = ctx->nblk, F = ctx->sq_nframes;
+    if (total > ctx->sym_sub_cap_frames) {
+        cudaFree(ctx->sym_lens); cudaFree(ctx->sym_offs);
+        ctx->sym_lens = ctx->sym_offs = nullptr; ctx->sym_sub_cap_frames = 0;
+        CU(cudaMalloc(&ctx->sym_lens, total * nblk * 4 * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->sym_offs, total * (nblk * 4 + 1) * sizeof(uint32_t)));
+        ctx->sym_sub_cap_frames = total;
+    }
+    cudaStream_t st = ctx->stream;
+    dim3 grid(nblk, (unsigned)total);
+    const int nt = nthreads_px(g.bs);
+    for (int emit = 0; emit < 2; ++emit) {
+        if (g.bs == 16) rle_symbols_kernel<16><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, 0, F, F);
+        else if (g.bs == 8) rle_symbols_kernel<8><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, 0, F, F);
+        else rle_symbols_kernel<4><<<grid, nt, 0, st>>>(ctx->sq_levels, ctx->sq_split, ctx->sym_lens, ctx->sym_offs, ctx->sym_data, ctx->sym_frame_stride, g.W, g.nbx, nblk, emit, 0, F, F);
+        if (!emit) scan_lens_kernel<<<(unsigned)total, 1024, 0, st>>>(ctx->sym_lens, ctx->sym_offs, nblk * 4, ctx->sym_tot, 0, F, F);
+    }
+    ctx->launches += 3;
+    CU(cudaGetLastError());
     ctx->sym_resident = true;
     return SO_OK;
 }

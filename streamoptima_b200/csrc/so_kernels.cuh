@@ -128,6 +128,8 @@ struct FlowArgs {
     size_t scratch_stride;       // per-unit stride of res_frame / band (one frame)
     const short4* mvp_in;        // fast ME, table-driven chain: predictor (x, y, ref) of every block, [unit][nblk]; else nullptr
     size_t mvp_in_stride;
+    uint32_t* blk_len;           // optional: RLE symbols of every block (all its sub-blocks), [unit][nblk] -- the count pass of the
+    size_t blk_len_stride;       // symbol packer comes for free from the size statistics
 };
 
 // ME results are either plain MeResult records (fast ME, intra search) or the packed 64-bit keys the exhaustive search
@@ -346,6 +348,7 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
         if (blk == 0) { st->mae_den = a.mae_den; st->frame_type = a.frame_type; }
         atomicAdd(reinterpret_cast<unsigned long long*>(&st->sse), se);
         atomicAdd(&st->qsize, (unsigned)len);
+        if (a.blk_len) a.blk_len[unit * a.blk_len_stride + blk] = (uint32_t)len;
         atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
         // MAE numerator in units of 1/mae_den: full search 1/BS^2 (sub MAEs: sum sad_k/S^2/4 = sum sad_k/BS^2),
         // fast ME 1/4 (values are reference indices; VBS averages four of them)
@@ -629,6 +632,7 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
         if (blk == 0) { st->mae_den = a.mae_den; st->frame_type = a.frame_type; }
         atomicAdd(reinterpret_cast<unsigned long long*>(&st->sse), se);
         atomicAdd(&st->qsize, (unsigned)len);
+        if (a.blk_len) a.blk_len[unit * a.blk_len_stride + blk] = (uint32_t)len;
         atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
         if (a.fast) {
             unsigned long long n = (unsigned long long)mp.sad * 4ull;
@@ -1056,6 +1060,136 @@ __global__ void __launch_bounds__(576) fast_chain16_kernel(const FlowArgs a, con
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// The chain as a scan.  A block's transition table is a FUNCTION predictor -> predictor, and function composition is
+// associative: the chain over all blocks of a frame (Encoder.py:581) does not have to be walked block by block.
+//   A. fast_scan_chunk_kernel (parallel over chunks of L consecutive blocks): the composition F_c of the chunk's tables for
+//      every predictor of the first block's window (81 inputs, one thread each, L dependent shared-memory lookups): where
+//      the chain leaves the chunk, or "escaped" when it runs out of some block's window on the way;
+//   B. fast_scan_walk_kernel (one CTA per unit): walks the <= 256 CHUNKS -- one lookup in F_c per chunk (all F_c sit in
+//      shared memory) -- and records the predictor every chunk is entered with.  A chunk whose F_c has no answer for the
+//      incoming predictor (cold start, scene change) is walked block by block right here, with the cooperative step of
+//      fast_me16_run for blocks whose window the predictor has left, and marked as done;
+//   C. fast_scan_fill_kernel (parallel over chunks): replays each chunk from its entry predictor and records the
+//      predictor of every block in `state` -- what fast_me16_kernel (mvp_in = state) then turns into results.
+// Serial depth: L + nchunks + L table lookups (1080p: 32 + 255 + 32) instead of 8160 dependent steps.
+// F_c entry: .x = px | py << 16 (predictor after the chunk), .y = ref (0xFF: unchanged) | escaped << 8; entry 81 of a
+// chunk holds the centre of its first block.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FS_STATES = FT_S * FT_S;          // 81
+constexpr int FS_ROW = FS_STATES + 1;           // + the first centre
+
+__device__ __forceinline__ int fs_pack(int x, int y) { return (x & 0xFFFF) | (y << 16); }
+__device__ __forceinline__ int fs_x(int v) { return (int)(short)(v & 0xFFFF); }
+__device__ __forceinline__ int fs_y(int v) { return v >> 16; }
+
+// stage the tables and centres of blocks [b0, b0 + n) of one unit in shared memory: sm = [n][FT_TRANS] tables, then n centres
+__device__ __forceinline__ int* fs_stage(unsigned char* sm, int L, const uint8_t* trans_u, const short4* state_u, int b0, int n) {
+    const uint4* src = reinterpret_cast<const uint4*>(trans_u + (size_t)b0 * FT_TRANS);
+    for (int e = threadIdx.x; e < n * (FT_TRANS / 16); e += blockDim.x) reinterpret_cast<uint4*>(sm)[e] = src[e];
+    int* cen = reinterpret_cast<int*>(sm + (size_t)L * FT_TRANS);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) { const short4 c = state_u[b0 + e]; cen[e] = fs_pack(c.x, c.y); }
+    return cen;
+}
+
+__global__ void __launch_bounds__(96) fast_scan_chunk_kernel(const uint8_t* trans, size_t trans_unit_stride, const short4* state,
+                                                             size_t state_unit_stride, int unit0, int nblk, int L, int2* F, size_t F_unit_stride) {
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    const int chunk = blockIdx.x, unit = unit0 + blockIdx.y;
+    const int b0 = chunk * L, n = min(L, nblk - b0);
+    const int* cen = fs_stage(fs_smem, L, trans + unit * trans_unit_stride, state + unit * state_unit_stride, b0, n);
+    __syncthreads();
+    int2* out = F + unit * F_unit_stride + (size_t)chunk * FS_ROW;
+    const int t = threadIdx.x;
+    if (t == FS_STATES) out[t] = make_int2(cen[0], 0);
+    if (t >= FS_STATES) return;
+    int px = fs_x(cen[0]) - FT_K + t / FT_S, py = fs_y(cen[0]) - FT_K + t % FT_S, ref = 0xFF, esc = 0;
+    for (int i = 0; i < n; ++i) {
+        const int c = cen[i];
+        const int rx = px - fs_x(c) + FT_K, ry = py - fs_y(c) + FT_K;
+        if ((unsigned)rx >= (unsigned)FT_S || (unsigned)ry >= (unsigned)FT_S) { esc = 1; break; }
+        const int tr = fs_smem[i * FT_TRANS + rx * FT_S + ry];
+        if (tr != 0xFF) { ref = tr >> 4; px += ((tr >> 2) & 3) - 1; py += (tr & 3) - 1; }
+    }
+    out[t] = make_int2(fs_pack(px, py), ref | (esc << 8));
+}
+
+template <int BS>
+__global__ void __launch_bounds__(576) fast_scan_walk_kernel(const FlowArgs a, const uint8_t* trans, size_t trans_unit_stride, short4* state,
+                                                             size_t state_unit_stride, int L, int nchunks, const int2* F, size_t F_unit_stride,
+                                                             int2* entry, size_t entry_unit_stride) {
+    extern __shared__ __align__(16) unsigned char fs_smem[];        // [nchunks][FS_ROW] int2, then the centres of one chunk
+    __shared__ int s_mvout[3];
+    const FrameGeom& g = a.g;
+    const int unit = a.unit0 + blockIdx.y;
+    const int nblk = g.nbx * g.nby;
+    int2* sF = reinterpret_cast<int2*>(fs_smem);
+    int* cen = reinterpret_cast<int*>(sF + (size_t)nchunks * FS_ROW);
+    const int2* Fu = F + unit * F_unit_stride;
+    for (int e = threadIdx.x; e < nchunks * FS_ROW; e += blockDim.x) sF[e] = Fu[e];
+    __syncthreads();
+    const uint8_t* tr_u = trans + unit * trans_unit_stride;
+    short4* st = state + unit * state_unit_stride;
+    int2* en = entry + unit * entry_unit_stride;
+    // every thread walks the same chain (scalar work, broadcast reads): no hand-off when a block needs the whole CTA
+    int px = 0, py = 0, ref = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int2* row = sF + (size_t)c * FS_ROW;
+        const int c0 = row[FS_STATES].x;
+        const int sx = px - fs_x(c0) + FT_K, sy = py - fs_y(c0) + FT_K;
+        bool ok = (unsigned)sx < (unsigned)FT_S && (unsigned)sy < (unsigned)FT_S;
+        int2 f = make_int2(0, 0);
+        if (ok) { f = row[sx * FT_S + sy]; ok = ((f.y >> 8) & 1) == 0; }
+        if (ok) {
+            if (threadIdx.x == 0) en[c] = make_int2(fs_pack(px, py), ref);
+            px = fs_x(f.x); py = fs_y(f.x);
+            if ((f.y & 0xFF) != 0xFF) ref = f.y & 0xFF;
+            continue;
+        }
+        // no answer for this predictor: walk the chunk block by block (its centres are copied first -- `state` is overwritten
+        // with the predictors as we go)
+        if (threadIdx.x == 0) en[c] = make_int2(0, -1);
+        const int b0 = c * L, n = min(L, nblk - b0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < n; e += blockDim.x) { const short4 cc = st[b0 + e]; cen[e] = fs_pack(cc.x, cc.y); }
+        __syncthreads();
+        for (int i = 0; i < n; ++i) {
+            const int cb = cen[i];
+            const int rx = px - fs_x(cb) + FT_K, ry = py - fs_y(cb) + FT_K;
+            if ((unsigned)rx < (unsigned)FT_S && (unsigned)ry < (unsigned)FT_S) {
+                const int tr = __ldg(tr_u + (size_t)(b0 + i) * FT_TRANS + rx * FT_S + ry);
+                if (threadIdx.x == 0) st[b0 + i] = make_short4((short)px, (short)py, (short)ref, 0);
+                if (tr != 0xFF) { ref = tr >> 4; px += ((tr >> 2) & 3) - 1; py += (tr & 3) - 1; }
+            } else {
+                fast_me16_run<BS>(a, unit, b0 + i, b0 + i + 1, true, px, py, ref, st, s_mvout);     // records st[b0 + i], ends with a barrier
+                px = s_mvout[0]; py = s_mvout[1]; ref = s_mvout[2];
+                __syncthreads();                                                                    // s_mvout is rewritten by the next step
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) fast_scan_fill_kernel(const uint8_t* trans, size_t trans_unit_stride, short4* state, size_t state_unit_stride,
+                                                            int unit0, int nblk, int L, const int2* entry, size_t entry_unit_stride) {
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    const int chunk = blockIdx.x, unit = unit0 + blockIdx.y;
+    const int2 e = entry[unit * entry_unit_stride + chunk];
+    if (e.y == -1) return;                                  // the walker went through this chunk block by block
+    const int b0 = chunk * L, n = min(L, nblk - b0);
+    short4* st = state + unit * state_unit_stride;
+    const int* cen = fs_stage(fs_smem, L, trans + unit * trans_unit_stride, st, b0, n);
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    int px = fs_x(e.x), py = fs_y(e.x), ref = e.y;
+    for (int i = 0; i < n; ++i) {
+        const int c = cen[i];
+        const int rx = px - fs_x(c) + FT_K, ry = py - fs_y(c) + FT_K;         // inside the window: the walker checked this path
+        st[b0 + i] = make_short4((short)px, (short)py, (short)ref, 0);
+        const int tr = fs_smem[i * FT_TRANS + rx * FT_S + ry];
+        if (tr != 0xFF) { ref = tr >> 4; px += ((tr >> 2) & 3) - 1; py += (tr & 3) - 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // intra search (intra_find_best_match_horizontal, Encoder.py:1010-1045; intra_prediction :1272-1338)
 // The search frame holds ORIGINAL pixels left of the current parent block and 128 elsewhere, so all blocks are
 // independent.  Sub-block SADs are the quadrant sums of the parent's candidates (same dx, same pixels).
@@ -1281,6 +1415,7 @@ __global__ void intra_finish_kernel(const FlowArgs a) {
         so_frame_stats* st = a.stats + unit * a.stats_stride;
         if (blk == 0) { st->mae_den = a.mae_den; st->frame_type = a.frame_type; }
         atomicAdd(&st->qsize, (unsigned)len);
+        if (a.blk_len) a.blk_len[unit * a.blk_len_stride + blk] = (uint32_t)len;
         atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
         if (mae_inf) atomicOr(&st->mae_inf, 1u); else atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), mae_n);
     }
@@ -1535,6 +1670,83 @@ __global__ void rle_symbols_kernel(const int16_t* levels, const uint8_t* split, 
         out[nzb + stb] = (int16_t)(nz ? -len : (trailing ? 0 : len));
     }
     if (nz) out[nzb + (sst[t + 1] - sst[lo])] = (int16_t)val;
+}
+
+// Emit pass of the symbol packer used on the end-to-end path: one WARP per block.  The per-block symbol counts come from the
+// finish kernels (blk_len), their exclusive scan per frame (scan_lens_kernel) gives every block its place in the frame's
+// packed stream.  Lane l owns scan positions l, l + 32, ...: a ballot per 32 positions yields the block's non-zero bitmap
+// in scan order, replicated in every lane, and everything else is bit arithmetic on it --
+//   run starts   S = nz ^ (nz << 1)  |  segment starts (a split block is four consecutive segments)
+//   slot(header of the run starting at p) = #nz before p + #starts before p
+//   slot(value at p)                      = #nz before p + #starts up to and including p
+//   run length = distance to the next start (or the block end); a zero run that reaches its segment's end is the symbol 0.
+template <int BS>
+__global__ void __launch_bounds__(256) rle_emit_warp_kernel(const int16_t* levels, const uint8_t* split, const uint32_t* boffs, int16_t* syms,
+                                                            size_t sym_frame_stride, int W, int H, int nbx, int nblk, int f0, int nf, int F) {
+    constexpr int NN = BS * BS, NW = (NN + 31) / 32, S = BS / 2;
+    __shared__ uint8_t inv_full[NN], inv_sub[NN / 4];          // scan position -> pixel index inside the (sub-)block, row-major
+    for (int t = threadIdx.x; t < NN; t += blockDim.x) inv_full[c_scanpos[tbl_off(BS) + t]] = (uint8_t)t;
+    for (int t = threadIdx.x; t < NN / 4; t += blockDim.x) inv_sub[c_scanpos[tbl_off(S) + t]] = (uint8_t)t;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * 8 + warp;
+    if (blk >= nblk) return;
+    const int frame = seq_frame(blockIdx.y, f0, nf, F);
+    const int sp = split[(size_t)frame * nblk + blk];
+    const int bx = blk % nbx, by = blk / nbx;
+    const int16_t* lv = levels + (size_t)frame * W * H + (size_t)(by * BS) * W + bx * BS;
+    const int seglen = sp ? NN / 4 : NN;
+    int val[NW];
+    uint32_t nzw[NW], stw[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        const int p = lane + 32 * k;
+        int v = 0;
+        if (p < NN) {
+            int i, j;
+            if (sp) {
+                const int seg = p / (NN / 4), pix = inv_sub[p % (NN / 4)];
+                i = pix / S + (seg >> 1) * S; j = pix % S + (seg & 1) * S;
+            } else {
+                const int pix = inv_full[p];
+                i = pix / BS; j = pix % BS;
+            }
+            v = lv[(size_t)i * W + j];
+        }
+        val[k] = v;
+        nzw[k] = __ballot_sync(0xFFFFFFFFu, v != 0);
+    }
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        const uint32_t prev = (nzw[k] << 1) | (k ? (nzw[k > 0 ? k - 1 : 0] >> 31) : 0u);
+        uint32_t segm;
+        if (seglen >= 32) segm = ((32 * k) % seglen == 0) ? 1u : 0u;
+        else segm = seglen == 16 ? 0x00010001u : (seglen == 8 ? 0x01010101u : 0x11111111u);
+        const uint32_t act = (NN - 32 * k >= 32) ? 0xFFFFFFFFu : ((1u << (NN - 32 * k > 0 ? NN - 32 * k : 0)) - 1u);
+        stw[k] = ((nzw[k] ^ prev) | segm) & act;
+    }
+    int16_t* out = syms + (size_t)frame * sym_frame_stride + boffs[(size_t)frame * (nblk + 1) + blk];
+    const uint32_t below = (1u << lane) - 1u;
+    int nzpre = 0, stpre = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        const int p = lane + 32 * k;
+        const int nz = (nzw[k] >> lane) & 1, st = (stw[k] >> lane) & 1;
+        const int nzb = nzpre + __popc(nzw[k] & below), stb = stpre + __popc(stw[k] & below);
+        if (st) {
+            const uint32_t m = lane == 31 ? 0u : (stw[k] >> (lane + 1));
+            int q = NN;                                  // next run start (or the end of the block)
+            if (m) q = p + __ffs(m);
+            else {
+#pragma unroll
+                for (int w = NW - 1; w > k; --w) if (stw[w]) q = 32 * w + __ffs(stw[w]) - 1;
+            }
+            const int len = q - p;
+            out[nzb + stb] = (int16_t)(nz ? -len : ((q % seglen == 0) ? 0 : len));
+        }
+        if (nz) out[nzb + stb + st] = (int16_t)val[k];
+        nzpre += __popc(nzw[k]); stpre += __popc(stw[k]);
+    }
 }
 
 // exclusive prefix sum of n entries per frame (one CTA per frame): offs[frame][0..n], offs[frame][n] = totals[frame] = total

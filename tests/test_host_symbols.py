@@ -104,18 +104,25 @@ def test_corrupt_symbol_streams_are_rejected():
 
 
 def test_results_own_their_buffers():
-    """EncodeResult semantics without a GPU: buffers go back to the pool only when nothing references them any more."""
-    from streamoptima_b200.Encoder import _Lease, _PinnedPool
+    """EncodeResult semantics without a GPU: buffers are recycled only when nothing references them any more."""
+    from streamoptima_b200.Encoder import EncodeResult, _Lease, _PinnedPool
     pool = _PinnedPool()
-    lease = _Lease(pool)
-    a = lease.array((4, 8), np.int16)
-    b = lease.array((16,), np.uint8)
-    a[:] = 5
-    keep = a[1]                       # a view survives the lease
-    del a, b, lease
-    assert len(pool.free) == 1        # b's buffer was recycled, a's was not: `keep` still reads it
-    lease2 = _Lease(pool)
-    c = lease2.array((16,), np.uint8)
-    c[:] = 9
+
+    def make(fill):
+        lease = _Lease(pool)
+        r = EncodeResult(a=lease.array((4, 8), np.int16), b=lease.array((16,), np.uint8))
+        r.lease = lease
+        r["a"][:] = fill
+        return r
+
+    r1 = make(5)
+    keep = r1["a"][1]                 # a view survives the result
+    ptr_a, ptr_b = r1["a"].ctypes.data, r1["b"].ctypes.data
+    del r1
+    r2 = make(9)                      # b's buffer is recycled, a's is not: `keep` still reads it
+    assert r2["b"].ctypes.data == ptr_b and r2["a"].ctypes.data != ptr_a
     assert (keep == 5).all()
-    del keep
+    del keep, r2
+    r3 = make(1)                      # now everything is reusable
+    assert {r3["a"].ctypes.data, r3["b"].ctypes.data} <= {ptr_a, ptr_b} | {r3["a"].ctypes.data}
+    assert len(pool.pending) == 0
