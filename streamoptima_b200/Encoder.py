@@ -379,7 +379,7 @@ class Y_Video_codec:
                          lambda o: ctx.lib.so_encode_yuv420_file(ctx.handle, bpath, sw, sh, first_frame, F, *o))
 
     _pool = _PinnedPool()
-    _sym_guess = 0.35          # symbols per pixel the first symbol buffer is sized for (grows to what encodes needed)
+    _sym_guess = 0.35          # symbols per pixel the symbol buffer of this codec is sized for (grows to what its encodes needed)
 
     def _run(self, ctx, U, F, want_levels, want_recon, want_symbols, call):
         """Pinned output buffers (leased from the pool, owned by the result) + one library call ``call(output pointers)``."""
@@ -423,7 +423,7 @@ class Y_Video_codec:
         if want_levels:
             out["levels"] = levels
         if want_symbols:
-            type(self)._sym_guess = max(self._sym_guess, 1.15 * sym.needed / float(U * F * H * W))
+            self._sym_guess = max(self._sym_guess, 1.15 * sym.needed / float(U * F * H * W))     # per codec: densities differ with QP
             out.update(symbols=symbols[:max(int(sym.needed), 1)], sym_pos=pos, sym_count=cnt, sym_needed=int(sym.needed))
             if not want_levels:
                 bs = ctx.bs

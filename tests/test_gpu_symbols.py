@@ -59,7 +59,7 @@ def test_packed_symbol_output_of_sequence_encode(name):
     try:
         outs = []
         for guess in (old_guess, 1e-6):               # second run: buffer far too small -> fetched after the encode
-            Y_Video_codec._sym_guess = guess
+            c._sym_guess = guess
             o = c.encode_arrays(frames, want_levels=False, want_recon=False, want_symbols=True)
             outs.append(o)
             assert o["sym_needed"] == int(wcnt.sum())
@@ -74,7 +74,7 @@ def test_packed_symbol_output_of_sequence_encode(name):
         c.encode_arrays(frames2, want_levels=False, want_symbols=True)
         np.testing.assert_array_equal(outs[0]["symbols"], a)     # the earlier result still holds its own data
     finally:
-        Y_Video_codec._sym_guess = old_guess
+        assert Y_Video_codec._sym_guess == old_guess          # the density estimate is per codec
 
 
 def test_two_encodes_on_one_codec_do_not_alias():
