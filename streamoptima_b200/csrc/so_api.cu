@@ -865,23 +865,29 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
             const int L = ctx->fs_L, nch = ctx->fs_nchunks;
             const size_t tstride = nblk_pad * FT_TRANS, fstride = (size_t)nch * FS_ROW;
             const size_t csm = (size_t)L * FT_TRANS + (size_t)L * 4, wsm = (size_t)nch * FS_ROW * sizeof(int2) + (size_t)L * 4;
+            // without VBS the whole-block results are all that is needed and the scan knows them: no search kernel afterwards
+            static const bool always_me16 = std::getenv("SO_FAST_ALWAYS_ME16") != nullptr;      // A/B switch and cross-check in the tests
+            const bool results_from_scan = !chain_walk && !a.vbs && !always_me16;
             auto scan = [&](auto walk_kernel) {
                 fast_scan_chunk_kernel<<<dim3(nch, units), 96, csm, st>>>(ctx->fm_table, tstride, ctx->fm_state, nblk_pad, a.unit0, ctx->nblk, L, ctx->fs_F, fstride);
-                walk_kernel<<<dim3(1, units), 576, wsm, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad, L, nch, ctx->fs_F, fstride, ctx->fs_entry, (size_t)nch);
-                fast_scan_fill_kernel<<<dim3(nch, units), 32, csm, st>>>(ctx->fm_table, tstride, ctx->fm_state, nblk_pad, a.unit0, ctx->nblk, L, ctx->fs_entry, (size_t)nch);
+                walk_kernel<<<dim3(1, units), 576, wsm, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad, L, nch, ctx->fs_F, fstride, ctx->fs_entry, (size_t)nch,
+                                                              results_from_scan ? 1 : 0);
+                fast_scan_fill_kernel<<<dim3(nch, units), 32, csm, st>>>(ctx->fm_table, tstride, ctx->fm_state, nblk_pad, a.unit0, ctx->nblk, L, ctx->fs_entry, (size_t)nch,
+                                                                        results_from_scan ? ctx->me_parent : nullptr, (size_t)ctx->nblk);
                 ctx->launches += 2;
             };
             if (g.bs == 16) {
                 fast_table16_kernel<16><<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad);
                 if (chain_walk) fast_chain16_kernel<16><<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad);
                 else scan(fast_scan_walk_kernel<16>);
-                fast_me16_kernel<16><<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
+                if (!results_from_scan) fast_me16_kernel<16><<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
             } else {
                 fast_table16_kernel<8><<<dim3(ctx->nblk, units), 128, tsm, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad);
                 if (chain_walk) fast_chain16_kernel<8><<<dim3(1, units), 576, 0, st>>>(a, ctx->fm_table, tstride, ctx->fm_state, nblk_pad);
                 else scan(fast_scan_walk_kernel<8>);
-                fast_me16_kernel<8><<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
+                if (!results_from_scan) fast_me16_kernel<8><<<dim3(ctx->nblk, units), 576, 0, st>>>(b);
             }
+            if (results_from_scan) ctx->launches--;
             ctx->launches += 2;
         }
         else if (packed && g.bs == 16) fast_me16_kernel<16><<<grid, 576, 0, st>>>(a);

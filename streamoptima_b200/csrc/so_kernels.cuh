@@ -929,8 +929,10 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
     __syncthreads();
     uint16_t* s_sad = reinterpret_cast<uint16_t*>(s_cur + BS * WPR);         // [nref][FT_N][FT_N]
     for (int e = threadIdx.x; e < nref * FT_N * FT_N; e += blockDim.x) {
+        // horizontal offset fastest: the lanes of a warp then read the SAME few region rows (shared-memory broadcast, and the
+        // two or three rows a warp spans sit in disjoint banks); vertical-fastest made every row load a 3-way bank conflict
         const int ref = e / (FT_N * FT_N), rem = e - ref * (FT_N * FT_N);
-        const int ix = rem / FT_N, iy = rem - ix * FT_N;
+        const int iy = rem / FT_N, ix = rem - iy * FT_N;
         // invalid offsets (Encoder.py:728-730: 0 <= p and p + 2*bs < size - bs on both axes) get 0xFFFF (> any SAD)
         const int dx = dx0 + ix, dy = dy0 + iy;
         const int px = x * mult + dx, py = y * mult + dy;
@@ -951,7 +953,7 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
                 for (int w = 0; w < WPR; ++w) sad = sad4_acc(s_cur[row * WPR + w], __funnelshift_r(q[w], q[w + 1], sh), sad);
             }
         }
-        s_sad[e] = (uint16_t)sad;
+        s_sad[ref * (FT_N * FT_N) + ix * FT_N + iy] = (uint16_t)sad;
     }
     __syncthreads();
     // transition table: for every predictor within K of the centre, the winner of fast_motion_estimation's scan (ref, dx,
@@ -1113,43 +1115,62 @@ __global__ void __launch_bounds__(96) fast_scan_chunk_kernel(const uint8_t* tran
     out[t] = make_int2(fs_pack(px, py), ref | (esc << 8));
 }
 
+// whole-block result of fast_motion_estimation for a block entered with predictor (px, py, ref) whose table says `tr`
+// (Encoder.py:722-742; the second return value is the reference index, quirk Q4)
+__device__ __forceinline__ MeResult fs_result(int px, int py, int ref, int tr) {
+    MeResult r;
+    r.none = 0;
+    if (tr != 0xFF) { r.ref = (int16_t)(tr >> 4); r.dx = (int16_t)(px + ((tr >> 2) & 3) - 1); r.dy = (int16_t)(py + (tr & 3) - 1); r.sad = (uint32_t)(tr >> 4); }
+    else { r.dx = (int16_t)px; r.dy = (int16_t)py; r.ref = (int16_t)ref; r.sad = 0u; }          // no valid candidate: best_mv = mvp, best_ref_idx = 0
+    return r;
+}
+
 template <int BS>
 __global__ void __launch_bounds__(576) fast_scan_walk_kernel(const FlowArgs a, const uint8_t* trans, size_t trans_unit_stride, short4* state,
                                                              size_t state_unit_stride, int L, int nchunks, const int2* F, size_t F_unit_stride,
-                                                             int2* entry, size_t entry_unit_stride) {
+                                                             int2* entry, size_t entry_unit_stride, int write_results) {
     extern __shared__ __align__(16) unsigned char fs_smem[];        // [nchunks][FS_ROW] int2, then the centres of one chunk
     __shared__ int s_mvout[3];
+    __shared__ int s_req[4];                                        // {chunk that needs the whole CTA (nchunks: done), predictor x, y, ref}
     const FrameGeom& g = a.g;
     const int unit = a.unit0 + blockIdx.y;
     const int nblk = g.nbx * g.nby;
     int2* sF = reinterpret_cast<int2*>(fs_smem);
     int* cen = reinterpret_cast<int*>(sF + (size_t)nchunks * FS_ROW);
-    const int2* Fu = F + unit * F_unit_stride;
-    for (int e = threadIdx.x; e < nchunks * FS_ROW; e += blockDim.x) sF[e] = Fu[e];
+    {
+        const int4* src = reinterpret_cast<const int4*>(F + unit * F_unit_stride);          // FS_ROW is even: whole int4s
+        for (int e = threadIdx.x; e < nchunks * FS_ROW / 2; e += blockDim.x) reinterpret_cast<int4*>(sF)[e] = src[e];
+    }
     __syncthreads();
     const uint8_t* tr_u = trans + unit * trans_unit_stride;
     short4* st = state + unit * state_unit_stride;
     int2* en = entry + unit * entry_unit_stride;
-    // every thread walks the same chain (scalar work, broadcast reads): no hand-off when a block needs the whole CTA
-    int px = 0, py = 0, ref = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int2* row = sF + (size_t)c * FS_ROW;
-        const int c0 = row[FS_STATES].x;
-        const int sx = px - fs_x(c0) + FT_K, sy = py - fs_y(c0) + FT_K;
-        bool ok = (unsigned)sx < (unsigned)FT_S && (unsigned)sy < (unsigned)FT_S;
-        int2 f = make_int2(0, 0);
-        if (ok) { f = row[sx * FT_S + sy]; ok = ((f.y >> 8) & 1) == 0; }
-        if (ok) {
-            if (threadIdx.x == 0) en[c] = make_int2(fs_pack(px, py), ref);
-            px = fs_x(f.x); py = fs_y(f.x);
-            if ((f.y & 0xFF) != 0xFF) ref = f.y & 0xFF;
-            continue;
+    MeResult* res = a.me_parent + unit * a.me_parent_stride;
+    int px = 0, py = 0, ref = 0, c = 0;
+    while (true) {
+        if (threadIdx.x < 32) {
+            // warp 0 walks the chunks: one lookup in the chunk's composed table per step
+            while (c < nchunks) {
+                const int2* row = sF + (size_t)c * FS_ROW;
+                const int c0 = row[FS_STATES].x;
+                const int sx = px - fs_x(c0) + FT_K, sy = py - fs_y(c0) + FT_K;
+                if (!((unsigned)sx < (unsigned)FT_S && (unsigned)sy < (unsigned)FT_S)) break;
+                const int2 f = row[sx * FT_S + sy];
+                if ((f.y >> 8) & 1) break;
+                if (threadIdx.x == 0) en[c] = make_int2(fs_pack(px, py), ref);
+                px = fs_x(f.x); py = fs_y(f.x);
+                if ((f.y & 0xFF) != 0xFF) ref = f.y & 0xFF;
+                ++c;
+            }
+            if (threadIdx.x == 0) { s_req[0] = c; s_req[1] = px; s_req[2] = py; s_req[3] = ref; }
         }
-        // no answer for this predictor: walk the chunk block by block (its centres are copied first -- `state` is overwritten
-        // with the predictors as we go)
+        __syncthreads();
+        c = s_req[0]; px = s_req[1]; py = s_req[2]; ref = s_req[3];
+        if (c >= nchunks) break;
+        // this chunk has no answer for the incoming predictor (cold start, scene change): block by block, all threads in step
+        // (its centres are copied first -- `state` is overwritten with the predictors as we go)
         if (threadIdx.x == 0) en[c] = make_int2(0, -1);
         const int b0 = c * L, n = min(L, nblk - b0);
-        __syncthreads();
         for (int e = threadIdx.x; e < n; e += blockDim.x) { const short4 cc = st[b0 + e]; cen[e] = fs_pack(cc.x, cc.y); }
         __syncthreads();
         for (int i = 0; i < n; ++i) {
@@ -1157,19 +1178,26 @@ __global__ void __launch_bounds__(576) fast_scan_walk_kernel(const FlowArgs a, c
             const int rx = px - fs_x(cb) + FT_K, ry = py - fs_y(cb) + FT_K;
             if ((unsigned)rx < (unsigned)FT_S && (unsigned)ry < (unsigned)FT_S) {
                 const int tr = __ldg(tr_u + (size_t)(b0 + i) * FT_TRANS + rx * FT_S + ry);
-                if (threadIdx.x == 0) st[b0 + i] = make_short4((short)px, (short)py, (short)ref, 0);
+                if (threadIdx.x == 0) {
+                    st[b0 + i] = make_short4((short)px, (short)py, (short)ref, 0);
+                    if (write_results) res[b0 + i] = fs_result(px, py, ref, tr);
+                }
                 if (tr != 0xFF) { ref = tr >> 4; px += ((tr >> 2) & 3) - 1; py += (tr & 3) - 1; }
             } else {
-                fast_me16_run<BS>(a, unit, b0 + i, b0 + i + 1, true, px, py, ref, st, s_mvout);     // records st[b0 + i], ends with a barrier
+                fast_me16_run<BS>(a, unit, b0 + i, b0 + i + 1, true, px, py, ref, st, s_mvout);     // records st[] and the result, ends with a barrier
                 px = s_mvout[0]; py = s_mvout[1]; ref = s_mvout[2];
                 __syncthreads();                                                                    // s_mvout is rewritten by the next step
             }
         }
+        ++c;
+        __syncthreads();                                                                            // s_req is rewritten by warp 0
     }
 }
 
+// res != nullptr: the whole-block results are written here as well (no VBS: nothing else is needed from a search kernel)
 __global__ void __launch_bounds__(32) fast_scan_fill_kernel(const uint8_t* trans, size_t trans_unit_stride, short4* state, size_t state_unit_stride,
-                                                            int unit0, int nblk, int L, const int2* entry, size_t entry_unit_stride) {
+                                                            int unit0, int nblk, int L, const int2* entry, size_t entry_unit_stride,
+                                                            MeResult* res, size_t res_unit_stride) {
     extern __shared__ __align__(16) unsigned char fs_smem[];
     const int chunk = blockIdx.x, unit = unit0 + blockIdx.y;
     const int2 e = entry[unit * entry_unit_stride + chunk];
@@ -1185,6 +1213,7 @@ __global__ void __launch_bounds__(32) fast_scan_fill_kernel(const uint8_t* trans
         const int rx = px - fs_x(c) + FT_K, ry = py - fs_y(c) + FT_K;         // inside the window: the walker checked this path
         st[b0 + i] = make_short4((short)px, (short)py, (short)ref, 0);
         const int tr = fs_smem[i * FT_TRANS + rx * FT_S + ry];
+        if (res) res[unit * res_unit_stride + b0 + i] = fs_result(px, py, ref, tr);
         if (tr != 0xFF) { ref = tr >> 4; px += ((tr >> 2) & 3) - 1; py += (tr & 3) - 1; }
     }
 }
