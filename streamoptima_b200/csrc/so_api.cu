@@ -10,6 +10,7 @@
 #include "so_kernels.cuh"
 #include "so_me_tma.cuh"
 #include "so_me_ring.cuh"
+#include "so_me_ring2.cuh"
 #include <cstdlib>
 #include <fcntl.h>
 #include <unistd.h>
@@ -531,13 +532,12 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
     if (rc) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const long long total = (long long)units * a.items_per_unit;
-    const long long nchunks = (total + MR_CHUNK - 1) / MR_CHUNK;
-    const int grid = nchunks < sms ? (int)nchunks : sms;
     static bool attr_done[64] = {};
     if (ctx->device >= 64 || !attr_done[ctx->device]) {
         CU(cudaFuncSetAttribute(me_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
         CU(cudaFuncSetAttribute(me_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
+        CU(cudaFuncSetAttribute(me_ring2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR2_SMEM));
+        CU(cudaFuncSetAttribute(me_ring2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MR2_SMEM));
         if (ctx->device < 64) attr_done[ctx->device] = true;
     }
     if (!ctx->me_work) {      // {chunk counter, finished CTAs}: zero at every launch -- the last CTA of a launch resets both
@@ -545,11 +545,26 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
         CU(cudaMemsetAsync(ctx->me_work, 0, 256, st));
     }
     a.work = ctx->me_work;
+    static const bool ring_v1 = std::getenv("SO_ME_RING_V1") != nullptr;      // A/B switch and cross-check: the first item-ring kernel
     ev_pair(ctx, ctx->ev_me, st, true);
     if (ctx->timing_on) ctx->ev_xs.push_back(ctx->ev_me.size() - 1);
     cudaError_t e;
-    if (out_sub) e = launch_pdl(me_ring_kernel<true>, dim3(grid), dim3(384), MR_SMEM, st, map, cmap, a);
-    else e = launch_pdl(me_ring_kernel<false>, dim3(grid), dim3(512), MR_SMEM, st, map, cmap, a);
+    if (ring_v1) {
+        const long long total = (long long)units * a.items_per_unit;
+        const long long nchunks = (total + MR_CHUNK - 1) / MR_CHUNK;
+        const int grid = nchunks < sms ? (int)nchunks : sms;
+        if (out_sub) e = launch_pdl(me_ring_kernel<true>, dim3(grid), dim3(384), MR_SMEM, st, map, cmap, a);
+        else e = launch_pdl(me_ring_kernel<false>, dim3(grid), dim3(512), MR_SMEM, st, map, cmap, a);
+    } else {
+        MeRing2Args a2{};
+        a2.b = a;
+        a2.npairs = a.g.nbx * a.g.nby * a.g.nref;
+        a2.chunks_per_unit = a.g.fme ? ((a2.npairs + 3) / 4) * 2 : (a2.npairs + 7) / 8;
+        const long long nchunks = (long long)units * a2.chunks_per_unit;
+        const int grid = nchunks < sms ? (int)nchunks : sms;
+        if (out_sub) e = launch_pdl(me_ring2_kernel<true>, dim3(grid), dim3(384), MR2_SMEM, st, map, cmap, a2);
+        else e = launch_pdl(me_ring2_kernel<false>, dim3(grid), dim3(512), MR2_SMEM, st, map, cmap, a2);
+    }
     if (e == cudaSuccess) e = cudaGetLastError();
     ev_pair(ctx, ctx->ev_me, st, false);
     if (e != cudaSuccess) { set_err(ctx, std::string("me_ring_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }

@@ -1,0 +1,486 @@
+// Exhaustive motion search for 16x16 blocks at r = 16 (BASELINE configs 2-5), item-ring kernel, second version (sm_100a).
+//
+// Same arithmetic, ring planes, TMA boxes and shared-memory layout as so_me_ring.cuh; what changes is how work is cut:
+//   * work is handed out in HOMOGENEOUS CHUNKS of 8 items: four consecutive (block, reference) pairs x the two phase planes
+//     of ONE horizontal parity.  A chunk of interior blocks is 8 x 44 tasks = exactly 11 bundles, so no bundle mixes even and
+//     odd horizontal phases any more: the 33rd-offset pass (dx = +32, even phases only) runs exactly where it is needed;
+//   * a chunk only carries the vertical groups that hold a valid offset for at least one of its items (edge block rows:
+//     Encoder.py:695-698): tasks per item = 4 x groups, tasks ordered [item][group][shift] as before.  The producer records
+//     every chunk in a small ring of chunk entries {first bundle, groups, first group, items}; a search warp finds the chunk
+//     of its bundle with a cursor that only moves forward;
+//   * a bundle may now cover several items (edge chunks have few tasks per item): the per-item merge uses
+//     __match_any_sync + REDUX over the lanes of an item, and each item's lanes arrive on its `empty` barrier together
+//     (the producer pre-arrives for the groups a chunk does not carry, so the barrier count stays 44).
+#pragma once
+#include "so_me_ring.cuh"
+
+constexpr int MR2_CE = 32;                      // chunk entries in flight (ring)
+constexpr int MR2_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 2048;      // + barriers, item meta, chunk entries, counters
+
+struct MeRing2Args {
+    MeRingArgs b;                // geometry, outputs, units, nph, z_*, slot_packed, work counters (items_per_unit unused)
+    int npairs;                  // (block, reference) pairs per unit = blocks * nref
+    int chunks_per_unit;         // fme: ceil(npairs / 4) * 2 (pair group x horizontal parity); else ceil(npairs / 8)
+};
+
+template <bool QUAD>
+__global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __grid_constant__ CUtensorMap ring_map,
+                                                                       const __grid_constant__ CUtensorMap cur_map, const MeRing2Args a2) {
+    const MeRingArgs& a = a2.b;
+    constexpr int BS = 16, WPR = 4, G = 3;
+    extern __shared__ __align__(1024) unsigned char smem_r[];
+    unsigned char* const wins = smem_r;                                        // [NS][4][MR_PLANE]
+    unsigned char* const curs = wins + MR_NS * MR_SLOT;                        // [NS][256]
+    uint64_t* const ready = reinterpret_cast<uint64_t*>(curs + MR_NS * MR_CUR);
+    uint64_t* const empty = ready + MR_NS;
+    int4* const meta = reinterpret_cast<int4*>(empty + MR_NS);                  // [NS]: {out index, bx, by, ref | ph << 8 | interior << 16}
+    int4* const centry = meta + MR_NS;                                          // [MR2_CE]: {first bundle, ng | g_lo << 8 | nit << 16 | bundles << 24, first item, 0}
+    volatile int* const cseq = reinterpret_cast<volatile int*>(centry + MR2_CE); // [MR2_CE]: chunk sequence number the entry holds (seqlock; -1 while written)
+    unsigned int* const counter = reinterpret_cast<unsigned int*>(const_cast<int*>(cseq) + MR2_CE);
+    volatile int* const issued = reinterpret_cast<volatile int*>(counter + 1);  // items whose loads have been issued
+    volatile int* const chunks_pub = issued + 1;                                // chunk entries published
+    volatile int* const final_bundles = chunks_pub + 1;                         // number of bundles of this CTA, once known
+
+    const FrameGeom& g = a.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (int)(blockDim.x >> 5);
+    if (tid == 0) {
+        for (int s = 0; s < MR_NS; ++s) { mbar_init(&ready[s], 1); mbar_init(&empty[s], MR_TPI); }
+        *counter = 0;
+        *issued = 0;
+        *chunks_pub = 0;
+        *final_bundles = 0x7FFFFFFF;
+        for (int s = 0; s < MR2_CE; ++s) cseq[s] = -1;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_trigger();
+    __syncthreads();
+    pdl_wait();          // everything below reads what earlier kernels of the stream wrote (ring planes, keys, the work counter)
+
+    const int cpu = a2.chunks_per_unit;
+    const int nchunks = a.units * cpu;
+    const int mul = g.fme ? 2 : 1;
+
+    if (warp == nwarps - 1) {
+        // ================================= producer =================================
+        // chunks are handed out by a device-wide counter: all CTAs stay in the same neighbourhood of the frame (window rows
+        // are re-read from L2, not DRAM) and the tail balances itself
+        int q = 0, qn = 0;
+        if (lane == 0) q = (int)atomicAdd(a.work, 1u);
+        q = __shfl_sync(0xFFFFFFFFu, q, 0);
+        int slot = 0, n = 0, jchunk = 0, bundle_base = 0;
+        uint32_t par = 1;                       // parity of (use - 1) for the wait on `empty`
+        bool first_round = true;
+        while (q < nchunks) {
+            if (lane == 0) qn = (int)atomicAdd(a.work, 1u);             // next chunk: the latency hides behind this one
+            const int unit = q / cpu, qq = q - unit * cpu;
+            int pair0, nit, hpar = 0;
+            if (a.nph == 4) { pair0 = (qq >> 1) * 4; hpar = qq & 1; nit = 2 * min(4, a2.npairs - pair0); }
+            else { pair0 = qq * 8; nit = min(8, a2.npairs - pair0); }
+            // item k of the chunk (lane k < nit works it out; the issuing loop below reads it with shuffles)
+            int i_blk = 0, i_ref = 0, i_ph = 0, i_bx = 0, i_by = 0, i_int = 0, glo = 99, ghi = -1;
+            if (lane < nit) {
+                const int pair = pair0 + (a.nph == 4 ? (lane >> 1) : lane);
+                i_ph = a.nph == 4 ? hpar + 2 * (lane & 1) : 0;          // phase plane = (py << 1) | px
+                i_blk = pair / g.nref; i_ref = pair - i_blk * g.nref;
+                i_by = i_blk / g.nbx; i_bx = i_blk - i_by * g.nbx;
+                int l0, h0, l1, h1;
+                valid_range(i_bx * BS, g.W, BS, g.fme, g.fme, l0, h0);
+                valid_range(i_by * BS, g.H, BS, g.fme, g.fme, l1, h1);
+                i_int = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;       // every offset of the range is valid
+                // vertical groups with a valid offset: dy = mul * oy + py in [max(l1, -R), min(h1, R)], group = (oy + 16) / 3
+                const int py = g.fme ? (i_ph >> 1) : 0;
+                const int dlo = max(l1, -g.R) - py, dhi = min(h1, g.R) - py;
+                const int olo = max(-16, dlo >= 0 ? (dlo + mul - 1) / mul : -((-dlo) / mul));     // ceil(dlo / mul)
+                const int ohi = min(16, dhi >= 0 ? dhi / mul : -((-dhi + mul - 1) / mul));       // floor(dhi / mul)
+                if (olo <= ohi) { glo = (olo + 16) / 3; ghi = (ohi + 16) / 3; }
+            }
+            glo = __reduce_min_sync(0xFFFFFFFFu, glo);
+            ghi = __reduce_max_sync(0xFFFFFFFFu, ghi);
+            if (ghi >= glo) {                   // else: no item of the chunk has a valid candidate -- the keys stay all ones
+                const int ng = ghi - glo + 1, tpi = 4 * ng, nb = (nit * tpi + 31) >> 5;
+                if (lane == 0) {
+                    const int e = jchunk & (MR2_CE - 1);
+                    cseq[e] = -1;
+                    __threadfence_block();
+                    centry[e] = make_int4(bundle_base, ng | (glo << 8) | (nit << 16) | (nb << 24), n, 0);
+                    __threadfence_block();
+                    cseq[e] = jchunk;
+                    __threadfence_block();
+                    *chunks_pub = jchunk + 1;
+                }
+                __syncwarp();
+                for (int k = 0; k < nit; ++k) {
+                    if (!first_round) {
+                        while (!mbar_try(&empty[slot], par)) __nanosleep(40);
+                    }
+                    const int blk = __shfl_sync(0xFFFFFFFFu, i_blk, k), ref = __shfl_sync(0xFFFFFFFFu, i_ref, k);
+                    const int phz = __shfl_sync(0xFFFFFFFFu, i_ph, k), bx = __shfl_sync(0xFFFFFFFFu, i_bx, k), by = __shfl_sync(0xFFFFFFFFu, i_by, k);
+                    const int interior = __shfl_sync(0xFFFFFFFFu, i_int, k);
+                    if (lane == 0) meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (phz << 8) | (interior << 16) | (unit << 17));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&ready[slot], (uint32_t)(4 * MR_BOXROWS * MR_WP + BS * BS));
+                        if (tpi < MR_TPI) mbar_arrive_cnt(&empty[slot], (uint32_t)(MR_TPI - tpi));     // the groups this chunk does not carry
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int z = a.z_unit0 + unit * a.z_per_unit + (int)((a.slot_packed >> (4 * ref)) & 15u) * 16 + phz * 4;
+                        tma_load_3d(wins + slot * MR_SLOT, &ring_map, &ready[slot], bx * BS - 16, by * BS - 16 - (slot & 1), z);
+                    } else if (lane == 1) {
+                        tma_load_3d(curs + slot * MR_CUR, &cur_map, &ready[slot], bx * BS, by * BS, unit);
+                    }
+                    ++n;
+                    if (lane == 0) *issued = n;
+                    if (++slot == MR_NS) { slot = 0; par ^= 1; first_round = false; }
+                }
+                bundle_base += nb;
+                ++jchunk;
+            }
+            q = __shfl_sync(0xFFFFFFFFu, qn, 0);
+        }
+        if (lane == 0) { __threadfence_block(); *final_bundles = bundle_base; }      // no bundle with index >= bundle_base will ever exist
+    } else {
+    // ================================= search warps =================================
+    unsigned b = 0;
+    if (lane == 0) b = atomicAdd(counter, 1u);
+    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+    int jc = 0;                                 // chunk cursor of this warp: bundles are fetched in increasing order
+    while (true) {
+        // ---- the chunk that holds bundle b (seqlock read of its entry; wait for the producer if it is not published yet)
+        int4 ce;
+        {
+            SpinWait sw;
+            bool none = false;
+            while (true) {
+                if (jc < *chunks_pub) {
+                    const int e = jc & (MR2_CE - 1);
+                    const int s1 = cseq[e];
+                    __threadfence_block();
+                    ce = centry[e];
+                    __threadfence_block();
+                    const int s2 = cseq[e];
+                    if (s1 == jc && s2 == jc && b < (unsigned)ce.x + ((unsigned)ce.y >> 24)) break;
+                    ++jc;                       // this chunk ends before bundle b (or its entry was recycled long ago)
+                    continue;
+                }
+                if ((int)b >= *final_bundles) { none = true; break; }
+                sw.pause();
+            }
+            if (none) break;
+        }
+        const int ng = ce.y & 255, g_lo = (ce.y >> 8) & 255, nit = (ce.y >> 16) & 255;
+        const unsigned lb = b - (unsigned)ce.x;
+        const unsigned tq = (32u * lb + lane) >> 2;                             // (item, group) pair of this lane inside the chunk
+        const unsigned mg = (1024u + ng - 1) / (unsigned)ng;                     // exact division by ng for tq < 96 (ng <= 11)
+        unsigned ki = (tq * mg) >> 10;
+        const unsigned gl = tq - ki * ng;
+        const bool has = ki < (unsigned)nit;                                    // lanes past the chunk's last task shadow its last item
+        if (!has) ki = (unsigned)nit - 1u;
+        const unsigned item = (unsigned)ce.z + ki;                              // CTA-local item index
+        const int grp = g_lo + (has ? (int)gl : 0), c = (int)(lane & 3u);
+        {   // every item the bundle touches must have been issued (ready[] is then in the phase of this use, never an older one)
+            const unsigned last = (unsigned)ce.z + min((unsigned)nit - 1u, (((32u * lb + 31u) >> 2) * mg) >> 10);
+            SpinWait sw;
+            while (*issued <= (int)last) sw.pause();
+        }
+        unsigned nb = 0;
+        if (lane == 0) nb = atomicAdd(counter, 1u);         // next bundle index: consumed at the end of this iteration
+        const unsigned use = __umulhi(item, 0xBA2E8BA3u) >> 4, slot = item - use * MR_NS;       // item / 22
+        mbar_wait(&ready[slot], use & 1u);
+        __syncwarp();
+        const unsigned seg = __match_any_sync(0xFFFFFFFFu, has ? ki : 0xFFu);      // the lanes of my item
+        const bool leader = has && (int)lane == __ffs(seg) - 1;
+        const int4 mt = meta[slot];
+        const int bx = mt.y, by = mt.z;
+        const int ph = (mt.w >> 8) & 255;
+        const int px = g.fme ? (ph & 1) : 0, py = g.fme ? (ph >> 1) : 0;
+        const int p = (int)(slot & 1u);
+        const unsigned char* wslot = wins + slot * MR_SLOT;
+        const unsigned char* win = wslot + c * MR_PLANE + (p + G * grp) * MR_WP;
+        const uint32_t* cb = reinterpret_cast<const uint32_t*>(curs + slot * MR_CUR);
+        const int oy0 = -16 + G * grp;
+
+        if constexpr (QUAD) {
+            // ---- VBS: the four 8x8 sub-blocks search the same offsets, so their SADs are the quadrant sums of the parent's
+            // candidates (Encoder.py:517-536 vs :558).  Two half passes (top / bottom 8 rows), left and right words in
+            // separate accumulators; quadrant minima are folded after each half, the parent sums are kept.
+            uint32_t par[3][8];
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) par[gg][k] = 0;
+            // 33rd horizontal offset first: lane c takes block rows 4c..4c+3 (c = 0, 1: top half; 2, 3: bottom half)
+            uint32_t exq[5][3];                      // parent, TL, TR, BL, BR sums of candidate k = 8, complete on every lane
+#pragma unroll
+            for (int e = 0; e < 5; ++e)
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) exq[e][gg] = 0u;
+            if (__any_sync(0xFFFFFFFFu, px == 0)) {  // odd horizontal phases have no 33rd offset (dx = 33 > R): masked below
+                uint32_t eL[3] = {0u, 0u, 0u}, eR[3] = {0u, 0u, 0u};
+                const unsigned char* w0 = wslot + (p + G * grp + 4 * c) * MR_WP + 32;
+                uint4 cr[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cr[i] = reinterpret_cast<const uint4*>(cb)[4 * c + i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(w0 + i * MR_WP);
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg) {
+                        const int r = i - gg;
+                        if (r >= 0 && r < 4) {
+                            eL[gg] = sad4_acc(w.x, cr[r].x, eL[gg]); eL[gg] = sad4_acc(w.y, cr[r].y, eL[gg]);
+                            eR[gg] = sad4_acc(w.z, cr[r].z, eR[gg]); eR[gg] = sad4_acc(w.w, cr[r].w, eR[gg]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    const uint32_t hl = eL[gg] + __shfl_xor_sync(0xFFFFFFFFu, eL[gg], 1);      // my half (top for c < 2)
+                    const uint32_t hr = eR[gg] + __shfl_xor_sync(0xFFFFFFFFu, eR[gg], 1);
+                    const uint32_t ol = __shfl_xor_sync(0xFFFFFFFFu, hl, 2), orr = __shfl_xor_sync(0xFFFFFFFFu, hr, 2);   // the other half
+                    const bool top = c < 2;
+                    exq[1][gg] = top ? hl : ol; exq[2][gg] = top ? hr : orr;
+                    exq[3][gg] = top ? ol : hl; exq[4][gg] = top ? orr : hr;
+                    exq[0][gg] = hl + hr + ol + orr;
+                }
+            }
+            uint32_t bq[5] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // parent, TL, TR, BL, BR
+            const bool fast_valid = __all_sync(0xFFFFFFFFu, (mt.w >> 16) & 1);
+            // distance parts of the keys
+            uint32_t ly8[3], lx8[9];
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative
+                lx8[k] = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
+            }
+            // interior block: parent and sub-blocks share the two special cases (ox = 16 on odd horizontal phases, oy = 16
+            // on odd vertical ones); keys are folded rows-first like in the plain search (3 IMAD + min3 + add per column)
+            const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;
+            const uint32_t ybl = (grp == MR_NG - 1 && py) ? 0xFFFFFFFFu : 0u;
+            auto fold = [&](uint32_t s0, uint32_t s1, uint32_t s2, int k) {
+                const uint32_t t0 = s0 * 65536u + ly8[0], t1 = s1 * 65536u + ly8[1], t2 = (s2 * 65536u + ly8[2]) | ybl;
+                uint32_t v = min(min(t0, t1), t2) + lx8[k];
+                if (k == 8) v |= xbl;
+                return v;
+            };
+            // edge block: parent and sub-blocks have their own rectangles (Encoder.py:695-698 with their own size / position)
+            auto xbad = [&](int k, int pos, int n) {
+                int l, h;
+                valid_range(pos, g.W, n, g.fme, g.fme, l, h);
+                const int dx = mul * (-16 + c + 4 * k) + px;
+                return ((k < 8 || c == 0) && dx >= -g.R && dx <= g.R && dx >= l && dx <= h) ? 0u : 0xFFFFFFFFu;
+            };
+            auto ybad = [&](int gg, int pos, int n) {
+                int l, h;
+                valid_range(pos, g.H, n, g.fme, g.fme, l, h);
+                const int dy = mul * (oy0 + gg) + py;
+                return (dy >= -g.R && dy <= g.R && dy >= l && dy <= h) ? 0u : 0xFFFFFFFFu;
+            };
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {            // rolled: one copy of the SAD pass in the instruction stream
+                uint32_t aL[3][8], aR[3][8];
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { aL[gg][k] = 0; aR[gg][k] = 0; }
+                sad_pass_g3<WPR, 8, 8, BS / 2, MR_WP, true>(win + half * (BS / 2) * MR_WP, cb + half * (BS / 2) * WPR, aL, aR);
+                uint32_t eL[3], eR[3];
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) { eL[gg] = half ? exq[3][gg] : exq[1][gg]; eR[gg] = half ? exq[4][gg] : exq[2][gg]; }
+                uint32_t bl = 0xFFFFFFFFu, br = 0xFFFFFFFFu;
+                if (fast_valid) {
+                    bl = fold(eL[0], eL[1], eL[2], 8);
+                    br = fold(eR[0], eR[1], eR[2], 8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        bl = min(bl, fold(aL[0][k], aL[1][k], aL[2][k], k));
+                        br = min(br, fold(aR[0][k], aR[1][k], aR[2][k], k));
+                    }
+                } else {
+                    uint32_t yb[3];
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg) yb[gg] = ybad(gg, by * BS + half * (BS / 2), BS / 2);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const uint32_t xl = xbad(k, bx * BS, BS / 2), xr = xbad(k, bx * BS + BS / 2, BS / 2);
+#pragma unroll
+                        for (int gg = 0; gg < 3; ++gg) {
+                            const uint32_t l1v = lx8[k] + ly8[gg];
+                            const uint32_t sl = k < 8 ? aL[gg][k < 8 ? k : 0] : eL[gg], sr = k < 8 ? aR[gg][k < 8 ? k : 0] : eR[gg];
+                            bl = min(bl, (sl * 65536u + l1v) | xl | yb[gg]);
+                            br = min(br, (sr * 65536u + l1v) | xr | yb[gg]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg) par[gg][k] += aL[gg][k] + aR[gg][k];
+                if (half == 0) { bq[1] = bl; bq[2] = br; } else { bq[3] = bl; bq[4] = br; }
+            }
+            if (fast_valid) {
+                uint32_t bp = fold(exq[0][0], exq[0][1], exq[0][2], 8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bp = min(bp, fold(par[0][k], par[1][k], par[2][k], k));
+                bq[0] = bp;
+            } else {
+                uint32_t yb[3];
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) yb[gg] = ybad(gg, by * BS, BS);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const uint32_t xp = xbad(k, bx * BS, BS);
+#pragma unroll
+                    for (int gg = 0; gg < 3; ++gg) {
+                        const uint32_t sp = k < 8 ? par[gg][k < 8 ? k : 0] : exq[0][gg];
+                        bq[0] = min(bq[0], (sp * 65536u + (lx8[k] + ly8[gg])) | xp | yb[gg]);
+                    }
+                }
+            }
+            // ---- merge: five keys per segment
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                const uint32_t best = bq[e];
+                const int idx = (int)(best & 0xFFu), k = (idx * 11) >> 5, gg = idx - 3 * k;
+                const int dx = mul * (-16 + c + 4 * k) + px, dy = mul * (oy0 + gg) + py;
+                const uint32_t xy = ((uint32_t)(dx + g.R) << 8) | (uint32_t)(dy + g.R);
+                const uint32_t v1 = (has && best != 0xFFFFFFFFu) ? (best >> 8) : 0xFFFFFFFFu;
+                {
+                    const uint32_t m1 = __reduce_min_sync(seg, v1);
+                    const uint32_t m2 = __reduce_min_sync(seg, v1 == m1 ? xy : 0xFFFFFFFFu);
+                    if (leader && m1 != 0xFFFFFFFFu) {
+                        const int4 ms = mt;
+                        const unsigned long long key = ((unsigned long long)(m1 >> 8) << 40) | ((unsigned long long)(m1 & 0xFFu) << 24) |
+                                                       ((unsigned long long)(ms.w & 255) << 16) | (unsigned long long)m2;
+                        unsigned long long* okey;
+                        if (e == 0) okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + ms.x);
+                        else {
+                            const int kx = (e - 1) & 1, ky = (e - 1) >> 1, un = ms.w >> 17;
+                            okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out_sub) + un * a.out_sub_unit_stride +
+                                                                         (size_t)(ms.z * 2 + ky) * (g.nbx * 2) + ms.y * 2 + kx);
+                        }
+                        atomicMin(okey, key);
+                    }
+                }
+            }
+        } else {
+        // ---- main pass: 8 horizontal x 3 vertical offsets
+        uint32_t acc[3][8];
+#pragma unroll
+        for (int gg = 0; gg < 3; ++gg)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[gg][k] = 0;
+        {
+            uint32_t unused[3][8];
+            sad_pass_g3<WPR, 8, 8, BS, MR_WP, false>(win, cb, acc, unused);
+        }
+        // ---- 33rd horizontal offset (ox = +16: words 8..11 of the shift-0 copy): lane c of the four takes block rows 4c..4c+3
+        uint32_t ex[3] = {0u, 0u, 0u};
+        if (__any_sync(0xFFFFFFFFu, px == 0)) {
+            const unsigned char* w0 = wslot + (p + G * grp + 4 * c) * MR_WP + 32;
+            uint4 cr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cr[i] = reinterpret_cast<const uint4*>(cb)[4 * c + i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const uint4 w = *reinterpret_cast<const uint4*>(w0 + i * MR_WP);
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    const int r = i - gg;
+                    if (r >= 0 && r < 4) {
+                        ex[gg] = sad4_acc(w.x, cr[r].x, ex[gg]); ex[gg] = sad4_acc(w.y, cr[r].y, ex[gg]);
+                        ex[gg] = sad4_acc(w.z, cr[r].z, ex[gg]); ex[gg] = sad4_acc(w.w, cr[r].w, ex[gg]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) {
+                ex[gg] += __shfl_xor_sync(0xFFFFFFFFu, ex[gg], 1);
+                ex[gg] += __shfl_xor_sync(0xFFFFFFFFu, ex[gg], 2);
+            }
+        }
+
+        // ---- thread-local argmin.  key32 = sad << 16 | (|dx| + |dy|) << 8 | (k * 3 + g); invalid candidates are OR-ed to all ones.
+        uint32_t best = 0xFFFFFFFFu;
+        const bool fast_valid = __all_sync(0xFFFFFFFFu, (mt.w >> 16) & 1);
+        if (fast_valid) {
+            // interior block: the only invalid candidates are ox = 16 on odd horizontal phases and oy = 16 on odd vertical ones
+            const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;          // candidate k = 8
+            const uint32_t ybl = (grp == MR_NG - 1 && py) ? 0xFFFFFFFFu : 0u;     // candidate g = 2 of the last group
+            uint32_t ly8[3];
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
+            // min over the three vertical offsets first (their keys differ by SAD and ly8 only), then add the horizontal part:
+            // 3 IMAD (FMA pipe) + one 3-input min + one add per column instead of 3 adds + 3 mins on the ALU pipe
+            uint32_t kk[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative (c <= 3)
+                const uint32_t lx8 = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
+                const uint32_t t0 = (k < 8 ? acc[0][k < 8 ? k : 0] : ex[0]) * 65536u + ly8[0];
+                const uint32_t t1 = (k < 8 ? acc[1][k < 8 ? k : 0] : ex[1]) * 65536u + ly8[1];
+                const uint32_t t2 = ((k < 8 ? acc[2][k < 8 ? k : 0] : ex[2]) * 65536u + ly8[2]) | ybl;
+                kk[k] = min(min(t0, t1), t2) + lx8;
+            }
+            kk[8] |= xbl;
+            best = min(min(min(kk[0], kk[1]), min(kk[2], kk[3])), min(min(kk[4], kk[5]), min(kk[6], min(kk[7], kk[8]))));
+        } else {
+            int xlo, xhi, ylo, yhi;
+            valid_range(bx * BS, g.W, BS, g.fme, g.fme, xlo, xhi);
+            valid_range(by * BS, g.H, BS, g.fme, g.fme, ylo, yhi);
+            xlo = max(xlo, -g.R); xhi = min(xhi, g.R);
+            ylo = max(ylo, -g.R); yhi = min(yhi, g.R);
+            uint32_t ly8[3], ybad[3];
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) {
+                const int dy = mul * (oy0 + gg) + py;
+                ly8[gg] = (uint32_t)(abs(dy) << 8) + gg;
+                ybad[gg] = (dy >= ylo && dy <= yhi) ? 0u : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int dx = mul * (-16 + c + 4 * k) + px;
+                const uint32_t lx8 = (uint32_t)(abs(dx) << 8) + k * 3;
+                const uint32_t xbad = ((k < 8 || c == 0) && dx >= xlo && dx <= xhi) ? 0u : 0xFFFFFFFFu;
+#pragma unroll
+                for (int gg = 0; gg < 3; ++gg) {
+                    const uint32_t key = ((k < 8 ? acc[gg][k < 8 ? k : 0] : ex[gg]) * 65536u + (lx8 + ly8[gg])) | xbad | ybad[gg];
+                    best = min(best, key);
+                }
+            }
+        }
+        // ---- merge per item: order (SAD, |dx|+|dy|, ref, dx, dy); all lanes of a segment share ref, so two REDUX steps
+        //      ((SAD, L1), then (dx, dy) among the lanes that tie) give the winner of the segment
+        uint32_t xy;
+        {
+            const int idx = (int)(best & 0xFFu), k = (idx * 11) >> 5, gg = idx - 3 * k;
+            const int dx = mul * (-16 + c + 4 * k) + px, dy = mul * (oy0 + gg) + py;
+            xy = ((uint32_t)(dx + g.R) << 8) | (uint32_t)(dy + g.R);
+        }
+        const uint32_t v1 = (has && best != 0xFFFFFFFFu) ? (best >> 8) : 0xFFFFFFFFu;
+        {
+            const uint32_t m1 = __reduce_min_sync(seg, v1);
+            const uint32_t m2 = __reduce_min_sync(seg, v1 == m1 ? xy : 0xFFFFFFFFu);
+            if (leader && m1 != 0xFFFFFFFFu) {
+                const unsigned long long key = ((unsigned long long)(m1 >> 8) << 40) | ((unsigned long long)(m1 & 0xFFu) << 24) |
+                                               ((unsigned long long)(mt.w & 255) << 16) | (unsigned long long)m2;
+                atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + mt.x), key);
+            }
+        }
+        }   // !QUAD
+        __syncwarp();
+        if (leader) mbar_arrive_cnt(&empty[slot], (uint32_t)__popc(seg));        // the tasks of this item done by this bundle
+        b = __shfl_sync(0xFFFFFFFFu, nb, 0);
+    }
+    }   // search warps
+    // the last CTA to get here resets the device-wide counters for the next launch (every producer has stopped fetching)
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(a.work + 1, 1u);
+        if (prev == gridDim.x - 1) { a.work[0] = 0u; a.work[1] = 0u; }
+    }
+}

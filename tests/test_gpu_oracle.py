@@ -113,6 +113,43 @@ def test_full_size_direct_equals_expand_staging():
     assert outs[0] == outs[1]
 
 
+_RING_SCRIPT = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+from streamoptima_b200 import synth
+from streamoptima_b200.Encoder import Y_Video_codec
+Y_Video_codec.write_recon_yuv = False
+h = hashlib.sha256()
+for (F, H, W, kw) in ((6, 1088, 1920, dict(nRefFrames=4, FMEEnable=True)),
+                      (4, 1088, 1920, dict(nRefFrames=3, FMEEnable=True, VBSEnable=True, lam=0.02)),
+                      (3, 544, 976, dict(nRefFrames=1)),                                  # integer search, odd number of block columns
+                      (4, 272, 400, dict(nRefFrames=3, VBSEnable=True, lam=0.02)),
+                      (4, 160, 1936, dict(nRefFrames=2, FMEEnable=True))):
+    frames = synth.zooming(F, H, W, seed=21)
+    c = Y_Video_codec(H, W, F, 16, 16, 3, 30, 0, y_only_frame_arr=frames, **kw)
+    c.encode()
+    p = c.encoded_package.packed
+    for k in ("split", "mv", "levels", "recon"):
+        h.update(np.ascontiguousarray(p[k]).tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_ring_kernel_v2_equals_v1():
+    """The chunked item-ring search kernel (homogeneous chunks, only the valid vertical groups of edge rows, per-item merge with
+    match + REDUX) against the first item-ring kernel (SO_ME_RING_V1), which the strip goldens and the oracle tests pinned
+    in round 1: 1080p half-pel with 4 references, fused VBS search, integer search, widths whose pair count is not a
+    multiple of the chunk size."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for extra in ({}, {"SO_ME_RING_V1": "1"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", _RING_SCRIPT % root], capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
+
+
 def test_full_size_crop_matches_oracle_interior():
     """1080p P frame against the oracle on a crop: blocks whose whole search window lies inside the crop must get the
     same motion vector when the crop is encoded on its own with the same reference pixels (integer search, 1 ref)."""
