@@ -90,6 +90,13 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                 i_int = (l0 <= -g.R && h0 >= g.R && l1 <= -g.R && h1 >= g.R) ? 1 : 0;       // every offset of the range is valid
                 // vertical groups with a valid offset: dy = mul * oy + py in [max(l1, -R), min(h1, R)], group = (oy + 16) / 3
                 const int py = g.fme ? (i_ph >> 1) : 0;
+                if constexpr (QUAD) {           // the 8x8 sub-blocks searched in the same pass have wider valid ranges: union of all three
+                    int ls, hs;
+                    valid_range(i_by * BS, g.H, BS / 2, g.fme, g.fme, ls, hs);
+                    l1 = min(l1, ls); h1 = max(h1, hs);
+                    valid_range(i_by * BS + BS / 2, g.H, BS / 2, g.fme, g.fme, ls, hs);
+                    l1 = min(l1, ls); h1 = max(h1, hs);
+                }
                 const int dlo = max(l1, -g.R) - py, dhi = min(h1, g.R) - py;
                 const int olo = max(-16, dlo >= 0 ? (dlo + mul - 1) / mul : -((-dlo) / mul));     // ceil(dlo / mul)
                 const int ohi = min(16, dhi >= 0 ? dhi / mul : -((-dhi + mul - 1) / mul));       // floor(dhi / mul)
@@ -101,12 +108,10 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                 const int ng = ghi - glo + 1, tpi = 4 * ng, nb = (nit * tpi + 31) >> 5;
                 if (lane == 0) {
                     const int e = jchunk & (MR2_CE - 1);
+                    volatile int* cv = reinterpret_cast<volatile int*>(centry + e);
                     cseq[e] = -1;
-                    __threadfence_block();
-                    centry[e] = make_int4(bundle_base, ng | (glo << 8) | (nit << 16) | (nb << 24), n, 0);
-                    __threadfence_block();
+                    cv[0] = bundle_base; cv[1] = ng | (glo << 8) | (nit << 16) | (nb << 24); cv[2] = n;
                     cseq[e] = jchunk;
-                    __threadfence_block();
                     *chunks_pub = jchunk + 1;
                 }
                 __syncwarp();
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
             }
             q = __shfl_sync(0xFFFFFFFFu, qn, 0);
         }
-        if (lane == 0) { __threadfence_block(); *final_bundles = bundle_base; }      // no bundle with index >= bundle_base will ever exist
+        if (lane == 0) *final_bundles = bundle_base;      // no bundle with index >= bundle_base will ever exist
     } else {
     // ================================= search warps =================================
     unsigned b = 0;
@@ -155,11 +160,13 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
             bool none = false;
             while (true) {
                 if (jc < *chunks_pub) {
+                    // shared-memory accesses of a warp are performed in program order and the producer writes seq = -1, data,
+                    // seq = j in that order: reading seq, data, seq (volatile, no reordering by the compiler) is a seqlock
+                    // without fences (a membar here costs more than the whole rest of the bundle header)
                     const int e = jc & (MR2_CE - 1);
                     const int s1 = cseq[e];
-                    __threadfence_block();
-                    ce = centry[e];
-                    __threadfence_block();
+                    const volatile int* cv = reinterpret_cast<const volatile int*>(centry + e);
+                    ce = make_int4(cv[0], cv[1], cv[2], 0);
                     const int s2 = cseq[e];
                     if (s1 == jc && s2 == jc && b < (unsigned)ce.x + ((unsigned)ce.y >> 24)) break;
                     ++jc;                       // this chunk ends before bundle b (or its entry was recycled long ago)
