@@ -281,13 +281,9 @@ def c5_sharded(rank, world, local_rank, dist, reps=2):
         torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    dev_ms = tq_ms = 0.0
-    timed_frames = 0
     d2h = 0
     for _ in range(reps):
         out = c.encode_arrays(frames, **kw)
-        t = c.last_timing
-        dev_ms += t["device_ms"]; tq_ms += t["tq_ms"]; timed_frames += t["timed_frames"]
         d2h += out["sym_needed"] * 2 + out["split"].nbytes + out["mv"].nbytes + out["row_sizes"].nbytes + out["stats"].nbytes
         if world > 1:       # the statistics two-pass rate control consumes, all-gathered
             st = out["stats"]
@@ -297,7 +293,22 @@ def c5_sharded(rank, world, local_rank, dist, reps=2):
             dist.all_gather(parts, mine_t)
     barrier()
     wall = time.perf_counter() - t0
-    tm = torch.tensor([dev_ms, wall * 1e3, float(d2h), tq_ms], dtype=torch.float64, device=dev)
+    # kernels alone: the same batch resident in HBM (no copies inside the region), CUDA events of so_seq_run
+    from streamoptima_b200 import _native
+    ctx = c._ctx
+    _native.check(ctx.handle, ctx.lib.so_seq_upload(ctx.handle, frames.ctypes.data, len(mine), IP))
+    _native.check(ctx.handle, ctx.lib.so_seq_sync(ctx.handle))
+    _native.check(ctx.handle, ctx.lib.so_seq_run(ctx.handle))
+    ctx.last_timing()
+    barrier()
+    dev_ms = fin_ms = 0.0
+    fin_launches = 0
+    for _ in range(reps):
+        _native.check(ctx.handle, ctx.lib.so_seq_run(ctx.handle))
+        t = ctx.last_timing()
+        dev_ms += t["device_ms"]; fin_ms += t["finish_inter_ms"]; fin_launches += t["finish_inter_launches"]
+    barrier()
+    tm = torch.tensor([dev_ms, wall * 1e3, float(d2h), fin_ms], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tm.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -311,19 +322,24 @@ def c5_sharded(rank, world, local_rank, dist, reps=2):
     total = S * F * reps
     e2e_s = float(mx[1]) / 1e3
     hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    # the finish kernels of rank 0 on the frames that carry per-kernel events: 5*H*W algorithmic bytes per frame and unit
-    fin_gbs = 5.0 * H * W * len(mine) * timed_frames / (tq_ms / 1e3) / 1e9 if tq_ms > 0 else None
+    # rank 0's inter finish kernel (transform / quantisation / RLE size / reconstruction), one launch = one P frame of all its units:
+    # 5*H*W algorithmic bytes per frame and unit (cur 1 + predictor 1 + levels 2 + recon 1)
+    fin_gbs = 5.0 * H * W * len(mine) * fin_launches / (fin_ms / 1e3) / 1e9 if fin_ms > 0 else None
     return {"workload": f"C5: {S} x 4K (3840x2160) streams x {F} frames, I_Period {IP}, i=16 r=16 integer search, nRef=1, QP {C5['qp']}: "
                         f"{len(units)} closed GOPs dealt round-robin to {world} rank(s), one batched call per rank",
             "scaling": "strong", "n_gpus": world, "units": len(units), "reps": reps,
             "device_frames_per_s": total / (float(mx[0]) / 1e3), "e2e_frames_per_s": total / e2e_s,
+            "device_note": "kernels alone: the rank's GOPs resident in HBM, CUDA events around so_seq_run, max over ranks",
             "h2d_GBps_aggregate": total * H * W / e2e_s / 1e9, "d2h_GBps_aggregate": float(sm[2]) / e2e_s / 1e9,
             "d2h_bytes_per_frame": float(sm[2]) / total, "h2d_bytes_per_frame": H * W,
-            "limiter": "e2e is bounded by the host->device copy of the raw frames (8.3 MB per 4K frame over this rank's PCIe link; "
-                       "h2d_GBps_aggregate / n_gpus is the per-link rate reached) -- the device-side number is what the kernels sustain",
-            "roofline_transform_batched": {"bound": "hbm", "kernel": "inter_finish16_kernel<false> / intra_finish_kernel<16>, %d units per launch" % len(mine),
+            "limiter": "e2e is bounded by the host->device copy of the raw frames: 8.3 MB in per 4K frame against %.1f MB out; h2d_GBps_aggregate / "
+                       "n_gpus is the rate every rank's copies reach while all ranks share the host's memory system (one rank alone: ~21 GB/s)"
+                       % (float(sm[2]) / total / 1e6),
+            "roofline_transform_batched": {"bound": "hbm by bytes; instruction-bound in practice (FP64 replay of SciPy's DCT: ~1100 warp instructions per block, "
+                                                    "DRAM traffic = algorithmic bytes, profiles/r02_inter_finish16_batched_ncu_summary.txt)",
+                                           "kernel": "inter_finish16_kernel<false>, %d units (4K frames) per launch" % len(mine),
                                            "achieved": fin_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fin_gbs / hbm_peak if fin_gbs else None,
-                                           "algorithmic_bytes_per_frame": 5 * H * W}}
+                                           "algorithmic_bytes_per_frame": 5 * H * W, "launches_timed": fin_launches}}
 
 
 def main():
@@ -432,11 +448,12 @@ def main():
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
-    dev_ms = me_ms = tq_ms = xs_ms = 0.0
-    launches = me_launches = xs_launches = timed_frames = 0
+    dev_ms = me_ms = tq_ms = xs_ms = fin_ms = 0.0
+    launches = me_launches = xs_launches = timed_frames = fin_launches = 0
     for k in range(args.steps):
         t = step_resident(k)
         dev_ms += t["device_ms"]; me_ms += t["me_ms"]; tq_ms += t["tq_ms"]; xs_ms += t["search_ms"]
+        fin_ms += t["finish_inter_ms"]; fin_launches += t["finish_inter_launches"]
         launches += t["launches"]; me_launches += t["me_launches"]; xs_launches += t["search_launches"]
         timed_frames += t["timed_frames"]
     barrier()
@@ -515,10 +532,11 @@ def main():
                              "avg_launch_ms": avg_launch_ms, "launches_timed": xs_launches,
                              "me_share_of_step": avg_launch_ms * me_l * args.steps / dev_ms,
                              "traffic": traffic, "traffic_detail": traffic_detail},
-                "roofline_transform": {"bound": "hbm", "achieved": 5.0 * H * W * timed_frames / (tq_ms / 1e3) / 1e9,
+                "roofline_transform": {"bound": "hbm", "kernel": "inter_finish16_kernel<false>", "achieved": 5.0 * H * W * fin_launches / (fin_ms / 1e3) / 1e9,
                                        "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                                        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
-                                       "unit": "GB/s", "note": "5*H*W algorithmic bytes per frame (SURVEY 8d) over the transform/quant/recon kernels of the frames that carry per-kernel events; ONE 1080p frame per launch is latency-bound -- c5_sharded.roofline_transform_batched is the same kernel on a batched launch"},
+                                       "unit": "GB/s", "launches_timed": fin_launches,
+                                       "note": "5*H*W algorithmic bytes per P frame (SURVEY 8d) over the CUDA-event time of the finish kernel's timed launches; ONE 1080p frame per launch (1020 CTAs) -- c5_sharded.roofline_transform_batched is the same kernel on a batched launch"},
                 "e2e": {"value": total_frames / (e2e_ms_max / 1e3), "unit": "frames/s", "h2d_bytes_per_step": F * H * W,
                         "d2h_bytes_per_step": d2h / args.steps, "wall_ms_per_step": e2e_ms_max / args.steps,
                         "device_ms_per_step_rank0": e2e_dev_ms / args.steps,

@@ -237,6 +237,10 @@ int so_last_me_launches(so_ctx* ctx);    /* number of launches covered by timing
  * its timed launches (ms), out[1] = number of timed launches, out[2] = frames with per-kernel events, out[3] = frames of
  * the run.  out[0] / out[1] is the per-launch duration bench.py's roofline uses. */
 int so_last_search_timing(so_ctx* ctx, double out[4]);
+/* The inter finish kernel (transform / quantisation / RLE size / reconstruction of P frames, Encoder.py:779-827, :1086) alone:
+ * out[0] = summed event time of its timed launches (ms), out[1] = timed launches (all units of a frame are one launch),
+ * out[2] = the sum over all transform kernels incl. intra frames (= so_last_timing [2]), out[3] = frames with events. */
+int so_last_finish_timing(so_ctx* ctx, double out[4]);
 
 /* Host-side text formatters, byte-identical to the reference's (Encoder.py:1419-1542 with canonical integers).
  * Return the number of bytes written (excluding the terminating NUL), or the required size (negative) when cap

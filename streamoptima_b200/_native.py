@@ -52,7 +52,7 @@ EXPORTS = ["so_abi_version", "so_last_error", "so_device_count", "so_ctx_create"
            "so_format_residual_frame_symbols", "so_write_bitstream_files", "so_parse_bitstream_files",
            "so_set_symbol_output", "so_fetch_symbols", "so_format_residual_frame_packed", "so_symbols_to_levels",
            "so_write_bitstream_files_symbols",
-           "so_last_timing", "so_last_me_launches", "so_last_search_timing",
+           "so_last_timing", "so_last_me_launches", "so_last_search_timing", "so_last_finish_timing",
            "so_format_mv_frame", "so_format_residual_frame"]
 
 _lib = None
@@ -106,6 +106,7 @@ def load():
     lib.so_write_bitstream_files_symbols.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_char_p, C.c_char_p, i32]
     lib.so_parse_bitstream_files.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32]
     lib.so_last_search_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.so_last_finish_timing.argtypes = [vp, C.POINTER(C.c_double)]
     lib.so_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
     lib.so_last_me_launches.argtypes = [vp]
     lib.so_format_mv_frame.restype = i64
@@ -178,6 +179,8 @@ class Context:
         xs = (C.c_double * 4)()
         check(self.handle, self.lib.so_last_search_timing(self.handle, xs))
         # me_ms / tq_ms / search_ms are sums over the frames that carry per-kernel events (timed_frames of frames)
-        return dict(device_ms=out[0], me_ms=out[1], tq_ms=out[2], launches=int(out[3]),
+        fi = (C.c_double * 4)()
+        check(self.handle, self.lib.so_last_finish_timing(self.handle, fi))
+        return dict(device_ms=out[0], me_ms=out[1], tq_ms=out[2], launches=int(out[3]), finish_inter_ms=fi[0], finish_inter_launches=int(fi[1]),
                     me_launches=int(self.lib.so_last_me_launches(self.handle)), search_ms=xs[0], search_launches=int(xs[1]),
                     timed_frames=int(xs[2]), frames=int(xs[3]))

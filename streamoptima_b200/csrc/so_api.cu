@@ -100,7 +100,7 @@ struct so_ctx {
     so_symbol_out* sym_out = nullptr;       // armed by so_set_symbol_output: sequence encodes deliver packed symbols
     uint64_t sym_used = 0;                  // symbols handed out so far in the running sequence encode
     bool sym_overflow = false;
-    double timing[7] = {0, 0, 0, 0, 0, 0, 0};
+    double timing[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     bool timing_pending = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sq_units = 0, sq_nframes = 0;
@@ -127,6 +127,7 @@ struct so_ctx {
     size_t ev_used = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_me, ev_tq;
     std::vector<size_t> ev_xs;              // indices into ev_me of the exhaustive-search kernel launches
+    std::vector<size_t> ev_tq_inter;        // indices into ev_tq of the inter finish kernel launches (the rest are intra frames)
     bool timing_on = false;
     int timed_frames = 0, total_frames = 0;    // frames of the last so_seq_run with / without per-kernel events
     const int* cur_qp_blocks = nullptr;     // per-block QPs of the frame being encoded (ROI extension)
@@ -923,6 +924,7 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
         }
     }
     ev_pair(ctx, ctx->ev_tq, st, true);
+    if (ctx->timing_on) ctx->ev_tq_inter.push_back(ctx->ev_tq.size() - 1);
     dim3 grid(ctx->nblk, units);
     static const bool generic16 = std::getenv("SO_FINISH_GENERIC") != nullptr;      // tests: force the generic kernel
     if (g.bs == 16 && g.W % 16 == 0 && !generic16) {
@@ -1081,7 +1083,7 @@ extern "C" int so_seq_run(so_ctx* ctx) {
     const size_t px = ctx->frame_px;
     const int nby = ctx->g.nby;
     ctx->launches = 0;
-    ctx->ev_used = 0; ctx->ev_me.clear(); ctx->ev_tq.clear(); ctx->ev_xs.clear();
+    ctx->ev_used = 0; ctx->ev_me.clear(); ctx->ev_tq.clear(); ctx->ev_xs.clear(); ctx->ev_tq_inter.clear();
     ctx->timing_on = true;
     while (ctx->ev_pool.size() < 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev_pool.push_back(e); }
     ctx->ev0 = ctx->ev_pool[ctx->ev_used++]; ctx->ev1 = ctx->ev_pool[ctx->ev_used++];
@@ -1519,6 +1521,9 @@ extern "C" int so_last_timing(so_ctx* ctx, double out[4]) {
         double xs = 0;
         for (size_t i : ctx->ev_xs) { float t = 0; cudaEventElapsedTime(&t, ctx->ev_me[i].first, ctx->ev_me[i].second); xs += t; }
         ctx->timing[5] = xs; ctx->timing[6] = (double)ctx->ev_xs.size();
+        double fi = 0;
+        for (size_t i : ctx->ev_tq_inter) { float t = 0; cudaEventElapsedTime(&t, ctx->ev_tq[i].first, ctx->ev_tq[i].second); fi += t; }
+        ctx->timing[7] = fi; ctx->timing[8] = (double)ctx->ev_tq_inter.size();
         ctx->timing_pending = false;
     }
     for (int i = 0; i < 4; ++i) out[i] = ctx->timing[i];
@@ -1531,6 +1536,18 @@ extern "C" int so_last_me_launches(so_ctx* ctx) {
     if (!ctx) return SO_E_INVALID;
     int rc = so_last_timing(ctx, t);
     return rc ? rc : (int)ctx->timing[4];
+}
+
+// the inter finish kernel (transform / quantisation / RLE size / reconstruction of P frames) alone in the last so_seq_run:
+// out[0] = summed CUDA-event time (ms) of its timed launches, out[1] = timed launches (one per timed P frame, all units in
+// one launch), out[2] = the same sum over all transform kernels incl. intra frames, out[3] = timed frames
+extern "C" int so_last_finish_timing(so_ctx* ctx, double out[4]) {
+    double t[4];
+    if (!ctx || !out) return SO_E_INVALID;
+    int rc = so_last_timing(ctx, t);
+    if (rc) return rc;
+    out[0] = ctx->timing[7]; out[1] = ctx->timing[8]; out[2] = ctx->timing[2]; out[3] = (double)ctx->timed_frames;
+    return SO_OK;
 }
 
 // exhaustive-search kernels alone (me_ring_kernel / me_tma_kernel): out[0] = summed CUDA-event time (ms) of the timed

@@ -111,13 +111,14 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                     volatile int* cv = reinterpret_cast<volatile int*>(centry + e);
                     cseq[e] = -1;
                     cv[0] = bundle_base; cv[1] = ng | (glo << 8) | (nit << 16) | (nb << 24); cv[2] = n;
+                    cv[3] = (1024 + ng - 1) / ng;          // exact division by ng of any (item, group) index of a chunk: (x * m) >> 10, x < 96
                     cseq[e] = jchunk;
                     *chunks_pub = jchunk + 1;
                 }
                 __syncwarp();
                 for (int k = 0; k < nit; ++k) {
                     if (!first_round) {
-                        while (!mbar_try(&empty[slot], par)) __nanosleep(40);
+                        while (!mbar_try(&empty[slot], par)) __nanosleep(200);      // 22 items ahead: a slot frees up every ~0.6 us
                     }
                     const int blk = __shfl_sync(0xFFFFFFFFu, i_blk, k), ref = __shfl_sync(0xFFFFFFFFu, i_ref, k);
                     const int phz = __shfl_sync(0xFFFFFFFFu, i_ph, k), bx = __shfl_sync(0xFFFFFFFFu, i_bx, k), by = __shfl_sync(0xFFFFFFFFu, i_by, k);
@@ -152,8 +153,11 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
     if (lane == 0) b = atomicAdd(counter, 1u);
     b = __shfl_sync(0xFFFFFFFFu, b, 0);
     int jc = 0;                                 // chunk cursor of this warp: bundles are fetched in increasing order
+    unsigned last_base = 0;                     // first bundle of the chunk the cursor points at
     while (true) {
         // ---- the chunk that holds bundle b (seqlock read of its entry; wait for the producer if it is not published yet)
+        // a chunk holds at most 11 bundles, so the chunk of bundle b is at least (b - first bundle of the last chunk) / 11 entries ahead
+        jc += (int)(__umulhi(b - last_base, 0xBA2E8BA3u) >> 3);
         int4 ce;
         {
             SpinWait sw;
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                     const int e = jc & (MR2_CE - 1);
                     const int s1 = cseq[e];
                     const volatile int* cv = reinterpret_cast<const volatile int*>(centry + e);
-                    ce = make_int4(cv[0], cv[1], cv[2], 0);
+                    ce = make_int4(cv[0], cv[1], cv[2], cv[3]);
                     const int s2 = cseq[e];
                     if (s1 == jc && s2 == jc && b < (unsigned)ce.x + ((unsigned)ce.y >> 24)) break;
                     ++jc;                       // this chunk ends before bundle b (or its entry was recycled long ago)
@@ -177,10 +181,11 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
             }
             if (none) break;
         }
+        last_base = (unsigned)ce.x;
         const int ng = ce.y & 255, g_lo = (ce.y >> 8) & 255, nit = (ce.y >> 16) & 255;
         const unsigned lb = b - (unsigned)ce.x;
         const unsigned tq = (32u * lb + lane) >> 2;                             // (item, group) pair of this lane inside the chunk
-        const unsigned mg = (1024u + ng - 1) / (unsigned)ng;                     // exact division by ng for tq < 96 (ng <= 11)
+        const unsigned mg = (unsigned)ce.w;                                     // exact division by ng for tq < 96 (ng <= 11)
         unsigned ki = (tq * mg) >> 10;
         const unsigned gl = tq - ki * ng;
         const bool has = ki < (unsigned)nit;                                    // lanes past the chunk's last task shadow its last item
