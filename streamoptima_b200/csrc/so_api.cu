@@ -1192,6 +1192,17 @@ extern "C" int so_seq_sync(so_ctx* ctx) {
     return SO_OK;
 }
 
+// Frames per pipeline chunk (the unit of upload, symbol packing and download): 8, fewer when many units are batched so that a
+// chunk stays around 256 MB of input -- the first chunk's upload is the only copy the encode cannot hide, and with 64 4K
+// units an 8-frame chunk would be 4 GB of it.  SO_PIPE_CHUNK=n overrides (tests, A/B).
+static int pipe_chunk_frames(so_ctx* ctx, int n_units) {
+    static const int forced = std::getenv("SO_PIPE_CHUNK") ? atoi(std::getenv("SO_PIPE_CHUNK")) : 0;
+    if (forced > 0) return forced;
+    const size_t per_frame = (size_t)n_units * ctx->frame_px;
+    size_t c = ((size_t)256 << 20) / std::max<size_t>(per_frame, 1);
+    return (int)std::min<size_t>(8, std::max<size_t>(1, c));
+}
+
 // The chunked pipeline shared by so_encode_sequence and so_encode_yuv420_file (pipe.* and sq_units / sq_nframes are set):
 // uploads two chunks ahead, the frame loop, downloads one chunk behind; with so_set_symbol_output the packed run-level
 // symbols are produced per chunk on the device and copied out with their exact sizes.
@@ -1240,7 +1251,7 @@ extern "C" int so_encode_sequence(so_ctx* ctx, const uint8_t* frames, int n_unit
     if (rc) return rc;
     ctx->sq_units = n_units; ctx->sq_nframes = n_frames;
     auto& P = ctx->pipe;
-    P.chunk = 8;
+    P.chunk = pipe_chunk_frames(ctx, n_units);
     P.nchunks = (n_frames + P.chunk - 1) / P.chunk;
     P.h_frames = frames; P.h_split = split; P.h_mv = mv; P.h_levels = levels; P.h_recon = recon; P.h_rows = row_sizes; P.h_stats = stats;
     return pipe_run(ctx);

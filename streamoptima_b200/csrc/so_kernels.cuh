@@ -928,32 +928,60 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
         s_cur[threadIdx.x] = *reinterpret_cast<const uint32_t*>(a.cur + unit * a.cur_unit_stride + (size_t)(y + threadIdx.x / WPR) * g.W + x + (threadIdx.x % WPR) * 4);
     __syncthreads();
     uint16_t* s_sad = reinterpret_cast<uint16_t*>(s_cur + BS * WPR);         // [nref][FT_N][FT_N]
-    for (int e = threadIdx.x; e < nref * FT_N * FT_N; e += blockDim.x) {
-        // horizontal offset fastest: the lanes of a warp then read the SAME few region rows (shared-memory broadcast, and the
-        // two or three rows a warp spans sit in disjoint banks); vertical-fastest made every row load a 3-way bank conflict
-        const int ref = e / (FT_N * FT_N), rem = e - ref * (FT_N * FT_N);
-        const int iy = rem / FT_N, ix = rem - iy * FT_N;
-        // invalid offsets (Encoder.py:728-730: 0 <= p and p + 2*bs < size - bs on both axes) get 0xFFFF (> any SAD)
-        const int dx = dx0 + ix, dy = dy0 + iy;
-        const int px = x * mult + dx, py = y * mult + dy;
-        uint32_t sad = 0xFFFFu;
-        if (px >= 0 && px <= Wr - 3 * BS - 1 && py >= 0 && py <= Hr - 3 * BS - 1) {
-            const int ph = g.fme ? (((py & 1) << 1) | (px & 1)) : 0;
-            const int co = (g.fme ? (px >> 1) : px) - XA, ro = (g.fme ? (py >> 1) : py) - Y0;     // half-pel: co <= 8, ro <= 5; integer: co <= 13, ro <= 10
-            const unsigned char* rg = ft_smem + ((size_t)(ref * nph + ph) * FTR_H + ro) * FTR_W + (co & ~3);
+    // Work item = (reference, horizontal offset, vertical set): the up-to-six vertical offsets of a set lie in ONE phase plane
+    // one row apart (half-pel: the even / the odd offsets; integer: the first six / the last five), so a thread walks the
+    // region rows once -- five aligned words per row, shifted into place -- and feeds every row to all the offsets it belongs
+    // to, with the current block held in registers: 1/7 of the shared-memory loads of one-candidate-per-thread.  The
+    // horizontal offset is the fastest index: the lanes of a warp read the same few rows (broadcast, disjoint banks).
+    {
+        uint32_t cw[BS][WPR];
+#pragma unroll
+        for (int r = 0; r < BS; ++r)
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) cw[r][w] = s_cur[r * WPR + w];
+        constexpr int VT = 6;
+        for (int it = threadIdx.x; it < nref * FT_N * 2; it += blockDim.x) {
+            const int ref = it / (FT_N * 2), rem = it - ref * (FT_N * 2);
+            const int vs = rem / FT_N, ix = rem - vs * FT_N;
+            const int iy0 = g.fme ? vs : vs * VT, stepi = g.fme ? 2 : 1, n = vs ? FT_N - VT : VT;
+            const int dx = dx0 + ix, px = x * mult + dx;
+            const int py0 = y * mult + dy0 + iy0;
+            const bool xok = px >= 0 && px <= Wr - 3 * BS - 1;       // Encoder.py:728-730 on the x axis
+            const int ph = g.fme ? (((py0 & 1) << 1) | (px & 1)) : 0;
+            const int co = (g.fme ? (px >> 1) : px) - XA, ro0 = (g.fme ? (py0 >> 1) : py0) - Y0;
+            const unsigned char* rg = ft_smem + ((size_t)(ref * nph + ph) * FTR_H + ro0) * FTR_W + (co & ~3);
             const int sh = (co & 3) * 8;
-            sad = 0;
-#pragma unroll 4
-            for (int row = 0; row < BS; ++row) {
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(rg + row * FTR_W);
-                uint32_t q[WPR + 1];
+            uint32_t acc[VT];
 #pragma unroll
-                for (int w = 0; w <= WPR; ++w) q[w] = rw[w];
+            for (int t = 0; t < VT; ++t) acc[t] = 0u;
 #pragma unroll
-                for (int w = 0; w < WPR; ++w) sad = sad4_acc(s_cur[row * WPR + w], __funnelshift_r(q[w], q[w + 1], sh), sad);
+            for (int r = 0; r < BS + VT - 1; ++r) {
+                if (r < BS + n - 1) {
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(rg + r * FTR_W);
+                    uint32_t q[WPR + 1], wv[WPR];
+#pragma unroll
+                    for (int w = 0; w <= WPR; ++w) q[w] = rw[w];
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) wv[w] = __funnelshift_r(q[w], q[w + 1], sh);
+#pragma unroll
+                    for (int t = 0; t < VT; ++t) {
+                        const int cr = r - t;                       // current-block row this region row meets at vertical offset t
+                        if (cr >= 0 && cr < BS && t < n) {
+#pragma unroll
+                            for (int w = 0; w < WPR; ++w) acc[t] = sad4_acc(cw[cr][w], wv[w], acc[t]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < VT; ++t) {
+                if (t < n) {
+                    const int py = py0 + t * stepi;
+                    const bool ok = xok && py >= 0 && py <= Hr - 3 * BS - 1;       // invalid offsets get 0xFFFF (> any SAD)
+                    s_sad[ref * (FT_N * FT_N) + ix * FT_N + iy0 + t * stepi] = ok ? (uint16_t)acc[t] : (uint16_t)0xFFFFu;
+                }
             }
         }
-        s_sad[ref * (FT_N * FT_N) + ix * FT_N + iy] = (uint16_t)sad;
     }
     __syncthreads();
     // transition table: for every predictor within K of the centre, the winner of fast_motion_estimation's scan (ref, dx,
