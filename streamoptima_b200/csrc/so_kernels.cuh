@@ -909,20 +909,34 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
     const int X0 = g.fme ? ((x * 2 + dx0) >> 1) : x + dx0, Y0 = g.fme ? ((y * 2 + dy0) >> 1) : y + dy0;
     const int XA = X0 & ~3;
     uint32_t* s_cur = reinterpret_cast<uint32_t*>(ft_smem + (size_t)nref * nph * FTR_H * FTR_W);
-    for (int e = threadIdx.x; e < nref * nph * FTR_H * (FTR_W / 4); e += blockDim.x) {
-        const int w = e % (FTR_W / 4), row = (e / (FTR_W / 4)) % FTR_H, rp = e / ((FTR_W / 4) * FTR_H);
-        const int ref = rp / nph, ph = rp % nph;
-        const int X = XA + 4 * w, Y = Y0 + row;
-        uint32_t v = 0u;
-        if (Y >= 0 && Y < g.H) {
-            const uint8_t* pl = a.ring.plane(unit, ref, ph) + (size_t)Y * g.pitch;
-            if (X >= 0 && X + 3 < g.W) v = __ldg(reinterpret_cast<const uint32_t*>(pl + X));
-            else {
+    {   // staging.  Thread = (word of the row, row): no divisions in the loop, and the two loads a thread makes per plane
+        // (rows r and r + 16) are independent -- the kernel is bound by the latency of these L2 reads, not by their volume
+        const int w = threadIdx.x & 7, r0 = threadIdx.x >> 3;                 // 128 threads: 8 words x 16 rows
+        const int X = XA + 4 * w;
+        const bool xin = X >= 0 && X + 3 < g.W;
+        for (int ref = 0; ref < nref; ++ref) {
+#pragma unroll 4
+            for (int ph = 0; ph < nph; ++ph) {
+                const uint8_t* plane = a.ring.plane(unit, ref, ph);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(ft_smem) + (size_t)(ref * nph + ph) * FTR_H * (FTR_W / 4);
 #pragma unroll
-                for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < g.W) v |= (uint32_t)pl[X + b] << (8 * b);
+                for (int k = 0; k < 2; ++k) {
+                    const int row = r0 + 16 * k, Y = Y0 + row;
+                    if (row < FTR_H) {
+                        uint32_t v = 0u;
+                        if (Y >= 0 && Y < g.H) {
+                            const uint8_t* pl = plane + (size_t)Y * g.pitch;
+                            if (xin) v = __ldg(reinterpret_cast<const uint32_t*>(pl + X));
+                            else {
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) if (X + b >= 0 && X + b < g.W) v |= (uint32_t)pl[X + b] << (8 * b);
+                            }
+                        }
+                        dst[row * (FTR_W / 4) + w] = v;
+                    }
+                }
             }
         }
-        reinterpret_cast<uint32_t*>(ft_smem)[e] = v;
     }
     if (threadIdx.x < BS * WPR)
         s_cur[threadIdx.x] = *reinterpret_cast<const uint32_t*>(a.cur + unit * a.cur_unit_stride + (size_t)(y + threadIdx.x / WPR) * g.W + x + (threadIdx.x % WPR) * 4);
@@ -934,11 +948,6 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
     // to, with the current block held in registers: 1/7 of the shared-memory loads of one-candidate-per-thread.  The
     // horizontal offset is the fastest index: the lanes of a warp read the same few rows (broadcast, disjoint banks).
     {
-        uint32_t cw[BS][WPR];
-#pragma unroll
-        for (int r = 0; r < BS; ++r)
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) cw[r][w] = s_cur[r * WPR + w];
         constexpr int VT = 6;
         for (int it = threadIdx.x; it < nref * FT_N * 2; it += blockDim.x) {
             const int ref = it / (FT_N * 2), rem = it - ref * (FT_N * 2);
@@ -954,8 +963,13 @@ __global__ void __launch_bounds__(128) fast_table16_kernel(const FlowArgs a, uin
             uint32_t acc[VT];
 #pragma unroll
             for (int t = 0; t < VT; ++t) acc[t] = 0u;
+            uint32_t cw[BS][WPR];                   // current rows are loaded when first needed: at most VT of them are live
 #pragma unroll
             for (int r = 0; r < BS + VT - 1; ++r) {
+                if (r < BS) {
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) cw[r][w] = s_cur[r * WPR + w];
+                }
                 if (r < BS + n - 1) {
                     const uint32_t* rw = reinterpret_cast<const uint32_t*>(rg + r * FTR_W);
                     uint32_t q[WPR + 1], wv[WPR];
@@ -1167,7 +1181,14 @@ __global__ void __launch_bounds__(576) fast_scan_walk_kernel(const FlowArgs a, c
     int* cen = reinterpret_cast<int*>(sF + (size_t)nchunks * FS_ROW);
     {
         const int4* src = reinterpret_cast<const int4*>(F + unit * F_unit_stride);          // FS_ROW is even: whole int4s
-        for (int e = threadIdx.x; e < nchunks * FS_ROW / 2; e += blockDim.x) reinterpret_cast<int4*>(sF)[e] = src[e];
+        const int n4 = nchunks * FS_ROW / 2;
+        for (int e0 = threadIdx.x; e0 < n4; e0 += blockDim.x * 4) {                         // four loads in flight per thread
+            int4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = e0 + u * blockDim.x; if (e < n4) v[u] = __ldg(src + e); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int e = e0 + u * blockDim.x; if (e < n4) reinterpret_cast<int4*>(sF)[e] = v[u]; }
+        }
     }
     __syncthreads();
     const uint8_t* tr_u = trans + unit * trans_unit_stride;
@@ -1177,10 +1198,12 @@ __global__ void __launch_bounds__(576) fast_scan_walk_kernel(const FlowArgs a, c
     int px = 0, py = 0, ref = 0, c = 0;
     while (true) {
         if (threadIdx.x < 32) {
-            // warp 0 walks the chunks: one lookup in the chunk's composed table per step
+            // warp 0 walks the chunks: one dependent lookup in the chunk's composed table per step (the centre of the next
+            // chunk does not depend on the walk and is fetched alongside)
+            int c0 = c < nchunks ? sF[(size_t)c * FS_ROW + FS_STATES].x : 0;
             while (c < nchunks) {
                 const int2* row = sF + (size_t)c * FS_ROW;
-                const int c0 = row[FS_STATES].x;
+                const int c0n = c + 1 < nchunks ? row[FS_ROW + FS_STATES].x : 0;
                 const int sx = px - fs_x(c0) + FT_K, sy = py - fs_y(c0) + FT_K;
                 if (!((unsigned)sx < (unsigned)FT_S && (unsigned)sy < (unsigned)FT_S)) break;
                 const int2 f = row[sx * FT_S + sy];
@@ -1189,6 +1212,7 @@ __global__ void __launch_bounds__(576) fast_scan_walk_kernel(const FlowArgs a, c
                 px = fs_x(f.x); py = fs_y(f.x);
                 if ((f.y & 0xFF) != 0xFF) ref = f.y & 0xFF;
                 ++c;
+                c0 = c0n;
             }
             if (threadIdx.x == 0) { s_req[0] = c; s_req[1] = px; s_req[2] = py; s_req[3] = ref; }
         }
