@@ -564,7 +564,10 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
         const long long nchunks = (long long)units * a2.chunks_per_unit;
         const int grid = nchunks < sms ? (int)nchunks : sms;
         if (out_sub) e = launch_pdl(me_ring2_kernel<true>, dim3(grid), dim3(384), MR2_SMEM, st, map, cmap, a2);
-        else e = launch_pdl(me_ring2_kernel<false>, dim3(grid), dim3(512), MR2_SMEM, st, map, cmap, a2);
+        else {
+            static const int nthr = std::getenv("SO_ME_RING_THREADS") ? atoi(std::getenv("SO_ME_RING_THREADS")) : 512;      // experiments: fewer search warps
+            e = launch_pdl(me_ring2_kernel<false>, dim3(grid), dim3(nthr), MR2_SMEM, st, map, cmap, a2);
+        }
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     ev_pair(ctx, ctx->ev_me, st, false);
