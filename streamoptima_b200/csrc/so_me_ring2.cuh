@@ -5,17 +5,20 @@
 //     of ONE horizontal parity.  A chunk of interior blocks is 8 x 44 tasks = exactly 11 bundles, so no bundle mixes even and
 //     odd horizontal phases any more: the 33rd-offset pass (dx = +32, even phases only) runs exactly where it is needed;
 //   * a chunk only carries the vertical groups that hold a valid offset for at least one of its items (edge block rows:
-//     Encoder.py:695-698): tasks per item = 4 x groups, tasks ordered [item][group][shift] as before.  The producer records
-//     every chunk in a small ring of chunk entries {first bundle, groups, first group, items}; a search warp finds the chunk
-//     of its bundle with a cursor that only moves forward;
+//     Encoder.py:695-698): tasks per item = 4 x groups, tasks ordered [item][group][shift] as before.  The producer writes,
+//     for every bundle, one DESCRIPTOR WORD per lane quad {slot, phase parity of the slot's use, group, valid} into a ring
+//     indexed by the bundle number and publishes the bundle count once the chunk's loads are issued: a search warp's
+//     header is one shared-memory load -- no cursor, no division, no "issued" check;
+//   * the producer issues the (up to) eight items of a chunk lane-parallel: lane k waits for its own slot, writes the item
+//     meta and launches both TMA boxes;
 //   * a bundle may now cover several items (edge chunks have few tasks per item): the per-item merge uses
 //     __match_any_sync + REDUX over the lanes of an item, and each item's lanes arrive on its `empty` barrier together
 //     (the producer pre-arrives for the groups a chunk does not carry, so the barrier count stays 44).
 #pragma once
 #include "so_me_ring.cuh"
 
-constexpr int MR2_CE = 32;                      // chunk entries in flight (ring)
-constexpr int MR2_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 2048;      // + barriers, item meta, chunk entries, counters
+constexpr int MR2_BD = 64;                      // bundles whose descriptors are kept (ring; at most 55 are live, see the producer)
+constexpr int MR2_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 3072;      // + barriers, item meta, bundle descriptors, counters
 
 struct MeRing2Args {
     MeRingArgs b;                // geometry, outputs, units, nph, z_*, slot_packed, work counters (items_per_unit unused)
@@ -34,12 +37,10 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
     uint64_t* const ready = reinterpret_cast<uint64_t*>(curs + MR_NS * MR_CUR);
     uint64_t* const empty = ready + MR_NS;
     int4* const meta = reinterpret_cast<int4*>(empty + MR_NS);                  // [NS]: {out index, bx, by, ref | ph << 8 | interior << 16}
-    int4* const centry = meta + MR_NS;                                          // [MR2_CE]: {first bundle, ng | g_lo << 8 | nit << 16 | bundles << 24, first item, 0}
-    volatile int* const cseq = reinterpret_cast<volatile int*>(centry + MR2_CE); // [MR2_CE]: chunk sequence number the entry holds (seqlock; -1 while written)
-    unsigned int* const counter = reinterpret_cast<unsigned int*>(const_cast<int*>(cseq) + MR2_CE);
-    volatile int* const issued = reinterpret_cast<volatile int*>(counter + 1);  // items whose loads have been issued
-    volatile int* const chunks_pub = issued + 1;                                // chunk entries published
-    volatile int* const final_bundles = chunks_pub + 1;                         // number of bundles of this CTA, once known
+    volatile uint32_t* const bdesc = reinterpret_cast<volatile uint32_t*>(meta + MR_NS);   // [MR2_BD][8]: slot | use parity << 5 | group << 6 | valid << 10
+    unsigned int* const counter = const_cast<unsigned int*>(bdesc) + MR2_BD * 8;
+    volatile int* const bundles_pub = reinterpret_cast<volatile int*>(counter + 1);   // bundles whose descriptors are written AND whose items are issued
+    volatile int* const final_bundles = bundles_pub + 1;                        // number of bundles of this CTA, once known
 
     const FrameGeom& g = a.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -47,10 +48,8 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
     if (tid == 0) {
         for (int s = 0; s < MR_NS; ++s) { mbar_init(&ready[s], 1); mbar_init(&empty[s], MR_TPI); }
         *counter = 0;
-        *issued = 0;
-        *chunks_pub = 0;
+        *bundles_pub = 0;
         *final_bundles = 0x7FFFFFFF;
-        for (int s = 0; s < MR2_CE; ++s) cseq[s] = -1;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_trigger();
@@ -68,16 +67,15 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
         int q = 0, qn = 0;
         if (lane == 0) q = (int)atomicAdd(a.work, 1u);
         q = __shfl_sync(0xFFFFFFFFu, q, 0);
-        int slot = 0, n = 0, jchunk = 0, bundle_base = 0;
-        uint32_t par = 1;                       // parity of (use - 1) for the wait on `empty`
-        bool first_round = true;
+        int slot = 0, n = 0, bundle_base = 0;
+        uint32_t upar = 0;                      // parity of the use (n / MR_NS) of `slot`
         while (q < nchunks) {
             if (lane == 0) qn = (int)atomicAdd(a.work, 1u);             // next chunk: the latency hides behind this one
             const int unit = q / cpu, qq = q - unit * cpu;
             int pair0, nit, hpar = 0;
             if (a.nph == 4) { pair0 = (qq >> 1) * 4; hpar = qq & 1; nit = 2 * min(4, a2.npairs - pair0); }
             else { pair0 = qq * 8; nit = min(8, a2.npairs - pair0); }
-            // item k of the chunk (lane k < nit works it out; the issuing loop below reads it with shuffles)
+            // item k of the chunk belongs to lane k < nit
             int i_blk = 0, i_ref = 0, i_ph = 0, i_bx = 0, i_by = 0, i_int = 0, glo = 99, ghi = -1;
             if (lane < nit) {
                 const int pair = pair0 + (a.nph == 4 ? (lane >> 1) : lane);
@@ -106,43 +104,48 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
             ghi = __reduce_max_sync(0xFFFFFFFFu, ghi);
             if (ghi >= glo) {                   // else: no item of the chunk has a valid candidate -- the keys stay all ones
                 const int ng = ghi - glo + 1, tpi = 4 * ng, nb = (nit * tpi + 31) >> 5;
-                if (lane == 0) {
-                    const int e = jchunk & (MR2_CE - 1);
-                    volatile int* cv = reinterpret_cast<volatile int*>(centry + e);
-                    cseq[e] = -1;
-                    cv[0] = bundle_base; cv[1] = ng | (glo << 8) | (nit << 16) | (nb << 24); cv[2] = n;
-                    cv[3] = (1024 + ng - 1) / ng;          // exact division by ng of any (item, group) index of a chunk: (x * m) >> 10, x < 96
-                    cseq[e] = jchunk;
-                    *chunks_pub = jchunk + 1;
+                // ---- bundle descriptors: entry e = 8 * (bundle in chunk) + lane quad = the (item, group) pair index of the quad.
+                // Ring safety: when these are written every item up to n - 1 has been issued, so every item up to n - 1 - MR_NS has
+                // been consumed; the live bundles are those of the last MR_NS items (they lie in at most 4 chunks = 44 bundles) plus
+                // the 11 of this chunk: 55 <= MR2_BD.
+                const int mg = (1024 + ng - 1) / ng;        // exact division by ng of any e < 96 (ng <= 11): (e * mg) >> 10
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int e = lane + 32 * j;
+                    if (e < nb * 8) {
+                        int ki = (e * mg) >> 10, gl = e - ki * ng;
+                        const bool has = ki < nit;          // quads past the chunk's last task shadow its last item
+                        if (!has) { ki = nit - 1; gl = 0; }
+                        int s = slot + ki;
+                        const bool wrap = s >= MR_NS;
+                        if (wrap) s -= MR_NS;
+                        bdesc[(bundle_base * 8 + e) & (MR2_BD * 8 - 1)] =
+                            (uint32_t)s | ((upar ^ (wrap ? 1u : 0u)) << 5) | ((uint32_t)(glo + gl) << 6) | (has ? 1u << 10 : 0u);
+                    }
+                }
+                // ---- the chunk's items, one lane each
+                if (lane < nit) {
+                    int s = slot + lane;
+                    const bool wrap = s >= MR_NS;
+                    if (wrap) s -= MR_NS;
+                    if (n + lane >= MR_NS) {            // not the first use of the slot: wait until its previous item is consumed
+                        const uint32_t par = upar ^ (wrap ? 1u : 0u) ^ 1u;
+                        while (!mbar_try(&empty[s], par)) __nanosleep(200);      // 22 items ahead: a slot frees up every ~0.6 us
+                    }
+                    meta[s] = make_int4((int)(unit * a.out_unit_stride) + i_blk, i_bx, i_by, i_ref | (i_ph << 8) | (i_int << 16) | (unit << 17));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
+                    mbar_arrive_expect_tx(&ready[s], (uint32_t)(4 * MR_BOXROWS * MR_WP + BS * BS));
+                    if (tpi < MR_TPI) mbar_arrive_cnt(&empty[s], (uint32_t)(MR_TPI - tpi));     // the groups this chunk does not carry
+                    const int z = a.z_unit0 + unit * a.z_per_unit + (int)((a.slot_packed >> (4 * i_ref)) & 15u) * 16 + i_ph * 4;
+                    tma_load_3d(wins + s * MR_SLOT, &ring_map, &ready[s], i_bx * BS - 16, i_by * BS - 16 - (s & 1), z);
+                    tma_load_3d(curs + s * MR_CUR, &cur_map, &ready[s], i_bx * BS, i_by * BS, unit);
                 }
                 __syncwarp();
-                for (int k = 0; k < nit; ++k) {
-                    if (!first_round) {
-                        while (!mbar_try(&empty[slot], par)) __nanosleep(200);      // 22 items ahead: a slot frees up every ~0.6 us
-                    }
-                    const int blk = __shfl_sync(0xFFFFFFFFu, i_blk, k), ref = __shfl_sync(0xFFFFFFFFu, i_ref, k);
-                    const int phz = __shfl_sync(0xFFFFFFFFu, i_ph, k), bx = __shfl_sync(0xFFFFFFFFu, i_bx, k), by = __shfl_sync(0xFFFFFFFFu, i_by, k);
-                    const int interior = __shfl_sync(0xFFFFFFFFu, i_int, k);
-                    if (lane == 0) meta[slot] = make_int4((int)(unit * a.out_unit_stride) + blk, bx, by, ref | (phz << 8) | (interior << 16) | (unit << 17));
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&ready[slot], (uint32_t)(4 * MR_BOXROWS * MR_WP + BS * BS));
-                        if (tpi < MR_TPI) mbar_arrive_cnt(&empty[slot], (uint32_t)(MR_TPI - tpi));     // the groups this chunk does not carry
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int z = a.z_unit0 + unit * a.z_per_unit + (int)((a.slot_packed >> (4 * ref)) & 15u) * 16 + phz * 4;
-                        tma_load_3d(wins + slot * MR_SLOT, &ring_map, &ready[slot], bx * BS - 16, by * BS - 16 - (slot & 1), z);
-                    } else if (lane == 1) {
-                        tma_load_3d(curs + slot * MR_CUR, &cur_map, &ready[slot], bx * BS, by * BS, unit);
-                    }
-                    ++n;
-                    if (lane == 0) *issued = n;
-                    if (++slot == MR_NS) { slot = 0; par ^= 1; first_round = false; }
-                }
+                n += nit;
+                slot += nit;
+                if (slot >= MR_NS) { slot -= MR_NS; upar ^= 1u; }
                 bundle_base += nb;
-                ++jchunk;
+                if (lane == 0) *bundles_pub = bundle_base;          // descriptors written, meta written, loads issued
             }
             q = __shfl_sync(0xFFFFFFFFu, qn, 0);
         }
@@ -152,57 +155,26 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
     unsigned b = 0;
     if (lane == 0) b = atomicAdd(counter, 1u);
     b = __shfl_sync(0xFFFFFFFFu, b, 0);
-    int jc = 0;                                 // chunk cursor of this warp: bundles are fetched in increasing order
-    unsigned last_base = 0;                     // first bundle of the chunk the cursor points at
     while (true) {
-        // ---- the chunk that holds bundle b (seqlock read of its entry; wait for the producer if it is not published yet)
-        // a chunk holds at most 11 bundles, so the chunk of bundle b is at least (b - first bundle of the last chunk) / 11 entries ahead
-        jc += (int)(__umulhi(b - last_base, 0xBA2E8BA3u) >> 3);
-        int4 ce;
+        // ---- wait until bundle b is published (its descriptors are written and its items' loads issued)
         {
             SpinWait sw;
             bool none = false;
-            while (true) {
-                if (jc < *chunks_pub) {
-                    // shared-memory accesses of a warp are performed in program order and the producer writes seq = -1, data,
-                    // seq = j in that order: reading seq, data, seq (volatile, no reordering by the compiler) is a seqlock
-                    // without fences (a membar here costs more than the whole rest of the bundle header)
-                    const int e = jc & (MR2_CE - 1);
-                    const int s1 = cseq[e];
-                    const volatile int* cv = reinterpret_cast<const volatile int*>(centry + e);
-                    ce = make_int4(cv[0], cv[1], cv[2], cv[3]);
-                    const int s2 = cseq[e];
-                    if (s1 == jc && s2 == jc && b < (unsigned)ce.x + ((unsigned)ce.y >> 24)) break;
-                    ++jc;                       // this chunk ends before bundle b (or its entry was recycled long ago)
-                    continue;
-                }
-                if ((int)b >= *final_bundles) { none = true; break; }
+            while ((int)b >= *bundles_pub) {
+                if ((int)b >= *final_bundles) { none = true; break; }      // written after the last publication
                 sw.pause();
             }
             if (none) break;
         }
-        last_base = (unsigned)ce.x;
-        const int ng = ce.y & 255, g_lo = (ce.y >> 8) & 255, nit = (ce.y >> 16) & 255;
-        const unsigned lb = b - (unsigned)ce.x;
-        const unsigned tq = (32u * lb + lane) >> 2;                             // (item, group) pair of this lane inside the chunk
-        const unsigned mg = (unsigned)ce.w;                                     // exact division by ng for tq < 96 (ng <= 11)
-        unsigned ki = (tq * mg) >> 10;
-        const unsigned gl = tq - ki * ng;
-        const bool has = ki < (unsigned)nit;                                    // lanes past the chunk's last task shadow its last item
-        if (!has) ki = (unsigned)nit - 1u;
-        const unsigned item = (unsigned)ce.z + ki;                              // CTA-local item index
-        const int grp = g_lo + (has ? (int)gl : 0), c = (int)(lane & 3u);
-        {   // every item the bundle touches must have been issued (ready[] is then in the phase of this use, never an older one)
-            const unsigned last = (unsigned)ce.z + min((unsigned)nit - 1u, (((32u * lb + 31u) >> 2) * mg) >> 10);
-            SpinWait sw;
-            while (*issued <= (int)last) sw.pause();
-        }
+        const uint32_t dsc = bdesc[((b & (MR2_BD - 1)) << 3) | (lane >> 2)];
+        const unsigned slot = dsc & 31u;
+        const int grp = (int)((dsc >> 6) & 15u), c = (int)(lane & 3u);
+        const bool has = (dsc >> 10) & 1u;
         unsigned nb = 0;
         if (lane == 0) nb = atomicAdd(counter, 1u);         // next bundle index: consumed at the end of this iteration
-        const unsigned use = __umulhi(item, 0xBA2E8BA3u) >> 4, slot = item - use * MR_NS;       // item / 22
-        mbar_wait(&ready[slot], use & 1u);
+        mbar_wait(&ready[slot], (dsc >> 5) & 1u);
         __syncwarp();
-        const unsigned seg = __match_any_sync(0xFFFFFFFFu, has ? ki : 0xFFu);      // the lanes of my item
+        const unsigned seg = __match_any_sync(0xFFFFFFFFu, has ? slot : 0xFFu);    // the lanes of my item (one slot each)
         const bool leader = has && (int)lane == __ffs(seg) - 1;
         const int4 mt = meta[slot];
         const int bx = mt.y, by = mt.z;
