@@ -26,6 +26,23 @@ struct MeRing2Args {
     int chunks_per_unit;         // fme: ceil(npairs / 4) * 2 (pair group x horizontal parity); else ceil(npairs / 8)
 };
 
+// One 32-bit key per candidate for the per-item warp merge: SAD (16) | |dx|+|dy| (8) | dx + R (7) | dy > 0 (1).  Given the
+// L1 distance and dx, dy is known up to its sign, so the lexicographic order (SAD, L1, dx, dy) of Encoder.py:771 survives.
+__device__ __forceinline__ uint32_t mr2_key32(uint32_t best, int dx, int dy, int R) {
+    return (best & 0xFFFFFF00u) | ((uint32_t)(dx + R) << 1) | (dy > 0 ? 1u : 0u);
+}
+__device__ __forceinline__ unsigned long long mr2_key64(uint32_t m, int ref, int R) {
+    const int l1 = (int)((m >> 8) & 0xFFu), dxr = (int)((m >> 1) & 0x7Fu);
+    const int ady = l1 - abs(dxr - R), dy = (m & 1u) ? ady : -ady;
+    return ((unsigned long long)(m >> 16) << 40) | ((unsigned long long)l1 << 24) | ((unsigned long long)ref << 16) |
+           ((unsigned long long)dxr << 8) | (unsigned long long)(dy + R);
+}
+__device__ __forceinline__ unsigned int mr2_next(unsigned int* counter) {       // one lane: no warp-aggregation code around it
+    unsigned int v;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(smem_u32(counter)) : "memory");
+    return v;
+}
+
 template <bool QUAD>
 __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __grid_constant__ CUtensorMap ring_map,
                                                                        const __grid_constant__ CUtensorMap cur_map, const MeRing2Args a2) {
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
     } else {
     // ================================= search warps =================================
     unsigned b = 0;
-    if (lane == 0) b = atomicAdd(counter, 1u);
+    if (lane == 0) b = mr2_next(counter);
     b = __shfl_sync(0xFFFFFFFFu, b, 0);
     while (true) {
         // ---- wait until bundle b is published (its descriptors are written and its items' loads issued)
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
         const int grp = (int)((dsc >> 6) & 15u), c = (int)(lane & 3u);
         const bool has = (dsc >> 10) & 1u;
         unsigned nb = 0;
-        if (lane == 0) nb = atomicAdd(counter, 1u);         // next bundle index: consumed at the end of this iteration
+        if (lane == 0) nb = mr2_next(counter);              // next bundle index: consumed at the end of this iteration
         mbar_wait(&ready[slot], (dsc >> 5) & 1u);
         __syncwarp();
         const unsigned seg = __match_any_sync(0xFFFFFFFFu, has ? slot : 0xFFu);    // the lanes of my item (one slot each)
@@ -331,24 +348,19 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                 const uint32_t best = bq[e];
                 const int idx = (int)(best & 0xFFu), k = (idx * 11) >> 5, gg = idx - 3 * k;
                 const int dx = mul * (-16 + c + 4 * k) + px, dy = mul * (oy0 + gg) + py;
-                const uint32_t xy = ((uint32_t)(dx + g.R) << 8) | (uint32_t)(dy + g.R);
-                const uint32_t v1 = (has && best != 0xFFFFFFFFu) ? (best >> 8) : 0xFFFFFFFFu;
-                {
-                    const uint32_t m1 = __reduce_min_sync(seg, v1);
-                    const uint32_t m2 = __reduce_min_sync(seg, v1 == m1 ? xy : 0xFFFFFFFFu);
-                    if (leader && m1 != 0xFFFFFFFFu) {
-                        const int4 ms = mt;
-                        const unsigned long long key = ((unsigned long long)(m1 >> 8) << 40) | ((unsigned long long)(m1 & 0xFFu) << 24) |
-                                                       ((unsigned long long)(ms.w & 255) << 16) | (unsigned long long)m2;
-                        unsigned long long* okey;
-                        if (e == 0) okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + ms.x);
-                        else {
-                            const int kx = (e - 1) & 1, ky = (e - 1) >> 1, un = ms.w >> 17;
-                            okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out_sub) + un * a.out_sub_unit_stride +
-                                                                         (size_t)(ms.z * 2 + ky) * (g.nbx * 2) + ms.y * 2 + kx);
-                        }
-                        atomicMin(okey, key);
+                const uint32_t v1 = (has && best != 0xFFFFFFFFu) ? mr2_key32(best, dx, dy, g.R) : 0xFFFFFFFFu;
+                const uint32_t m1 = __reduce_min_sync(seg, v1);
+                if (leader && m1 != 0xFFFFFFFFu) {
+                    const int4 ms = mt;
+                    const unsigned long long key = mr2_key64(m1, ms.w & 255, g.R);
+                    unsigned long long* okey;
+                    if (e == 0) okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + ms.x);
+                    else {
+                        const int kx = (e - 1) & 1, ky = (e - 1) >> 1, un = ms.w >> 17;
+                        okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out_sub) + un * a.out_sub_unit_stride +
+                                                                     (size_t)(ms.z * 2 + ky) * (g.nbx * 2) + ms.y * 2 + kx);
                     }
+                    atomicMin(okey, key);
                 }
             }
         } else {
@@ -364,7 +376,8 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
         }
         // ---- 33rd horizontal offset (ox = +16: words 8..11 of the shift-0 copy): lane c of the four takes block rows 4c..4c+3
         uint32_t ex[3] = {0u, 0u, 0u};
-        if (__any_sync(0xFFFFFFFFu, px == 0)) {
+        const bool any_px0 = __any_sync(0xFFFFFFFFu, px == 0);
+        if (any_px0) {
             const unsigned char* w0 = wslot + (p + G * grp + 4 * c) * MR_WP + 32;
             uint4 cr[4];
 #pragma unroll
@@ -394,24 +407,30 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
         if (fast_valid) {
             // interior block: the only invalid candidates are ox = 16 on odd horizontal phases and oy = 16 on odd vertical ones
             const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;          // candidate k = 8
-            const uint32_t ybl = (grp == MR_NG - 1 && py) ? 0xFFFFFFFFu : 0u;     // candidate g = 2 of the last group
+            const bool ybl = grp == MR_NG - 1 && py;                              // candidate g = 2 of the last group
             uint32_t ly8[3];
 #pragma unroll
             for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
             // min over the three vertical offsets first (their keys differ by SAD and ly8 only), then add the horizontal part:
-            // 3 IMAD (FMA pipe) + one 3-input min + one add per column instead of 3 adds + 3 mins on the ALU pipe
-            uint32_t kk[9];
+            // 3 IMAD (FMA pipe) + ONE 3-input min + one add per column on the ALU pipe.  The invalid third row of the last group
+            // on odd vertical phases is taken out through its multiplier (0) and addend (all ones but the index): no predicated
+            // 2-input mins
+            uint32_t m2 = 65536u;
+            if (ybl) { m2 = 0u; ly8[2] = 0xFFFFFF02u; }
+            uint32_t kk[8];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
+            for (int k = 0; k < 8; ++k) {
                 const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative (c <= 3)
                 const uint32_t lx8 = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
-                const uint32_t t0 = (k < 8 ? acc[0][k < 8 ? k : 0] : ex[0]) * 65536u + ly8[0];
-                const uint32_t t1 = (k < 8 ? acc[1][k < 8 ? k : 0] : ex[1]) * 65536u + ly8[1];
-                const uint32_t t2 = ((k < 8 ? acc[2][k < 8 ? k : 0] : ex[2]) * 65536u + ly8[2]) | ybl;
+                const uint32_t t0 = acc[0][k] * 65536u + ly8[0], t1 = acc[1][k] * 65536u + ly8[1], t2 = acc[2][k] * m2 + ly8[2];
                 kk[k] = min(min(t0, t1), t2) + lx8;
             }
-            kk[8] |= xbl;
-            best = min(min(min(kk[0], kk[1]), min(kk[2], kk[3])), min(min(kk[4], kk[5]), min(kk[6], min(kk[7], kk[8]))));
+            best = min(min(min(kk[0], kk[1]), min(kk[2], kk[3])), min(min(kk[4], kk[5]), min(kk[6], kk[7])));
+            if (any_px0) {                      // the 33rd horizontal offset exists on even horizontal phases only (uniform per bundle)
+                const int dx = mul * (16 + c) + px;
+                const uint32_t t0 = ex[0] * 65536u + ly8[0], t1 = ex[1] * 65536u + ly8[1], t2 = ex[2] * m2 + ly8[2];
+                best = min(best, (min(min(t0, t1), t2) + ((uint32_t)dx << 8) + 24u) | xbl);
+            }
         } else {
             int xlo, xhi, ylo, yhi;
             valid_range(bx * BS, g.W, BS, g.fme, g.fme, xlo, xhi);
@@ -437,23 +456,18 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                 }
             }
         }
-        // ---- merge per item: order (SAD, |dx|+|dy|, ref, dx, dy); all lanes of a segment share ref, so two REDUX steps
-        //      ((SAD, L1), then (dx, dy) among the lanes that tie) give the winner of the segment
-        uint32_t xy;
-        {
+        // ---- merge per item: order (SAD, |dx|+|dy|, ref, dx, dy); all lanes of a segment share ref, so ONE REDUX over the
+        //      32-bit key (SAD, L1, dx, sign of dy) gives the winner of the segment
+        uint32_t v1 = 0xFFFFFFFFu;
+        if (has && best != 0xFFFFFFFFu) {
             const int idx = (int)(best & 0xFFu), k = (idx * 11) >> 5, gg = idx - 3 * k;
             const int dx = mul * (-16 + c + 4 * k) + px, dy = mul * (oy0 + gg) + py;
-            xy = ((uint32_t)(dx + g.R) << 8) | (uint32_t)(dy + g.R);
+            v1 = mr2_key32(best, dx, dy, g.R);
         }
-        const uint32_t v1 = (has && best != 0xFFFFFFFFu) ? (best >> 8) : 0xFFFFFFFFu;
         {
             const uint32_t m1 = __reduce_min_sync(seg, v1);
-            const uint32_t m2 = __reduce_min_sync(seg, v1 == m1 ? xy : 0xFFFFFFFFu);
-            if (leader && m1 != 0xFFFFFFFFu) {
-                const unsigned long long key = ((unsigned long long)(m1 >> 8) << 40) | ((unsigned long long)(m1 & 0xFFu) << 24) |
-                                               ((unsigned long long)(mt.w & 255) << 16) | (unsigned long long)m2;
-                atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + mt.x), key);
-            }
+            if (leader && m1 != 0xFFFFFFFFu)
+                atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + mt.x), mr2_key64(m1, mt.w & 255, g.R));
         }
         }   // !QUAD
         __syncwarp();
