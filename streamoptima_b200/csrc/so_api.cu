@@ -931,8 +931,9 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
     dim3 grid(ctx->nblk, units);
     static const bool generic16 = std::getenv("SO_FINISH_GENERIC") != nullptr;      // tests: force the generic kernel
     if (g.bs == 16 && g.W % 16 == 0 && !generic16) {
-        if (a.vbs) CU(launch_pdl(inter_finish16_kernel<true>, dim3((ctx->nblk + 7) / 8, units), dim3(128), 0, st, a));
-        else CU(launch_pdl(inter_finish16_kernel<false>, dim3((ctx->nblk + 7) / 8, units), dim3(128), 0, st, a));
+        const dim3 fg((ctx->nblk + 7) / 8, units);
+        if (a.vbs) CU(launch_pdl(inter_finish16_kernel<true>, fg, dim3(128), 0, st, a));
+        else CU(launch_pdl(inter_finish16_kernel<false>, fg, dim3(128), 0, st, a));
     }
     else if (g.bs == 16) inter_finish_kernel<16><<<grid, nt, 0, st>>>(a);
     else if (g.bs == 8) inter_finish_kernel<8><<<grid, nt, 0, st>>>(a);

@@ -23,6 +23,17 @@ struct RefList {
     const uint8_t* plane[SO_MAX_REF][4];
 };
 
+// Exact int <-> double conversions on the FP64 add pipe.  I2F.F64 / F2I.F64 run on the XU pipe at a small fraction of a
+// lane per clock; with 64 of them per 16x16 block they -- not the transform -- bounded the finish kernels (ncu:
+// sm__inst_executed_pipe_xu 89 %).  so_i2d: bits (0x43300000, v ^ 0x80000000) are the double 2^52 + 2^31 + v; so_d2i_rint:
+// d + 1.5 * 2^52 rounds to nearest-even like rint() and leaves the integer in the low word (|d| < 2^31).
+__device__ __forceinline__ double so_i2d(int v) {
+    return __dadd_rn(__hiloint2double(0x43300000, v ^ (int)0x80000000), -4503601774854144.0);
+}
+__device__ __forceinline__ int so_d2i_rint(double d) {
+    return __double2loint(__dadd_rn(d, 6755399441055744.0));
+}
+
 // The reference ring as the kernels address it: [unit][slot][phase 0..3][byte shift 0..3][H][pitch].  Shift plane c of
 // a phase holds the phase plane moved left by c bytes (plane_c[x] = plane[x + c], zero past the frame edge): a TMA box
 // load at a 16-byte aligned x of plane c delivers a search window whose candidates at x = c (mod 4) are word aligned.

@@ -270,9 +270,9 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
     const int predp = pred_sample(g, rl, selp, mp.ref, i, j);
     const int resp = c - predp;
 
-    if (active) ws[j * P + i] = (double)resp;
+    if (active) ws[j * P + i] = so_i2d(resp);
     transform2d<BS, BS, false>(ws, t);
-    const int tcp = active ? (int)rint(ws[j * P + i]) : 0;
+    const int tcp = active ? so_d2i_rint(ws[j * P + i]) : 0;
 
     const bool eligible = a.vbs && bx != 0 && by != 0;
     const int qrow = a.qp_blocks ? a.qp_blocks[blk] : (a.qp_rows ? a.qp_rows[by] : a.qp_final);
@@ -290,9 +290,9 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
         const int preds = pred_sample(g, rl, sels, ms.ref, si, sj);
         const PredSel selq = pred_select(g, xs * mult, ys * mult, ms.dx, ms.dy, S, BS);     // quirk Q5
         preds_q5 = pred_sample(g, rl, selq, ms.ref, si, sj);
-        if (active) ws[j * P + i] = (double)(c - preds);
+        if (active) ws[j * P + i] = so_i2d(c - preds);
         transform2d<BS, S, false>(ws, t);
-        tcs = active ? (int)rint(ws[j * P + i]) : 0;
+        tcs = active ? so_d2i_rint(ws[j * P + i]) : 0;
         // RD costs with the prediction-time QP (calculate_RD_cost, Encoder.py:1133-1158)
         const int lenp = rle_len_cta<BS, BS>(quant_rhe(tcp, q_shift(j, i, BS, a.qp_rd)), j, i, 0, nzbuf, active);
         const int qs = a.qp_rd > 0 ? a.qp_rd - 1 : a.qp_rd;
@@ -324,12 +324,12 @@ __global__ void inter_finish_kernel(const FlowArgs a) {
                           : rle_len_cta<BS, BS>(level, j, i, 0, nzbuf, active);
     if (active) {
         a.levels[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)level;
-        ws[j * P + i] = (double)(level * (1 << shift));          // rescale_QTC, Encoder.py:820
+        ws[j * P + i] = so_i2d(level * (1 << shift));          // rescale_QTC, Encoder.py:820
     }
     if (split) transform2d<BS, S, true>(ws, t); else transform2d<BS, BS, true>(ws, t);
     unsigned long long se = 0;
     if (active) {
-        const int rec = (pred_rec + (int)rint(ws[j * P + i])) & 0xFF;     // astype(np.uint8) wraps (A5)
+        const int rec = (pred_rec + so_d2i_rint(ws[j * P + i])) & 0xFF;     // astype(np.uint8) wraps (A5)
         a.recon[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (uint8_t)rec;
         const int d = rec - c;
         se = (unsigned long long)(d * d);
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
         }
     }
 #pragma unroll
-    for (int i = 0; i < BS; ++i) ws[r * P + i] = (double)(c[i] - predp[i]);
+    for (int i = 0; i < BS; ++i) ws[r * P + i] = so_i2d(c[i] - predp[i]);
     // column r, then row r: one copy of the straight-line transform in the instruction stream (the kernel is latency-bound
     // and its code does not fit the instruction cache when every pass is inlined separately)
     if constexpr (VBS) {                       // the VBS variant is register-bound: run-time strides cost it 29 registers
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
     }
     int tcp[BS];
 #pragma unroll
-    for (int i = 0; i < BS; ++i) tcp[i] = (int)rint(ws[r * P + i]);
+    for (int i = 0; i < BS; ++i) tcp[i] = so_d2i_rint(ws[r * P + i]);
     __syncwarp();
 
     const bool eligible = VBS && a.vbs && bx != 0 && by != 0;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
                 const PredSel selq = pred_select(g, xs * mult, ys * mult, ms.dx, ms.dy, S, BS);      // quirk Q5
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
-                    ws[r * P + kx * S + i] = (double)(c[kx * S + i] - pred_sample(g, rl, sels, ms.ref, i, sr));
+                    ws[r * P + kx * S + i] = so_i2d(c[kx * S + i] - pred_sample(g, rl, sels, ms.ref, i, sr));
                     predq5[kx * S + i] = pred_sample(g, rl, selq, ms.ref, i, sr);
                 }
             }
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
         if (eligible) { dct1d<S>(ws + r * P, 1); dct1d<S>(ws + r * P + S, 1); }      // row r of the left and right sub-blocks
         if (eligible) {
 #pragma unroll
-            for (int i = 0; i < BS; ++i) tcs[i] = (int)rint(ws[r * P + i]);
+            for (int i = 0; i < BS; ++i) tcs[i] = so_d2i_rint(ws[r * P + i]);
         }
         __syncwarp();
         // RD costs at the prediction-time QP (calculate_RD_cost, Encoder.py:1133-1158)
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
         for (int i = 0; i < BS; ++i) {
             const int shift = split ? q_shift(sr, i & 7, S, qs) : q_shift(r, i, BS, qrow);
             level[i] = quant_rhe(split ? tcs[i] : tcp[i], shift);
-            ws[r * P + i] = (double)(level[i] * (1 << shift));
+            ws[r * P + i] = so_i2d(level[i] * (1 << shift));
             if (level[i] != 0) { if (!split) m0 |= 1u << i; else if (i < S) m0 |= 1u << i; else m1 |= 1u << (i - S); }
         }
     }
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
         uint32_t pk[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < BS; ++i) {
-            const int rec = ((split ? predq5[i] : predp[i]) + (int)rint(ws[r * P + i])) & 0xFF;      // astype(np.uint8) wraps (A5)
+            const int rec = ((split ? predq5[i] : predp[i]) + so_d2i_rint(ws[r * P + i])) & 0xFF;      // astype(np.uint8) wraps (A5)
             pk[i >> 2] |= (uint32_t)rec << (8 * (i & 3));
             const int d = rec - c[i];
             se += (unsigned long long)(d * d);
@@ -628,22 +628,57 @@ __global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
             const bool on = split || kk == 0;
             mvo[kk * 3 + 0] = on ? m.dx : 0; mvo[kk * 3 + 1] = on ? m.dy : 0; mvo[kk * 3 + 2] = on ? m.ref : 0;
         }
-        so_frame_stats* st = a.stats + unit * a.stats_stride;
-        if (blk == 0) { st->mae_den = a.mae_den; st->frame_type = a.frame_type; }
-        atomicAdd(reinterpret_cast<unsigned long long*>(&st->sse), se);
-        atomicAdd(&st->qsize, (unsigned)len);
         if (a.blk_len) a.blk_len[unit * a.blk_len_stride + blk] = (uint32_t)len;
-        atomicAdd(a.row_sizes + unit * a.rows_stride + by, (unsigned)len);
+    }
+    // ---- frame statistics: the eight blocks of the CTA are summed in shared memory and leave as ONE set of atomics (the
+    //      counters of a frame live in one 128-byte line: 3 same-line atomics per block serialise in L2 -- they, not the
+    //      arithmetic, bounded this kernel)
+    __shared__ unsigned long long red_se[8], red_n[8];
+    __shared__ unsigned int red_len[8];
+    __shared__ int red_by[8];
+    if (r == 0) {
+        const int slot = warp * 2 + h;
+        unsigned long long n = 0;
+        bool inf = false;
         if (a.fast) {
-            unsigned long long n = (unsigned long long)mp.sad * 4ull;
+            n = (unsigned long long)mp.sad * 4ull;
             if (eligible) { n = 0; for (int kk = 0; kk < 4; ++kk) n += msub[kk].sad; }
-            atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), n);
         } else {
-            unsigned long long n = mp.sad;
-            bool inf = mp.none;
+            n = mp.sad;
+            inf = mp.none;
             if (eligible) { n = 0; inf = false; for (int kk = 0; kk < 4; ++kk) { n += msub[kk].sad; inf = inf || msub[kk].none; } }
-            if (inf) atomicOr(&st->mae_inf, 1u); else atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), n);
         }
+        red_se[slot] = live ? se : 0ull;
+        red_len[slot] = live ? (unsigned)len : 0u;
+        red_n[slot] = (live && !inf) ? n : 0ull;
+        red_by[slot] = live ? (inf ? (by | 0x40000000) : by) : -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        so_frame_stats* st = a.stats + unit * a.stats_stride;
+        if (blockIdx.x == 0) { st->mae_den = a.mae_den; st->frame_type = a.frame_type; }
+        unsigned long long sse = 0, num = 0;
+        unsigned int tl = 0, rowl = 0;
+        bool inf = false;
+        int row = -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int b = red_by[k];
+            if (b < 0) continue;
+            sse += red_se[k]; num += red_n[k]; tl += red_len[k];
+            inf = inf || (b & 0x40000000);
+            const int rb = b & 0x3FFFFFFF;
+            if (rb != row) {
+                if (row >= 0) atomicAdd(a.row_sizes + unit * a.rows_stride + row, rowl);
+                row = rb; rowl = 0;
+            }
+            rowl += red_len[k];
+        }
+        if (row >= 0) atomicAdd(a.row_sizes + unit * a.rows_stride + row, rowl);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&st->sse), sse);
+        atomicAdd(&st->qsize, tl);
+        if (inf) atomicOr(&st->mae_inf, 1u);
+        if (num) atomicAdd(reinterpret_cast<unsigned long long*>(&st->mae_num), num);
     }
 }
 
@@ -1437,9 +1472,9 @@ __global__ void intra_finish_kernel(const FlowArgs a) {
     const int c = row[x + i];
     const MeResult mp = a.me_parent[unit * a.me_parent_stride + blk];
     const int resp = c - intra_pred(row, x, mp.dx, i, x, bx == 0);
-    if (active) ws[j * P + i] = (double)resp;
+    if (active) ws[j * P + i] = so_i2d(resp);
     transform2d<BS, BS, false>(ws, t);
-    const int tcp = active ? (int)rint(ws[j * P + i]) : 0;
+    const int tcp = active ? so_d2i_rint(ws[j * P + i]) : 0;
 
     const bool eligible = a.vbs && bx != 0 && by != 0;
     const int qrow = a.qp_blocks ? a.qp_blocks[blk] : (a.qp_rows ? a.qp_rows[by] : a.qp_final);
@@ -1454,9 +1489,9 @@ __global__ void intra_finish_kernel(const FlowArgs a) {
         const MeResult ms = a.me_sub[unit * a.me_sub_stride + sb];
         const int xs = x + (k & 1) * S;
         const int ress = c - intra_pred(row, xs, ms.dx, si, x, false);
-        if (active) ws[j * P + i] = (double)ress;
+        if (active) ws[j * P + i] = so_i2d(ress);
         transform2d<BS, S, false>(ws, t);
-        tcs = active ? (int)rint(ws[j * P + i]) : 0;
+        tcs = active ? so_d2i_rint(ws[j * P + i]) : 0;
         const int lenp = rle_len_cta<BS, BS>(quant_rhe(tcp, q_shift(j, i, BS, a.qp_rd)), j, i, 0, nzbuf, active);
         const int qs = a.qp_rd > 0 ? a.qp_rd - 1 : a.qp_rd;
         const int lens = rle_len_cta<BS, S>(quant_rhe(tcs, q_shift(sj, si, S, qs)), sj, si, k, nzbuf, active);
@@ -1480,10 +1515,10 @@ __global__ void intra_finish_kernel(const FlowArgs a) {
                           : rle_len_cta<BS, BS>(level, j, i, 0, nzbuf, active);
     if (active) {
         a.levels[unit * a.frame_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)level;
-        ws[j * P + i] = (double)(level * (1 << shift));
+        ws[j * P + i] = so_i2d(level * (1 << shift));
     }
     if (split) transform2d<BS, S, true>(ws, t); else transform2d<BS, BS, true>(ws, t);
-    if (active) a.res_frame[unit * a.scratch_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)rint(ws[j * P + i]);
+    if (active) a.res_frame[unit * a.scratch_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)so_d2i_rint(ws[j * P + i]);
     if (t == 0) {
         a.split[unit * a.split_stride + blk] = (uint8_t)split;
         int16_t* mvo = a.mv + unit * a.mv_stride + (size_t)blk * 12;
@@ -1645,10 +1680,10 @@ __global__ void decode_block_kernel(const FlowArgs a, int intra) {
     int shift;
     if (!split) shift = q_shift(j, i, BS, qrow);
     else { const int qs = qrow > 0 ? qrow - 1 : qrow; shift = q_shift(sj, si, S, qs); }
-    if (active) ws[j * P + i] = (double)(level * (1 << shift));
+    if (active) ws[j * P + i] = so_i2d(level * (1 << shift));
     if (split) transform2d<BS, S, true>(ws, t); else transform2d<BS, BS, true>(ws, t);
     if (!active) return;
-    const int r = (int)rint(ws[j * P + i]);
+    const int r = so_d2i_rint(ws[j * P + i]);
     if (intra) {
         a.res_frame[unit * a.scratch_stride + (size_t)(y + j) * g.W + x + i] = (int16_t)r;
         return;
