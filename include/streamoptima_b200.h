@@ -42,6 +42,10 @@ extern "C" {
 #define SO_FLAG_FME     1u   /* FMEEnable : half-pel search (Encoder.py:388, :697)     */
 #define SO_FLAG_FAST_ME 2u   /* fast_me   : 3x3 around the predictor (Encoder.py:719)  */
 #define SO_FLAG_VBS     4u   /* VBSEnable : 4-way split with RD decision (Encoder.py:512-573) */
+#define SO_FLAG_SEA     8u   /* extension, results unchanged: the exhaustive search of find_best_match (Encoder.py:678-717)
+                              * skips candidates whose SAD lower bound (8x8 quadrant sums) exceeds the exact SAD of a predictor
+                              * candidate -- same minimum key, ties included.  Applies to 16x16 blocks at r = 16 without VBS;
+                              * ignored elsewhere.  Off by default. */
 
 #define SO_MAX_REF 8
 #define SO_ALL_UNITS (-1)    /* `unit` argument of the per-frame calls: every unit of the context in lock step */
@@ -241,6 +245,10 @@ int so_last_search_timing(so_ctx* ctx, double out[4]);
  * out[0] = summed event time of its timed launches (ms), out[1] = timed launches (all units of a frame are one launch),
  * out[2] = the sum over all transform kernels incl. intra frames (= so_last_timing [2]), out[3] = frames with events. */
 int so_last_finish_timing(so_ctx* ctx, double out[4]);
+/* Counters of the SO_FLAG_SEA search since the context was created (waits for the device): out[0] = exact SADs computed
+ * (predictor candidates + candidates that passed the bound; the plain search computes one per valid candidate), out[1] = launches
+ * (one per P frame, all units), out[2] = out[3] = 0 (reserved). */
+int so_sea_stats(so_ctx* ctx, uint64_t out[4]);
 
 /* Host-side text formatters, byte-identical to the reference's (Encoder.py:1419-1542 with canonical integers).
  * Return the number of bytes written (excluding the terminating NUL), or the required size (negative) when cap

@@ -11,7 +11,7 @@ import os
 _LIB_NAME = "libstreamoptima_b200.so"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-SO_FLAG_FME, SO_FLAG_FAST_ME, SO_FLAG_VBS = 1, 2, 4
+SO_FLAG_FME, SO_FLAG_FAST_ME, SO_FLAG_VBS, SO_FLAG_SEA = 1, 2, 4, 8
 SO_MAX_REF = 8
 
 
@@ -52,7 +52,7 @@ EXPORTS = ["so_abi_version", "so_last_error", "so_device_count", "so_ctx_create"
            "so_format_residual_frame_symbols", "so_write_bitstream_files", "so_parse_bitstream_files",
            "so_set_symbol_output", "so_fetch_symbols", "so_format_residual_frame_packed", "so_symbols_to_levels",
            "so_write_bitstream_files_symbols",
-           "so_last_timing", "so_last_me_launches", "so_last_search_timing", "so_last_finish_timing",
+           "so_last_timing", "so_last_me_launches", "so_last_search_timing", "so_last_finish_timing", "so_sea_stats",
            "so_format_mv_frame", "so_format_residual_frame"]
 
 _lib = None
@@ -108,6 +108,7 @@ def load():
     lib.so_last_search_timing.argtypes = [vp, C.POINTER(C.c_double)]
     lib.so_last_finish_timing.argtypes = [vp, C.POINTER(C.c_double)]
     lib.so_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.so_sea_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.so_last_me_launches.argtypes = [vp]
     lib.so_format_mv_frame.restype = i64
     lib.so_format_mv_frame.argtypes = [i32, vp, vp, i32, i32, vp, C.c_char_p, i64]
@@ -129,11 +130,12 @@ class Context:
     """Owns one ``so_ctx`` (one CUDA device, not thread-safe)."""
 
     def __init__(self, *, width, height, block_size, search_range, qp, intra_dur, n_ref_frames=1, fme=False, fast_me=False,
-                 vbs=False, rc_flag=0, parallel_mode=0, lam=0.0, intra_thresh=0, max_batch=1, device=0):
+                 vbs=False, rc_flag=0, parallel_mode=0, lam=0.0, intra_thresh=0, max_batch=1, device=0, sea=False):
         self.lib = load()
         p = so_params(width=width, height=height, block_size=block_size, search_range=search_range, qp=qp,
                       intra_dur=intra_dur, n_ref_frames=n_ref_frames,
-                      flags=(SO_FLAG_FME if fme else 0) | (SO_FLAG_FAST_ME if fast_me else 0) | (SO_FLAG_VBS if vbs else 0),
+                      flags=(SO_FLAG_FME if fme else 0) | (SO_FLAG_FAST_ME if fast_me else 0) | (SO_FLAG_VBS if vbs else 0) |
+                      (SO_FLAG_SEA if sea else 0),
                       rc_flag=rc_flag or 0, parallel_mode=parallel_mode, lam=float(lam or 0.0),
                       intra_thresh=int(intra_thresh or 0), max_batch=max_batch, reserved=0)
         self.params = p
@@ -172,6 +174,12 @@ class Context:
         a = np.ascontiguousarray(qp_blocks, np.int32)
         assert a.ndim == 2 and a.shape[1] == self.nblk
         check(self.handle, self.lib.so_set_block_qps(self.handle, a.ctypes.data, a.shape[0]))
+
+    def sea_stats(self):
+        """Counters of the pruned exhaustive search (``sea=True``) since the context was created."""
+        out = (C.c_uint64 * 4)()
+        check(self.handle, self.lib.so_sea_stats(self.handle, out))
+        return dict(exact_sads=int(out[0]), p_frames=int(out[1]))
 
     def last_timing(self):
         out = (C.c_double * 4)()

@@ -11,6 +11,7 @@
 #include "so_me_tma.cuh"
 #include "so_me_ring.cuh"
 #include "so_me_ring2.cuh"
+#include "so_me_sea.cuh"
 #include <cstdlib>
 #include <fcntl.h>
 #include <unistd.h>
@@ -61,6 +62,7 @@ struct so_ctx {
         std::vector<int> list;              // ring slots in list order (oldest first)
         std::vector<char> slot_u8;          // slot holds a uint8 reconstruction (false: the float 128 frame)
         std::vector<int> slot_wrap;         // wrap mode the half-pel planes of the slot were built with (-1 none)
+        std::vector<char> slot_sea;         // the slot's packed quadrant bytes (successive elimination) match its planes
         bool operator==(const RingState& o) const { return list == o.list && slot_u8 == o.slot_u8 && slot_wrap == o.slot_wrap; }
     };
     std::vector<RingState> rstates;
@@ -77,6 +79,9 @@ struct so_ctx {
     int* qp_rows_dev = nullptr;
     std::vector<int> qp_rows;
     unsigned int* me_work = nullptr;        // chunk counter of the item-ring search kernel
+    // successive elimination (so_me_sea.cuh, SO_FLAG_SEA): packed quadrant bytes [unit][slot][phase][H][W], last winners, counters
+    uint32_t *sea_pq = nullptr, *sea_prev = nullptr;
+    unsigned int* sea_ctr = nullptr;
     uint8_t* fm_table = nullptr;            // fast ME: per-block transition tables around the previous frame's predictors
     short4* fm_state = nullptr;             // fast ME: predictor (x, y, ref) every block used in the last P frame, [batch][nblk]
     int2 *fs_F = nullptr, *fs_entry = nullptr;   // fast ME scan: per-chunk composed transition functions / chunk entry predictors
@@ -193,7 +198,8 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     free_seq(c);
     cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->in_parent); cudaFree(c->in_sub);
     cudaFree(c->res_frame); cudaFree(c->band);
-    cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev); cudaFree(c->me_work); cudaFree(c->fm_table); cudaFree(c->fm_state);
+    cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev); cudaFree(c->me_work); cudaFree(c->sea_pq); cudaFree(c->sea_prev); cudaFree(c->sea_ctr);
+    cudaFree(c->fm_table); cudaFree(c->fm_state);
     cudaFree(c->fs_F); cudaFree(c->fs_entry);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto b : c->pipe.stage) if (b) cudaFreeHost(b);
@@ -266,7 +272,7 @@ extern "C" int so_ctx_create(so_ctx** out, const so_params* p, int device) {
     CUC(cudaMalloc(&ctx->band, sizeof(int32_t) * ctx->frame_px * ctx->batch));
     CUC(cudaMalloc(&ctx->qp_rows_dev, sizeof(int) * g.nby));
     ctx->rstates.resize(ctx->batch);
-    for (auto& r : ctx->rstates) { r.slot_u8.assign(ctx->nslots, 0); r.slot_wrap.assign(ctx->nslots, -1); }
+    for (auto& r : ctx->rstates) { r.slot_u8.assign(ctx->nslots, 0); r.slot_wrap.assign(ctx->nslots, -1); r.slot_sea.assign(ctx->nslots, 0); }
     if (upload_tables(ctx) != SO_OK) return fail(SO_E_CUDA);
     *out = ctx;
     return SO_OK;
@@ -377,6 +383,7 @@ static int ref_reset_impl(so_ctx* ctx, cudaStream_t st, bool reset_keys) {
     R.list.push_back(s);
     R.slot_u8[s] = 0;
     R.slot_wrap[s] = 0;          // planes of a constant frame are the constant in both modes
+    R.slot_sea[s] = 0;
     return SO_OK;
 }
 
@@ -401,6 +408,7 @@ static int ring_push(so_ctx* ctx, const uint8_t* recon_dev, size_t src_unit_stri
     ctx->launches++;
     CU(cudaGetLastError());
     R.slot_wrap[s] = wrap;
+    R.slot_sea[s] = 0;
     return SO_OK;
 }
 
@@ -508,6 +516,67 @@ static cudaError_t launch_me_tma_n(int NDX, int G, const CUtensorMap& map, const
     }
 }
 
+// ---- successive elimination (so_me_sea.cuh) -----------------------------------------------------------------------------------
+static bool sea_enabled(const so_ctx* ctx) {
+    static const char* env = std::getenv("SO_ME_SEA");             // tests / A-B: "1" forces it on, "0" off
+    if (env && env[0] == '1') return true;
+    if (env && env[0] == '0') return false;
+    return (ctx->p.flags & SO_FLAG_SEA) != 0;
+}
+
+static int run_sea(so_ctx* ctx, const MeRingArgs& a, const uint8_t* cur, size_t cur_stride, int unit0, int units, cudaStream_t st) {
+    const FrameGeom& g = ctx->g;
+    const int nph = a.nph;
+    if (!ctx->sea_pq) {
+        const size_t nb = (size_t)ctx->nblk * ctx->batch;
+        CU(cudaMalloc(&ctx->sea_pq, (size_t)ctx->batch * ctx->nslots * nph * ctx->frame_px * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->sea_prev, nb * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->sea_ctr, 256));
+        CU(cudaMemsetAsync(ctx->sea_prev, 0xFF, nb * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(ctx->sea_ctr, 0, 256, st));
+    }
+    SeaArgs s{};
+    s.g = a.g;
+    s.ring = ctx->ring; s.unit_stride = ctx->unit_stride; s.slot_stride = ctx->slot_stride; s.plane_bytes = ctx->plane_bytes;
+    s.nph = nph;
+    s.pq = ctx->sea_pq;
+    s.pq_plane_stride = ctx->frame_px;
+    s.pq_slot_stride = s.pq_plane_stride * (size_t)nph;
+    s.pq_unit_stride = s.pq_slot_stride * (size_t)ctx->nslots;
+    s.slot_packed = a.slot_packed;
+    s.cur = cur + (size_t)unit0 * cur_stride; s.cur_unit_stride = cur_stride;
+    s.out = a.out; s.out_unit_stride = a.out_unit_stride;
+    s.prev = ctx->sea_prev; s.ctr = ctx->sea_ctr;
+    s.unit0 = unit0; s.units = units; s.nblk = ctx->nblk;
+    // quadrant bytes of the references whose planes changed since they were last derived
+    so_ctx::RingState& R = ctx->rs();
+    for (int sl : R.list) {
+        if (R.slot_sea[sl]) continue;
+        CU(launch_pdl(sea_qplane_kernel, dim3((g.W + SQ_TX - 1) / SQ_TX, (g.H + SQ_TY - 1) / SQ_TY, units * nph), dim3(SQ_THREADS), 0, st,
+                      (const uint8_t*)(slot_ptr(ctx, sl) + (size_t)unit0 * ctx->unit_stride), ctx->unit_stride, ctx->plane_bytes,
+                      ctx->sea_pq + (size_t)unit0 * s.pq_unit_stride + (size_t)sl * s.pq_slot_stride, s.pq_unit_stride, s.pq_plane_stride,
+                      g.W, g.H, g.pitch, nph));
+        ctx->launches++;
+        R.slot_sea[sl] = 1;
+    }
+    const int gpr = (s.g.nbx + SEA_NB - 1) / SEA_NB;
+    CU(launch_pdl(sea_search_kernel, dim3(gpr * s.g.nby, units), dim3(256), 0, st, s));
+    return SO_OK;
+}
+
+// counters of the successive-elimination search since the context was created: out[0] = exact SADs computed (predictors +
+// candidates that passed the bound), out[1] = launches (one per P frame, all units), out[2], out[3] = 0 (reserved)
+extern "C" int so_sea_stats(so_ctx* ctx, uint64_t* out4) {
+    if (!ctx || !out4) return SO_E_INVALID;
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (!ctx->sea_ctr) return SO_OK;
+    CU(cudaSetDevice(ctx->device));
+    unsigned int h[4];
+    CU(cudaMemcpy(h, ctx->sea_ctr, sizeof(h), cudaMemcpyDeviceToHost));
+    out4[0] = (uint64_t)h[0] | ((uint64_t)h[1] << 32); out4[1] = h[2];
+    return SO_OK;
+}
+
 // Item-ring search kernel (so_me_ring.cuh): 16x16 blocks, r = 16, DIRECT staging
 static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, MeResult* out, size_t out_stride,
                        cudaStream_t st, MeResult* out_sub = nullptr, size_t out_sub_stride = 0) {
@@ -557,16 +626,23 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
         if (out_sub) e = launch_pdl(me_ring_kernel<true>, dim3(grid), dim3(384), MR_SMEM, st, map, cmap, a);
         else e = launch_pdl(me_ring_kernel<false>, dim3(grid), dim3(512), MR_SMEM, st, map, cmap, a);
     } else {
-        MeRing2Args a2{};
-        a2.b = a;
-        a2.npairs = a.g.nbx * a.g.nby * a.g.nref;
-        a2.chunks_per_unit = a.g.fme ? ((a2.npairs + 3) / 4) * 2 : (a2.npairs + 7) / 8;
-        const long long nchunks = (long long)units * a2.chunks_per_unit;
-        const int grid = nchunks < sms ? (int)nchunks : sms;
-        if (out_sub) e = launch_pdl(me_ring2_kernel<true>, dim3(grid), dim3(384), MR2_SMEM, st, map, cmap, a2);
-        else {
-            static const int nthr = std::getenv("SO_ME_RING_THREADS") ? atoi(std::getenv("SO_ME_RING_THREADS")) : 512;      // experiments: fewer search warps
-            e = launch_pdl(me_ring2_kernel<false>, dim3(grid), dim3(nthr), MR2_SMEM, st, map, cmap, a2);
+        if (!out_sub && sea_enabled(ctx)) {
+            // successive elimination (so_me_sea.cuh): predictors -> bound filter -> exact SADs of the survivors, one kernel
+            const int rc2 = run_sea(ctx, a, cur, cur_stride, unit0, units, st);
+            if (rc2) return rc2;
+            e = cudaSuccess;
+        } else {
+            MeRing2Args a2{};
+            a2.b = a;
+            a2.npairs = a.g.nbx * a.g.nby * a.g.nref;
+            a2.chunks_per_unit = a.g.fme ? ((a2.npairs + 3) / 4) * 2 : (a2.npairs + 7) / 8;
+            const long long nchunks = (long long)units * a2.chunks_per_unit;
+            const int grid = nchunks < sms ? (int)nchunks : sms;
+            if (out_sub) e = launch_pdl(me_ring2_kernel<true>, dim3(grid), dim3(384), MR2_SMEM, st, map, cmap, a2);
+            else {
+                static const int nthr = std::getenv("SO_ME_RING_THREADS") ? atoi(std::getenv("SO_ME_RING_THREADS")) : 512;      // experiments: fewer search warps
+                e = launch_pdl(me_ring2_kernel<false>, dim3(grid), dim3(nthr), MR2_SMEM, st, map, cmap, a2);
+            }
         }
     }
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -826,6 +902,7 @@ static int ensure_planes(so_ctx* ctx, int units, cudaStream_t st) {
                                                                                   g.W, g.H, g.pitch, g.fme, wrap, 0);
         ctx->launches++;
         R.slot_wrap[s] = wrap;
+        R.slot_sea[s] = 0;
     }
     CU(cudaGetLastError());
     return SO_OK;
