@@ -247,6 +247,54 @@ def full_flow(codec, frames, qp):
                     "written (tmpfs/disk of the box), residual text formatted from the packed symbols on host threads"}
 
 
+def sea_experiment(frames, cfg, device, steps=2):
+    """VERDICT r1 item 6(c), reported on its own and never folded into `value` / `roofline`: the same C2 steps with the
+    exhaustive search pruned by SAD lower bounds (Y_Video_codec.sea_prune -> SO_FLAG_SEA, csrc/so_me_sea.cuh).  The output is
+    the plain search's bit for bit (checked here on split / MVs / statistics); what changes is how many candidates get an exact SAD."""
+    from streamoptima_b200 import _native
+    from streamoptima_b200.Encoder import Y_Video_codec
+    F, H, W = frames.shape
+    res = {}
+    sig = {}
+    for sea in (False, True):
+        c = Y_Video_codec(H, W, F, cfg["bs"], cfg["r"], 4, cfg["intra_dur"], 0, nRefFrames=cfg["nref"], FMEEnable=cfg["fme"])
+        c.device = device
+        c.sea_prune = sea
+        kw = dict(want_levels=False, want_recon=False, want_symbols=True)
+        out = c.encode_arrays(frames, **kw)
+        sig[sea] = (np.array(out["split"]), np.array(out["mv"]), np.array(out["stats"]["sse"]), np.array(out["stats"]["qsize"]))
+        c.encode_arrays(frames, **kw)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            c.const_init_Qp = 4 + k
+            c.encode_arrays(frames, **kw)
+        e2e = (time.perf_counter() - t0) / steps
+        ctx = c._ctx
+        _native.check(ctx.handle, ctx.lib.so_seq_upload(ctx.handle, frames.ctypes.data, 1, F))
+        _native.check(ctx.handle, ctx.lib.so_seq_sync(ctx.handle))
+        ms = 0.0
+        s0 = ctx.sea_stats()
+        for k in range(steps):
+            ctx.set_qp(4 + k)
+            _native.check(ctx.handle, ctx.lib.so_seq_run(ctx.handle))
+            ms += ctx.last_timing()["device_ms"]
+        s1 = ctx.sea_stats()
+        res["pruned" if sea else "plain"] = {"frames_per_s": steps * F / (ms / 1e3), "e2e_frames_per_s": F / e2e}
+        if sea:
+            w_me, me_l = me_work_per_sequence(cfg)
+            res["exact_sads_per_p_frame"] = (s1["exact_sads"] - s0["exact_sads"]) / max(1, s1["p_frames"] - s0["p_frames"])
+            res["candidates_per_p_frame"] = w_me / (cfg["bs"] * cfg["bs"]) / me_l          # what the plain search evaluates (algorithmic)
+        c._ctx.close()
+        c._ctx = None
+    res["identical_output"] = all(np.array_equal(a, b) for a, b in zip(sig[False], sig[True]))
+    res["speedup"] = res["pruned"]["frames_per_s"] / res["plain"]["frames_per_s"]
+    res["what"] = ("C2 at QP 4-5, kernels alone (CUDA events of so_seq_run, frames resident) and end to end (encode_arrays), plain vs pruned "
+                   "exhaustive search.  Content dependent: this is the translating texture of the bench; on the zooming texture the "
+                   "pruned search ties with the plain one, on C5 (integer search, 1 reference) it is 15 % slower "
+                   "(profiles/r02_sea_experiment.json).  Off by default; roofline.achieved above is the plain kernel only")
+    return res
+
+
 def c5_sharded(rank, world, local_rank, dist, reps=2):
     """BASELINE configs[4]: FIXED batch (strong scaling) of C5.S 4K streams x C5.F frames, I_Period 16, nRefFrames 1 (closed GOPs,
     quirk Q7), r=16 integer search; the S*F/16 GOPs are dealt round-robin to the ranks (streamoptima_b200/sharding.py), every
@@ -553,6 +601,7 @@ def main():
                 full_flow(codec, frames, 4)                  # the next encode(), so two sets of pinned buffers come into being here
             line["e2e_full_flow"] = full_flow(codec, frames, 4)
             line["c1"] = {"gpu": gpu_c1(local_rank)}
+            line["sea_experiment"] = sea_experiment(frames, cfg, local_rank)
             if not args.no_cpu_baseline:
                 line["c1"]["cpu"] = cpu_c1_full()
         # free the C2 buffers, then the fixed 4K batch sharded over all ranks

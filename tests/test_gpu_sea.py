@@ -87,3 +87,23 @@ def test_batched_units_equal_single_sequences():
             one, _ = _encode(seqs[u], False, qp=3, **kw)
             for k in KEYS:
                 np.testing.assert_array_equal(np.asarray(res[k])[u], one[k], err_msg=f"unit {u} {k}")
+
+
+def test_per_frame_seam_two_units_one_frame_apart():
+    """The pruned search through the per-frame C ABI (so_encode_inter with SO_FLAG_SEA), teacher-forced against the reference strip:
+    unit 1 runs one frame behind unit 0, so the predictor memory and the quadrant planes of the two chains differ at every call."""
+    from tests.test_gpu_seam import Seam, _assert_frame
+    frames, enc, g = load_case("w1920_fme_nref4")
+    F, H, W = frames.shape
+    s = Seam(H, W, enc, max_batch=2, sea=True)
+    s.reset(0)
+    s.reset(1)
+    for step in range(F + 1):
+        for unit, f in ((0, step), (1, step - 1)):
+            if not 0 <= f < F:
+                continue
+            out = s.encode(unit, frames[f], int(g["frame_types"][f]) == 0)
+            _assert_frame(out, g, f)
+            s.push(unit, g["recon"][f])
+    assert s.ctx.sea_stats()["p_frames"] > 0
+    s.ctx.close()

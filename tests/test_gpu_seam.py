@@ -35,7 +35,7 @@ def _seam_cases():
 class Seam:
     """Minimal binding of the per-frame calls -- the same few lines INTEGRATION.md shows."""
 
-    def __init__(self, H, W, enc, max_batch=1):
+    def __init__(self, H, W, enc, max_batch=1, sea=False):
         import torch
         from streamoptima_b200 import _native
         from streamoptima_b200.Encoder import Y_Video_codec
@@ -45,7 +45,7 @@ class Seam:
         self.ctx = _native.Context(width=W, height=H, block_size=self.bs, search_range=e["search_range"], qp=e["Qp"],
                                    intra_dur=e["intra_dur"], n_ref_frames=e.get("nRefFrames", 1), fme=e.get("FMEEnable", False),
                                    fast_me=e.get("fast_me", False), vbs=e.get("VBSEnable", False), rc_flag=e.get("RCFlag") or 0,
-                                   parallel_mode=0, lam=e.get("lam") or 0.0, max_batch=max_batch)
+                                   parallel_mode=0, lam=e.get("lam") or 0.0, max_batch=max_batch, sea=sea)
         if (e.get("RCFlag") or 0) > 0:        # data-independent row QPs (quirk Q9), computed by the host class like the reference does
             helper = Y_Video_codec(H, W, 1, self.bs, e["search_range"], e["Qp"], e["intra_dur"], 0, RCFlag=e["RCFlag"],
                                    targetBR=e["targetBR"], qp_rate_tables=e["qp_rate_tables"])
