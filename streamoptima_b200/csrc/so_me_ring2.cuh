@@ -18,7 +18,7 @@
 #include "so_me_ring.cuh"
 
 constexpr int MR2_BD = 64;                      // bundles whose descriptors are kept (ring; at most 55 are live, see the producer)
-constexpr int MR2_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 3072;      // + barriers, item meta, bundle descriptors, counters
+constexpr int MR2_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 3072 + 512; // + barriers, item meta, bundle descriptors, counters, vertical addends
 
 struct MeRing2Args {
     MeRingArgs b;                // geometry, outputs, units, nph, z_*, slot_packed, work counters (items_per_unit unused)
@@ -26,11 +26,10 @@ struct MeRing2Args {
     int chunks_per_unit;         // fme: ceil(npairs / 4) * 2 (pair group x horizontal parity); else ceil(npairs / 8)
 };
 
-// One 32-bit key per candidate for the per-item warp merge: SAD (16) | |dx|+|dy| (8) | dx + R (7) | dy > 0 (1).  Given the
-// L1 distance and dx, dy is known up to its sign, so the lexicographic order (SAD, L1, dx, dy) of Encoder.py:771 survives.
-__device__ __forceinline__ uint32_t mr2_key32(uint32_t best, int dx, int dy, int R) {
-    return (best & 0xFFFFFF00u) | ((uint32_t)(dx + R) << 1) | (dy > 0 ? 1u : 0u);
-}
+// One 32-bit key per candidate, thread-local argmin and per-item warp merge alike: SAD (16) | |dx|+|dy| (8) | dx + R (7) | dy > 0 (1).
+// Given the L1 distance and dx, dy is known up to its sign, so the lexicographic order (SAD, L1, dx, dy) of Encoder.py:771
+// survives; the low byte is additive -- 2 dx + (2 R + (dy > 0)) -- so it rides along in the addends of the key fold and the
+// winner needs no index decode.
 __device__ __forceinline__ unsigned long long mr2_key64(uint32_t m, int ref, int R) {
     const int l1 = (int)((m >> 8) & 0xFFu), dxr = (int)((m >> 1) & 0x7Fu);
     const int ady = l1 - abs(dxr - R), dy = (m & 1u) ? ady : -ady;
@@ -58,10 +57,24 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
     unsigned int* const counter = const_cast<unsigned int*>(bdesc) + MR2_BD * 8;
     volatile int* const bundles_pub = reinterpret_cast<volatile int*>(counter + 1);   // bundles whose descriptors are written AND whose items are issued
     volatile int* const final_bundles = bundles_pub + 1;                        // number of bundles of this CTA, once known
+    // vertical parts of the keys per (group, vertical phase): {|dy| << 8 | 2R + (dy > 0)} of the three offsets of the group and the
+    // multiplier of the third SAD (0 with an all-ones addend where oy = 16 does not exist: odd vertical phases, last group)
+    uint4* const lytab = reinterpret_cast<uint4*>(smem_r + MR_NS * (MR_SLOT + MR_CUR) + 3072);      // [MR_NG][2]
 
     const FrameGeom& g = a.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = (int)(blockDim.x >> 5);
+    if (tid >= 32 && tid < 32 + 2 * MR_NG) {
+        const int grp = (tid - 32) >> 1, py = (tid - 32) & 1, m = g.fme ? 2 : 1;
+        uint32_t v[3];
+#pragma unroll
+        for (int gg = 0; gg < 3; ++gg) {
+            const int dy = m * (-16 + 3 * grp + gg) + (g.fme ? py : 0);
+            v[gg] = ((uint32_t)abs(dy) << 8) + (uint32_t)(2 * g.R) + (dy > 0 ? 1u : 0u);
+        }
+        const bool ybl = grp == MR_NG - 1 && py && g.fme;
+        lytab[tid - 32] = make_uint4(v[0], v[1], ybl ? 0xFFFFFF00u : v[2], ybl ? 0u : 65536u);
+    }
     if (tid == 0) {
         for (int s = 0; s < MR_NS; ++s) { mbar_init(&ready[s], 1); mbar_init(&empty[s], MR_TPI); }
         *counter = 0;
@@ -252,11 +265,14 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
             // distance parts of the keys
             uint32_t ly8[3], lx8[9];
 #pragma unroll
-            for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
+            for (int gg = 0; gg < 3; ++gg) {
+                const int dy = mul * (oy0 + gg) + py;
+                ly8[gg] = ((uint32_t)abs(dy) << 8) + (uint32_t)(2 * g.R) + (dy > 0 ? 1u : 0u);
+            }
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative
-                lx8[k] = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
+                lx8[k] = (uint32_t)(dx * (k < 4 ? -254 : 258));              // |dx| << 8 | 2 dx
             }
             // interior block: parent and sub-blocks share the two special cases (ox = 16 on odd horizontal phases, oy = 16
             // on odd vertical ones); keys are folded rows-first like in the plain search (3 IMAD + min3 + add per column)
@@ -345,10 +361,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
             // ---- merge: five keys per segment
 #pragma unroll
             for (int e = 0; e < 5; ++e) {
-                const uint32_t best = bq[e];
-                const int idx = (int)(best & 0xFFu), k = (idx * 11) >> 5, gg = idx - 3 * k;
-                const int dx = mul * (-16 + c + 4 * k) + px, dy = mul * (oy0 + gg) + py;
-                const uint32_t v1 = (has && best != 0xFFFFFFFFu) ? mr2_key32(best, dx, dy, g.R) : 0xFFFFFFFFu;
+                const uint32_t v1 = has ? bq[e] : 0xFFFFFFFFu;
                 const uint32_t m1 = __reduce_min_sync(seg, v1);
                 if (leader && m1 != 0xFFFFFFFFu) {
                     const int4 ms = mt;
@@ -407,29 +420,24 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
         if (fast_valid) {
             // interior block: the only invalid candidates are ox = 16 on odd horizontal phases and oy = 16 on odd vertical ones
             const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;          // candidate k = 8
-            const bool ybl = grp == MR_NG - 1 && py;                              // candidate g = 2 of the last group
-            uint32_t ly8[3];
-#pragma unroll
-            for (int gg = 0; gg < 3; ++gg) ly8[gg] = (uint32_t)(abs(mul * (oy0 + gg) + py) << 8) + gg;
-            // min over the three vertical offsets first (their keys differ by SAD and ly8 only), then add the horizontal part:
-            // 3 IMAD (FMA pipe) + ONE 3-input min + one add per column on the ALU pipe.  The invalid third row of the last group
-            // on odd vertical phases is taken out through its multiplier (0) and addend (all ones but the index): no predicated
-            // 2-input mins
-            uint32_t m2 = 65536u;
-            if (ybl) { m2 = 0u; ly8[2] = 0xFFFFFF02u; }
+            // min over the three vertical offsets first (their keys differ by SAD and the vertical addend only), then the horizontal
+            // part: 3 IMAD (FMA pipe) + ONE 3-input min on the ALU pipe + one IMAD (dx * -254 = |dx| << 8 | 2 dx for dx < 0, dx * 258
+            // for dx >= 0) per column.  The invalid third row of the last group on odd vertical phases is taken out through its
+            // multiplier (0) and addend (all ones) in the table: no predicated 2-input mins
+            const uint4 ly = lytab[grp * 2 + py];
+            const int dx0 = mul * (c - 16) + px, dxs = 4 * mul;
             uint32_t kk[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int dx = mul * (-16 + c + 4 * k) + px;                 // k < 4: negative, k >= 4: non-negative (c <= 3)
-                const uint32_t lx8 = ((uint32_t)(k < 4 ? -dx : dx) << 8) + k * 3;
-                const uint32_t t0 = acc[0][k] * 65536u + ly8[0], t1 = acc[1][k] * 65536u + ly8[1], t2 = acc[2][k] * m2 + ly8[2];
-                kk[k] = min(min(t0, t1), t2) + lx8;
+                const int dx = dx0 + k * dxs;                                // k < 4: negative, k >= 4: non-negative (c <= 3)
+                const uint32_t t0 = acc[0][k] * 65536u + ly.x, t1 = acc[1][k] * 65536u + ly.y, t2 = acc[2][k] * ly.w + ly.z;
+                kk[k] = (uint32_t)(dx * (k < 4 ? -254 : 258)) + min(min(t0, t1), t2);
             }
             best = min(min(min(kk[0], kk[1]), min(kk[2], kk[3])), min(min(kk[4], kk[5]), min(kk[6], kk[7])));
             if (any_px0) {                      // the 33rd horizontal offset exists on even horizontal phases only (uniform per bundle)
-                const int dx = mul * (16 + c) + px;
-                const uint32_t t0 = ex[0] * 65536u + ly8[0], t1 = ex[1] * 65536u + ly8[1], t2 = ex[2] * m2 + ly8[2];
-                best = min(best, (min(min(t0, t1), t2) + ((uint32_t)dx << 8) + 24u) | xbl);
+                const int dx = dx0 + 8 * dxs;
+                const uint32_t t0 = ex[0] * 65536u + ly.x, t1 = ex[1] * 65536u + ly.y, t2 = ex[2] * ly.w + ly.z;
+                best = min(best, ((uint32_t)(dx * 258) + min(min(t0, t1), t2)) | xbl);
             }
         } else {
             int xlo, xhi, ylo, yhi;
@@ -441,13 +449,13 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
 #pragma unroll
             for (int gg = 0; gg < 3; ++gg) {
                 const int dy = mul * (oy0 + gg) + py;
-                ly8[gg] = (uint32_t)(abs(dy) << 8) + gg;
+                ly8[gg] = ((uint32_t)abs(dy) << 8) + (uint32_t)(2 * g.R) + (dy > 0 ? 1u : 0u);
                 ybad[gg] = (dy >= ylo && dy <= yhi) ? 0u : 0xFFFFFFFFu;
             }
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 const int dx = mul * (-16 + c + 4 * k) + px;
-                const uint32_t lx8 = (uint32_t)(abs(dx) << 8) + k * 3;
+                const uint32_t lx8 = ((uint32_t)abs(dx) << 8) + (uint32_t)(2 * dx);
                 const uint32_t xbad = ((k < 8 || c == 0) && dx >= xlo && dx <= xhi) ? 0u : 0xFFFFFFFFu;
 #pragma unroll
                 for (int gg = 0; gg < 3; ++gg) {
@@ -458,12 +466,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
         }
         // ---- merge per item: order (SAD, |dx|+|dy|, ref, dx, dy); all lanes of a segment share ref, so ONE REDUX over the
         //      32-bit key (SAD, L1, dx, sign of dy) gives the winner of the segment
-        uint32_t v1 = 0xFFFFFFFFu;
-        if (has && best != 0xFFFFFFFFu) {
-            const int idx = (int)(best & 0xFFu), k = (idx * 11) >> 5, gg = idx - 3 * k;
-            const int dx = mul * (-16 + c + 4 * k) + px, dy = mul * (oy0 + gg) + py;
-            v1 = mr2_key32(best, dx, dy, g.R);
-        }
+        const uint32_t v1 = has ? best : 0xFFFFFFFFu;
         {
             const uint32_t m1 = __reduce_min_sync(seg, v1);
             if (leader && m1 != 0xFFFFFFFFu)
