@@ -79,6 +79,7 @@ struct so_ctx {
     int* qp_rows_dev = nullptr;
     std::vector<int> qp_rows;
     unsigned int* me_work = nullptr;        // chunk counter of the item-ring search kernel
+    int me_key_fmt = 1;                     // format of the packed keys the last exhaustive search left (FlowArgs::me_packed)
     // successive elimination (so_me_sea.cuh, SO_FLAG_SEA): packed quadrant bytes [unit][slot][phase][H][W], last winners, counters
     uint32_t *sea_pq = nullptr, *sea_prev = nullptr;
     unsigned int* sea_ctr = nullptr;
@@ -638,6 +639,7 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
             a2.chunks_per_unit = a.g.fme ? ((a2.npairs + 3) / 4) * 2 : (a2.npairs + 7) / 8;
             const long long nchunks = (long long)units * a2.chunks_per_unit;
             const int grid = nchunks < sms ? (int)nchunks : sms;
+            ctx->me_key_fmt = 2;            // compact keys (me_get format 2)
             if (out_sub) e = launch_pdl(me_ring2_kernel<true>, dim3(grid), dim3(384), MR2_SMEM, st, map, cmap, a2);
             else {
                 static const int nthr = std::getenv("SO_ME_RING_THREADS") ? atoi(std::getenv("SO_ME_RING_THREADS")) : 512;      // experiments: fewer search warps
@@ -657,6 +659,7 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
 static int run_me_tma(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int unit0, int units, int bs, MeResult* out,
                       size_t out_stride, cudaStream_t st, MeResult* out_sub = nullptr, size_t out_sub_stride = 0, bool* used_quad = nullptr) {
     static const bool force_simple = std::getenv("SO_ME_SIMPLE") != nullptr;      // tests: cross-check of the packed kernels
+    ctx->me_key_fmt = 1;
     if (bs < 4 || force_simple) {
         // 2x2 sub-blocks of VBS with block_size 4 (or the test switch): plain one-warp-per-block search
         if (used_quad) *used_quad = false;
@@ -1003,6 +1006,7 @@ static int encode_inter_impl(so_ctx* ctx, const uint8_t* cur, size_t cur_stride,
             if (rc) return rc;
         }
     }
+    if (!use_fast) a.me_packed = ctx->me_key_fmt;
     ev_pair(ctx, ctx->ev_tq, st, true);
     if (ctx->timing_on) ctx->ev_tq_inter.push_back(ctx->ev_tq.size() - 1);
     dim3 grid(ctx->nblk, units);

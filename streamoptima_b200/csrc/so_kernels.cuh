@@ -110,7 +110,7 @@ struct FlowArgs {
     int unit0;                   // first unit processed by this launch (grid.y / grid.x index is added)
     int vbs, fast, chain;        // chain: fast ME carries mvp across blocks (ParallelMode 0)
     uint32_t mae_den, frame_type; // written into the frame's statistics by block 0 of the finish kernels
-    int me_packed;               // me_parent / me_sub hold packed search keys; the finish kernel decodes and resets them
+    int me_packed;               // me_parent / me_sub hold packed search keys (1: 64-bit keys, 2: compact keys of so_me_ring2.cuh); the finish kernel decodes and resets them
     int nref_fast;               // refs[:nRefFrames] of fast ME (1 in ParallelMode 2, Encoder.py:590)
     int qp_final;                // QP when no rate control
     int qp_rd;                   // QP of self.Q during prediction (RD cost)
@@ -139,7 +139,13 @@ __device__ __forceinline__ MeResult me_get(const MeResult* p, int packed, int R)
     const unsigned long long key = *reinterpret_cast<const unsigned long long*>(p);
     MeResult r;
     if (key == ~0ull) { r.dx = 0; r.dy = 0; r.ref = 0; r.none = 1; r.sad = 0; }          // (0,0,0), MAE = inf (Encoder.py:684-685)
-    else {
+    else if (packed == 2) {
+        // compact key of the item-ring search kernel (so_me_ring2.cuh): SAD (16) | |dx|+|dy| (8) | ref (8) | dx + R (7) | dy > 0 (1)
+        const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+        const int l1 = (int)((lo >> 16) & 0xFFu), dx = (int)((lo >> 1) & 0x7Fu) - R, ady = l1 - abs(dx);
+        r.sad = ((hi & 0xFFu) << 8) | (lo >> 24); r.ref = (int16_t)((lo >> 8) & 0xFFu);
+        r.dx = (int16_t)dx; r.dy = (int16_t)((lo & 1u) ? ady : -ady); r.none = 0;
+    } else {
         r.sad = (uint32_t)(key >> 40); r.ref = (int16_t)((key >> 16) & 0xFF);
         r.dx = (int16_t)((int)((key >> 8) & 0xFF) - R); r.dy = (int16_t)((int)(key & 0xFF) - R); r.none = 0;
     }

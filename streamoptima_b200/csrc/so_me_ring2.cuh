@@ -30,11 +30,12 @@ struct MeRing2Args {
 // Given the L1 distance and dx, dy is known up to its sign, so the lexicographic order (SAD, L1, dx, dy) of Encoder.py:771
 // survives; the low byte is additive -- 2 dx + (2 R + (dy > 0)) -- so it rides along in the addends of the key fold and the
 // winner needs no index decode.
-__device__ __forceinline__ unsigned long long mr2_key64(uint32_t m, int ref, int R) {
-    const int l1 = (int)((m >> 8) & 0xFFu), dxr = (int)((m >> 1) & 0x7Fu);
-    const int ady = l1 - abs(dxr - R), dy = (m & 1u) ? ady : -ady;
-    return ((unsigned long long)(m >> 16) << 40) | ((unsigned long long)l1 << 24) | ((unsigned long long)ref << 16) |
-           ((unsigned long long)dxr << 8) | (unsigned long long)(dy + R);
+// The 64-bit key merged with atomicMin: the 32-bit key with the reference between its L1 byte and its low byte -- the order
+// (SAD, L1, ref, dx, dy) of Encoder.py:771 -- put together with two byte permutes; me_get (so_kernels.cuh, format 2) decodes it
+// once per block.  refw: a word whose byte 0 is the reference index.
+__device__ __forceinline__ unsigned long long mr2_key64(uint32_t m, uint32_t refw) {
+    const uint32_t lo = __byte_perm(m, refw, 0x2140), hi = __byte_perm(m, 0u, 0x4443);
+    return ((unsigned long long)hi << 32) | lo;
 }
 __device__ __forceinline__ unsigned int mr2_next(unsigned int* counter) {       // one lane: no warp-aggregation code around it
     unsigned int v;
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                 const uint32_t m1 = __reduce_min_sync(seg, v1);
                 if (leader && m1 != 0xFFFFFFFFu) {
                     const int4 ms = mt;
-                    const unsigned long long key = mr2_key64(m1, ms.w & 255, g.R);
+                    const unsigned long long key = mr2_key64(m1, (uint32_t)ms.w);
                     unsigned long long* okey;
                     if (e == 0) okey = reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + ms.x);
                     else {
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
         {
             const uint32_t m1 = __reduce_min_sync(seg, v1);
             if (leader && m1 != 0xFFFFFFFFu)
-                atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + mt.x), mr2_key64(m1, mt.w & 255, g.R));
+                atomicMin(reinterpret_cast<unsigned long long*>(reinterpret_cast<MeResult*>(a.out) + mt.x), mr2_key64(m1, (uint32_t)mt.w));
         }
         }   // !QUAD
         __syncwarp();

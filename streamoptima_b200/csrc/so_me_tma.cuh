@@ -153,6 +153,13 @@ __device__ __forceinline__ void load_cur_row(const uint32_t* cb, int row, uint32
     }
 }
 
+#ifndef SAD_TRIPLE_UNROLL
+#define SAD_TRIPLE_UNROLL 2      // unroll factor of the steady loop (three window rows per iteration)
+#endif
+#ifndef SAD_TRIPLE_UNROLL
+#define SAD_TRIPLE_UNROLL 1      // unroll factor of the steady loop of sad_pass_g3 (three window rows per iteration)
+#endif
+constexpr int SAD_TRIPLE_UNROLL_N = SAD_TRIPLE_UNROLL;
 template <int WPR, int NDX, int KM, int ROWS, int WP, bool SPLIT>
 __device__ __forceinline__ void sad_pass_g3(const unsigned char* win, const uint32_t* cb, uint32_t (&accA)[3][NDX], uint32_t (&accB)[3][NDX]) {
     static_assert(ROWS >= 4, "needs two ramp rows on each side");
@@ -167,7 +174,7 @@ __device__ __forceinline__ void sad_pass_g3(const unsigned char* win, const uint
     sad_row_g3<WPR, NDX, KM, WP, SPLIT, 1, 3>(win + WP, cq, accA, accB);
     constexpr int STEADY = ROWS - 2, TRIPLES = STEADY / 3, REM = STEADY % 3;
     const unsigned char* wr = win + 2 * WP;
-#pragma unroll 1
+#pragma unroll SAD_TRIPLE_UNROLL_N
     for (int t3 = 0; t3 < TRIPLES; ++t3) {
         const int rho = 2 + 3 * t3;
         load_cur_row<WPR>(cb, rho, cq[2]);
