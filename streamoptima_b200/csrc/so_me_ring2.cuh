@@ -17,8 +17,12 @@
 #pragma once
 #include "so_me_ring.cuh"
 
+#ifndef MR2_PRODUCER_SLEEP
+#define MR2_PRODUCER_SLEEP 200          // ns between two polls of a slot's `empty` barrier by the producer
+#endif
 constexpr int MR2_BD = 64;                      // bundles whose descriptors are kept (ring; at most 55 are live, see the producer)
-constexpr int MR2_SMEM = MR_NS * (MR_SLOT + MR_CUR) + 3072 + 512; // + barriers, item meta, bundle descriptors, counters, vertical addends
+constexpr int MR2_CTRL = 1024 + MR2_BD * 8 * 16;                 // barriers, item meta, counters | bundle descriptors
+constexpr int MR2_SMEM = MR_NS * (MR_SLOT + MR_CUR) + MR2_CTRL + 512;   // + vertical addends
 
 struct MeRing2Args {
     MeRingArgs b;                // geometry, outputs, units, nph, z_*, slot_packed, work counters (items_per_unit unused)
@@ -37,6 +41,14 @@ __device__ __forceinline__ unsigned long long mr2_key64(uint32_t m, uint32_t ref
     const uint32_t lo = __byte_perm(m, refw, 0x2140), hi = __byte_perm(m, 0u, 0x4443);
     return ((unsigned long long)hi << 32) | lo;
 }
+__device__ __forceinline__ uint4 mr2_lds_v4(const volatile void* p) {       // one volatile 128-bit shared load (descriptor ring)
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(const_cast<const void*>(p))) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mr2_sts_v4(volatile void* p, const uint4& v) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(const_cast<const void*>(p))), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ unsigned int mr2_next(unsigned int* counter) {       // one lane: no warp-aggregation code around it
     unsigned int v;
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(smem_u32(counter)) : "memory");
@@ -54,13 +66,19 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
     uint64_t* const ready = reinterpret_cast<uint64_t*>(curs + MR_NS * MR_CUR);
     uint64_t* const empty = ready + MR_NS;
     int4* const meta = reinterpret_cast<int4*>(empty + MR_NS);                  // [NS]: {out index, bx, by, ref | ph << 8 | interior << 16}
-    volatile uint32_t* const bdesc = reinterpret_cast<volatile uint32_t*>(meta + MR_NS);   // [MR2_BD][8]: slot | use parity << 5 | group << 6 | valid << 10
-    unsigned int* const counter = const_cast<unsigned int*>(bdesc) + MR2_BD * 8;
+    unsigned int* const counter = reinterpret_cast<unsigned int*>(meta + MR_NS);
     volatile int* const bundles_pub = reinterpret_cast<volatile int*>(counter + 1);   // bundles whose descriptors are written AND whose items are issued
     volatile int* const final_bundles = bundles_pub + 1;                        // number of bundles of this CTA, once known
+    // [MR2_BD][8] descriptors, one per lane quad of a bundle, everything a search warp needs before the SAD loop ready-made:
+    //   x: slot | use parity of the slot << 8 | flags << 16 (1 valid, 2 every offset of the item is valid, 4 odd horizontal phase,
+    //      8 odd vertical phase) | vertical group << 24
+    //   y, z, w: byte offsets from smem_r of the window row (slot parity + 3 * group) of shift plane 0, of the group's vertical
+    //      addends (lytab) and of the current block
+    volatile uint4* const bdesc = reinterpret_cast<volatile uint4*>(smem_r + MR_NS * (MR_SLOT + MR_CUR) + 1024);
     // vertical parts of the keys per (group, vertical phase): {|dy| << 8 | 2R + (dy > 0)} of the three offsets of the group and the
     // multiplier of the third SAD (0 with an all-ones addend where oy = 16 does not exist: odd vertical phases, last group)
-    uint4* const lytab = reinterpret_cast<uint4*>(smem_r + MR_NS * (MR_SLOT + MR_CUR) + 3072);      // [MR_NG][2]
+    constexpr int LYTAB_OFF = MR_NS * (MR_SLOT + MR_CUR) + MR2_CTRL;
+    uint4* const lytab = reinterpret_cast<uint4*>(smem_r + LYTAB_OFF);      // [MR_NG][2]
 
     const FrameGeom& g = a.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,18 +158,26 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                 // been consumed; the live bundles are those of the last MR_NS items (they lie in at most 4 chunks = 44 bundles) plus
                 // the 11 of this chunk: 55 <= MR2_BD.
                 const int mg = (1024 + ng - 1) / ng;        // exact division by ng of any e < 96 (ng <= 11): (e * mg) >> 10
+                const int i_info = i_ph | (i_int << 8);
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int e = lane + 32 * j;
+                    int ki = (e * mg) >> 10, gl = e - ki * ng;
+                    const bool has = ki < nit;              // quads past the chunk's last task shadow its last item
+                    if (!has) { ki = nit - 1; gl = 0; }
+                    const int info = __shfl_sync(0xFFFFFFFFu, i_info, ki);       // phase plane and interior flag of the quad's item
                     if (e < nb * 8) {
-                        int ki = (e * mg) >> 10, gl = e - ki * ng;
-                        const bool has = ki < nit;          // quads past the chunk's last task shadow its last item
-                        if (!has) { ki = nit - 1; gl = 0; }
                         int s = slot + ki;
                         const bool wrap = s >= MR_NS;
                         if (wrap) s -= MR_NS;
-                        bdesc[(bundle_base * 8 + e) & (MR2_BD * 8 - 1)] =
-                            (uint32_t)s | ((upar ^ (wrap ? 1u : 0u)) << 5) | ((uint32_t)(glo + gl) << 6) | (has ? 1u << 10 : 0u);
+                        const int grp = glo + gl, ph = info & 255;
+                        const uint32_t flags = (has ? 1u : 0u) | ((info >> 8) ? 2u : 0u) | ((g.fme && (ph & 1)) ? 4u : 0u) | ((g.fme && (ph >> 1)) ? 8u : 0u);
+                        uint4 d;
+                        d.x = (uint32_t)s | ((upar ^ (wrap ? 1u : 0u)) << 8) | (flags << 16) | ((uint32_t)grp << 24);
+                        d.y = (uint32_t)(s * MR_SLOT + ((s & 1) + G * grp) * MR_WP);
+                        d.z = (uint32_t)(LYTAB_OFF + (grp * 2 + ((flags >> 3) & 1u)) * 16);
+                        d.w = (uint32_t)(MR_NS * MR_SLOT + s * MR_CUR);
+                        mr2_sts_v4(&bdesc[(bundle_base * 8 + e) & (MR2_BD * 8 - 1)], d);
                     }
                 }
                 // ---- the chunk's items, one lane each
@@ -161,7 +187,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                     if (wrap) s -= MR_NS;
                     if (n + lane >= MR_NS) {            // not the first use of the slot: wait until its previous item is consumed
                         const uint32_t par = upar ^ (wrap ? 1u : 0u) ^ 1u;
-                        while (!mbar_try(&empty[s], par)) __nanosleep(200);      // 22 items ahead: a slot frees up every ~0.6 us
+                        while (!mbar_try(&empty[s], par)) __nanosleep(MR2_PRODUCER_SLEEP);      // 22 items ahead: a slot frees up every ~0.6 us
                     }
                     meta[s] = make_int4((int)(unit * a.out_unit_stride) + i_blk, i_bx, i_by, i_ref | (i_ph << 8) | (i_int << 16) | (unit << 17));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the slot was read through the generic proxy
@@ -197,24 +223,21 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
             }
             if (none) break;
         }
-        const uint32_t dsc = bdesc[((b & (MR2_BD - 1)) << 3) | (lane >> 2)];
-        const unsigned slot = dsc & 31u;
-        const int grp = (int)((dsc >> 6) & 15u), c = (int)(lane & 3u);
-        const bool has = (dsc >> 10) & 1u;
+        const uint4 dsc = mr2_lds_v4(&bdesc[((b & (MR2_BD - 1)) << 3) | (lane >> 2)]);
+        const unsigned slot = dsc.x & 0xFFu;
+        const int grp = (int)(dsc.x >> 24), c = (int)(lane & 3u);
+        const bool has = dsc.x & 0x10000u;
         unsigned nb = 0;
         if (lane == 0) nb = mr2_next(counter);              // next bundle index: consumed at the end of this iteration
-        mbar_wait(&ready[slot], (dsc >> 5) & 1u);
+        mbar_wait(&ready[slot], (dsc.x >> 8) & 1u);
         __syncwarp();
         const unsigned seg = __match_any_sync(0xFFFFFFFFu, has ? slot : 0xFFu);    // the lanes of my item (one slot each)
         const bool leader = has && (int)lane == __ffs(seg) - 1;
         const int4 mt = meta[slot];
         const int bx = mt.y, by = mt.z;
-        const int ph = (mt.w >> 8) & 255;
-        const int px = g.fme ? (ph & 1) : 0, py = g.fme ? (ph >> 1) : 0;
-        const int p = (int)(slot & 1u);
-        const unsigned char* wslot = wins + slot * MR_SLOT;
-        const unsigned char* win = wslot + c * MR_PLANE + (p + G * grp) * MR_WP;
-        const uint32_t* cb = reinterpret_cast<const uint32_t*>(curs + slot * MR_CUR);
+        const int px = (dsc.x >> 18) & 1u, py = (dsc.x >> 19) & 1u;          // 0 without half-pel search
+        const unsigned char* win = smem_r + (dsc.y + (unsigned)(c * MR_PLANE));
+        const uint32_t* cb = reinterpret_cast<const uint32_t*>(smem_r + dsc.w);
         const int oy0 = -16 + G * grp;
 
         if constexpr (QUAD) {
@@ -234,7 +257,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                 for (int gg = 0; gg < 3; ++gg) exq[e][gg] = 0u;
             if (__any_sync(0xFFFFFFFFu, px == 0)) {  // odd horizontal phases have no 33rd offset (dx = 33 > R): masked below
                 uint32_t eL[3] = {0u, 0u, 0u}, eR[3] = {0u, 0u, 0u};
-                const unsigned char* w0 = wslot + (p + G * grp + 4 * c) * MR_WP + 32;
+                const unsigned char* w0 = smem_r + (dsc.y + (unsigned)(4 * c * MR_WP + 32));
                 uint4 cr[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) cr[i] = reinterpret_cast<const uint4*>(cb)[4 * c + i];
@@ -262,7 +285,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
                 }
             }
             uint32_t bq[5] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // parent, TL, TR, BL, BR
-            const bool fast_valid = __all_sync(0xFFFFFFFFu, (mt.w >> 16) & 1);
+            const bool fast_valid = __all_sync(0xFFFFFFFFu, dsc.x & 0x20000u);
             // distance parts of the keys
             uint32_t ly8[3], lx8[9];
 #pragma unroll
@@ -392,7 +415,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
         uint32_t ex[3] = {0u, 0u, 0u};
         const bool any_px0 = __any_sync(0xFFFFFFFFu, px == 0);
         if (any_px0) {
-            const unsigned char* w0 = wslot + (p + G * grp + 4 * c) * MR_WP + 32;
+            const unsigned char* w0 = smem_r + (dsc.y + (unsigned)(4 * c * MR_WP + 32));
             uint4 cr[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) cr[i] = reinterpret_cast<const uint4*>(cb)[4 * c + i];
@@ -417,7 +440,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
 
         // ---- thread-local argmin.  key32 = sad << 16 | (|dx| + |dy|) << 8 | (k * 3 + g); invalid candidates are OR-ed to all ones.
         uint32_t best = 0xFFFFFFFFu;
-        const bool fast_valid = __all_sync(0xFFFFFFFFu, (mt.w >> 16) & 1);
+        const bool fast_valid = __all_sync(0xFFFFFFFFu, dsc.x & 0x20000u);
         if (fast_valid) {
             // interior block: the only invalid candidates are ox = 16 on odd horizontal phases and oy = 16 on odd vertical ones
             const uint32_t xbl = (c == 0 && px == 0) ? 0u : 0xFFFFFFFFu;          // candidate k = 8
@@ -425,7 +448,7 @@ __global__ void __launch_bounds__(QUAD ? 384 : 512, 1) me_ring2_kernel(const __g
             // part: 3 IMAD (FMA pipe) + ONE 3-input min on the ALU pipe + one IMAD (dx * -254 = |dx| << 8 | 2 dx for dx < 0, dx * 258
             // for dx >= 0) per column.  The invalid third row of the last group on odd vertical phases is taken out through its
             // multiplier (0) and addend (all ones) in the table: no predicated 2-input mins
-            const uint4 ly = lytab[grp * 2 + py];
+            const uint4 ly = *reinterpret_cast<const uint4*>(smem_r + dsc.z);
             const int dx0 = mul * (c - 16) + px, dxs = 4 * mul;
             uint32_t kk[8];
 #pragma unroll
