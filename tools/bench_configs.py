@@ -21,15 +21,26 @@ TAB = [[90000, 70000, 52000, 39000, 28000, 19000, 13000, 9000, 6000, 4000, 2500,
 def run(name, U, F, H, W, args, kw, reps=2):
     frames = torch.stack([synth_frames_torch(F, H, W, seed=u, device=dev) for u in range(U)]).cpu().numpy()
     c = Y_Video_codec(H, W, F, *args, 0, **kw)
-    c.encode_arrays(frames, want_levels=True, want_recon=True)
+    kw_e2e = dict(want_levels=False, want_recon=False, want_symbols=True)      # the residual travels as packed run-level symbols
+    for _ in range(2):
+        c.encode_arrays(frames, **kw_e2e)
     t0 = time.perf_counter()
-    dev_ms = 0.0
     for _ in range(reps):
-        c.encode_arrays(frames)
-        dev_ms += c.last_timing["device_ms"]
+        c.encode_arrays(frames, **kw_e2e)
     wall = (time.perf_counter() - t0) / reps
+    # kernels alone: the sequence(s) resident in HBM, CUDA events around so_seq_run
+    from streamoptima_b200 import _native
+    ctx = c._ctx
+    _native.check(ctx.handle, ctx.lib.so_seq_upload(ctx.handle, frames.ctypes.data, U, F))
+    _native.check(ctx.handle, ctx.lib.so_seq_sync(ctx.handle))
+    dev_ms, t = 0.0, None
+    for i in range(reps + 1):
+        _native.check(ctx.handle, ctx.lib.so_seq_run(ctx.handle))
+        t = ctx.last_timing()
+        if i:
+            dev_ms += t["device_ms"]
     out = dict(config=name, units=U, frames=F, size=f"{W}x{H}", fps_kernel=U * F / (dev_ms / reps / 1e3), fps_e2e=U * F / wall,
-               me_ms_per_frame=c.last_timing["me_ms"] / max(1, c.last_timing["timed_frames"]) / U, launches=c.last_timing["launches"])
+               me_ms_per_frame=t["me_ms"] / max(1, t["timed_frames"]) / U, launches=t["launches"])
     print(json.dumps(out), flush=True)
     c._ctx.close()
 
