@@ -1,6 +1,8 @@
 """Randomised differential test: small random configurations, CUDA path vs the CPU oracle, everything bit for bit (packed
 outputs, both text streams, device-generated symbols, decode round trip).
-    python tools/fuzz_vs_oracle.py [n_cases] [seed] [big]        (GPU box; about 0.1 s per case, 1 s with `big`)"""
+    python tools/fuzz_vs_oracle.py [n_cases] [seed] [big|ring]   (GPU box; about 0.1 s per case, 1 s with `big`)
+`ring`: only the geometry of the bench kernels (16x16 blocks, r = 16: item-ring search kernel, fused VBS search, and -- on half of
+the non-VBS cases -- the pruned search `sea_prune`), frames up to 208 x 304, several seconds of oracle per case."""
 import os, sys, time, traceback
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,6 +14,7 @@ Y_Video_codec.write_recon_yuv = False
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 BIG = len(sys.argv) > 3 and sys.argv[3] == "big"       # frames up to 160 x 224: several CTAs / chunks per launch (slower oracle)
+RING = len(sys.argv) > 3 and sys.argv[3] == "ring"
 TAB = [[9000, 7000, 5200, 3900, 2800, 1900, 1300, 900, 600, 400, 250, 100], [6000, 4600, 3400, 2500, 1800, 1200, 800, 560, 380, 250, 160, 60]]
 bad = skipped = 0
 t0 = time.time()
@@ -24,10 +27,14 @@ for n in range(n_cases):
     kw = dict(block_size=bs, search_range=r, Qp=int(rng.integers(0, {4: 10, 8: 11, 16: 12}[bs])), intra_dur=int(rng.integers(1, 6)))
     if rng.random() < 0.5: kw["FMEEnable"] = True
     if rng.random() < 0.5: kw["nRefFrames"] = int(rng.integers(2, 5)) if rng.random() < 0.85 else int(rng.integers(5, 9))
+    if RING:
+        bs, r = 16, 16
+        H = 16 * int(rng.integers(2, 14)); W = 16 * int(rng.integers(3, 20))
+        kw.update(block_size=16, search_range=16, Qp=int(rng.integers(0, 12)))
     if r > 16: F = min(F, 3)
     if rng.random() < 0.4: kw.update(VBSEnable=True, lam=float(rng.choice([0.005, 0.02, 0.3])))
     mode = rng.random()
-    if mode < 0.3: kw["fast_me"] = True
+    if mode < (0.0 if RING else 0.3): kw["fast_me"] = True
     pm = rng.random()
     if pm < 0.15 and not (kw.get("VBSEnable") and kw.get("fast_me")): kw["ParallelMode"] = 2
     elif pm < 0.25 and not (kw.get("VBSEnable") and kw.get("fast_me")): kw["ParallelMode"] = 1
@@ -45,6 +52,8 @@ for n in range(n_cases):
             continue
         e = dict(kw)
         c = Y_Video_codec(H, W, F, e.pop("block_size"), e.pop("search_range"), e.pop("Qp"), e.pop("intra_dur"), 0, y_only_frame_arr=frames, **e)
+        sea = bs == 16 and r == 16 and not kw.get("VBSEnable") and rng.random() < 0.5
+        c.sea_prune = bool(sea)
         c.encode()
         p = c.encoded_package.packed
         split, mv, lev = package_to_arrays(o["frame_types"], o["mvs"], o["levels"], H, W, bs)
@@ -66,6 +75,6 @@ for n in range(n_cases):
         ok = False
     if not ok:
         bad += 1
-        print("MISMATCH", n, kind, (F, H, W), kw, flush=True)
+        print("MISMATCH", n, kind, (F, H, W), kw, "sea" if c.sea_prune else "", flush=True)
 print(f"{n_cases} cases ({skipped} skipped: no QP fits the rate budget), {bad} mismatches, {time.time() - t0:.0f} s")
 sys.exit(1 if bad else 0)
