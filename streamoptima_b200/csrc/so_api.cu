@@ -403,6 +403,11 @@ static int ring_push(so_ctx* ctx, const uint8_t* recon_dev, size_t src_unit_stri
     bool all_u8 = true;
     for (int l : R.list) all_u8 = all_u8 && R.slot_u8[l];
     const int wrap = (g.fme && all_u8) ? 1 : 0;
+    if (!g.fme && g.W % 16 == 0 && reinterpret_cast<uintptr_t>(recon_dev) % 16 == 0 && src_unit_stride % 16 == 0)
+        CU(launch_pdl(ring_shift_kernel, dim3((g.W / 16 + 127) / 128, g.H, units), dim3(128), 0, st,
+                      slot_ptr(ctx, s) + (size_t)ctx->u0() * ctx->unit_stride, ctx->unit_stride,
+                      ctx->plane_bytes, recon_dev, src_unit_stride, g.W, g.W, g.pitch));
+    else
     CU(launch_pdl(ring_planes_kernel, dim3((g.W / 4 + 127) / 128, g.H, units), dim3(128), 0, st,
                   slot_ptr(ctx, s) + (size_t)ctx->u0() * ctx->unit_stride, ctx->unit_stride,
                   ctx->plane_bytes, recon_dev, src_unit_stride, g.W, g.W, g.H, g.pitch, g.fme, wrap, 1));

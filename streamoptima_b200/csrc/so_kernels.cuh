@@ -94,6 +94,26 @@ __global__ void ring_planes_kernel(uint8_t* slot0, size_t unit_stride, size_t pl
     }
 }
 
+// Integer search only (no half-pel phases): the frame and its three byte-shifted copies, 16 pixels per thread with 128-bit
+// stores (the generic kernel above computes all four phases per pixel before it knows that only phase 0 is stored).  W % 16 == 0.
+__global__ void __launch_bounds__(128) ring_shift_kernel(uint8_t* slot0, size_t unit_stride, size_t plane_bytes, const uint8_t* src,
+                                                         size_t src_unit_stride, int src_pitch, int W, int pitch) {
+    pdl_trigger();
+    pdl_wait();
+    const int x16 = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, x = x16 * 16;
+    if (x >= W) return;
+    const uint8_t* srow = src + blockIdx.z * src_unit_stride + (size_t)y * src_pitch + x;
+    const uint4 v = *reinterpret_cast<const uint4*>(srow);
+    // word past the 16 pixels; past the frame edge the last column is replicated (only invalid candidates see it)
+    const uint32_t nx = x + 16 < W ? *reinterpret_cast<const uint32_t*>(srow + 16) : (v.w >> 24) * 0x01010101u;
+    uint8_t* base = slot0 + blockIdx.z * unit_stride + (size_t)y * pitch + x;
+    *reinterpret_cast<uint4*>(base) = v;
+#pragma unroll
+    for (int c = 1; c < 4; ++c)
+        *reinterpret_cast<uint4*>(base + (size_t)c * plane_bytes) =
+            make_uint4(__funnelshift_r(v.x, v.y, 8 * c), __funnelshift_r(v.y, v.z, 8 * c), __funnelshift_r(v.z, v.w, 8 * c), __funnelshift_r(v.w, nx, 8 * c));
+}
+
 __global__ void ring_fill_kernel(uint8_t* dst, size_t dst_unit_stride, size_t bytes16, uint32_t v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < bytes16) reinterpret_cast<uint4*>(dst + blockIdx.y * dst_unit_stride)[i] = make_uint4(v, v, v, v);
@@ -398,8 +418,11 @@ __device__ __forceinline__ int rle_rows_partial(uint32_t m, int rr, uint32_t m_p
     return v;
 }
 
+#ifndef FIN16_MINB
+#define FIN16_MINB 1                  // resident CTAs per SM the non-VBS finish kernel is compiled for (register cap)
+#endif
 template <bool VBS>
-__global__ void __launch_bounds__(128) inter_finish16_kernel(const FlowArgs a) {
+__global__ void __launch_bounds__(128, VBS ? 1 : FIN16_MINB) inter_finish16_kernel(const FlowArgs a) {
     constexpr int BS = 16, S = 8, P = 17;
     __shared__ double tiles[4][2][BS * P];
     pdl_trigger();
