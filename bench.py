@@ -570,7 +570,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "wall_ms_per_step": wall_ms_max / args.steps,
-                "roofline": {"bound": "int32-alu (VABSDIFF4 pipe)", "kernel": "me_ring_kernel<false>", "achieved": achieved,
+                "roofline": {"bound": "int32-alu (VABSDIFF4 pipe)", "kernel": "me_ring2_kernel<false>", "achieved": achieved,
                              "peak": peak, "unit": "T lane-instr/s (1 instr = 4 pixel SADs)", "frac": achieved / peak,
                              "peak_int32": peak_iadd, "frac_int32": achieved / peak_iadd,
                              "peak_source": "measured: tools/int_peak.cu, profiles/int_peak_r01.json (MEASURED_PEAKS.json has no integer figure); "
