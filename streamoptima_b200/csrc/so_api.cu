@@ -566,7 +566,9 @@ static int run_sea(so_ctx* ctx, const MeRingArgs& a, const uint8_t* cur, size_t 
         R.slot_sea[sl] = 1;
     }
     const int gpr = (s.g.nbx + SEA_NB - 1) / SEA_NB;
-    CU(launch_pdl(sea_search_kernel, dim3(gpr * s.g.nby, units), dim3(256), 0, st, s));
+    // one warp per (reference, phase plane, block) triple in flight: 4 blocks x 1 plane (integer search, one reference) fill 4 warps
+    const int sea_threads = s.g.nref * nph * SEA_NB <= 4 ? 128 : 256;
+    CU(launch_pdl(sea_search_kernel, dim3(gpr * s.g.nby, units), dim3(sea_threads), 0, st, s));
     return SO_OK;
 }
 

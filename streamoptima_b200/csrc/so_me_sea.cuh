@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(256, SEA_MINB) sea_search_kernel(const SeaArgs
         if (g.fme) { lo = (lo - py + 1) >> 1; hi = (hi - py) >> 1; }
         s_ylo[py] = lo; s_yhi[py] = hi;
     }
-    if (tid >= 128 && tid < 128 + SEA_NB) { s_key[tid - 128] = ~0ull; s_thr[tid - 128] = 1023u; }     // D <= 1020: everything passes
-    if (tid == 255) { s_evals = 0u; s_n = 0u; }
+    if (tid >= 96 && tid < 96 + SEA_NB) { s_key[tid - 96] = ~0ull; s_thr[tid - 96] = 1023u; }       // D <= 1020: everything passes
+    if (tid == 127) { s_evals = 0u; s_n = 0u; }
     __syncthreads();
     unsigned int evals = 0;
     if (warp < SEA_NB && bx0 + warp < g.nbx) {
@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(256, SEA_MINB) sea_search_kernel(const SeaArgs
     const int ox0 = 4 * quad - 16;
     const uint32_t* pq_u = a.pq + (size_t)(a.unit0 + u) * a.pq_unit_stride;
     const int off0 = (rsub - 16) * g.W + ox0, rowstep = 3 * g.W;
-    for (int pair = warp; pair < npairs; pair += 8) {
+    const int nwarps = (int)(blockDim.x >> 5);             // 8, or 4 when there is one (reference, phase plane) only
+    for (int pair = warp; pair < npairs; pair += nwarps) {
         const int item = pair / SEA_NB, b = pair - item * SEA_NB, bx = bx0 + b;
         if (bx >= g.nbx) continue;
         const int ref = item / a.nph, ph = item - ref * a.nph;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256, SEA_MINB) sea_search_kernel(const SeaArgs
     // ================================= phase B: exact SADs of the listed survivors =================================
     {
         const int n = (int)min(s_n, (unsigned)SEA_LCAP);
-        evals += sea_eval_thread(a, ring_u, bx0, by, s_cur, s_thr, s_key, s_list, tid, 256, n);
+        evals += sea_eval_thread(a, ring_u, bx0, by, s_cur, s_thr, s_key, s_list, tid, (int)blockDim.x, n);
     }
     evals = __reduce_add_sync(0xFFFFFFFFu, evals);
     if (lane == 0 && evals) atomicAdd(&s_evals, evals);
