@@ -290,7 +290,7 @@ def sea_experiment(frames, cfg, device, steps=2):
     res["speedup"] = res["pruned"]["frames_per_s"] / res["plain"]["frames_per_s"]
     res["what"] = ("C2 at QP 4-5, kernels alone (CUDA events of so_seq_run, frames resident) and end to end (encode_arrays), plain vs pruned "
                    "exhaustive search.  Content dependent: this is the translating texture of the bench; on the zooming texture the "
-                   "pruned search ties with the plain one, on C5 (integer search, 1 reference) it is 1.14x faster "
+                   "pruned search is 3 % slower than the plain one, on C5 (integer search, 1 reference) it is 1.14x faster "
                    "(profiles/r02_sea_experiment.json).  Off by default; roofline.achieved above is the plain kernel only")
     return res
 

@@ -175,20 +175,28 @@ __device__ __forceinline__ unsigned int sea_eval_thread(const SeaArgs& a, const 
         const uint32_t* w = reinterpret_cast<const uint32_t*>(sea_window(a, ring_u, bx0 + b, by, ref, dx, dy));
         const int p4 = g.pitch >> 2;
         uint32_t s0 = 0, s1 = 0;
+        bool hopeless = false;
 #pragma unroll
-        for (int r = 0; r < 16; r += 2) {
-            const uint4 c0 = *reinterpret_cast<const uint4*>(&cur[b][r * 16]), c1 = *reinterpret_cast<const uint4*>(&cur[b][r * 16 + 16]);
-            const uint32_t* w0 = w + r * p4;
-            const uint32_t* w1 = w0 + p4;
-            s0 = sad4_acc(__ldg(w0), c0.x, s0); s0 = sad4_acc(__ldg(w0 + 1), c0.y, s0);
-            s0 = sad4_acc(__ldg(w0 + 2), c0.z, s0); s0 = sad4_acc(__ldg(w0 + 3), c0.w, s0);
-            s1 = sad4_acc(__ldg(w1), c1.x, s1); s1 = sad4_acc(__ldg(w1 + 1), c1.y, s1);
-            s1 = sad4_acc(__ldg(w1 + 2), c1.z, s1); s1 = sad4_acc(__ldg(w1 + 3), c1.w, s1);
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int r = 8 * half; r < 8 * half + 8; r += 2) {
+                const uint4 c0 = *reinterpret_cast<const uint4*>(&cur[b][r * 16]), c1 = *reinterpret_cast<const uint4*>(&cur[b][r * 16 + 16]);
+                const uint32_t* w0 = w + r * p4;
+                const uint32_t* w1 = w0 + p4;
+                s0 = sad4_acc(__ldg(w0), c0.x, s0); s0 = sad4_acc(__ldg(w0 + 1), c0.y, s0);
+                s0 = sad4_acc(__ldg(w0 + 2), c0.z, s0); s0 = sad4_acc(__ldg(w0 + 3), c0.w, s0);
+                s1 = sad4_acc(__ldg(w1), c1.x, s1); s1 = sad4_acc(__ldg(w1 + 1), c1.y, s1);
+                s1 = sad4_acc(__ldg(w1 + 2), c1.z, s1); s1 = sad4_acc(__ldg(w1 + 3), c1.w, s1);
+            }
+            // the SAD of the upper half alone already exceeds the block's best SAD so far (top 24 bits of its key): this candidate
+            // cannot win, not even a tie -- skip its lower half
+            if (half == 0 && s0 + s1 > (reinterpret_cast<volatile uint32_t*>(key + b)[1] >> 8)) { hopeless = true; break; }
         }
+        ++evals;
+        if (hopeless) continue;
         const uint32_t sad = s0 + s1;
         atomicMin(key + b, sea_key64(sad, ref, dx, dy, g.R));
         atomicMin(thr + b, (sad + 252u) >> 6);
-        ++evals;
     }
     return evals;
 }
