@@ -46,6 +46,12 @@ extern "C" {
                               * skips candidates whose SAD lower bound (8x8 quadrant sums) exceeds the exact SAD of a predictor
                               * candidate -- same minimum key, ties included.  Applies to 16x16 blocks at r = 16 without VBS;
                               * ignored elsewhere.  Off by default. */
+#define SO_FLAG_SEA_AUTO 16u /* with SO_FLAG_SEA: the library watches how many exact SADs the pruned launches that have FINISHED took
+                              * per (block, reference, phase plane) (read from mapped host memory, no synchronisation) and runs the
+                              * plain kernel for the next 60 P frames whenever their running average says pruning does not pay on the
+                              * content, then probes again.  The host enqueues a resident sequence far ahead of the GPU, so the
+                              * feedback acts across calls (GOP after GOP, sequence after sequence), not inside one short call.
+                              * Results are identical either way. */
 
 #define SO_MAX_REF 8
 #define SO_ALL_UNITS (-1)    /* `unit` argument of the per-frame calls: every unit of the context in lock step */

@@ -215,7 +215,8 @@ class Y_Video_codec:
     write_recon_yuv = True      # encode() writes yuv/y_only_reconstructed.yuv like the reference (Encoder.py:1894)
     roi_qp_map = None           # EXTENSION (not in the reference): int [F, n_blocks] per-block QPs for the final quantisation
     device = 0                  # CUDA device ordinal used by encode()
-    sea_prune = False           # EXTENSION, results unchanged: prune the exhaustive search with SAD lower bounds (SO_FLAG_SEA)
+    sea_prune = False           # EXTENSION, results unchanged: prune the exhaustive search with SAD lower bounds (SO_FLAG_SEA);
+                                # "auto": only while it pays on the content (SO_FLAG_SEA_AUTO)
 
     def __init__(self, h_pixels, w_pixels, frames, block_size, search_range, Qp, intra_dur, intra_mode, lam=None,
                  VBSEnable=False, nRefFrames=1, yuv_file=None, y_only_frame_arr=None, fast_me=False, FMEEnable=False,
@@ -300,6 +301,9 @@ class Y_Video_codec:
             qps.append(qp)
         return qps
 
+    def _sea_mode(self):
+        return "auto" if self.sea_prune == "auto" else bool(self.sea_prune)
+
     def _context(self, block_size, search_range, intra_dur, max_batch=1):
         """Native context for the CURRENT attribute values: the reference reads ``self.*`` every frame, so everything a
         context is created from is part of the cache key (only ``const_init_Qp`` is re-pushed on reuse)."""
@@ -312,7 +316,7 @@ class Y_Video_codec:
         row_qps = tuple(self._rc_row_qps(self.h_pixels // block_size)) if rc_on else ()
         key = (block_size, search_range, intra_dur, max_batch, self.device, self.h_pixels, self.w_pixels, self.nRefFrames,
                bool(self.FMEEnable), bool(self.fast_me), bool(self.VBSEnable), self.RCFlag or 0, self.ParallelMode,
-               float(self.lam or 0.0), int(self.intra_thresh or 0), row_qps, bool(self.sea_prune))
+               float(self.lam or 0.0), int(self.intra_thresh or 0), row_qps, self._sea_mode())
         if self._ctx is not None and self._ctx_key == key:
             self._ctx.set_qp(self.const_init_Qp)
             return self._ctx
@@ -322,7 +326,7 @@ class Y_Video_codec:
                                     qp=self.const_init_Qp, intra_dur=intra_dur, n_ref_frames=self.nRefFrames,
                                     fme=self.FMEEnable, fast_me=self.fast_me, vbs=self.VBSEnable, rc_flag=self.RCFlag or 0,
                                     parallel_mode=self.ParallelMode, lam=self.lam or 0.0, intra_thresh=self.intra_thresh or 0,
-                                    max_batch=max_batch, device=self.device, sea=bool(self.sea_prune))
+                                    max_batch=max_batch, device=self.device, sea=self._sea_mode())
         self._ctx_key = key
         if rc_on:
             self._ctx.set_row_qps(list(row_qps))

@@ -11,7 +11,7 @@ import os
 _LIB_NAME = "libstreamoptima_b200.so"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-SO_FLAG_FME, SO_FLAG_FAST_ME, SO_FLAG_VBS, SO_FLAG_SEA = 1, 2, 4, 8
+SO_FLAG_FME, SO_FLAG_FAST_ME, SO_FLAG_VBS, SO_FLAG_SEA, SO_FLAG_SEA_AUTO = 1, 2, 4, 8, 16
 SO_MAX_REF = 8
 
 
@@ -135,7 +135,7 @@ class Context:
         p = so_params(width=width, height=height, block_size=block_size, search_range=search_range, qp=qp,
                       intra_dur=intra_dur, n_ref_frames=n_ref_frames,
                       flags=(SO_FLAG_FME if fme else 0) | (SO_FLAG_FAST_ME if fast_me else 0) | (SO_FLAG_VBS if vbs else 0) |
-                      (SO_FLAG_SEA if sea else 0),
+                      (SO_FLAG_SEA if sea else 0) | (SO_FLAG_SEA_AUTO if sea == "auto" else 0),
                       rc_flag=rc_flag or 0, parallel_mode=parallel_mode, lam=float(lam or 0.0),
                       intra_thresh=int(intra_thresh or 0), max_batch=max_batch, reserved=0)
         self.params = p

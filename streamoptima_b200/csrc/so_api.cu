@@ -83,6 +83,13 @@ struct so_ctx {
     // successive elimination (so_me_sea.cuh, SO_FLAG_SEA): packed quadrant bytes [unit][slot][phase][H][W], last winners, counters
     uint32_t *sea_pq = nullptr, *sea_prev = nullptr;
     unsigned int* sea_ctr = nullptr;
+    // SO_FLAG_SEA_AUTO: mapped host words {exact SADs of the last finished pruned launch, its sequence number}, what the host
+    // has seen of them, candidates-per-launch bookkeeping and the number of frames the plain kernel still runs
+    unsigned int *sea_host = nullptr, *sea_host_dev = nullptr;
+    unsigned int sea_seq = 0, sea_seen = 0;
+    double sea_items[64] = {};
+    int sea_cooldown = 0, sea_skip = 2;     // the first pruned frames of a context start without predictors: not judged
+    double sea_avg = -1.0;                  // running average of exact SADs per (block, reference, phase plane)
     uint8_t* fm_table = nullptr;            // fast ME: per-block transition tables around the previous frame's predictors
     short4* fm_state = nullptr;             // fast ME: predictor (x, y, ref) every block used in the last P frame, [batch][nblk]
     int2 *fs_F = nullptr, *fs_entry = nullptr;   // fast ME scan: per-chunk composed transition functions / chunk entry predictors
@@ -200,6 +207,7 @@ extern "C" void so_ctx_destroy(so_ctx* c) {
     cudaFree(c->ring); cudaFree(c->me_parent); cudaFree(c->me_sub); cudaFree(c->in_parent); cudaFree(c->in_sub);
     cudaFree(c->res_frame); cudaFree(c->band);
     cudaFree(c->qp_rows_dev); cudaFree(c->qp_blocks_dev); cudaFree(c->me_work); cudaFree(c->sea_pq); cudaFree(c->sea_prev); cudaFree(c->sea_ctr);
+    if (c->sea_host) cudaFreeHost(c->sea_host);
     cudaFree(c->fm_table); cudaFree(c->fm_state);
     cudaFree(c->fs_F); cudaFree(c->fs_entry);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -530,6 +538,36 @@ static bool sea_enabled(const so_ctx* ctx) {
     return (ctx->p.flags & SO_FLAG_SEA) != 0;
 }
 
+// SO_FLAG_SEA_AUTO: pruning pays while the pruned launches take few exact SADs per (block, reference, phase plane).  The count of
+// the last FINISHED launch is read from mapped host memory without synchronising; when its running average exceeds the threshold
+// the plain kernel runs for the next SEA_COOLDOWN P frames, then pruning is probed again (the first probe frame starts from stale
+// predictors and is not judged).
+static bool sea_pays(so_ctx* ctx) {
+    if (!(ctx->p.flags & SO_FLAG_SEA_AUTO)) return true;
+    constexpr double SEA_MAX_PER_ITEM = 7.0, SEA_EMA = 0.2;
+    constexpr int SEA_COOLDOWN = 60;
+    if (ctx->sea_host) {
+        const unsigned int seq = reinterpret_cast<volatile unsigned int*>(ctx->sea_host)[1];
+        if (seq != ctx->sea_seen) {
+            const unsigned int evals = reinterpret_cast<volatile unsigned int*>(ctx->sea_host)[0];
+            ctx->sea_seen = seq;
+            const double items = ctx->sea_items[seq & 63u];
+            if (ctx->sea_skip > 0) --ctx->sea_skip;
+            else if (ctx->sea_cooldown == 0 && items > 0) {
+                // exponential average: one expensive frame (cold predictors after an I frame) does not switch the search
+                const double x = std::min(evals / items, 3.0 * SEA_MAX_PER_ITEM);
+                ctx->sea_avg = ctx->sea_avg < 0 ? x : (1.0 - SEA_EMA) * ctx->sea_avg + SEA_EMA * x;
+                if (ctx->sea_avg > SEA_MAX_PER_ITEM) ctx->sea_cooldown = SEA_COOLDOWN;
+            }
+        }
+    }
+    if (ctx->sea_cooldown > 0) {
+        if (--ctx->sea_cooldown == 0) ctx->sea_skip = 1;       // the probe frame that follows is not judged
+        return false;
+    }
+    return true;
+}
+
 static int run_sea(so_ctx* ctx, const MeRingArgs& a, const uint8_t* cur, size_t cur_stride, int unit0, int units, cudaStream_t st) {
     const FrameGeom& g = ctx->g;
     const int nph = a.nph;
@@ -540,6 +578,11 @@ static int run_sea(so_ctx* ctx, const MeRingArgs& a, const uint8_t* cur, size_t 
         CU(cudaMalloc(&ctx->sea_ctr, 256));
         CU(cudaMemsetAsync(ctx->sea_prev, 0xFF, nb * sizeof(uint32_t), st));
         CU(cudaMemsetAsync(ctx->sea_ctr, 0, 256, st));
+        if (ctx->p.flags & SO_FLAG_SEA_AUTO) {
+            CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->sea_host), 64, cudaHostAllocMapped));
+            ctx->sea_host[0] = ctx->sea_host[1] = 0u;
+            CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->sea_host_dev), ctx->sea_host, 0));
+        }
     }
     SeaArgs s{};
     s.g = a.g;
@@ -553,6 +596,9 @@ static int run_sea(so_ctx* ctx, const MeRingArgs& a, const uint8_t* cur, size_t 
     s.cur = cur + (size_t)unit0 * cur_stride; s.cur_unit_stride = cur_stride;
     s.out = a.out; s.out_unit_stride = a.out_unit_stride;
     s.prev = ctx->sea_prev; s.ctr = ctx->sea_ctr;
+    s.host_stat = ctx->sea_host_dev;
+    s.seq = ++ctx->sea_seq;
+    ctx->sea_items[s.seq & 63u] = (double)units * ctx->nblk * a.g.nref * nph;
     s.unit0 = unit0; s.units = units; s.nblk = ctx->nblk;
     // quadrant bytes of the references whose planes changed since they were last derived
     so_ctx::RingState& R = ctx->rs();
@@ -634,7 +680,7 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
         if (out_sub) e = launch_pdl(me_ring_kernel<true>, dim3(grid), dim3(384), MR_SMEM, st, map, cmap, a);
         else e = launch_pdl(me_ring_kernel<false>, dim3(grid), dim3(512), MR_SMEM, st, map, cmap, a);
     } else {
-        if (!out_sub && sea_enabled(ctx)) {
+        if (!out_sub && sea_enabled(ctx) && sea_pays(ctx)) {
             // successive elimination (so_me_sea.cuh): predictors -> bound filter -> exact SADs of the survivors, one kernel
             const int rc2 = run_sea(ctx, a, cur, cur_stride, unit0, units, st);
             if (rc2) return rc2;
@@ -655,6 +701,14 @@ static int run_me_ring(so_ctx* ctx, const uint8_t* cur, size_t cur_stride, int u
         }
     }
     if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && ctx->me_key_fmt == 2 && !out_sub && ctx->sea_prev && (ctx->p.flags & SO_FLAG_SEA_AUTO) && sea_enabled(ctx)) {
+        // the plain kernel ran in auto mode: keep the pruned search's predictors fresh for the next probe
+        SeaArgs sv{};
+        sv.g = a.g; sv.out = a.out; sv.out_unit_stride = a.out_unit_stride; sv.prev = ctx->sea_prev;
+        sv.unit0 = unit0; sv.units = units; sv.nblk = ctx->nblk;
+        e = launch_pdl(sea_save_kernel, dim3((ctx->nblk + 255) / 256, units), dim3(256), 0, st, sv);
+        ctx->launches++;
+    }
     ev_pair(ctx, ctx->ev_me, st, false);
     if (e != cudaSuccess) { set_err(ctx, std::string("me_ring_kernel: ") + cudaGetErrorString(e)); return SO_E_CUDA; }
     ctx->launches++;

@@ -39,7 +39,9 @@ struct SeaArgs {
     unsigned long long* out;           // packed keys of the first unit of the launch, stride of MeResult (16 B) per block
     size_t out_unit_stride;            // in MeResult elements
     uint32_t* prev;                    // [unit][nblk]: winner of the last P frame (ref << 16 | dx + R << 8 | dy + R), all ones = none
-    unsigned int* ctr;                 // [0..1] 64-bit count of exact SADs, [2] launches
+    unsigned int* ctr;                 // [0..1] 64-bit count of exact SADs, [2] launches, [6] finished CTAs / [7] exact SADs of this launch
+    unsigned int* host_stat;           // mapped host memory or null: {exact SADs of the last finished launch, its sequence number}
+    unsigned int seq;                  // sequence number of this launch
     int unit0, units, nph, nblk;
 };
 
@@ -381,5 +383,35 @@ __global__ void __launch_bounds__(256, SEA_MINB) sea_search_kernel(const SeaArgs
     if (tid == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(a.ctr), (unsigned long long)s_evals);
         if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&a.ctr[2], 1u);
+        if (a.host_stat) {
+            // the last CTA of the launch reports how many exact SADs the launch took: the host reads it without synchronising
+            // (a few frames late) and decides whether pruning pays on this content (SO_FLAG_SEA_AUTO)
+            atomicAdd(&a.ctr[7], s_evals);
+            __threadfence();
+            if (atomicAdd(&a.ctr[6], 1u) == gridDim.x * gridDim.y - 1u) {
+                const unsigned int v = atomicExch(&a.ctr[7], 0u);
+                a.ctr[6] = 0u;
+                *reinterpret_cast<volatile unsigned int*>(a.host_stat) = v;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(a.host_stat + 1) = a.seq;
+            }
+        }
     }
+}
+
+// SO_FLAG_SEA_AUTO while the plain kernel runs: keep the pruned search's predictors fresh (winners of the frame, read from the
+// compact keys of me_ring2_kernel -- me_get format 2) so that the next probe does not start cold.
+__global__ void __launch_bounds__(256) sea_save_kernel(const SeaArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    const int blk = blockIdx.x * 256 + threadIdx.x, u = blockIdx.y;
+    if (blk >= a.nblk) return;
+    const unsigned long long key = *reinterpret_cast<const unsigned long long*>(reinterpret_cast<const MeResult*>(a.out) + u * a.out_unit_stride + blk);
+    uint32_t pv = 0xFFFFFFFFu;
+    if (key != ~0ull) {
+        const uint32_t lo = (uint32_t)key;
+        const int l1 = (int)((lo >> 16) & 0xFFu), dxr = (int)((lo >> 1) & 0x7Fu), ady = l1 - abs(dxr - a.g.R);
+        pv = (((lo >> 8) & 0xFFu) << 16) | ((uint32_t)dxr << 8) | (uint32_t)(((lo & 1u) ? ady : -ady) + a.g.R);
+    }
+    a.prev[(size_t)(a.unit0 + u) * a.nblk + blk] = pv;
 }

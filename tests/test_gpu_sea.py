@@ -107,3 +107,17 @@ def test_per_frame_seam_two_units_one_frame_apart():
             s.push(unit, g["recon"][f])
     assert s.ctx.sea_stats()["p_frames"] > 0
     s.ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["translating", "zooming", "scene_cut"])
+def test_auto_mode_switches_between_the_two_searches_without_changing_the_output(kind):
+    """``sea_prune = "auto"`` (SO_FLAG_SEA_AUTO) runs the plain kernel while pruning does not pay: whatever it decides per frame,
+    the output is the plain search's."""
+    F, H, W = 48, 272, 640
+    frames = synth.make(kind, F=F, H=H, W=W, seed=17)
+    kw = dict(nRefFrames=2, FMEEnable=True)
+    a, _ = _encode(frames, False, intra_dur=16, **kw)
+    b, st = _encode(frames, "auto", intra_dur=16, **kw)
+    for k in KEYS:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert 0 < st["p_frames"] <= F - 3
