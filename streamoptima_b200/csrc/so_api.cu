@@ -87,7 +87,7 @@ struct so_ctx {
     // has seen of them, candidates-per-launch bookkeeping and the number of frames the plain kernel still runs
     unsigned int *sea_host = nullptr, *sea_host_dev = nullptr;
     unsigned int sea_seq = 0, sea_seen = 0;
-    double sea_items[64] = {};
+    double sea_items[1024] = {};            // candidates of the launches in flight (the host runs up to a sequence ahead), by sequence number
     int sea_cooldown = 0, sea_skip = 2;     // the first pruned frames of a context start without predictors: not judged
     double sea_avg = -1.0;                  // running average of exact SADs per (block, reference, phase plane)
     uint8_t* fm_table = nullptr;            // fast ME: per-block transition tables around the previous frame's predictors
@@ -551,7 +551,7 @@ static bool sea_pays(so_ctx* ctx) {
         if (seq != ctx->sea_seen) {
             const unsigned int evals = reinterpret_cast<volatile unsigned int*>(ctx->sea_host)[0];
             ctx->sea_seen = seq;
-            const double items = ctx->sea_items[seq & 63u];
+            const double items = ctx->sea_items[seq & 1023u];
             if (ctx->sea_skip > 0) --ctx->sea_skip;
             else if (ctx->sea_cooldown == 0 && items > 0) {
                 // exponential average: one expensive frame (cold predictors after an I frame) does not switch the search
@@ -598,7 +598,7 @@ static int run_sea(so_ctx* ctx, const MeRingArgs& a, const uint8_t* cur, size_t 
     s.prev = ctx->sea_prev; s.ctr = ctx->sea_ctr;
     s.host_stat = ctx->sea_host_dev;
     s.seq = ++ctx->sea_seq;
-    ctx->sea_items[s.seq & 63u] = (double)units * ctx->nblk * a.g.nref * nph;
+    ctx->sea_items[s.seq & 1023u] = (double)units * ctx->nblk * a.g.nref * nph;
     s.unit0 = unit0; s.units = units; s.nblk = ctx->nblk;
     // quadrant bytes of the references whose planes changed since they were last derived
     so_ctx::RingState& R = ctx->rs();
